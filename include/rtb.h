@@ -1,0 +1,262 @@
+/*
+ * rtb.h — C ABI of librtb.so, the B200 (sm_100a) replacement for the reference's
+ * per-pixel sample job.
+ *
+ * What it replaces (paths relative to /root/reference/RaytracingInOneWeekend/Assets/Scripts):
+ *   Runtime/Jobs/SampleBatchJob.cs:17-164   struct SampleBatchJob : IJobParallelFor   (the job)
+ *   Unity/Raytracer.cs:671-736              the host fills the job's fields and schedules it
+ * The reference has no FFI for this path (it is a Burst job).  Its only native-call
+ * precedent — and the style this header follows — is the denoiser binding:
+ *   Assets/ThirdParty/nVidia OptiX Denoiser/OptixApi.cs:154-251   [DllImport] externs on IntPtr handles
+ *   OptixDenoiser/OptixDenoiser/OptixDenoiser.h:1-10              extern "C" exports returning an int code
+ *   Runtime/Jobs/DenoiseJobs.cs:10-39                             a non-Burst IJob making the blocking call
+ * The P/Invoke stub a maintainer would add is in INTEGRATION.md and
+ * raytracing-in-one-weekend_b200/bindings/B200PathTracerApi.cs.
+ *
+ * Conventions: every call returns 0 on success or an rtb_status code; never throws,
+ * never aborts.  Only PODs and plain pointers cross the boundary.  One call in flight
+ * per context (the host serialises batches through job dependencies,
+ * Raytracer.cs:809-811); callable from any thread.  Host pointers are borrowed for
+ * the duration of the call only (DenoiseJobs.cs:26-37 precedent).
+ *
+ * Pixel layout is the reference's: index = row * W + col, row 0 = bottom
+ * (SampleBatchJob.cs:64-67).  float3 arrays are packed 12-byte elements.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RTB_API __declspec(dllexport)
+#else
+#define RTB_API __attribute__((visibility("default")))
+#endif
+
+#define RTB_ABI_VERSION 1
+
+typedef enum rtb_status {
+  RTB_OK = 0,
+  RTB_ERR_INVALID_ARGUMENT = 1,
+  RTB_ERR_NO_SCENE = 2,
+  RTB_ERR_CANCELLED = 3,        /* the cancellation token was set; outputs unspecified (SampleBatchJob.cs:61) */
+  RTB_ERR_UNSUPPORTED = 4,      /* entity/material/sky type outside the supported hot path */
+  RTB_ERR_OUT_OF_MEMORY = 5,
+  RTB_ERR_CUDA = 100            /* 100 + cudaError_t */
+} rtb_status;
+
+/* ---- scene (uploaded once per world change; Raytracer.cs:1167-1183) ------------------- */
+
+/* Entity of EntityType.Sphere (Entity.cs:13-20, EntityTypes/Sphere.cs:6-24) with a static
+ * rigid transform.  `radius` may be NEGATIVE: the intersection uses radius^2 and the normal
+ * is point/radius, so a negative radius flips the normal (hollow glass; HitTests.cs:43).
+ * The reference keeps a quaternion per entity; a sphere is rotation-invariant, so the
+ * host's flattener passes only the translation (Entity.OriginTransform.pos). */
+typedef struct rtb_sphere {
+  float center[3];
+  float radius;
+  uint32_t material;            /* index into the material array (Entity.Material - materialBuffer.ptr) */
+  uint32_t reserved[3];
+} rtb_sphere;                   /* 32 bytes */
+
+typedef enum rtb_material_type {     /* Material.cs:9-14 */
+  RTB_MATERIAL_STANDARD = 0,
+  RTB_MATERIAL_DIELECTRIC = 1,
+  RTB_MATERIAL_PROBABILISTIC_VOLUME = 2   /* not on the hot path: rtb_upload_scene returns RTB_ERR_UNSUPPORTED */
+} rtb_material_type;
+
+/* Material with constant textures only (Material.cs:16-26, Texture.cs:50-59,101-108:
+ * TextureType.Constant / ConstantScalar).  "Lambertian" = STANDARD{metallic 0, glossiness 0};
+ * "Metal(fuzz)" = STANDARD{metallic 1, glossiness 1-fuzz}; glass = DIELECTRIC{glossiness 1}. */
+typedef struct rtb_material {
+  uint32_t type;                /* rtb_material_type */
+  float albedo[3];              /* Albedo.MainColor */
+  float emission[3];            /* Emission.MainColor */
+  float glossiness;             /* Glossiness scalar */
+  float metallic;               /* Metallic scalar */
+  float index_of_refraction;    /* Material.parameter (Dielectric) */
+  uint32_t reserved[2];
+} rtb_material;                 /* 48 bytes */
+
+/* Flattened BvhNode (BvhNode.cs:5-22): pointers become indices into the node array
+ * (root = node 0, the order BuildRuntimeBvhJob.cs:18-39 produces) and into the sphere array
+ * (the reference's leaves point into a contiguous BVH-ordered entity copy,
+ * BvhNodeData.cs:157-160).  Leaf iff first_entity >= 0 (BvhNode.IsLeaf: EntitiesStart != null). */
+typedef struct rtb_bvh_node {
+  float bounds_min[3];
+  float bounds_max[3];
+  int32_t left;                 /* node index or -1 */
+  int32_t right;                /* node index or -1 */
+  int32_t first_entity;         /* sphere index or -1 for inner nodes */
+  int32_t entity_count;
+} rtb_bvh_node;                 /* 40 bytes */
+
+/* ---- per-batch uniforms (the public fields of SampleBatchJob, SampleBatchJob.cs:23-39) - */
+
+typedef struct rtb_view {       /* View.cs:8-14, 88 bytes */
+  float origin[3];
+  float lower_left_corner[3];
+  float horizontal[3];
+  float vertical[3];
+  float forward[3];
+  float up[3];
+  float right[3];
+  float lens_radius;
+} rtb_view;
+
+typedef enum rtb_sky_type {     /* Environment.cs:5-10 */
+  RTB_SKY_NONE = 0,
+  RTB_SKY_GRADIENT = 1,
+  RTB_SKY_CUBEMAP = 2           /* not on the hot path: RTB_ERR_UNSUPPORTED */
+} rtb_sky_type;
+
+typedef struct rtb_environment {/* Environment.cs:12-18 */
+  uint32_t sky_type;
+  float sky_bottom_color[3];
+  float sky_top_color[3];
+} rtb_environment;
+
+typedef struct rtb_batch_params {
+  float size[2];                        /* Size (float2: W, H) */
+  int32_t slice_offset;                 /* SliceOffset */
+  int32_t slice_divider;                /* SliceDivider (>= 1); rows with row % divider != offset are skipped */
+  uint32_t seed;                        /* Seed (frameSeed, Raytracer.cs:660) — the Philox key */
+  rtb_view view;                        /* View */
+  rtb_environment environment;          /* Environment */
+  uint32_t sample_count_range[2];       /* SampleCountRange */
+  int32_t trace_depth;                  /* TraceDepth (1..500, Raytracer.cs:90) */
+  uint32_t sub_pixel_jitter;            /* SubPixelJitter (bool) */
+  float sample_count_weight_extrema[2]; /* SampleCountWeightExtrema */
+  /* Extension (not a SampleBatchJob field): restrict the batch to rows [row_begin, row_end).
+   * Both 0 = all rows.  Used for row-tile sharding across GPUs; composes with the slice test. */
+  int32_t row_begin;
+  int32_t row_end;
+} rtb_batch_params;
+
+/* Diagnostics under FULL_DIAGNOSTICS (Raytracer.cs:54-64; the define is on in
+ * ProjectSettings.asset:590).  ray_count matches the reference exactly (one per bounce-loop
+ * iteration, SampleBatchJob.cs:203).  bounds_hit_count / candidate_count are what THIS
+ * traversal executed (a pruned closest-hit walk visits fewer nodes than the reference's
+ * collect-all walk, SampleBatchJob.cs:420-447). */
+typedef struct rtb_diagnostics {
+  float ray_count;
+  float bounds_hit_count;
+  float candidate_count;
+  float sample_count_weight;
+} rtb_diagnostics;
+
+/* The accumulation buffers of one batch (SampleBatchJob.cs:41-51).  All eight point to
+ * W*H elements.  `diagnostics` may be NULL.  in_* and out_* may not alias (the reference
+ * ping-pongs two sets, Raytracer.cs:798-802). */
+typedef struct rtb_batch_buffers {
+  const float* in_color;                /* float4: xyz = sum of radiance, w = #successful samples */
+  const float* in_sample_count_weight;  /* float */
+  const float* in_normal;               /* float3 */
+  const float* in_albedo;               /* float3 */
+  float* out_color;                     /* float4 */
+  float* out_sample_count_weight;       /* float */
+  float* out_normal;                    /* float3 */
+  float* out_albedo;                    /* float3 */
+  rtb_diagnostics* out_diagnostics;     /* may be NULL */
+} rtb_batch_buffers;
+
+typedef struct rtb_ctx rtb_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+RTB_API int rtb_abi_version(void);
+/* Creates a context bound to CUDA device `device`.  Fails with RTB_ERR_CUDA+code when no
+ * sm_100 device/driver is present: there is no CPU fallback. */
+RTB_API int rtb_create(int device, rtb_ctx** out_ctx);
+RTB_API int rtb_destroy(rtb_ctx* ctx);
+/* Last error text of this context (or of the calling thread when ctx is NULL). */
+RTB_API const char* rtb_last_error(const rtb_ctx* ctx);
+typedef void (*rtb_log_fn)(int level, const char* message, void* user);
+RTB_API int rtb_set_log_callback(rtb_ctx* ctx, rtb_log_fn fn, void* user);
+
+/* ---- scene ----------------------------------------------------------------------------- */
+/* Copies the flattened world to the device (replaces BvhRoot + the pointer graph behind it,
+ * SampleBatchJob.cs:34).  The host may free its arrays on return. */
+RTB_API int rtb_upload_scene(rtb_ctx* ctx,
+                             const rtb_sphere* spheres, size_t sphere_count,
+                             const rtb_material* materials, size_t material_count,
+                             const rtb_bvh_node* nodes, size_t node_count);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* Replaces `sampleBatchJob.Schedule(W*H, 1, dep).Complete()` (Raytracer.cs:730-736) with HOST
+ * buffers: uploads the four input accumulators, runs the megakernel, downloads the four
+ * outputs (+diagnostics), returns when the out_* arrays are fully written.
+ * `cancel` (may be NULL) is the CancellationToken (SampleBatchJob.cs:23,61): polled between
+ * kernel chunks; when set the call returns RTB_ERR_CANCELLED promptly. */
+RTB_API int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params,
+                             const rtb_batch_buffers* host_buffers,
+                             const volatile uint8_t* cancel);
+
+/* Same batch on DEVICE-resident buffers, enqueued on `cuda_stream` (a cudaStream_t passed as
+ * void*; NULL = the context's own stream) without synchronising: the caller owns the
+ * buffers and the stream (used for multi-batch accumulation that never leaves HBM, and for
+ * row-tile sharding where each rank renders into its slice of a gather buffer). */
+RTB_API int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params,
+                                    const rtb_batch_buffers* device_buffers,
+                                    void* cuda_stream);
+
+/* Optional: pin (cudaHostRegister) the host's pooled accumulation arrays so that
+ * rtb_sample_batch copies at full PCIe rate; the same 8 pointers recur every batch
+ * (Raytracer.cs:279-303 pools). */
+RTB_API int rtb_register_host_buffer(rtb_ctx* ctx, void* ptr, size_t bytes);
+RTB_API int rtb_unregister_host_buffer(rtb_ctx* ctx, void* ptr);
+
+/* ---- adjacent jobs, device-side ("next" rows f1/f2 of SURVEY.md §8) --------------------- */
+/* CombineJob (CombineJob.cs:29-71): rgb = color.xyz / (int)color.w with the interlace
+ * look-around, NaN -> 0, albedo / max(n,1), normalizesafe(normal / max(n,1)).
+ * Device pointers; out_* are float3 arrays; any out may be NULL. */
+RTB_API int rtb_combine_device(rtb_ctx* ctx, int width, int height, int debug_mode, int ldr_albedo,
+                               const float* color4, const float* normal3, const float* albedo3,
+                               float* out_color3, float* out_normal3, float* out_albedo3,
+                               void* cuda_stream);
+
+/* ReduceMetricsJob (ReduceMetricsJob.cs:22-45) on device buffers. */
+typedef struct rtb_metrics {
+  int64_t total_ray_count;
+  int64_t total_samples;
+  float sample_count_weight_min, sample_count_weight_max;
+  int32_t sample_count_min, sample_count_max;
+} rtb_metrics;
+RTB_API int rtb_reduce_metrics_device(rtb_ctx* ctx, int width, int height,
+                                      const rtb_diagnostics* diagnostics, const float* color4,
+                                      const float* sample_count_weight, rtb_metrics* out_host,
+                                      void* cuda_stream);
+
+/* ---- measurement ----------------------------------------------------------------------- */
+/* Work counters of the last rtb_sample_batch*_ call made with counters enabled
+ * (rtb_set_option(ctx, RTB_OPT_COUNTERS, 1) selects the instrumented kernel build). */
+typedef struct rtb_counters {
+  uint64_t samples;             /* camera paths attempted */
+  uint64_t rays;                /* bounce-loop iterations (== sum of ray_count) */
+  uint64_t node_tests;          /* AABB slab tests executed */
+  uint64_t sphere_tests;        /* ray-sphere quadratics executed */
+  uint64_t shade_standard;      /* Standard scatter evaluations */
+  uint64_t shade_dielectric;    /* Dielectric scatter evaluations */
+  uint64_t sky_hits;            /* paths terminated by the sky */
+  uint64_t failed_samples;      /* depth == TraceDepth (SampleBatchJob.cs:379-381) */
+} rtb_counters;
+RTB_API int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out);
+
+typedef enum rtb_option {
+  RTB_OPT_COUNTERS = 1,         /* 0/1: run the instrumented kernel (slower) */
+  RTB_OPT_KERNEL = 2,           /* 0 = auto, 1 = simple (thread per pixel), 2 = persistent megakernel */
+  RTB_OPT_CANCEL_CHUNK_ROWS = 3 /* rows per launch when a cancel token is passed (0 = auto) */
+} rtb_option;
+RTB_API int rtb_set_option(rtb_ctx* ctx, int option, int64_t value);
+/* Milliseconds of the last kernel launch sequence on the context stream (CUDA events; the
+ * same bracket as the two RecordTimeJobs, Raytracer.cs:729-738).  Valid after a synchronising call. */
+RTB_API int rtb_last_kernel_ms(rtb_ctx* ctx, float* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */

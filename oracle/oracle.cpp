@@ -1,0 +1,695 @@
+// oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT.
+//
+// CPU restatement of the reference's per-pixel sample job, structured like the C# it
+// follows (collect all BVH candidates -> intersect all -> sort -> take the nearest;
+// emission/attenuation stacks unwound tail->head; failed samples dropped).  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+// it; nothing under raytracing-in-one-weekend_b200/ includes, links or calls it.
+//
+// PARITY UNPINNED: the reference has no tests, golden vectors or fixtures for this path
+//  and its Unity/Burst C# cannot be compiled or run in this image, so
+// this restatement is pinned only by our own known-answer tests (tests/test_oracle_kat.py:
+// Unity xorshift32 stream, Philox4x32-10 Random123 vectors, closed-form intersection and
+// shading cases, scene/BVH counts) — not by outputs of the reference itself.
+//
+// Paths below are relative to /root/reference/RaytracingInOneWeekend/Assets/Scripts.
+// Library math (Unity.Mathematics) comes from include/rtb/umath.h; everything else in
+// this file restates the reference's own code.  Float contraction: FMAs appear only
+// inside um:: functions and at the three places marked [FMA] (Burst FloatMode.Fast,
+// SampleBatchJob.cs:16, permits any contraction; we fix one).
+//
+// Build: oracle/Makefile (strict: -O2 -ffp-contract=off; fast: -O3 unsafe-math for timing).
+
+#include "rtb.h"
+#include "rtb/umath.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+using um::f3;
+
+namespace {
+
+// ======================================================================================
+// RNG
+// ======================================================================================
+
+// Unity.Mathematics.Random (package not vendored).
+struct UnityRandom {
+  uint32_t state;
+  void init(uint32_t seed) { state = seed; next_state(); }
+  uint32_t next_state() {
+    uint32_t t = state;
+    state ^= state << 13;
+    state ^= state >> 17;
+    state ^= state << 5;
+    return t;
+  }
+};
+
+// Philox4x32-10 (Salmon et al., SC'11), written from the paper's round function.
+void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Random-draw slots.  The reference's white-noise stream is sequential per pixel
+// (SampleBatchJob.cs:91), so data-dependent draws shift every later draw; the Philox
+// replacement (BASELINE.json north_star) gives each draw site a fixed slot so a skipped
+// draw does not move the others.
+//   camera  (bounce word 0xFFFFFFFF): block 0 = {jitter.x, jitter.y, lens theta, lens radius}, block 1 = {time}
+//   bounce d (bounce word d):         block 0 = {rough-normal / random-direction u, v, reflect-or-Schlick test, metal test}
+//                                     block 1 = {diffuse direction u, v}
+enum Slot {
+  SLOT_JITTER = 0,       // 2 floats: block 0 [0,1]
+  SLOT_LENS = 2,         // 2 floats: block 0 [2,3]
+  SLOT_TIME = 4,         // 1 float : block 1 [0]
+  SLOT_ROUGH = 0,        // 2 floats: block 0 [0,1]   (Material.cs:83 / :124)
+  SLOT_REFLECT = 2,      // 1 float : block 0 [2]     (Material.cs:91 / :143)
+  SLOT_METAL = 3,        // 1 float : block 0 [3]     (Material.cs:99)
+  SLOT_DIFFUSE = 4       // 2 floats: block 1 [0,1]   (Material.cs:107)
+};
+constexpr uint32_t BOUNCE_CAMERA = 0xFFFFFFFFu;
+constexpr uint32_t PHILOX_KEY1 = 0x52544232u;  // "RTB2"
+
+enum NoiseMode { NOISE_WHITE_XORSHIFT = 0, NOISE_PHILOX = 1 };
+
+// RandomSource.cs:15-151 (White case).  Every draw site passes its slot; the xorshift
+// mode ignores it and consumes the stream in call order exactly like the reference.
+struct RandomSource {
+  int mode = NOISE_WHITE_XORSHIFT;
+  UnityRandom white{};
+  uint32_t key[2] = {0, 0};
+  uint32_t pixel = 0, sample = 0, bounce = 0;
+  uint32_t cached_block_id = 0xFFFFFFFFu, cached_bounce = 0, cached_sample = 0;
+  uint32_t cached[4] = {0, 0, 0, 0};
+  float random_events = 0;  // RandomSource.cs:33-37
+
+  static float to_float(uint32_t u) { return um::asfloat(0x3f800000u | (u >> 9)) - 1.0f; }
+
+  uint32_t raw(int slot) {
+    if (mode == NOISE_WHITE_XORSHIFT) return white.next_state();
+    uint32_t block = (uint32_t)slot >> 2;
+    if (block != cached_block_id || bounce != cached_bounce || sample != cached_sample) {
+      uint32_t ctr[4] = {pixel, sample, bounce, block};
+      philox4x32_10(ctr, key, cached);
+      cached_block_id = block; cached_bounce = bounce; cached_sample = sample;
+    }
+    return cached[slot & 3];
+  }
+  float NextFloat(int slot) { return to_float(raw(slot)); }
+  void NextFloat2(int slot, float* x, float* y) { *x = to_float(raw(slot)); *y = to_float(raw(slot + 1)); }
+
+  // RandomSource.cs:40-61
+  void InUnitDisk(float* x, float* y) {
+    float theta = NextFloat(SLOT_LENS) * (2 * um::PI - 0) + 0;   // whiteNoise.NextFloat(0, 2 * PI)
+    float radius = um::sqrt(NextFloat(SLOT_LENS + 1));
+    float s, c;
+    um::sincos(theta, &s, &c);
+    *x = radius * c;
+    *y = radius * s;
+  }
+  f3 OnCosineWeightedHemisphere(f3 normal, int slot);
+  // RandomSource.cs:113-128
+  f3 NextFloat3Direction(int slot) {
+    float rx, ry;
+    NextFloat2(slot, &rx, &ry);
+    float z = rx * 2.0f - 1.0f;
+    float r = um::sqrt(um::max(1.0f - z * z, 0.0f));
+    float angle = ry * um::PI * 2.0f;
+    float s, c;
+    um::sincos(angle, &s, &c);
+    return um::mk(c * r, s * r, z);
+  }
+};
+
+// Tools.GetOrthonormalBasis (Util/Tools.cs:19-28)
+void GetOrthonormalBasis(f3 normal, f3* tangent, f3* bitangent) {
+  float s = normal.z >= 0 ? 1.0f : -1.0f;
+  float a = um::div(-1.0f, s + normal.z);
+  float b = normal.x * normal.y * a;
+  *tangent = um::mk(1 + s * normal.x * normal.x * a, s * b, -s * normal.x);
+  *bitangent = um::mk(b, s + normal.y * normal.y * a, -normal.y);
+}
+// Tools.TangentToWorldSpace (Util/Tools.cs:30-37)
+f3 TangentToWorldSpace(f3 v, f3 normal) {
+  f3 tangent, bitangent;
+  GetOrthonormalBasis(normal, &tangent, &bitangent);
+  return um::normalize(um::mul_cols(tangent, normal, bitangent, v));
+}
+// RandomSource.cs:63-89
+f3 RandomSource::OnCosineWeightedHemisphere(f3 normal, int slot) {
+  float ux, uy;
+  NextFloat2(slot, &ux, &uy);
+  float u = ux;
+  float radius = um::sqrt(u);
+  float theta = uy * 2 * um::PI;
+  float s, c;
+  um::sincos(theta, &s, &c);
+  f3 tangentSpaceDirection = um::mk(radius * c, um::sqrt(1 - u), radius * s);
+  return TangentToWorldSpace(tangentSpaceDirection, normal);
+}
+
+// ======================================================================================
+// Runtime structs
+// ======================================================================================
+
+struct Ray {  // Ray.cs
+  f3 Origin, Direction;
+  float Time;
+  Ray OffsetTowards(f3 normal) const { return Ray{um::mad(normal, 0.001f, Origin), Direction, Time}; }  // [FMA] Ray.cs:18
+  f3 GetPoint(float t) const { return um::mad(Direction, t, Origin); }                                     // [FMA] Ray.cs:20
+};
+
+struct HitRecord {  // HitRecord.cs
+  float Distance;
+  f3 Point, Normal;
+  int Entity;  // index instead of Entity*
+};
+
+struct Scene {
+  const rtb_sphere* spheres; size_t sphere_count;
+  const rtb_material* materials; size_t material_count;
+  const rtb_bvh_node* nodes; size_t node_count;
+  std::vector<um::rigid> origin_transform, inverse_transform;  // Entity.OriginTransform / InverseTransform
+};
+
+// HitTests.Hit(this AxisAlignedBoundingBox) (HitTests.cs:9-21)
+bool AabbHit(const rtb_bvh_node& n, f3 rayOrigin, f3 rayInvDirection) {
+  f3 mn = um::mk(n.bounds_min[0], n.bounds_min[1], n.bounds_min[2]);
+  f3 mx = um::mk(n.bounds_max[0], n.bounds_max[1], n.bounds_max[2]);
+  f3 t0 = (mn - rayOrigin) * rayInvDirection;
+  f3 t1 = (mx - rayOrigin) * rayInvDirection;
+  float tMin = um::max(0.0f, um::cmax(um::min(t0, t1)));
+  float tMax = um::cmin(um::max(t0, t1));
+  return tMin < tMax;
+}
+
+// HitTests.Hit(this Sphere) (HitTests.cs:23-60), in entity space
+bool SphereHit(float radius, const Ray& r, float tMin, float tMax, float* distance, f3* normal) {
+  float squaredRadius = radius * radius;  // Sphere ctor, Sphere.cs:10-14
+  f3 oc = r.Origin;
+  float a = um::dot(r.Direction, r.Direction);
+  float b = um::dot(oc, r.Direction);
+  float c = um::dot(oc, oc) - squaredRadius;
+  float discriminant = um::fma(b, b, -(a * c));  // [FMA] b*b - a*c
+  if (discriminant > 0) {
+    float sqrtDiscriminant = um::sqrt(discriminant);
+    float t = um::div(-b - sqrtDiscriminant, a);
+    if (t < tMax && t > tMin) {
+      *distance = t;
+      *normal = r.GetPoint(t) / radius;
+      return true;
+    }
+    t = um::div(-b + sqrtDiscriminant, a);
+    if (t < tMax && t > tMin) {
+      *distance = t;
+      *normal = r.GetPoint(t) / radius;
+      return true;
+    }
+  }
+  *distance = 0;
+  *normal = um::mk(0.0f);
+  return false;
+}
+
+// Entity.Hit -> HitInternal -> HitContent (Entity.cs:57-122), static sphere entity
+bool EntityHit(const Scene& sc, int entity, const Ray& ray, float tMin, float tMax, HitRecord* rec) {
+  const um::rigid& transformAtTime = sc.origin_transform[entity];
+  const um::rigid& inverseTransform = sc.inverse_transform[entity];
+  Ray entitySpaceRay{um::transform(inverseTransform, ray.Origin), um::rotate(inverseTransform.rot, ray.Direction), 0};
+  float distance;
+  f3 entityLocalNormal;
+  if (!SphereHit(sc.spheres[entity].radius, entitySpaceRay, tMin, tMax, &distance, &entityLocalNormal)) return false;
+  rec->Distance = distance;
+  rec->Point = ray.GetPoint(distance);
+  rec->Normal = um::normalize(um::rotate(transformAtTime.rot, entityLocalNormal));
+  rec->Entity = entity;
+  return true;
+}
+
+// ======================================================================================
+// Material (Material.cs, Microfacet.cs)
+// ======================================================================================
+
+float Schlick(float cosine, float refractiveIndex) {  // Material.cs:212-217
+  float r0 = um::div(1 - refractiveIndex, 1 + refractiveIndex);
+  r0 *= r0;
+  return r0 + (1 - r0) * um::pow5(1 - cosine);
+}
+bool Refract(f3 v, f3 n, float niOverNt, f3* refracted) {  // Material.cs:198-210
+  float dt = um::dot(v, n);
+  float discriminant = 1 - niOverNt * niOverNt * (1 - dt * dt);
+  if (discriminant > 0) {
+    *refracted = niOverNt * (v - n * dt) - n * um::sqrt(discriminant);
+    return true;
+  }
+  *refracted = um::mk(0.0f);
+  return false;
+}
+float RoughnessToAlpha(float roughness) {  // Microfacet.cs:71-80
+  roughness = um::max(roughness, 1e-3f);
+  float x = um::log(roughness);
+  return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+float Lambda(f3 w, f3 normal, float roughness) {  // Microfacet.cs:53-69
+  float cosTheta = um::dot(normal, w);
+  float sqCosTheta = cosTheta * cosTheta;
+  float sqSinTheta = um::max(0.0f, 1 - sqCosTheta);
+  float sinTheta = um::sqrt(sqSinTheta);
+  float tanTheta = um::div(sinTheta, cosTheta);
+  float absTanTheta = um::abs(tanTheta);
+  if (um::isinf(absTanTheta)) return 0;
+  float alpha = RoughnessToAlpha(roughness);
+  float alpha2Tan2Theta = (alpha * absTanTheta) * (alpha * absTanTheta);
+  return um::div(-1 + um::sqrt(1 + alpha2Tan2Theta), 2.0f);
+}
+float SmithMaskingShadowing(f3 w, f3 normal, float roughness) {  // Microfacet.cs:9-12
+  return um::div(1.0f, 1 + Lambda(w, normal, roughness));
+}
+
+bool AlmostEquals1(float v) { return um::abs(1.0f - v) < 1e-6f; }  // MathExtensions.cs:23-27
+bool IsPerfectSpecular(const rtb_material& m) {                    // Material.cs:181-196
+  switch (m.type) {
+    case RTB_MATERIAL_DIELECTRIC: return true;
+    case RTB_MATERIAL_STANDARD: return AlmostEquals1(m.metallic) && AlmostEquals1(m.glossiness);
+  }
+  return false;
+}
+
+// Material.Scatter (Material.cs:67-173), Standard and Dielectric; constant textures
+// (Texture.cs:50-59,101-108).
+void Scatter(const rtb_material& m, const Ray& ray, const HitRecord& rec, RandomSource& rng,
+             f3* reflectance, Ray* scattered) {
+  *reflectance = um::mk(m.albedo[0], m.albedo[1], m.albedo[2]);
+  switch (m.type) {
+    case RTB_MATERIAL_STANDARD: {
+      float metallic = m.metallic;
+      float glossiness = m.glossiness;
+      float roughness = um::pow2(1 - glossiness);
+      f3 roughNormal = roughness > 0
+          ? um::normalize(um::lerp(rec.Normal, rng.OnCosineWeightedHemisphere(rec.Normal, SLOT_ROUGH), roughness))
+          : rec.Normal;
+      float incidentCosine = -um::dot(ray.Direction, roughNormal);
+      float ior = um::lerp(1.5f, 1.1f, metallic);  // PlasticIor, MetalIor (Material.cs:18-19)
+      float fresnel = Schlick(incidentCosine, ior);
+      float maskingShadowing = SmithMaskingShadowing(ray.Direction, rec.Normal, roughness);
+      float reflectionChance = um::saturate(fresnel * glossiness * maskingShadowing);
+
+      if (reflectionChance > 0 && rng.NextFloat(SLOT_REFLECT) < reflectionChance) {
+        *scattered = Ray{rec.Point, um::reflect(ray.Direction, roughNormal), ray.Time};
+        *reflectance = um::mk(1.0f);
+      } else {
+        if (metallic > 0 && rng.NextFloat(SLOT_METAL) < metallic) {
+          *scattered = Ray{rec.Point, um::reflect(ray.Direction, roughNormal), ray.Time};
+        } else {
+          *scattered = Ray{rec.Point, rng.OnCosineWeightedHemisphere(rec.Normal, SLOT_DIFFUSE), ray.Time};
+        }
+      }
+      if (reflectionChance > 0 && reflectionChance < 1) rng.random_events++;
+      if (metallic > 0 && metallic < 1) rng.random_events++;
+      rng.random_events += roughness * (reflectionChance + (1 - reflectionChance) * metallic);
+      rng.random_events += (1 - reflectionChance) * (1 - metallic);
+      break;
+    }
+    case RTB_MATERIAL_DIELECTRIC: {
+      float roughness = 1 - m.glossiness;
+      f3 roughNormal = um::normalize(rec.Normal + roughness * rng.NextFloat3Direction(SLOT_ROUGH));
+      float niOverNt, cosine;
+      f3 outwardRoughNormal;
+      float ddn = um::dot(ray.Direction, roughNormal);
+      if (ddn > 0) {
+        outwardRoughNormal = -roughNormal;
+        niOverNt = m.index_of_refraction;
+        cosine = m.index_of_refraction * ddn;
+      } else {
+        outwardRoughNormal = roughNormal;
+        niOverNt = um::div(1.0f, m.index_of_refraction);
+        cosine = -ddn;
+      }
+      f3 scatterDirection, refracted;
+      if (Refract(ray.Direction, outwardRoughNormal, niOverNt, &refracted) &&
+          rng.NextFloat(SLOT_REFLECT) > Schlick(cosine, m.index_of_refraction)) {
+        scatterDirection = refracted;
+      } else {
+        scatterDirection = um::reflect(ray.Direction, roughNormal);
+        *reflectance = um::mk(1.0f);
+      }
+      *scattered = Ray{rec.Point, scatterDirection, ray.Time};
+      rng.random_events++;
+      rng.random_events += roughness;
+      break;
+    }
+    default:
+      *scattered = ray;
+      break;
+  }
+}
+
+// ======================================================================================
+// View (View.cs:38-48)
+// ======================================================================================
+f3 v3(const float* p) { return um::mk(p[0], p[1], p[2]); }
+
+Ray GetRay(const rtb_view& v, float nx, float ny, RandomSource& rng) {
+  float rdx = 0, rdy = 0;
+  if (v.lens_radius != 0) {
+    rng.InUnitDisk(&rdx, &rdy);
+    rdx = v.lens_radius * rdx;
+    rdy = v.lens_radius * rdy;
+  }
+  f3 offset = v3(v.right) * rdx + v3(v.up) * rdy;
+  f3 dir = um::normalize(v3(v.lower_left_corner) - offset + nx * v3(v.horizontal) + ny * v3(v.vertical));
+  return Ray{v3(v.origin) + offset, dir, rng.NextFloat(SLOT_TIME)};
+}
+
+// ======================================================================================
+// SampleBatchJob
+// ======================================================================================
+
+struct Job {
+  const rtb_batch_params* p;
+  const Scene* scene;
+  const rtb_batch_buffers* buf;
+  int noise;
+};
+
+struct Work {  // the stackalloc'd buffers of Execute (SampleBatchJob.cs:103-113); vectors grow like Hybrid* collections
+  std::vector<f3> emission, attenuation;
+  std::vector<int> node_stack, candidates;
+  std::vector<HitRecord> hits;
+};
+
+// SampleBatchJob.FindHitCandidates (:403-448)
+void FindHitCandidates(const Scene& sc, const Ray& ray, Work& w, rtb_diagnostics& diag) {
+  f3 rayInvDirection = um::rcp(ray.Direction);
+  rayInvDirection = um::mk(um::isnan(rayInvDirection.x) ? um::INF : rayInvDirection.x,
+                           um::isnan(rayInvDirection.y) ? um::INF : rayInvDirection.y,
+                           um::isnan(rayInvDirection.z) ? um::INF : rayInvDirection.z);
+  w.node_stack.clear();
+  w.candidates.clear();
+  if (sc.node_count == 0) return;
+  w.node_stack.push_back(0);
+  while (!w.node_stack.empty()) {
+    int ni = w.node_stack.back();
+    w.node_stack.pop_back();
+    const rtb_bvh_node& node = sc.nodes[ni];
+    if (!AabbHit(node, ray.Origin, rayInvDirection)) continue;
+    diag.bounds_hit_count++;
+    if (node.first_entity >= 0) {
+      for (int i = 0; i < node.entity_count; i++) w.candidates.push_back(node.first_entity + i);
+      diag.candidate_count += node.entity_count;
+    } else {
+      w.node_stack.push_back(node.left);
+      w.node_stack.push_back(node.right);
+    }
+  }
+}
+
+// SampleBatchJob.FindHits (:450-475)
+void FindHits(const Scene& sc, const Ray& ray, Work& w) {
+  w.hits.clear();
+  while (!w.candidates.empty()) {
+    int e = w.candidates.back();
+    w.candidates.pop_back();
+    HitRecord rec;
+    if (EntityHit(sc, e, ray, 0, um::INF, &rec)) w.hits.push_back(rec);
+  }
+  if (!w.hits.empty())
+    std::stable_sort(w.hits.begin(), w.hits.end(),
+                     [](const HitRecord& a, const HitRecord& b) { return a.Distance < b.Distance; });
+}
+
+// SampleBatchJob.Sample (:166-401).  The ProbabilisticVolume branches (:194-201, :212-303)
+// are unreachable without a volume material (upload rejects them), so they are omitted.
+bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleColor, f3* sampleNormal,
+            f3* sampleAlbedo, rtb_diagnostics& diag, float* randomEventsAcc) {
+  const Scene& sc = *job.scene;
+  const rtb_batch_params& p = *job.p;
+  w.emission.clear();
+  w.attenuation.clear();
+  float randomEventsLocalAcc = 0;
+  int depth = 0;
+  bool firstNonSpecularHit = false;
+  *sampleColor = *sampleNormal = *sampleAlbedo = um::mk(0.0f);
+  Ray ray = eyeRay;
+  float pow2depth = 1.0f;  // pow(2, depth), exact (inf from depth 128 on, like powf)
+
+  for (; depth < p.trace_depth; depth++) {
+    rng.bounce = (uint32_t)depth;
+    FindHitCandidates(sc, ray, w, diag);
+    FindHits(sc, ray, w);
+    diag.ray_count++;
+
+    if (!w.hits.empty()) {
+      const HitRecord rec = w.hits[0];
+      const rtb_material& material = sc.materials[sc.spheres[rec.Entity].material];
+      f3 albedo;
+      Ray scatteredRay;
+      Scatter(material, ray, rec, rng, &albedo, &scatteredRay);
+      f3 emission = v3(material.emission);  // Material.Emit (Material.cs:175-179)
+      w.emission.push_back(emission);
+      if (depth == 0) *sampleNormal = rec.Normal;
+      if (!firstNonSpecularHit) {
+        if (!IsPerfectSpecular(material)) {
+          *sampleAlbedo = emission + albedo;
+          *sampleNormal = rec.Normal;
+          firstNonSpecularHit = true;
+        }
+      }
+      w.attenuation.push_back(albedo);
+      randomEventsLocalAcc += um::div(rng.random_events, pow2depth);
+      rng.random_events = 0;
+      ray = scatteredRay;
+      ray = ray.OffsetTowards(um::dot(scatteredRay.Direction, rec.Normal) >= 0 ? rec.Normal : -rec.Normal);
+    } else {
+      f3 hitSkyColor = um::mk(0.0f);
+      if (p.environment.sky_type == RTB_SKY_GRADIENT)
+        hitSkyColor = um::lerp(v3(p.environment.sky_bottom_color), v3(p.environment.sky_top_color),
+                               0.5f * (ray.Direction.y + 1));
+      w.emission.push_back(hitSkyColor);
+      w.attenuation.push_back(um::mk(1.0f));
+      randomEventsLocalAcc += um::div(rng.random_events, pow2depth);
+      rng.random_events = 0;
+      if (!firstNonSpecularHit) {
+        *sampleAlbedo = hitSkyColor;
+        *sampleNormal = -ray.Direction;
+      }
+      break;
+    }
+    pow2depth *= 2.0f;
+  }
+
+  *sampleColor = um::mk(0.0f);
+  if (depth == p.trace_depth) return false;  // :379-381
+
+  for (size_t k = w.emission.size(); k-- > 0;) {  // :383-396
+    *sampleColor = *sampleColor * w.attenuation[k];
+    *sampleColor = *sampleColor + w.emission[k];
+  }
+  *randomEventsAcc += randomEventsLocalAcc;
+  return true;
+}
+
+// SampleBatchJob.Execute (:58-164)
+void Execute(const Job& job, int index, Work& w) {
+  const rtb_batch_params& p = *job.p;
+  const rtb_batch_buffers& b = *job.buf;
+  int width = (int)p.size[0];
+  int cx = index % width, cy = index / width;
+  if (cy % p.slice_divider != p.slice_offset) return;
+  if (p.row_end > p.row_begin && (cy < p.row_begin || cy >= p.row_end)) return;  // rtb extension
+
+  f3 colorAcc = v3(b.in_color + 4 * (size_t)index);
+  float lastW = b.in_color[4 * (size_t)index + 3];
+  f3 normalAcc = v3(b.in_normal + 3 * (size_t)index);
+  f3 albedoAcc = v3(b.in_albedo + 3 * (size_t)index);
+  float sampleCountWeightAcc = b.in_sample_count_weight[index];
+  int sampleCount = (int)lastW;
+
+  RandomSource rng;
+  rng.mode = job.noise;
+  if (job.noise == NOISE_WHITE_XORSHIFT) {
+    rng.white.init((p.seed * 0x8C4CA03Fu) ^ ((uint32_t)index * 0x7383ED49u));  // :91
+  } else {
+    rng.key[0] = p.seed;
+    rng.key[1] = PHILOX_KEY1;
+    rng.pixel = (uint32_t)index;
+  }
+
+  f3 fallbackAlbedo = um::mk(0.0f), fallbackNormal = um::mk(0.0f);
+  rtb_diagnostics diag{};
+
+  uint32_t samplesToAccumulate;
+  float sampleCountWeight = um::div(sampleCountWeightAcc, (float)sampleCount);
+  if (sampleCountWeight == 0) {
+    samplesToAccumulate = p.sample_count_range[0];
+  } else {
+    float normalized = um::saturate(um::unlerp(p.sample_count_weight_extrema[0], p.sample_count_weight_extrema[1], sampleCountWeight));
+    samplesToAccumulate = (uint32_t)um::round(um::lerp((float)p.sample_count_range[0], (float)p.sample_count_range[1], normalized));
+  }
+  diag.sample_count_weight = sampleCountWeight;
+
+  for (uint32_t s = 0; s < samplesToAccumulate; s++) {
+    rng.sample = s;
+    rng.bounce = BOUNCE_CAMERA;
+    float jx = 0.5f, jy = 0.5f;
+    if (p.sub_pixel_jitter) rng.NextFloat2(SLOT_JITTER, &jx, &jy);
+    float nx = um::div((float)cx + jx, p.size[0]);
+    float ny = um::div((float)cy + jy, p.size[1]);
+    Ray eyeRay = GetRay(p.view, nx, ny, rng);
+
+    f3 sampleColor, sampleNormal, sampleAlbedo;
+    if (Sample(job, eyeRay, rng, w, &sampleColor, &sampleNormal, &sampleAlbedo, diag, &sampleCountWeightAcc)) {
+      colorAcc = colorAcc + sampleColor;
+      normalAcc = normalAcc + sampleNormal;
+      albedoAcc = albedoAcc + sampleAlbedo;
+      sampleCount++;
+    }
+    if (s == 0) {
+      fallbackNormal = sampleNormal;
+      fallbackAlbedo = sampleAlbedo;
+    }
+  }
+
+  float* oc = b.out_color + 4 * (size_t)index;
+  oc[0] = colorAcc.x; oc[1] = colorAcc.y; oc[2] = colorAcc.z; oc[3] = (float)sampleCount;
+  f3 on = sampleCount == 0 ? fallbackNormal : normalAcc;
+  f3 oa = sampleCount == 0 ? fallbackAlbedo : albedoAcc;
+  float* pn = b.out_normal + 3 * (size_t)index;
+  float* pa = b.out_albedo + 3 * (size_t)index;
+  pn[0] = on.x; pn[1] = on.y; pn[2] = on.z;
+  pa[0] = oa.x; pa[1] = oa.y; pa[2] = oa.z;
+  b.out_sample_count_weight[index] = sampleCountWeightAcc;
+  if (b.out_diagnostics) b.out_diagnostics[index] = diag;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+// Runs one SampleBatchJob over pixel indices [index_begin, index_end) (0,0 = all) with
+// `threads` worker threads pulling one pixel at a time (== Schedule(W*H, 1, ...),
+// Raytracer.cs:730).  noise: 0 = the reference's xorshift32 white noise, 1 = Philox slots.
+ORACLE_API int oracle_sample_batch(const rtb_batch_params* params,
+                                   const rtb_sphere* spheres, size_t sphere_count,
+                                   const rtb_material* materials, size_t material_count,
+                                   const rtb_bvh_node* nodes, size_t node_count,
+                                   const rtb_batch_buffers* buffers, int noise, int threads,
+                                   int64_t index_begin, int64_t index_end) {
+  if (!params || !buffers || params->slice_divider < 1 || params->trace_depth < 0) return RTB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < material_count; i++)
+    if (materials[i].type > RTB_MATERIAL_DIELECTRIC) return RTB_ERR_UNSUPPORTED;
+  if (params->environment.sky_type == RTB_SKY_CUBEMAP) return RTB_ERR_UNSUPPORTED;
+  Scene sc{spheres, sphere_count, materials, material_count, nodes, node_count, {}, {}};
+  sc.origin_transform.resize(sphere_count);
+  sc.inverse_transform.resize(sphere_count);
+  for (size_t i = 0; i < sphere_count; i++) {
+    um::rigid t{um::quat_identity(), um::mk(spheres[i].center[0], spheres[i].center[1], spheres[i].center[2])};
+    sc.origin_transform[i] = t;
+    sc.inverse_transform[i] = um::inverse(t);  // Entity ctor, Entity.cs:52
+  }
+  Job job{params, &sc, buffers, noise};
+  int64_t total = (int64_t)params->size[0] * (int64_t)params->size[1];
+  if (index_end <= index_begin) { index_begin = 0; index_end = total; }
+  if (index_end > total) index_end = total;
+  if (threads < 1) threads = 1;
+  std::atomic<int64_t> next(index_begin);
+  auto worker = [&]() {
+    Work w;
+    for (;;) {
+      int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+      if (i >= index_end) break;
+      Execute(job, (int)i, w);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; t++) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+  return RTB_OK;
+}
+
+// ---- known-answer-test hooks (tests/test_oracle_kat.py) ---------------------------------
+ORACLE_API void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox4x32_10(ctr, key, out);
+}
+ORACLE_API void oracle_unity_random(uint32_t seed, uint32_t* out_states, float* out_floats, int n) {
+  UnityRandom r; r.init(seed);
+  for (int i = 0; i < n; i++) {
+    uint32_t s = r.next_state();
+    out_states[i] = s;
+    out_floats[i] = RandomSource::to_float(s);
+  }
+}
+ORACLE_API int oracle_sphere_hit(const float center[3], float radius, const float origin[3], const float dir[3],
+                                 float* distance, float point[3], float normal[3]) {
+  rtb_sphere s{};
+  s.center[0] = center[0]; s.center[1] = center[1]; s.center[2] = center[2]; s.radius = radius;
+  Scene sc{&s, 1, nullptr, 0, nullptr, 0, {}, {}};
+  um::rigid t{um::quat_identity(), v3(center)};
+  sc.origin_transform.push_back(t);
+  sc.inverse_transform.push_back(um::inverse(t));
+  HitRecord rec;
+  Ray ray{v3(origin), v3(dir), 0};
+  if (!EntityHit(sc, 0, ray, 0, um::INF, &rec)) return 0;
+  *distance = rec.Distance;
+  point[0] = rec.Point.x; point[1] = rec.Point.y; point[2] = rec.Point.z;
+  normal[0] = rec.Normal.x; normal[1] = rec.Normal.y; normal[2] = rec.Normal.z;
+  return 1;
+}
+ORACLE_API int oracle_aabb_hit(const float bmin[3], const float bmax[3], const float origin[3], const float dir[3]) {
+  rtb_bvh_node n{};
+  for (int i = 0; i < 3; i++) { n.bounds_min[i] = bmin[i]; n.bounds_max[i] = bmax[i]; }
+  f3 inv = um::rcp(v3(dir));
+  inv = um::mk(um::isnan(inv.x) ? um::INF : inv.x, um::isnan(inv.y) ? um::INF : inv.y, um::isnan(inv.z) ? um::INF : inv.z);
+  return AabbHit(n, v3(origin), inv) ? 1 : 0;
+}
+ORACLE_API float oracle_schlick(float cosine, float ior) { return Schlick(cosine, ior); }
+ORACLE_API float oracle_roughness_to_alpha(float r) { return RoughnessToAlpha(r); }
+ORACLE_API float oracle_lambda(const float w[3], const float n[3], float roughness) { return Lambda(v3(w), v3(n), roughness); }
+ORACLE_API int oracle_refract(const float v[3], const float n[3], float ni_over_nt, float out[3]) {
+  f3 r;
+  bool ok = Refract(v3(v), v3(n), ni_over_nt, &r);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z;
+  return ok ? 1 : 0;
+}
+ORACLE_API void oracle_get_ray(const rtb_view* view, float nx, float ny, uint32_t seed, uint32_t pixel, uint32_t sample,
+                               int noise, float origin[3], float dir[3]) {
+  RandomSource rng;
+  rng.mode = noise;
+  if (noise == NOISE_WHITE_XORSHIFT) rng.white.init(seed);
+  rng.key[0] = seed; rng.key[1] = PHILOX_KEY1; rng.pixel = pixel; rng.sample = sample; rng.bounce = BOUNCE_CAMERA;
+  Ray r = GetRay(*view, nx, ny, rng);
+  origin[0] = r.Origin.x; origin[1] = r.Origin.y; origin[2] = r.Origin.z;
+  dir[0] = r.Direction.x; dir[1] = r.Direction.y; dir[2] = r.Direction.z;
+}
+ORACLE_API void oracle_umath_sincos(const float* theta, float* s, float* c, int n) {
+  for (int i = 0; i < n; i++) um::sincos(theta[i], s + i, c + i);
+}
+ORACLE_API void oracle_umath_log(const float* x, float* y, int n) {
+  for (int i = 0; i < n; i++) y[i] = um::log(x[i]);
+}
+ORACLE_API void oracle_umath_pow(const float* x, float e, float* y, int n) {
+  for (int i = 0; i < n; i++) y[i] = um::pow_pos(x[i], e);
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""In-tree build of the two shared libraries (explicit nvcc / g++; no JIT cache).
+
+  lib/librtb_host.so   host-side producers (scene, BVH, view) — plain C++
+  lib/librtb.so        the sm_100a plugin: CUDA kernels + the C ABI of include/rtb.h
+
+nvcc cross-compiles sm_100a without a GPU, so this runs in the authoring container; the
+built .so files are git-ignored but travel to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "lib")
+INCLUDE = os.path.join(ROOT, "include")
+
+HOST_SOURCES = [os.path.join(CSRC, "host", "rtb_host.cpp")]
+CUDA_SOURCES = [os.path.join(CSRC, "plugin.cu")]
+CUDA_DEPS = [
+    os.path.join(CSRC, f)
+    for f in ("kernel_common.cuh", "sample_kernels.cuh", "aux_kernels.cuh")
+] + [os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
+HOST_DEPS = [os.path.join(INCLUDE, "rtb_host.h"), os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
+
+# -fmad=false: the parity contract of include/rtb/umath.h (FMAs only where written).
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-std=c++17", "-O3", "-lineinfo",
+    "-fmad=false",
+    "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
+    "-cudart", "static",
+    "-I", INCLUDE, "-I", CSRC,
+]
+GXX_FLAGS = [
+    "-std=c++17", "-O2", "-ffp-contract=off", "-march=x86-64-v3",
+    "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra",
+    "-I", INCLUDE,
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print("+", " ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    if verbose and (r.stdout or r.stderr):
+        print(r.stdout + r.stderr, flush=True)
+
+
+def host_lib_path():
+    return os.path.join(LIB, "librtb_host.so")
+
+
+def plugin_lib_path():
+    return os.path.join(LIB, "librtb.so")
+
+
+def build_host(force=False, verbose=False):
+    os.makedirs(LIB, exist_ok=True)
+    out = host_lib_path()
+    if force or _stale(out, HOST_SOURCES + HOST_DEPS):
+        gxx = shutil.which("g++") or "g++"
+        _run([gxx] + GXX_FLAGS + ["-o", out] + HOST_SOURCES, verbose)
+    return out
+
+
+def build_plugin(force=False, verbose=False, extra_flags=()):
+    os.makedirs(LIB, exist_ok=True)
+    out = plugin_lib_path()
+    if force or _stale(out, CUDA_SOURCES + CUDA_DEPS):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        _run([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + CUDA_SOURCES, verbose)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return build_host(force, verbose), build_plugin(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)
+    print("built:", host_lib_path(), plugin_lib_path())

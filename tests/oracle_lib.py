@@ -1,0 +1,117 @@
+"""Loader for the CPU oracle (oracle/liboracle*.so).  TEST-SIDE ONLY: the product package
+never imports this module or anything under oracle/."""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+rtb = importlib.import_module("raytracing-in-one-weekend_b200")
+abi = rtb.abi
+
+NOISE_XORSHIFT = 0  # the reference's Unity.Mathematics.Random stream
+NOISE_PHILOX = 1  # the slot-keyed Philox stream the GPU uses
+
+_libs = {}
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+
+
+def lib(fast=False):
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name not in _libs:
+        path = os.path.join(ORACLE_DIR, name)
+        src = os.path.join(ORACLE_DIR, "oracle.cpp")
+        if not os.path.exists(path) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(path)):
+            build_oracle()
+        L = C.CDLL(path)
+        L.oracle_sample_batch.argtypes = [
+            C.POINTER(abi.BatchParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+            C.POINTER(abi.BatchBuffers), C.c_int, C.c_int, C.c_int64, C.c_int64,
+        ]
+        L.oracle_sample_batch.restype = C.c_int
+        L.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.oracle_unity_random.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_sphere_hit.argtypes = [abi.f32x3, C.c_float, abi.f32x3, abi.f32x3, C.POINTER(C.c_float), abi.f32x3, abi.f32x3]
+        L.oracle_sphere_hit.restype = C.c_int
+        L.oracle_aabb_hit.argtypes = [abi.f32x3, abi.f32x3, abi.f32x3, abi.f32x3]
+        L.oracle_aabb_hit.restype = C.c_int
+        L.oracle_schlick.argtypes = [C.c_float, C.c_float]
+        L.oracle_schlick.restype = C.c_float
+        L.oracle_roughness_to_alpha.argtypes = [C.c_float]
+        L.oracle_roughness_to_alpha.restype = C.c_float
+        L.oracle_lambda.argtypes = [abi.f32x3, abi.f32x3, C.c_float]
+        L.oracle_lambda.restype = C.c_float
+        L.oracle_refract.argtypes = [abi.f32x3, abi.f32x3, C.c_float, abi.f32x3]
+        L.oracle_refract.restype = C.c_int
+        L.oracle_get_ray.argtypes = [
+            C.POINTER(abi.View), C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, abi.f32x3, abi.f32x3
+        ]
+        L.oracle_umath_sincos.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_umath_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_umath_pow.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_int]
+        _libs[name] = L
+    return _libs[name]
+
+
+class Buffers:
+    """The accumulation buffers of one batch as numpy arrays (SampleBatchJob.cs:41-51)."""
+
+    def __init__(self, width, height, diagnostics=True):
+        n = width * height
+        self.width, self.height = width, height
+        self.in_color = np.zeros((n, 4), np.float32)
+        self.in_weight = np.zeros(n, np.float32)
+        self.in_normal = np.zeros((n, 3), np.float32)
+        self.in_albedo = np.zeros((n, 3), np.float32)
+        self.out_color = np.zeros((n, 4), np.float32)
+        self.out_weight = np.zeros(n, np.float32)
+        self.out_normal = np.zeros((n, 3), np.float32)
+        self.out_albedo = np.zeros((n, 3), np.float32)
+        self.diagnostics = np.zeros(n, abi.DIAGNOSTICS_DTYPE) if diagnostics else None
+
+    def as_struct(self):
+        b = abi.BatchBuffers()
+        b.in_color = self.in_color.ctypes.data
+        b.in_sample_count_weight = self.in_weight.ctypes.data
+        b.in_normal = self.in_normal.ctypes.data
+        b.in_albedo = self.in_albedo.ctypes.data
+        b.out_color = self.out_color.ctypes.data
+        b.out_sample_count_weight = self.out_weight.ctypes.data
+        b.out_normal = self.out_normal.ctypes.data
+        b.out_albedo = self.out_albedo.ctypes.data
+        b.out_diagnostics = self.diagnostics.ctypes.data if self.diagnostics is not None else None
+        return b
+
+    def swap(self):
+        """Ping-pong: accumulation := output (Raytracer.cs:798-802)."""
+        self.in_color, self.out_color = self.out_color, self.in_color
+        self.in_weight, self.out_weight = self.out_weight, self.in_weight
+        self.in_normal, self.out_normal = self.out_normal, self.in_normal
+        self.in_albedo, self.out_albedo = self.out_albedo, self.in_albedo
+
+    def rgb(self):
+        """CombineJob's per-pixel colour (CombineJob.cs:34-54): xyz / (int)w, 0 when no samples."""
+        n = self.out_color[:, 3].astype(np.int32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rgb = self.out_color[:, :3] / np.maximum(n, 1)[:, None].astype(np.float32)
+        rgb[n == 0] = 0
+        return rgb.reshape(self.height, self.width, 3)
+
+
+def sample_batch(scene, params, buffers, noise=NOISE_PHILOX, threads=None, fast=False, index_range=(0, 0)):
+    threads = threads or os.cpu_count() or 1
+    b = buffers.as_struct()
+    rc = lib(fast).oracle_sample_batch(
+        C.byref(params), scene.spheres.ctypes.data, len(scene.spheres), scene.materials.ctypes.data, len(scene.materials),
+        scene.nodes.ctypes.data, len(scene.nodes), C.byref(b), noise, threads, index_range[0], index_range[1],
+    )
+    if rc != 0:
+        raise RuntimeError(f"oracle_sample_batch failed: {rc}")
+    return buffers
