@@ -1,0 +1,97 @@
+// aux_kernels.cuh — the two O(pixels) jobs that sit right after the sample job in the
+// reference's per-batch pipeline (Raytracer.cs:745-754, :844), as HBM-bound device kernels:
+//   combine_kernel         CombineJob.Execute        (Runtime/Jobs/CombineJob.cs:29-71)
+//   reduce_metrics_kernel  ReduceMetricsJob.Execute  (Runtime/Jobs/ReduceMetricsJob.cs:22-45)
+#pragma once
+
+#include "kernel_common.cuh"
+
+namespace rtbk {
+
+// CombineJob: colour / sample count with the interlace look-around, NaN -> 0 (or debug
+// colours), albedo / max(n,1) (optionally clamped to 1), normalizesafe(normal / max(n,1)).
+__global__ void combine_kernel(int width, int height, int debug_mode, int ldr_albedo,
+                               const float4* __restrict__ color, const float* __restrict__ normal,
+                               const float* __restrict__ albedo, float* __restrict__ out_color,
+                               float* __restrict__ out_normal, float* __restrict__ out_albedo) {
+  const int n = width * height;
+  for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < n; index += gridDim.x * blockDim.x) {
+    float4 c = color[index];
+    int real = (int)c.w;
+    f3 final_color;
+    if (!debug_mode) {
+      if (real == 0) {
+        int tentative = index;
+        while (real == 0 && (tentative -= width) >= 0) {   // look-around (interlaced buffer)
+          c = color[tentative];
+          real = (int)c.w;
+        }
+      }
+    }
+    const bool any_nan = um::isnan(c.x) || um::isnan(c.y) || um::isnan(c.z) || um::isnan(c.w);
+    if (real == 0) final_color = debug_mode ? um::mk(1.0f, 0.0f, 1.0f) : um::mk(0.0f);
+    else if (any_nan) final_color = debug_mode ? um::mk(0.0f, 1.0f, 1.0f) : um::mk(0.0f);
+    else final_color = um::mk(c.x, c.y, c.z) / (float)real;
+    const float denom = (float)max(real, 1);
+    if (out_color) { out_color[3 * (size_t)index] = final_color.x; out_color[3 * (size_t)index + 1] = final_color.y; out_color[3 * (size_t)index + 2] = final_color.z; }
+    if (out_albedo) {
+      f3 al = v3(albedo + 3 * (size_t)index) / denom;
+      if (ldr_albedo) al = um::min(al, um::mk(1.0f));
+      out_albedo[3 * (size_t)index] = al.x; out_albedo[3 * (size_t)index + 1] = al.y; out_albedo[3 * (size_t)index + 2] = al.z;
+    }
+    if (out_normal) {
+      f3 nn = v3(normal + 3 * (size_t)index) / denom;
+      float len2 = um::dot(nn, nn);               // math.normalizesafe: 0 when |v|^2 <= FLT_MIN_NORMAL
+      nn = len2 > 1.175494351e-38f ? nn * um::rsqrt(len2) : um::mk(0.0f);
+      out_normal[3 * (size_t)index] = nn.x; out_normal[3 * (size_t)index + 1] = nn.y; out_normal[3 * (size_t)index + 2] = nn.z;
+    }
+  }
+}
+
+struct MetricsAcc {
+  long long rays, samples;
+  float w_min, w_max;
+  int s_min, s_max;
+};
+
+// ReduceMetricsJob.  The reference is a serial loop; min/max/integer sums are order-free, so
+// a tree reduction returns the same values.  `partial` holds one MetricsAcc per block.
+__global__ void reduce_metrics_kernel(int n, const rtb_diagnostics* __restrict__ diag, const float4* __restrict__ color,
+                                      const float* __restrict__ weight, MetricsAcc* __restrict__ partial) {
+  MetricsAcc m{0, 0, um::INF, -um::INF, 0x7fffffff, (int)0x80000000};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (diag) m.rays += (int)diag[i].ray_count;
+    const int sc = (int)color[i].w;
+    m.samples += sc;
+    const float w = um::div(weight[i], (float)sc);
+    m.w_min = um::min(m.w_min, w);
+    m.w_max = um::max(m.w_max, w);
+    m.s_min = min(m.s_min, sc);
+    m.s_max = max(m.s_max, sc);
+  }
+  __shared__ MetricsAcc sh[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    m.rays += __shfl_down_sync(0xffffffffu, m.rays, o);
+    m.samples += __shfl_down_sync(0xffffffffu, m.samples, o);
+    m.w_min = um::min(m.w_min, __shfl_down_sync(0xffffffffu, m.w_min, o));
+    m.w_max = um::max(m.w_max, __shfl_down_sync(0xffffffffu, m.w_max, o));
+    m.s_min = min(m.s_min, __shfl_down_sync(0xffffffffu, m.s_min, o));
+    m.s_max = max(m.s_max, __shfl_down_sync(0xffffffffu, m.s_max, o));
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    MetricsAcc t = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+      t.rays += sh[w].rays;
+      t.samples += sh[w].samples;
+      t.w_min = um::min(t.w_min, sh[w].w_min);
+      t.w_max = um::max(t.w_max, sh[w].w_max);
+      t.s_min = min(t.s_min, sh[w].s_min);
+      t.s_max = max(t.s_max, sh[w].s_max);
+    }
+    partial[blockIdx.x] = t;
+  }
+}
+
+}  // namespace rtbk

@@ -1,0 +1,463 @@
+// kernel_common.cuh — device-side data layout, Philox RNG, TMA staging helpers and the
+// per-bounce building blocks (camera ray, closest-hit traversal, Material.Scatter) shared
+// by the kernels in sample_kernels.cuh.
+//
+// Reference paths are relative to /root/reference/RaytracingInOneWeekend/Assets/Scripts.
+//
+// Arithmetic contract (see include/rtb/umath.h): this translation unit is compiled with
+// -fmad=false, so an FMA exists only where um::fma / um::dot / um::mad is written.  Every
+// float expression below is written in the evaluation order of the CPU oracle so that the
+// discrete decisions of a path (hit / miss, reflect / refract, which sphere is nearest)
+// are bit-identical; the only tolerated differences are in sums and products whose order
+// the kernels change on purpose (per-pixel accumulation, attenuation product).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtb.h"
+#include "rtb/umath.h"
+
+namespace rtbk {
+
+using um::f3;
+
+// ---------------------------------------------------------------------------------------
+// Scene blob: one contiguous, 16-byte aligned byte array in HBM, copied verbatim into
+// shared memory by TMA bulk copies at CTA start (or read in place through the read-only
+// path when it does not fit).
+//
+//   inner nodes  : n_inner * 64 B   child boxes stored in the parent, 4 x float4:
+//                    q0 = (Lmin.x, Lmin.y, Lmin.z, Lmax.x)
+//                    q1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
+//                    q2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)
+//                    q3 = (left_ref, right_ref, -, -) as int32
+//                  ref >= 0: inner node index; ref < 0: leaf, first sphere = ~ref
+//   spheres      : n_spheres * 16 B  float4 (center.xyz, radius), BVH leaf order
+//   leaf_count   : n_spheres * 4 B   entity count of the leaf that STARTS at this sphere
+//   mat_index    : n_spheres * 4 B   material index of the sphere
+//   materials    : n_materials * 48 B  DevMaterial
+// ---------------------------------------------------------------------------------------
+struct DevMaterial {            // 48 bytes = 3 x float4
+  float albedo[3];
+  uint32_t type;                // rtb_material_type
+  float emission[3];
+  float glossiness;
+  float metallic;
+  float ior;
+  uint32_t perfect_specular;    // Material.IsPerfectSpecular (Material.cs:181-196), precomputed on upload
+  uint32_t pad;
+};
+static_assert(sizeof(DevMaterial) == 48, "DevMaterial layout");
+
+struct SceneDesc {
+  const unsigned char* blob;    // device pointer
+  uint32_t blob_bytes;          // multiple of 16
+  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, material_off;
+  uint32_t n_inner, n_spheres, n_materials;
+  int32_t root_ref;             // as child refs; meaningful when has_root
+  uint32_t has_root;            // 0: empty world (node_count == 0)
+  float root_min[3], root_max[3];
+  uint32_t max_depth;           // deepest root-to-leaf path (stack bound)
+};
+
+constexpr int kStackMax = 64;   // traversal stack entries (BVH depth bound; upload rejects deeper trees)
+constexpr int kTilePixelsMax = 16;
+constexpr uint32_t kPhiloxKey1 = 0x52544232u;   // "RTB2"
+constexpr uint32_t kBounceCamera = 0xFFFFFFFFu;
+
+// Kernel arguments (one __grid_constant__ struct).
+struct BatchArgs {
+  rtb_batch_params p;
+  rtb_batch_buffers b;          // DEVICE pointers
+  SceneDesc scene;
+  int width, height;
+  int first_row, row_step, n_rows;   // active rows: first_row + j * row_step, j < n_rows
+  uint32_t n_active_pixels;          // n_rows * width
+  int tile_pixels;                   // pixels per warp tile (<= kTilePixelsMax)
+  uint32_t n_tiles;
+  uint32_t* tile_counter;            // global work counter (zeroed before launch)
+  unsigned long long* counters;      // rtb_counters as 8 x u64, or nullptr
+};
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter = (pixel, sample, bounce, block),
+// key = (Seed, "RTB2").  Slots: see DESIGN.md "Random-draw slots".
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// RandomSource.NextFloat (RandomSource.cs:130-151 -> Unity.Mathematics.Random.NextFloat)
+__device__ __forceinline__ float u2f(uint32_t u) { return um::asfloat(0x3f800000u | (u >> 9)) - 1.0f; }
+
+// ---------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// Scene accessors.  SMEM = true: `base` points into shared memory (plain loads become LDS);
+// SMEM = false: `base` is the blob in HBM and loads go through the read-only path.
+// ---------------------------------------------------------------------------------------
+template <bool SMEM>
+struct SceneView {
+  const float4* inner;
+  const float4* spheres;
+  const uint32_t* leaf_count;
+  const uint32_t* mat_index;
+  const float4* materials;
+
+  __device__ __forceinline__ void bind(const unsigned char* base, const SceneDesc& s) {
+    inner = reinterpret_cast<const float4*>(base + s.inner_off);
+    spheres = reinterpret_cast<const float4*>(base + s.sphere_off);
+    leaf_count = reinterpret_cast<const uint32_t*>(base + s.leaf_count_off);
+    mat_index = reinterpret_cast<const uint32_t*>(base + s.mat_index_off);
+    materials = reinterpret_cast<const float4*>(base + s.material_off);
+  }
+  __device__ __forceinline__ float4 ld4(const float4* p) const {
+    if (SMEM) return *p;
+    return __ldg(p);
+  }
+  __device__ __forceinline__ uint32_t ld1(const uint32_t* p) const {
+    if (SMEM) return *p;
+    return __ldg(p);
+  }
+};
+
+struct WorkCounters {           // per-thread tallies of the instrumented build
+  uint32_t node_tests = 0, sphere_tests = 0, shade_standard = 0, shade_dielectric = 0;
+};
+
+__device__ __forceinline__ f3 v3(const float* p) { return um::mk(p[0], p[1], p[2]); }
+
+// HitTests.Hit(this AxisAlignedBoundingBox) (HitTests.cs:9-21): returns the decision and tMin.
+// fminf/fmaxf agree with math.min/max ("isnan(y) || x < y ? x : y") on every input except
+// the sign of a zero result, which no comparison below can observe.
+__device__ __forceinline__ bool aabb_hit(f3 mn, f3 mx, f3 o, f3 inv, float* t_enter) {
+  f3 t0 = (mn - o) * inv;
+  f3 t1 = (mx - o) * inv;
+  float tmin = fmaxf(0.0f, fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z)));
+  float tmax = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+  *t_enter = tmin;
+  return tmin < tmax;
+}
+
+// HitTests.Hit(this Sphere) (HitTests.cs:23-60) behind Entity.HitInternal (Entity.cs:74-103)
+// for a static, unrotated entity: entity-space origin = o + (-center), direction unchanged.
+// `a` = dot(d, d) is hoisted out by the caller.  Updates (best_t, best_idx) when this sphere
+// is hit nearer than best_t: the same record FindHits' sort would put first
+// (SampleBatchJob.cs:450-475) — a root is accepted iff 0 < t < +inf there, and the
+// second root is never nearer than the first, so clipping at best_t changes nothing.
+__device__ __forceinline__ void sphere_hit(float4 s, int idx, f3 o, f3 d, float a, float& best_t, int& best_idx) {
+  f3 oc = o + um::mk(-s.x, -s.y, -s.z);
+  float b = um::dot(oc, d);
+  float c = um::dot(oc, oc) - s.w * s.w;
+  float disc = um::fma(b, b, -(a * c));
+  if (disc > 0.0f) {
+    float sq = um::sqrt(disc);
+    float t = um::div(-b - sq, a);
+    if (!(t < best_t && t > 0.0f)) t = um::div(-b + sq, a);
+    if (t < best_t && t > 0.0f) {
+      best_t = t;
+      best_idx = idx;
+    }
+  }
+}
+
+// Closest hit over the whole world.  Replaces FindHitCandidates + FindHits
+// (SampleBatchJob.cs:403-475): the reference collects every entity of every leaf whose box
+// chain is hit, intersects all, sorts and takes index 0.  This walk applies the SAME box
+// test to the same boxes and the same sphere test, but visits the nearer child first and
+// skips a box whose entry distance lies beyond the best hit so far (with a safety margin
+// far larger than the rounding error of either distance), so it returns the same nearest
+// record while testing a fraction of the nodes.
+constexpr float kPruneMargin = 1.0005f;
+
+template <bool SMEM, bool COUNTERS>
+__device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
+                                            float& best_t, int& best_idx, WorkCounters& wc) {
+  best_t = um::INF;
+  best_idx = -1;
+  if (!sd.has_root) return;
+  // SampleBatchJob.cs:409-412
+  f3 inv = um::rcp(d);
+  inv = um::mk(um::isnan(inv.x) ? um::INF : inv.x, um::isnan(inv.y) ? um::INF : inv.y, um::isnan(inv.z) ? um::INF : inv.z);
+  const float a = um::dot(d, d);
+
+  float t_enter;
+  if (COUNTERS) wc.node_tests++;
+  if (!aabb_hit(v3(sd.root_min), v3(sd.root_max), o, inv, &t_enter)) return;
+
+  int stack[kStackMax];
+  int sp = 0;
+  int cur = sd.root_ref;
+  for (;;) {
+    if (cur >= 0) {
+      const float4* n = sv.inner + 4 * cur;
+      const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+      float tl, tr;
+      bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
+      bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
+      if (COUNTERS) wc.node_tests += 2;
+      const float limit = best_t * kPruneMargin;
+      hl = hl && tl < limit;
+      hr = hr && tr < limit;
+      const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+      if (hl && hr) {
+        const bool left_first = tl <= tr;
+        stack[sp++] = left_first ? right : left;
+        cur = left_first ? left : right;
+        continue;
+      }
+      if (hl) { cur = left; continue; }
+      if (hr) { cur = right; continue; }
+    } else {
+      const int first = ~cur;
+      const int count = (int)sv.ld1(sv.leaf_count + first);
+      for (int i = 0; i < count; i++) {
+        sphere_hit(sv.ld4(sv.spheres + first + i), first + i, o, d, a, best_t, best_idx);
+      }
+      if (COUNTERS) wc.sphere_tests += count;
+    }
+    if (sp == 0) break;
+    cur = stack[--sp];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Sampling transforms (RandomSource.cs) and basis helpers (Util/Tools.cs:19-37)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 tangent_to_world(f3 v, f3 normal) {
+  float s = normal.z >= 0 ? 1.0f : -1.0f;
+  float a = um::div(-1.0f, s + normal.z);
+  float b = normal.x * normal.y * a;
+  f3 tangent = um::mk(1 + s * normal.x * normal.x * a, s * b, -s * normal.x);
+  f3 bitangent = um::mk(b, s + normal.y * normal.y * a, -normal.y);
+  return um::normalize(um::mul_cols(tangent, normal, bitangent, v));
+}
+// RandomSource.OnCosineWeightedHemisphere (RandomSource.cs:63-89)
+__device__ __forceinline__ f3 cosine_hemisphere(f3 normal, float ux, float uy) {
+  float radius = um::sqrt(ux);
+  float theta = uy * 2 * um::PI;
+  float s, c;
+  um::sincos(theta, &s, &c);
+  f3 tangent_space = um::mk(radius * c, um::sqrt(1 - ux), radius * s);
+  return tangent_to_world(tangent_space, normal);
+}
+// RandomSource.NextFloat3Direction (RandomSource.cs:113-128)
+__device__ __forceinline__ f3 random_direction(float rx, float ry) {
+  float z = rx * 2.0f - 1.0f;
+  float r = um::sqrt(um::max(1.0f - z * z, 0.0f));
+  float angle = ry * um::PI * 2.0f;
+  float s, c;
+  um::sincos(angle, &s, &c);
+  return um::mk(c * r, s * r, z);
+}
+
+// Material.cs:212-217
+__device__ __forceinline__ float schlick(float cosine, float ior) {
+  float r0 = um::div(1 - ior, 1 + ior);
+  r0 *= r0;
+  return r0 + (1 - r0) * um::pow5(1 - cosine);
+}
+// Microfacet.cs:71-80
+__device__ __forceinline__ float roughness_to_alpha(float roughness) {
+  roughness = um::max(roughness, 1e-3f);
+  float x = um::log(roughness);
+  return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+// Microfacet.cs:9-12,53-69
+__device__ __forceinline__ float smith_masking_shadowing(f3 w, f3 normal, float roughness) {
+  float cos_theta = um::dot(normal, w);
+  float sq_cos = cos_theta * cos_theta;
+  float sq_sin = um::max(0.0f, 1 - sq_cos);
+  float sin_theta = um::sqrt(sq_sin);
+  float tan_theta = um::div(sin_theta, cos_theta);
+  float abs_tan = um::abs(tan_theta);
+  float lambda;
+  if (um::isinf(abs_tan)) {
+    lambda = 0;
+  } else {
+    float alpha = roughness_to_alpha(roughness);
+    float a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
+    lambda = um::div(-1 + um::sqrt(1 + a2t2), 2.0f);
+  }
+  return um::div(1.0f, 1 + lambda);
+}
+
+// ---------------------------------------------------------------------------------------
+// One path vertex
+// ---------------------------------------------------------------------------------------
+struct PathRay {
+  f3 o, d;
+};
+
+// View.GetRay (View.cs:38-48) with the uv of SampleBatchJob.cs:134.  The ray-time draw
+// (View.cs:47, slot 4) is not generated: nothing on the supported path reads Ray.Time.
+__device__ __forceinline__ PathRay camera_ray(const rtb_batch_params& p, int cx, int cy, uint32_t pixel, uint32_t sample) {
+  const rtb_view& v = p.view;
+  const bool lens = v.lens_radius != 0;
+  float jx = 0.5f, jy = 0.5f, rdx = 0, rdy = 0;
+  if (p.sub_pixel_jitter || lens) {
+    uint4 r = philox4x32_10(pixel, sample, kBounceCamera, 0, p.seed, kPhiloxKey1);
+    if (p.sub_pixel_jitter) { jx = u2f(r.x); jy = u2f(r.y); }
+    if (lens) {  // RandomSource.InUnitDisk (RandomSource.cs:40-61)
+      float theta = u2f(r.z) * (2 * um::PI - 0) + 0;
+      float radius = um::sqrt(u2f(r.w));
+      float s, c;
+      um::sincos(theta, &s, &c);
+      rdx = v.lens_radius * (radius * c);
+      rdy = v.lens_radius * (radius * s);
+    }
+  }
+  float nx = um::div((float)cx + jx, p.size[0]);
+  float ny = um::div((float)cy + jy, p.size[1]);
+  f3 offset = v3(v.right) * rdx + v3(v.up) * rdy;
+  PathRay r;
+  r.d = um::normalize(v3(v.lower_left_corner) - offset + nx * v3(v.horizontal) + ny * v3(v.vertical));
+  r.o = v3(v.origin) + offset;
+  return r;
+}
+
+struct ScatterResult {
+  f3 dir;           // scattered direction (not re-normalised, Material.cs:145,153)
+  f3 reflectance;   // attenuation
+  float random_events;
+};
+
+// Material.Scatter (Material.cs:67-173) for constant textures (Texture.cs:50-59,101-108).
+// m0 = (albedo.xyz, type), m1 = (emission.xyz, glossiness), m2 = (metallic, ior, perfect_specular, -)
+__device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2, f3 D, f3 N,
+                                                 uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
+  ScatterResult out;
+  out.reflectance = um::mk(m0.x, m0.y, m0.z);
+  const uint32_t type = __float_as_uint(m0.w);
+  if (type == RTB_MATERIAL_STANDARD) {
+    const float metallic = m2.x, glossiness = m1.w;
+    const float roughness = um::pow2(1 - glossiness);
+    float chance = 0.0f;
+    f3 rough_normal = N;
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    // With glossiness == 0 the reflection chance saturate(fresnel * 0 * G) is exactly 0
+    // and with metallic == 0 the rough normal has no other consumer: skip both (and the
+    // Philox block behind them).  Same result as evaluating Material.cs:83-89.
+    const bool pure_diffuse = glossiness == 0.0f && metallic == 0.0f;
+    if (!pure_diffuse) {
+      r0 = philox4x32_10(pixel, sample, bounce, 0, seed, kPhiloxKey1);
+      if (roughness > 0) rough_normal = um::normalize(um::lerp(N, cosine_hemisphere(N, u2f(r0.x), u2f(r0.y)), roughness));
+      float incident_cosine = -um::dot(D, rough_normal);
+      float ior = um::lerp(1.5f, 1.1f, metallic);
+      float fresnel = schlick(incident_cosine, ior);
+      float g = smith_masking_shadowing(D, N, roughness);
+      chance = um::saturate(fresnel * glossiness * g);
+    }
+    if (chance > 0 && u2f(r0.z) < chance) {
+      out.dir = um::reflect(D, rough_normal);
+      out.reflectance = um::mk(1.0f);
+    } else if (metallic > 0 && u2f(r0.w) < metallic) {
+      out.dir = um::reflect(D, rough_normal);
+    } else {
+      uint4 r1 = philox4x32_10(pixel, sample, bounce, 1, seed, kPhiloxKey1);
+      out.dir = cosine_hemisphere(N, u2f(r1.x), u2f(r1.y));
+    }
+    float ev = 0;
+    if (chance > 0 && chance < 1) ev++;
+    if (metallic > 0 && metallic < 1) ev++;
+    ev += roughness * (chance + (1 - chance) * metallic);
+    ev += (1 - chance) * (1 - metallic);
+    out.random_events = ev;
+  } else {  // RTB_MATERIAL_DIELECTRIC (upload rejects anything else)
+    const float ior = m2.y;
+    const float roughness = 1 - m1.w;
+    uint4 r0 = philox4x32_10(pixel, sample, bounce, 0, seed, kPhiloxKey1);
+    f3 rough_normal = um::normalize(N + roughness * random_direction(u2f(r0.x), u2f(r0.y)));
+    float ni_over_nt, cosine;
+    f3 outward;
+    float ddn = um::dot(D, rough_normal);
+    if (ddn > 0) {
+      outward = -rough_normal;
+      ni_over_nt = ior;
+      cosine = ior * ddn;
+    } else {
+      outward = rough_normal;
+      ni_over_nt = um::div(1.0f, ior);
+      cosine = -ddn;
+    }
+    // Material.Refract (Material.cs:198-210)
+    float dt = um::dot(D, outward);
+    float disc = 1 - ni_over_nt * ni_over_nt * (1 - dt * dt);
+    bool refracted = false;
+    if (disc > 0) {
+      if (u2f(r0.z) > schlick(cosine, ior)) {
+        out.dir = ni_over_nt * (D - outward * dt) - outward * um::sqrt(disc);
+        refracted = true;
+      }
+    }
+    if (!refracted) {
+      out.dir = um::reflect(D, rough_normal);
+      out.reflectance = um::mk(1.0f);
+    }
+    float ev = 0;
+    ev++;
+    ev += roughness;
+    out.random_events = ev;
+  }
+  return out;
+}
+
+// Sky (SampleBatchJob.cs:348-374; Environment.cs)
+__device__ __forceinline__ f3 sky_color(const rtb_environment& e, f3 d) {
+  if (e.sky_type == RTB_SKY_GRADIENT)
+    return um::lerp(v3(e.sky_bottom_color), v3(e.sky_top_color), 0.5f * (d.y + 1));
+  return um::mk(0.0f);
+}
+
+// Per-pixel prologue (SampleBatchJob.cs:72-126): how many samples this batch takes.
+__device__ __forceinline__ uint32_t samples_to_accumulate(const rtb_batch_params& p, float in_w, float in_weight,
+                                                          float* sample_count_weight) {
+  int sample_count = (int)in_w;
+  float w = um::div(in_weight, (float)sample_count);
+  *sample_count_weight = w;
+  if (w == 0) return p.sample_count_range[0];
+  float normalized = um::saturate(um::unlerp(p.sample_count_weight_extrema[0], p.sample_count_weight_extrema[1], w));
+  return (uint32_t)um::round(um::lerp((float)p.sample_count_range[0], (float)p.sample_count_range[1], normalized));
+}
+
+}  // namespace rtbk

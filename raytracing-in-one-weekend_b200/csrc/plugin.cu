@@ -1,0 +1,642 @@
+// plugin.cu — librtb.so: the C ABI of include/rtb.h over the sm_100a kernels.
+//
+// Replaces, behind one blocking call, what the reference's host does around the sample job
+// (Unity/Raytracer.cs:671-738): fill the job struct, schedule it over W*H pixels, wait.
+// Style precedent for the exports: OptixDenoiser/OptixDenoiser/OptixDenoiser.h:1-10 (extern
+// "C", int status codes) and Runtime/Jobs/DenoiseJobs.cs:10-39 (a blocking native call made
+// from a worker thread).  No CPU fallback: without a CUDA device every entry point fails.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "sample_kernels.cuh"
+
+using namespace rtbk;
+
+namespace {
+
+thread_local std::string g_thread_error;
+
+struct DeviceBuffers {
+  size_t capacity = 0;  // pixels
+  float *in_color = nullptr, *in_weight = nullptr, *in_normal = nullptr, *in_albedo = nullptr;
+  float *out_color = nullptr, *out_weight = nullptr, *out_normal = nullptr, *out_albedo = nullptr;
+  rtb_diagnostics* diagnostics = nullptr;
+};
+
+}  // namespace
+
+struct rtb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  std::string last_error;
+  rtb_log_fn log_fn = nullptr;
+  void* log_user = nullptr;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+
+  // scene
+  unsigned char* d_blob = nullptr;
+  SceneDesc scene{};
+  bool has_scene = false;
+
+  // work counters / options
+  uint32_t* d_tile_counter = nullptr;
+  unsigned long long* d_counters = nullptr;
+  rtb_counters counters{};
+  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0;
+  float last_ms = 0.0f;
+  bool smem_attr_set[2][2] = {{false, false}, {false, false}};
+
+  DeviceBuffers buf;
+  MetricsAcc* d_metrics_partial = nullptr;
+  rtb_diagnostics* d_scratch_diag = nullptr;
+  size_t scratch_diag_capacity = 0;
+  std::map<void*, size_t> registered;
+  std::mutex mu;
+};
+
+namespace {
+
+int fail(rtb_ctx* ctx, int code, const char* fmt, ...) {
+  char msg[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof msg, fmt, ap);
+  va_end(ap);
+  if (ctx) {
+    ctx->last_error = msg;
+    if (ctx->log_fn) ctx->log_fn(2, msg, ctx->log_user);
+  }
+  g_thread_error = msg;
+  return code;
+}
+
+#define RTB_CUDA(ctx, expr)                                                                           \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(ctx, _e == cudaErrorMemoryAllocation ? RTB_ERR_OUT_OF_MEMORY : RTB_ERR_CUDA + (int)_e, \
+                  "%s failed: %s", #expr, cudaGetErrorString(_e));                                    \
+  } while (0)
+
+// ---- scene flattening: rtb_bvh_node[] (reference order, root = 0) -> device blob ----------
+struct HostBlob {
+  std::vector<unsigned char> bytes;
+  SceneDesc desc{};
+};
+
+struct Flattener {
+  const rtb_bvh_node* nodes;
+  size_t node_count, sphere_count;
+  std::vector<uint8_t> visited;
+  std::vector<float> inner;          // 16 floats per inner node
+  std::vector<uint32_t> leaf_count;
+  uint32_t max_depth = 0;
+  const char* error = nullptr;
+
+  int32_t ref_of(int32_t n, uint32_t depth) {
+    if (error) return 0;
+    if (n < 0 || (size_t)n >= node_count) { error = "BVH child index out of range"; return 0; }
+    if (visited[n]) { error = "BVH is not a tree (node reachable twice)"; return 0; }
+    visited[n] = 1;
+    max_depth = std::max(max_depth, depth);
+    const rtb_bvh_node& nd = nodes[n];
+    if (nd.first_entity >= 0) {
+      if (nd.entity_count < 0 || (size_t)nd.first_entity + (size_t)nd.entity_count > sphere_count) {
+        error = "BVH leaf range outside the sphere array";
+        return 0;
+      }
+      if (nd.entity_count == 0) return ~(int32_t)sphere_count;  // sentinel slot: leaf_count == 0
+      leaf_count[nd.first_entity] = (uint32_t)nd.entity_count;
+      return ~nd.first_entity;
+    }
+    const int32_t self = (int32_t)(inner.size() / 16);
+    inner.resize(inner.size() + 16, 0.0f);
+    if (nd.left < 0 || nd.right < 0) { error = "BVH inner node without two children"; return 0; }
+    const rtb_bvh_node& l = nodes[std::min<size_t>((size_t)nd.left, node_count - 1)];
+    const rtb_bvh_node& r = nodes[std::min<size_t>((size_t)nd.right, node_count - 1)];
+    const int32_t lref = ref_of(nd.left, depth + 1);
+    const int32_t rref = ref_of(nd.right, depth + 1);
+    if (error) return 0;
+    float* q = &inner[(size_t)self * 16];
+    q[0] = l.bounds_min[0]; q[1] = l.bounds_min[1]; q[2] = l.bounds_min[2]; q[3] = l.bounds_max[0];
+    q[4] = l.bounds_max[1]; q[5] = l.bounds_max[2]; q[6] = r.bounds_min[0]; q[7] = r.bounds_min[1];
+    q[8] = r.bounds_min[2]; q[9] = r.bounds_max[0]; q[10] = r.bounds_max[1]; q[11] = r.bounds_max[2];
+    memcpy(&q[12], &lref, 4);
+    memcpy(&q[13], &rref, 4);
+    return self;
+  }
+};
+
+bool almost_equals_1(float v) { return std::fabs(1.0f - v) < 1e-6f; }  // MathExtensions.cs:23-27
+
+const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials,
+                       size_t material_count, const rtb_bvh_node* nodes, size_t node_count, HostBlob* out,
+                       int* status) {
+  *status = RTB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < material_count; i++) {
+    if (materials[i].type > RTB_MATERIAL_DIELECTRIC) {
+      *status = RTB_ERR_UNSUPPORTED;
+      return "material type outside the supported hot path (Standard, Dielectric)";
+    }
+  }
+  for (size_t i = 0; i < sphere_count; i++)
+    if (spheres[i].material >= material_count) return "sphere material index out of range";
+
+  Flattener f{nodes, node_count, sphere_count, std::vector<uint8_t>(node_count, 0), {}, std::vector<uint32_t>(sphere_count + 1, 0)};
+  SceneDesc& d = out->desc;
+  d = SceneDesc{};
+  if (node_count > 0) {
+    d.has_root = 1;
+    if (nodes[0].first_entity >= 0 && nodes[0].entity_count == 0) d.has_root = 0;  // empty world
+    if (d.has_root) {
+      d.root_ref = f.ref_of(0, 1);
+      if (f.error) return f.error;
+      for (int k = 0; k < 3; k++) { d.root_min[k] = nodes[0].bounds_min[k]; d.root_max[k] = nodes[0].bounds_max[k]; }
+    }
+  }
+  if (f.max_depth > (uint32_t)kStackMax) {
+    *status = RTB_ERR_UNSUPPORTED;
+    return "BVH deeper than 64 levels";
+  }
+  d.max_depth = f.max_depth;
+  d.n_inner = (uint32_t)(f.inner.size() / 16);
+  d.n_spheres = (uint32_t)sphere_count;
+  d.n_materials = (uint32_t)material_count;
+
+  auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t off = 0;
+  d.inner_off = (uint32_t)off; off = align16(off + (size_t)d.n_inner * 64);
+  d.sphere_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 16);
+  d.leaf_count_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 4);   // +1: the empty-leaf sentinel
+  d.mat_index_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 4);
+  d.material_off = (uint32_t)off; off = align16(off + material_count * sizeof(DevMaterial));
+  if (off == 0) off = 16;
+  d.blob_bytes = (uint32_t)off;
+  out->bytes.assign(off, 0);
+  unsigned char* b = out->bytes.data();
+  if (d.n_inner) memcpy(b + d.inner_off, f.inner.data(), (size_t)d.n_inner * 64);
+  for (size_t i = 0; i < sphere_count; i++) {
+    float s[4] = {spheres[i].center[0], spheres[i].center[1], spheres[i].center[2], spheres[i].radius};
+    memcpy(b + d.sphere_off + i * 16, s, 16);
+    memcpy(b + d.leaf_count_off + i * 4, &f.leaf_count[i], 4);
+    memcpy(b + d.mat_index_off + i * 4, &spheres[i].material, 4);
+  }
+  for (size_t i = 0; i < material_count; i++) {
+    DevMaterial m{};
+    const rtb_material& s = materials[i];
+    for (int k = 0; k < 3; k++) { m.albedo[k] = s.albedo[k]; m.emission[k] = s.emission[k]; }
+    m.type = s.type;
+    m.glossiness = s.glossiness;
+    m.metallic = s.metallic;
+    m.ior = s.index_of_refraction;
+    // Material.IsPerfectSpecular (Material.cs:181-196)
+    m.perfect_specular = s.type == RTB_MATERIAL_DIELECTRIC || (almost_equals_1(s.metallic) && almost_equals_1(s.glossiness));
+    memcpy(b + d.material_off + i * sizeof(DevMaterial), &m, sizeof m);
+  }
+  *status = RTB_OK;
+  return nullptr;
+}
+
+// ---- launch -----------------------------------------------------------------------------
+struct ActiveRows {
+  int first_row, row_step, n_rows;
+};
+
+// Rows this batch touches: the interlace test of SampleBatchJob.cs:69 intersected with the
+// [row_begin, row_end) extension.
+ActiveRows active_rows(const rtb_batch_params& p, int height, int range_begin, int range_end) {
+  int lo = 0, hi = height;
+  if (p.row_end > p.row_begin) { lo = std::max(lo, p.row_begin); hi = std::min(hi, p.row_end); }
+  if (range_end > range_begin) { lo = std::max(lo, range_begin); hi = std::min(hi, range_end); }
+  ActiveRows r{0, p.slice_divider, 0};
+  if (hi <= lo) return r;
+  int first = lo + ((p.slice_offset - lo) % p.slice_divider + p.slice_divider) % p.slice_divider;
+  if (first >= hi) return r;
+  r.first_row = first;
+  r.n_rows = (hi - 1 - first) / p.slice_divider + 1;
+  return r;
+}
+
+int validate_params(rtb_ctx* ctx, const rtb_batch_params* p, int* width, int* height) {
+  if (!p) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "params is NULL");
+  if (!(p->size[0] >= 1.0f && p->size[1] >= 1.0f && p->size[0] <= 65536.0f && p->size[1] <= 65536.0f))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "Size out of range");
+  *width = (int)p->size[0];
+  *height = (int)p->size[1];
+  if (p->slice_divider < 1 || p->slice_offset < 0 || p->slice_offset >= p->slice_divider)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "SliceOffset/SliceDivider invalid");
+  if (p->trace_depth < 0 || p->trace_depth > 65535) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "TraceDepth out of range");
+  if (p->environment.sky_type > RTB_SKY_GRADIENT)
+    return fail(ctx, RTB_ERR_UNSUPPORTED, "sky type outside the supported hot path (None, GradientSky)");
+  if (p->row_begin < 0 || p->row_end < 0 || p->row_end > *height)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "row_begin/row_end out of range");
+  return RTB_OK;
+}
+
+template <bool SMEM, bool COUNTERS>
+int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_spp) {
+  const size_t smem = mega_smem_bytes(a.scene.blob_bytes, SMEM);
+  auto kernel = sample_megakernel<SMEM, COUNTERS>;
+  if (!ctx->smem_attr_set[SMEM][COUNTERS]) {
+    RTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    ctx->smem_attr_set[SMEM][COUNTERS] = true;
+  }
+  int blocks_per_sm = 0;
+  RTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kMegaBlock, smem));
+  if (blocks_per_sm < 1) return fail(ctx, RTB_ERR_CUDA, "megakernel does not fit on an SM (smem %zu B)", smem);
+  const uint32_t n_warps_full = (uint32_t)(ctx->sm_count * blocks_per_sm * kMegaWarps);
+
+  // tile size: ~4096 samples per warp tile, at least ~6 tiles per resident warp when the
+  // image is small, never fewer than 1024 samples per tile unless the pixel count forces it
+  int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (4096 + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
+  while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
+  a.tile_pixels = tp;
+  a.n_tiles = (a.n_active_pixels + (uint32_t)tp - 1) / (uint32_t)tp;
+  const uint32_t ctas_needed = (a.n_tiles + kMegaWarps - 1) / kMegaWarps;
+  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
+  RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
+  kernel<<<grid, kMegaBlock, smem, stream>>>(a);
+  RTB_CUDA(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
+int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffers& dev, int width, int height,
+                 ActiveRows rows, cudaStream_t stream) {
+  if (rows.n_rows <= 0) return RTB_OK;
+  BatchArgs a{};
+  a.p = p;
+  a.b = dev;
+  a.scene = ctx->scene;
+  a.width = width;
+  a.height = height;
+  a.first_row = rows.first_row;
+  a.row_step = rows.row_step;
+  a.n_rows = rows.n_rows;
+  a.n_active_pixels = (uint32_t)rows.n_rows * (uint32_t)width;
+  a.tile_counter = ctx->d_tile_counter;
+  const bool counters = ctx->opt_counters != 0;
+  a.counters = counters ? ctx->d_counters : nullptr;
+  const uint32_t max_spp = std::max(p.sample_count_range[0], p.sample_count_range[1]);
+
+  rtb_diagnostics* user_diag = dev.out_diagnostics;
+  if (counters) {
+    if (!a.b.out_diagnostics) {  // the counter pass reads the per-pixel diagnostics
+      const size_t need = (size_t)width * height;
+      if (ctx->scratch_diag_capacity < need) {
+        if (ctx->d_scratch_diag) cudaFree(ctx->d_scratch_diag);
+        ctx->d_scratch_diag = nullptr;
+        ctx->scratch_diag_capacity = 0;
+        RTB_CUDA(ctx, cudaMalloc(&ctx->d_scratch_diag, need * sizeof(rtb_diagnostics)));
+        ctx->scratch_diag_capacity = need;
+      }
+      a.b.out_diagnostics = ctx->d_scratch_diag;
+    }
+    RTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+  }
+  (void)user_diag;
+
+  int kernel_kind = (int)ctx->opt_kernel;
+  if (kernel_kind == 0) kernel_kind = 2;
+  if (kernel_kind == 1) {
+    const uint32_t grid = (a.n_active_pixels + 127) / 128;
+    if (counters) sample_simple<true><<<grid, 128, 0, stream>>>(a);
+    else sample_simple<false><<<grid, 128, 0, stream>>>(a);
+    RTB_CUDA(ctx, cudaGetLastError());
+  } else {
+    const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
+                      ctx->scene.blob_bytes < (1u << 20);
+    int rc;
+    if (fits) rc = counters ? launch_mega_t<true, true>(ctx, a, stream, max_spp) : launch_mega_t<true, false>(ctx, a, stream, max_spp);
+    else rc = counters ? launch_mega_t<false, true>(ctx, a, stream, max_spp) : launch_mega_t<false, false>(ctx, a, stream, max_spp);
+    if (rc != RTB_OK) return rc;
+  }
+  if (counters) {
+    counters_from_diagnostics<<<ctx->sm_count * 4, 256, 0, stream>>>(a.b.out_diagnostics, a.b.out_color, a.b.in_color, a);
+    RTB_CUDA(ctx, cudaGetLastError());
+  }
+  return RTB_OK;
+}
+
+int ensure_buffers(rtb_ctx* ctx, size_t pixels) {
+  DeviceBuffers& b = ctx->buf;
+  if (b.capacity >= pixels) return RTB_OK;
+  float** ptrs[] = {&b.in_color, &b.in_weight, &b.in_normal, &b.in_albedo, &b.out_color, &b.out_weight, &b.out_normal, &b.out_albedo};
+  for (float** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (b.diagnostics) cudaFree(b.diagnostics);
+  b.diagnostics = nullptr;
+  b.capacity = 0;
+  const size_t elems[] = {4, 1, 3, 3, 4, 1, 3, 3};
+  for (int i = 0; i < 8; i++) RTB_CUDA(ctx, cudaMalloc(ptrs[i], pixels * elems[i] * sizeof(float)));
+  RTB_CUDA(ctx, cudaMalloc(&b.diagnostics, pixels * sizeof(rtb_diagnostics)));
+  b.capacity = pixels;
+  return RTB_OK;
+}
+
+// Copies the active rows of one per-pixel array between host and device.
+cudaError_t copy_rows(void* dst, const void* src, size_t elem_bytes, int width, ActiveRows rows, cudaMemcpyKind kind,
+                      cudaStream_t stream) {
+  const size_t row_bytes = (size_t)width * elem_bytes;
+  const size_t offset = (size_t)rows.first_row * row_bytes;
+  const size_t pitch = row_bytes * (size_t)rows.row_step;
+  if (rows.row_step == 1)
+    return cudaMemcpyAsync((char*)dst + offset, (const char*)src + offset, row_bytes * (size_t)rows.n_rows, kind, stream);
+  return cudaMemcpy2DAsync((char*)dst + offset, pitch, (const char*)src + offset, pitch, row_bytes, (size_t)rows.n_rows, kind, stream);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+int rtb_create(int device, rtb_ctx** out_ctx) {
+  if (!out_ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+  *out_ctx = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return fail(nullptr, RTB_ERR_CUDA + (int)e, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, RTB_ERR_CUDA + (int)e, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, RTB_ERR_UNSUPPORTED, "device %d is sm_%d%d; librtb is built for sm_100a only", device, prop.major, prop.minor);
+  rtb_ctx* ctx = new (std::nothrow) rtb_ctx();
+  if (!ctx) return fail(nullptr, RTB_ERR_OUT_OF_MEMORY, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  DeviceGuard g(device);
+  auto bail = [&](cudaError_t err, const char* what) {
+    int rc = fail(nullptr, RTB_ERR_CUDA + (int)err, "%s: %s", what, cudaGetErrorString(err));
+    rtb_destroy(ctx);
+    return rc;
+  };
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaMalloc(&ctx->d_tile_counter, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&ctx->d_metrics_partial, 1024 * sizeof(MetricsAcc))) != cudaSuccess) return bail(e, "cudaMalloc");
+  *out_ctx = ctx;
+  return RTB_OK;
+}
+
+int rtb_destroy(rtb_ctx* ctx) {
+  if (!ctx) return RTB_OK;
+  {
+    DeviceGuard g(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
+    DeviceBuffers& b = ctx->buf;
+    void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
+                    b.diagnostics, ctx->d_blob, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  }
+  delete ctx;
+  return RTB_OK;
+}
+
+const char* rtb_last_error(const rtb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_thread_error.c_str(); }
+
+int rtb_set_log_callback(rtb_ctx* ctx, rtb_log_fn fn, void* user) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  ctx->log_fn = fn;
+  ctx->log_user = user;
+  return RTB_OK;
+}
+
+int rtb_upload_scene(rtb_ctx* ctx, const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials,
+                     size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if ((sphere_count && !spheres) || (material_count && !materials) || (node_count && !nodes))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "NULL array with a non-zero count");
+  if (sphere_count > (1u << 28) || node_count > (1u << 29)) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "scene too large");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  HostBlob hb;
+  int status;
+  const char* err = build_blob(spheres, sphere_count, materials, material_count, nodes, node_count, &hb, &status);
+  if (err) return fail(ctx, status, "rtb_upload_scene: %s", err);
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_blob) cudaFree(ctx->d_blob);
+  ctx->d_blob = nullptr;
+  ctx->has_scene = false;
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_blob, hb.bytes.size()));
+  RTB_CUDA(ctx, cudaMemcpy(ctx->d_blob, hb.bytes.data(), hb.bytes.size(), cudaMemcpyHostToDevice));
+  ctx->scene = hb.desc;
+  ctx->scene.blob = ctx->d_blob;
+  ctx->has_scene = true;
+  return RTB_OK;
+}
+
+int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_batch_buffers* dev, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  int width, height;
+  int rc = validate_params(ctx, params, &width, &height);
+  if (rc != RTB_OK) return rc;
+  if (!ctx->has_scene) return fail(ctx, RTB_ERR_NO_SCENE, "rtb_upload_scene has not been called");
+  if (!dev || !dev->in_color || !dev->in_sample_count_weight || !dev->in_normal || !dev->in_albedo || !dev->out_color ||
+      !dev->out_sample_count_weight || !dev->out_normal || !dev->out_albedo)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "a batch buffer pointer is NULL");
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  return launch_batch(ctx, *params, *dev, width, height, active_rows(*params, height, 0, 0), stream);
+}
+
+int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_batch_buffers* host, const volatile uint8_t* cancel) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  int width, height;
+  int rc = validate_params(ctx, params, &width, &height);
+  if (rc != RTB_OK) return rc;
+  if (!ctx->has_scene) return fail(ctx, RTB_ERR_NO_SCENE, "rtb_upload_scene has not been called");
+  if (!host || !host->in_color || !host->in_sample_count_weight || !host->in_normal || !host->in_albedo || !host->out_color ||
+      !host->out_sample_count_weight || !host->out_normal || !host->out_albedo)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "a batch buffer pointer is NULL");
+  if (cancel && *cancel) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  DeviceGuard g(ctx->device);
+  const size_t pixels = (size_t)width * height;
+  if ((rc = ensure_buffers(ctx, pixels)) != RTB_OK) return rc;
+  DeviceBuffers& d = ctx->buf;
+  cudaStream_t s = ctx->stream;
+  const ActiveRows all = active_rows(*params, height, 0, 0);
+  if (all.n_rows <= 0) return RTB_OK;
+
+  RTB_CUDA(ctx, copy_rows(d.in_color, host->in_color, 16, width, all, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(ctx, copy_rows(d.in_weight, host->in_sample_count_weight, 4, width, all, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(ctx, copy_rows(d.in_normal, host->in_normal, 12, width, all, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(ctx, copy_rows(d.in_albedo, host->in_albedo, 12, width, all, cudaMemcpyHostToDevice, s));
+
+  rtb_batch_buffers dev{};
+  dev.in_color = d.in_color; dev.in_sample_count_weight = d.in_weight; dev.in_normal = d.in_normal; dev.in_albedo = d.in_albedo;
+  dev.out_color = d.out_color; dev.out_sample_count_weight = d.out_weight; dev.out_normal = d.out_normal; dev.out_albedo = d.out_albedo;
+  dev.out_diagnostics = host->out_diagnostics ? d.diagnostics : nullptr;
+
+  RTB_CUDA(ctx, cudaEventRecord(ctx->ev_start, s));
+  if (!cancel) {
+    if ((rc = launch_batch(ctx, *params, dev, width, height, all, s)) != RTB_OK) return rc;
+  } else {
+    // CancellationToken (SampleBatchJob.cs:61): the reference polls once per pixel; a kernel
+    // cannot be recalled, so the batch is issued in row chunks and the token is polled between them.
+    int chunk = ctx->opt_cancel_rows > 0 ? (int)ctx->opt_cancel_rows : std::max(1, height / 16);
+    if (ctx->opt_counters) chunk = height;  // counters describe one launch
+    int lo = params->row_end > params->row_begin ? params->row_begin : 0;
+    const int hi = params->row_end > params->row_begin ? params->row_end : height;
+    for (; lo < hi; lo += chunk) {
+      if (*cancel) {
+        cudaStreamSynchronize(s);
+        return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+      }
+      const ActiveRows part = active_rows(*params, height, lo, std::min(hi, lo + chunk));
+      if ((rc = launch_batch(ctx, *params, dev, width, height, part, s)) != RTB_OK) return rc;
+      RTB_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+  }
+  RTB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, s));
+
+  RTB_CUDA(ctx, copy_rows(host->out_color, d.out_color, 16, width, all, cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(ctx, copy_rows(host->out_sample_count_weight, d.out_weight, 4, width, all, cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(ctx, copy_rows(host->out_normal, d.out_normal, 12, width, all, cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(ctx, copy_rows(host->out_albedo, d.out_albedo, 12, width, all, cudaMemcpyDeviceToHost, s));
+  if (host->out_diagnostics)
+    RTB_CUDA(ctx, copy_rows(host->out_diagnostics, d.diagnostics, sizeof(rtb_diagnostics), width, all, cudaMemcpyDeviceToHost, s));
+  if (ctx->opt_counters)
+    RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(ctx, cudaStreamSynchronize(s));
+  RTB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
+  if (cancel && *cancel) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  return RTB_OK;
+}
+
+int rtb_register_host_buffer(rtb_ctx* ctx, void* ptr, size_t bytes) {
+  if (!ctx || !ptr || !bytes) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_register_host_buffer: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (ctx->registered.count(ptr)) return RTB_OK;
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  ctx->registered[ptr] = bytes;
+  return RTB_OK;
+}
+
+int rtb_unregister_host_buffer(rtb_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_unregister_host_buffer: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto it = ctx->registered.find(ptr);
+  if (it == ctx->registered.end()) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "buffer was not registered");
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaHostUnregister(ptr));
+  ctx->registered.erase(it);
+  return RTB_OK;
+}
+
+int rtb_combine_device(rtb_ctx* ctx, int width, int height, int debug_mode, int ldr_albedo, const float* color4,
+                       const float* normal3, const float* albedo3, float* out_color3, float* out_normal3,
+                       float* out_albedo3, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (width < 1 || height < 1 || !color4) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_combine_device: bad argument");
+  if ((out_normal3 && !normal3) || (out_albedo3 && !albedo3)) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_combine_device: missing input");
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  const int n = width * height;
+  const int grid = std::min((n + 255) / 256, ctx->sm_count * 8);
+  combine_kernel<<<grid, 256, 0, stream>>>(width, height, debug_mode, ldr_albedo, reinterpret_cast<const float4*>(color4),
+                                           normal3, albedo3, out_color3, out_normal3, out_albedo3);
+  RTB_CUDA(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
+int rtb_reduce_metrics_device(rtb_ctx* ctx, int width, int height, const rtb_diagnostics* diagnostics, const float* color4,
+                              const float* sample_count_weight, rtb_metrics* out_host, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (width < 1 || height < 1 || !color4 || !sample_count_weight || !out_host)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_reduce_metrics_device: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  const int n = width * height;
+  const int grid = std::max(1, std::min({(n + 255) / 256, ctx->sm_count * 4, 1024}));
+  reduce_metrics_kernel<<<grid, 256, 0, stream>>>(n, diagnostics, reinterpret_cast<const float4*>(color4), sample_count_weight,
+                                                  ctx->d_metrics_partial);
+  RTB_CUDA(ctx, cudaGetLastError());
+  std::vector<MetricsAcc> part(grid);
+  RTB_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->d_metrics_partial, grid * sizeof(MetricsAcc), cudaMemcpyDeviceToHost, stream));
+  RTB_CUDA(ctx, cudaStreamSynchronize(stream));
+  MetricsAcc t = part[0];
+  for (int i = 1; i < grid; i++) {
+    t.rays += part[i].rays;
+    t.samples += part[i].samples;
+    t.w_min = um::min(t.w_min, part[i].w_min);
+    t.w_max = um::max(t.w_max, part[i].w_max);
+    t.s_min = std::min(t.s_min, part[i].s_min);
+    t.s_max = std::max(t.s_max, part[i].s_max);
+  }
+  out_host->total_ray_count = t.rays;
+  out_host->total_samples = t.samples;
+  out_host->sample_count_weight_min = t.w_min;
+  out_host->sample_count_weight_max = t.w_max;
+  out_host->sample_count_min = t.s_min;
+  out_host->sample_count_max = t.s_max;
+  return RTB_OK;
+}
+
+int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out) {
+  if (!ctx || !out) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_get_counters: bad argument");
+  if (!ctx->opt_counters) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "counters are disabled (rtb_set_option(RTB_OPT_COUNTERS, 1))");
+  DeviceGuard g(ctx->device);
+  // device-buffer batches do not synchronise: fetch the counters of the last launch now
+  RTB_CUDA(ctx, cudaDeviceSynchronize());
+  RTB_CUDA(ctx, cudaMemcpy(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost));
+  *out = ctx->counters;
+  return RTB_OK;
+}
+
+int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  switch (option) {
+    case RTB_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; return RTB_OK;
+    case RTB_OPT_KERNEL:
+      if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_KERNEL must be 0, 1 or 2");
+      ctx->opt_kernel = value;
+      return RTB_OK;
+    case RTB_OPT_CANCEL_CHUNK_ROWS:
+      if (value < 0) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_CANCEL_CHUNK_ROWS must be >= 0");
+      ctx->opt_cancel_rows = value;
+      return RTB_OK;
+  }
+  return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "unknown option %d", option);
+}
+
+int rtb_last_kernel_ms(rtb_ctx* ctx, float* out_ms) {
+  if (!ctx || !out_ms) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_last_kernel_ms: bad argument");
+  *out_ms = ctx->last_ms;
+  return RTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,464 @@
+// sample_kernels.cuh — the two kernels that replace SampleBatchJob.Execute
+// (Runtime/Jobs/SampleBatchJob.cs:58-164) and SampleBatchJob.Sample (:166-401).
+//
+//   sample_megakernel   the product: persistent warps, one lane per pixel-sample, dead lanes
+//                       refilled from the warp's tile by ballot/popc compaction of the work
+//                       stream, scene + flattened BVH staged into shared memory by TMA bulk
+//                       copies, order-independent fixed-point accumulation in shared memory,
+//                       coalesced float4 stores when a tile retires.
+//   sample_simple       one thread per pixel looping over its samples in order; the
+//                       accumulation order is the reference's (bit-exact against the CPU
+//                       oracle up to TraceDepth 64).  Validation and tiny images only.
+#pragma once
+
+#include "kernel_common.cuh"
+
+namespace rtbk {
+
+constexpr int kMegaBlock = 256;          // threads per CTA (8 warps)
+constexpr int kMegaWarps = kMegaBlock / 32;
+constexpr float kFixedScale = 4294967296.0f;            // 2^32
+constexpr float kFixedInvScale = 2.3283064365386963e-10f;  // 2^-32
+constexpr int kAccValues = 10;           // color.xyz, normal.xyz, albedo.xyz, sampleCountWeight
+
+// Shared-memory state of one warp's tile.  Accumulators are 64-bit fixed point (2^-32)
+// split into two 32-bit words so that native 32-bit shared atomics can be used: the sum of
+// a pixel's samples does not depend on the order in which its paths finish, which makes
+// the image deterministic although lanes retire paths in data-dependent order.
+struct WarpTile {
+  uint32_t acc_lo[kTilePixelsMax][kAccValues];
+  uint32_t acc_hi[kTilePixelsMax][kAccValues];
+  uint32_t successes[kTilePixelsMax];
+  uint32_t rays[kTilePixelsMax];
+  uint32_t node_tests[kTilePixelsMax];
+  uint32_t sphere_tests[kTilePixelsMax];
+  uint32_t non_finite[kTilePixelsMax];
+  float fallback[kTilePixelsMax][6];     // first sample's normal/albedo (SampleBatchJob.cs:152-156)
+  uint32_t prefix[kTilePixelsMax + 1];   // exclusive prefix of per-pixel sample counts
+};
+
+__device__ __forceinline__ void fixed_add(WarpTile& t, int slot, int v, float x) {
+  long long q = __float2ll_rn(x * kFixedScale);
+  uint32_t lo = (uint32_t)q, hi = (uint32_t)((unsigned long long)q >> 32);
+  uint32_t old = atomicAdd(&t.acc_lo[slot][v], lo);
+  uint32_t carry = (old + lo) < old ? 1u : 0u;
+  if (hi + carry) atomicAdd(&t.acc_hi[slot][v], hi + carry);
+}
+__device__ __forceinline__ float fixed_read(const WarpTile& t, int slot, int v) {
+  long long q = (long long)(((unsigned long long)t.acc_hi[slot][v] << 32) | t.acc_lo[slot][v]);
+  return __ll2float_rn(q) * kFixedInvScale;
+}
+
+__host__ __device__ inline size_t mega_smem_bytes(uint32_t blob_bytes, bool scene_in_smem) {
+  size_t s = 16;  // mbarrier
+  if (scene_in_smem) s += blob_bytes;
+  s = (s + 15) & ~(size_t)15;
+  return s + sizeof(WarpTile) * kMegaWarps;
+}
+
+// Active pixel k (0 <= k < n_active_pixels) -> image coordinates and the reference's index.
+__device__ __forceinline__ void active_pixel(const BatchArgs& a, uint32_t k, int* cx, int* cy, uint32_t* index) {
+  uint32_t j = k / (uint32_t)a.width;
+  *cx = (int)(k - j * (uint32_t)a.width);
+  *cy = a.first_row + (int)j * a.row_step;
+  *index = (uint32_t)*cy * (uint32_t)a.width + (uint32_t)*cx;
+}
+
+template <bool SMEM, bool COUNTERS>
+__global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_constant__ BatchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  unsigned char* blob_smem = smem + 16;
+  const size_t tiles_off = (16 + (SMEM ? a.scene.blob_bytes : 0) + 15) & ~(size_t)15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpTile& tile = reinterpret_cast<WarpTile*>(smem + tiles_off)[warp];
+
+  // ---- stage the world into shared memory: TMA bulk copies signalled on one mbarrier ----
+  SceneView<SMEM> sv;
+  if (SMEM) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(bar, a.scene.blob_bytes);
+      constexpr uint32_t kChunk = 32768;
+      for (uint32_t off = 0; off < a.scene.blob_bytes; off += kChunk) {
+        uint32_t n = a.scene.blob_bytes - off < kChunk ? a.scene.blob_bytes - off : kChunk;
+        tma_bulk_g2s(blob_smem + off, a.scene.blob + off, n, bar);
+      }
+    }
+    __syncthreads();          // the barrier init is visible before anyone polls it
+    mbar_wait(bar, 0);
+    sv.bind(blob_smem, a.scene);
+  } else {
+    sv.bind(a.scene.blob, a.scene);
+  }
+
+  const rtb_batch_params& p = a.p;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // ---- per-lane path state ----
+  bool alive = false;
+  int slot = 0;               // pixel slot inside the warp tile
+  uint32_t pixel = 0, sample = 0;
+  int depth = 0;
+  bool first_non_specular = false;
+  PathRay ray{um::mk(0.0f), um::mk(0.0f)};
+  f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
+  f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
+  float events_acc = 0, pow2depth = 1;
+  uint32_t path_rays = 0;
+  WorkCounters wc;
+
+  // ---- warp-uniform tile state ----
+  uint32_t tile_base = 0, next_item = 0, total_items = 0;
+  int tile_n = 0;
+
+  for (;;) {
+    // (1) refill dead lanes from the tile's work stream
+    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+    if (need) {
+      const uint32_t my_item = next_item + __popc(need & lt_mask);
+      if (!alive && my_item < total_items) {
+        // item -> (pixel slot, sample) through the tile's prefix table
+        int lo = 0, hi = tile_n;   // find the last slot with prefix[slot] <= my_item
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (tile.prefix[mid] <= my_item) lo = mid; else hi = mid;
+        }
+        slot = lo;
+        sample = my_item - tile.prefix[lo];
+        int cx, cy;
+        active_pixel(a, tile_base + (uint32_t)slot, &cx, &cy, &pixel);
+        ray = camera_ray(p, cx, cy, pixel, sample);
+        alive = true;
+        depth = 0;
+        first_non_specular = false;
+        throughput = um::mk(1.0f);
+        radiance = um::mk(0.0f);
+        s_normal = um::mk(0.0f);
+        s_albedo = um::mk(0.0f);
+        events_acc = 0;
+        pow2depth = 1;
+        path_rays = 0;
+      }
+      next_item = min(next_item + (uint32_t)__popc(need), total_items);
+    }
+
+    // (2) nothing in flight and nothing left in the tile: retire it, fetch the next one
+    if (__ballot_sync(0xffffffffu, alive) == 0) {
+      __syncwarp();
+      if (tile_n > 0 && lane < tile_n) {
+        int cx, cy;
+        uint32_t index;
+        active_pixel(a, tile_base + (uint32_t)lane, &cx, &cy, &index);
+        const float4 in_color = reinterpret_cast<const float4*>(a.b.in_color)[index];
+        const float in_weight = a.b.in_sample_count_weight[index];
+        const int succ = (int)tile.successes[lane];
+        const int sample_count = (int)in_color.w + succ;
+        const bool bad = tile.non_finite[lane] != 0;
+        const float nan = um::asfloat(0x7fc00000u);
+        float v[kAccValues];
+#pragma unroll
+        for (int k = 0; k < kAccValues; k++) v[k] = bad ? nan : fixed_read(tile, lane, k);
+        float4 oc = make_float4(in_color.x + v[0], in_color.y + v[1], in_color.z + v[2], (float)sample_count);
+        reinterpret_cast<float4*>(a.b.out_color)[index] = oc;
+        const float* in_n = a.b.in_normal + 3 * (size_t)index;
+        const float* in_a = a.b.in_albedo + 3 * (size_t)index;
+        float* on = a.b.out_normal + 3 * (size_t)index;
+        float* oa = a.b.out_albedo + 3 * (size_t)index;
+        if (sample_count == 0) {
+          on[0] = tile.fallback[lane][0]; on[1] = tile.fallback[lane][1]; on[2] = tile.fallback[lane][2];
+          oa[0] = tile.fallback[lane][3]; oa[1] = tile.fallback[lane][4]; oa[2] = tile.fallback[lane][5];
+        } else {
+          on[0] = in_n[0] + v[3]; on[1] = in_n[1] + v[4]; on[2] = in_n[2] + v[5];
+          oa[0] = in_a[0] + v[6]; oa[1] = in_a[1] + v[7]; oa[2] = in_a[2] + v[8];
+        }
+        a.b.out_sample_count_weight[index] = in_weight + v[9];
+        if (a.b.out_diagnostics) {
+          rtb_diagnostics dg;
+          dg.ray_count = (float)tile.rays[lane];
+          dg.bounds_hit_count = (float)tile.node_tests[lane];
+          dg.candidate_count = (float)tile.sphere_tests[lane];
+          dg.sample_count_weight = um::div(in_weight, (float)(int)in_color.w);
+          a.b.out_diagnostics[index] = dg;
+        }
+      }
+      // next tile
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(a.tile_counter, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= a.n_tiles) break;
+      tile_base = t * (uint32_t)a.tile_pixels;
+      tile_n = (int)min((uint32_t)a.tile_pixels, a.n_active_pixels - tile_base);
+      uint32_t n_samples = 0;
+      if (lane < tile_n) {
+        int cx, cy;
+        uint32_t index;
+        active_pixel(a, tile_base + (uint32_t)lane, &cx, &cy, &index);
+        const float in_w = a.b.in_color[4 * (size_t)index + 3];
+        const float in_weight = a.b.in_sample_count_weight[index];
+        float scw;
+        n_samples = samples_to_accumulate(p, in_w, in_weight, &scw);
+#pragma unroll
+        for (int k = 0; k < kAccValues; k++) { tile.acc_lo[lane][k] = 0; tile.acc_hi[lane][k] = 0; }
+        tile.successes[lane] = 0;
+        tile.rays[lane] = 0;
+        tile.node_tests[lane] = 0;
+        tile.sphere_tests[lane] = 0;
+        tile.non_finite[lane] = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) tile.fallback[lane][k] = 0;
+      }
+      // exclusive prefix over the tile's pixels
+      uint32_t incl = n_samples;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane < tile_n) tile.prefix[lane] = incl - n_samples;
+      total_items = __shfl_sync(0xffffffffu, incl, 31);
+      if (lane == 0) tile.prefix[tile_n] = total_items;
+      next_item = 0;
+      __syncwarp();
+      continue;
+    }
+
+    // (3) one bounce for every live lane (SampleBatchJob.cs:184-377)
+    if (alive) {
+      float t_hit;
+      int hit_idx;
+      closest_hit<SMEM, COUNTERS>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      path_rays++;
+      bool finished = false, success = false;
+      if (hit_idx >= 0) {
+        const float4 s = sv.ld4(sv.spheres + hit_idx);
+        const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
+        const float4 m0 = sv.ld4(sv.materials + 3 * mi), m1 = sv.ld4(sv.materials + 3 * mi + 1),
+                     m2 = sv.ld4(sv.materials + 3 * mi + 2);
+        // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
+        const f3 oc = ray.o + um::mk(-s.x, -s.y, -s.z);
+        const f3 N = um::normalize(um::mad(ray.d, t_hit, oc) / s.w);
+        const f3 P = um::mad(ray.d, t_hit, ray.o);
+        const ScatterResult sc = scatter(m0, m1, m2, ray.d, N, pixel, sample, (uint32_t)depth, p.seed);
+        if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+        const f3 emission = um::mk(m1.x, m1.y, m1.z);
+        if (depth == 0) {
+          s_normal = N;
+          if (sample == 0) { tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z; }
+        }
+        if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
+          s_albedo = emission + sc.reflectance;
+          s_normal = N;
+          first_non_specular = true;
+          if (sample == 0) {
+            tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z;
+            tile.fallback[slot][3] = s_albedo.x; tile.fallback[slot][4] = s_albedo.y; tile.fallback[slot][5] = s_albedo.z;
+          }
+        }
+        // forward form of the emission/attenuation unstack (SampleBatchJob.cs:383-396)
+        radiance = um::mad(throughput, emission, radiance);
+        throughput = throughput * sc.reflectance;
+        events_acc += um::div(sc.random_events, pow2depth);
+        // next ray (SampleBatchJob.cs:335-336, Ray.cs:18)
+        const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
+        ray.o = um::mad(off_n, 0.001f, P);
+        ray.d = sc.dir;
+        depth++;
+        pow2depth *= 2.0f;
+        if (depth == p.trace_depth) finished = true;   // failed sample (:379-381)
+      } else {
+        const f3 sky = sky_color(p.environment, ray.d);
+        radiance = um::mad(throughput, sky, radiance);
+        if (!first_non_specular) {
+          s_albedo = sky;
+          s_normal = -ray.d;
+          if (sample == 0) {
+            tile.fallback[slot][0] = s_normal.x; tile.fallback[slot][1] = s_normal.y; tile.fallback[slot][2] = s_normal.z;
+            tile.fallback[slot][3] = sky.x; tile.fallback[slot][4] = sky.y; tile.fallback[slot][5] = sky.z;
+          }
+        }
+        finished = true;
+        success = true;
+      }
+      if (finished) {
+        alive = false;
+        atomicAdd(&tile.rays[slot], path_rays);
+        if (COUNTERS) {
+          atomicAdd(&tile.node_tests[slot], wc.node_tests);
+          atomicAdd(&tile.sphere_tests[slot], wc.sphere_tests);
+          if (a.counters) {
+            if (wc.shade_standard) atomicAdd(&a.counters[4], (unsigned long long)wc.shade_standard);
+            if (wc.shade_dielectric) atomicAdd(&a.counters[5], (unsigned long long)wc.shade_dielectric);
+          }
+          wc = WorkCounters();
+        }
+        if (success) {
+          const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, s_normal.x, s_normal.y, s_normal.z,
+                                          s_albedo.x, s_albedo.y, s_albedo.z, events_acc};
+          bool finite = true;
+#pragma unroll
+          for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
+          if (finite) {
+#pragma unroll
+            for (int k = 0; k < kAccValues; k++) fixed_add(tile, slot, k, vals[k]);
+          } else {
+            tile.non_finite[slot] = 1;
+          }
+          atomicAdd(&tile.successes[slot], 1u);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+}
+
+// Sums the per-pixel diagnostics into rtb_counters (instrumented runs only).
+__global__ void counters_from_diagnostics(const rtb_diagnostics* __restrict__ diag, const float* __restrict__ color4,
+                                          const float* __restrict__ in_color4, BatchArgs a) {
+  // grid-stride over active pixels
+  unsigned long long rays = 0, nodes = 0, spheres = 0, succ = 0, attempted = 0;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < a.n_active_pixels; k += gridDim.x * blockDim.x) {
+    int cx, cy;
+    uint32_t index;
+    active_pixel(a, k, &cx, &cy, &index);
+    float scw;
+    attempted += samples_to_accumulate(a.p, in_color4[4 * (size_t)index + 3], a.b.in_sample_count_weight[index], &scw);
+    rays += (unsigned long long)diag[index].ray_count;
+    nodes += (unsigned long long)diag[index].bounds_hit_count;
+    spheres += (unsigned long long)diag[index].candidate_count;
+    succ += (unsigned long long)((int)color4[4 * (size_t)index + 3] - (int)in_color4[4 * (size_t)index + 3]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    rays += __shfl_down_sync(0xffffffffu, rays, o);
+    nodes += __shfl_down_sync(0xffffffffu, nodes, o);
+    spheres += __shfl_down_sync(0xffffffffu, spheres, o);
+    succ += __shfl_down_sync(0xffffffffu, succ, o);
+    attempted += __shfl_down_sync(0xffffffffu, attempted, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&a.counters[0], attempted);
+    atomicAdd(&a.counters[7], attempted - succ);   // failed samples (SampleBatchJob.cs:379-381)
+    atomicAdd(&a.counters[1], rays);
+    atomicAdd(&a.counters[2], nodes);
+    atomicAdd(&a.counters[3], spheres);
+    atomicAdd(&a.counters[6], succ);   // successes == sky terminations
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sample_simple: thread per active pixel, samples in order.  Emission/attenuation stacks
+// are kept (up to 64 entries) and unwound tail -> head exactly like SampleBatchJob.cs:383-396,
+// and samples are added in index order, so colour sums are bit-identical to the oracle's.
+// ---------------------------------------------------------------------------------------
+constexpr int kSimpleStack = 64;
+
+template <bool COUNTERS>
+__global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ BatchArgs a) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.n_active_pixels) return;
+  const rtb_batch_params& p = a.p;
+  SceneView<false> sv;
+  sv.bind(a.scene.blob, a.scene);
+  int cx, cy;
+  uint32_t index;
+  active_pixel(a, k, &cx, &cy, &index);
+
+  const float4 in_color = reinterpret_cast<const float4*>(a.b.in_color)[index];
+  f3 color_acc = um::mk(in_color.x, in_color.y, in_color.z);
+  f3 normal_acc = v3(a.b.in_normal + 3 * (size_t)index);
+  f3 albedo_acc = v3(a.b.in_albedo + 3 * (size_t)index);
+  float weight_acc = a.b.in_sample_count_weight[index];
+  int sample_count = (int)in_color.w;
+  float scw;
+  const uint32_t n = samples_to_accumulate(p, in_color.w, weight_acc, &scw);
+  f3 fb_normal = um::mk(0.0f), fb_albedo = um::mk(0.0f);
+  uint32_t rays = 0;
+  WorkCounters wc;
+  const bool exact = p.trace_depth <= kSimpleStack;
+  f3 att[kSimpleStack], emi[kSimpleStack];
+
+  for (uint32_t s = 0; s < n; s++) {
+    PathRay ray = camera_ray(p, cx, cy, index, s);
+    f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
+    f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
+    bool first_non_specular = false;
+    float events_acc = 0, pow2depth = 1;
+    int depth = 0, entries = 0;
+    for (; depth < p.trace_depth; depth++) {
+      float t_hit;
+      int hit_idx;
+      closest_hit<false, COUNTERS>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      rays++;
+      if (hit_idx >= 0) {
+        const float4 sp = sv.ld4(sv.spheres + hit_idx);
+        const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
+        const float4 m0 = sv.ld4(sv.materials + 3 * mi), m1 = sv.ld4(sv.materials + 3 * mi + 1),
+                     m2 = sv.ld4(sv.materials + 3 * mi + 2);
+        const f3 oc = ray.o + um::mk(-sp.x, -sp.y, -sp.z);
+        const f3 N = um::normalize(um::mad(ray.d, t_hit, oc) / sp.w);
+        const f3 P = um::mad(ray.d, t_hit, ray.o);
+        const ScatterResult sc = scatter(m0, m1, m2, ray.d, N, index, s, (uint32_t)depth, p.seed);
+        if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+        const f3 emission = um::mk(m1.x, m1.y, m1.z);
+        if (depth == 0) s_normal = N;
+        if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
+          s_albedo = emission + sc.reflectance;
+          s_normal = N;
+          first_non_specular = true;
+        }
+        if (exact) { emi[entries] = emission; att[entries] = sc.reflectance; entries++; }
+        radiance = um::mad(throughput, emission, radiance);
+        throughput = throughput * sc.reflectance;
+        events_acc += um::div(sc.random_events, pow2depth);
+        const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
+        ray.o = um::mad(off_n, 0.001f, P);
+        ray.d = sc.dir;
+        pow2depth *= 2.0f;
+      } else {
+        const f3 sky = sky_color(p.environment, ray.d);
+        if (exact) { emi[entries] = sky; att[entries] = um::mk(1.0f); entries++; }
+        radiance = um::mad(throughput, sky, radiance);
+        if (!first_non_specular) { s_albedo = sky; s_normal = -ray.d; }
+        break;
+      }
+    }
+    if (depth != p.trace_depth) {
+      f3 c = radiance;
+      if (exact) {
+        c = um::mk(0.0f);
+        for (int e = entries; e-- > 0;) { c = c * att[e]; c = c + emi[e]; }
+      }
+      color_acc = color_acc + c;
+      normal_acc = normal_acc + s_normal;
+      albedo_acc = albedo_acc + s_albedo;
+      weight_acc += events_acc;
+      sample_count++;
+    }
+    if (s == 0) { fb_normal = s_normal; fb_albedo = s_albedo; }
+  }
+
+  reinterpret_cast<float4*>(a.b.out_color)[index] = make_float4(color_acc.x, color_acc.y, color_acc.z, (float)sample_count);
+  const f3 on = sample_count == 0 ? fb_normal : normal_acc;
+  const f3 oa = sample_count == 0 ? fb_albedo : albedo_acc;
+  float* pn = a.b.out_normal + 3 * (size_t)index;
+  float* pa = a.b.out_albedo + 3 * (size_t)index;
+  pn[0] = on.x; pn[1] = on.y; pn[2] = on.z;
+  pa[0] = oa.x; pa[1] = oa.y; pa[2] = oa.z;
+  a.b.out_sample_count_weight[index] = weight_acc;
+  if (COUNTERS && a.counters) {
+    if (wc.shade_standard) atomicAdd(&a.counters[4], (unsigned long long)wc.shade_standard);
+    if (wc.shade_dielectric) atomicAdd(&a.counters[5], (unsigned long long)wc.shade_dielectric);
+  }
+  if (a.b.out_diagnostics) {
+    rtb_diagnostics dg;
+    dg.ray_count = (float)rays;
+    dg.bounds_hit_count = (float)wc.node_tests;
+    dg.candidate_count = (float)wc.sphere_tests;
+    dg.sample_count_weight = scw;
+    a.b.out_diagnostics[index] = dg;
+  }
+}
+
+}  // namespace rtbk

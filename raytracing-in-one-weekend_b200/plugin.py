@@ -1,0 +1,229 @@
+"""ctypes binding of librtb.so (include/rtb.h) — the sm_100a plugin.
+
+This is the Python twin of the P/Invoke class a Unity maintainer would add
+(bindings/B200PathTracerApi.cs).  There is NO CPU fallback: loading
+fails loudly when the library has not been built, and `Context()` fails when no sm_100
+device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as abi
+from . import build as _build
+
+EXPORTS = [
+    "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
+    "rtb_upload_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_register_host_buffer", "rtb_unregister_host_buffer",
+    "rtb_combine_device", "rtb_reduce_metrics_device",
+    "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms",
+]
+
+_lib = None
+
+
+class RtbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"rtb error {code}: {message}")
+        self.code = code
+
+
+def lib():
+    """Loads lib/librtb.so (never builds it implicitly on a GPU box: the .so ships in-tree)."""
+    global _lib
+    if _lib is None:
+        path = _build.plugin_lib_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback"
+            )
+        L = C.CDLL(path)
+        vp, sz = C.c_void_p, C.c_size_t
+        L.rtb_abi_version.restype = C.c_int
+        L.rtb_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.rtb_destroy.argtypes = [vp]
+        L.rtb_last_error.argtypes = [vp]
+        L.rtb_last_error.restype = C.c_char_p
+        L.rtb_set_log_callback.argtypes = [vp, vp, vp]
+        L.rtb_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+        L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
+        L.rtb_sample_batch_device.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
+        L.rtb_register_host_buffer.argtypes = [vp, vp, sz]
+        L.rtb_unregister_host_buffer.argtypes = [vp, vp]
+        L.rtb_combine_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.rtb_reduce_metrics_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(abi.Metrics), vp]
+        L.rtb_get_counters.argtypes = [vp, C.POINTER(abi.Counters)]
+        L.rtb_set_option.argtypes = [vp, C.c_int, C.c_int64]
+        L.rtb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        for name in EXPORTS:
+            if name != "rtb_last_error":
+                getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+class HostBuffers:
+    """The eight accumulation arrays of one batch (SampleBatchJob.cs:41-51) + diagnostics, as
+    numpy arrays in the reference's layout (index = row * W + col, row 0 = bottom)."""
+
+    def __init__(self, width, height, diagnostics=True):
+        n = width * height
+        self.width, self.height = width, height
+        self.in_color = np.zeros((n, 4), np.float32)
+        self.in_weight = np.zeros(n, np.float32)
+        self.in_normal = np.zeros((n, 3), np.float32)
+        self.in_albedo = np.zeros((n, 3), np.float32)
+        self.out_color = np.zeros((n, 4), np.float32)
+        self.out_weight = np.zeros(n, np.float32)
+        self.out_normal = np.zeros((n, 3), np.float32)
+        self.out_albedo = np.zeros((n, 3), np.float32)
+        self.diagnostics = np.zeros(n, abi.DIAGNOSTICS_DTYPE) if diagnostics else None
+
+    def arrays(self):
+        a = [self.in_color, self.in_weight, self.in_normal, self.in_albedo,
+             self.out_color, self.out_weight, self.out_normal, self.out_albedo]
+        if self.diagnostics is not None:
+            a.append(self.diagnostics)
+        return a
+
+    def as_struct(self):
+        b = abi.BatchBuffers()
+        b.in_color = self.in_color.ctypes.data
+        b.in_sample_count_weight = self.in_weight.ctypes.data
+        b.in_normal = self.in_normal.ctypes.data
+        b.in_albedo = self.in_albedo.ctypes.data
+        b.out_color = self.out_color.ctypes.data
+        b.out_sample_count_weight = self.out_weight.ctypes.data
+        b.out_normal = self.out_normal.ctypes.data
+        b.out_albedo = self.out_albedo.ctypes.data
+        b.out_diagnostics = self.diagnostics.ctypes.data if self.diagnostics is not None else None
+        return b
+
+    def swap(self):
+        """accumulation := output (Raytracer.cs:798-802)."""
+        self.in_color, self.out_color = self.out_color, self.in_color
+        self.in_weight, self.out_weight = self.out_weight, self.in_weight
+        self.in_normal, self.out_normal = self.out_normal, self.in_normal
+        self.in_albedo, self.out_albedo = self.out_albedo, self.in_albedo
+
+    def rgb(self):
+        """Per-pixel colour as CombineJob defines it (CombineJob.cs:34-54)."""
+        n = self.out_color[:, 3].astype(np.int32)
+        rgb = self.out_color[:, :3] / np.maximum(n, 1)[:, None].astype(np.float32)
+        rgb[n == 0] = 0
+        return rgb.reshape(self.height, self.width, 3)
+
+
+def device_buffers_struct(in_color, in_weight, in_normal, in_albedo, out_color, out_weight, out_normal, out_albedo,
+                          diagnostics=None):
+    """rtb_batch_buffers from objects exposing `.data_ptr()` (torch CUDA tensors) or raw ints."""
+    def ptr(x):
+        if x is None:
+            return None
+        return x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+
+    b = abi.BatchBuffers()
+    b.in_color, b.in_sample_count_weight, b.in_normal, b.in_albedo = ptr(in_color), ptr(in_weight), ptr(in_normal), ptr(in_albedo)
+    b.out_color, b.out_sample_count_weight, b.out_normal, b.out_albedo = ptr(out_color), ptr(out_weight), ptr(out_normal), ptr(out_albedo)
+    b.out_diagnostics = ptr(diagnostics)
+    return b
+
+
+class Context:
+    """One rtb_ctx: a CUDA device, a stream, the uploaded world."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._L = lib()
+        rc = self._L.rtb_create(device, C.byref(self._h))
+        if rc != 0:
+            raise RtbError(rc, (self._L.rtb_last_error(None) or b"").decode())
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RtbError(rc, (self._L.rtb_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            self._L.rtb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene -------------------------------------------------------------------------
+    def upload_scene(self, spheres, materials, nodes):
+        spheres = np.ascontiguousarray(spheres, dtype=abi.SPHERE_DTYPE)
+        materials = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DTYPE)
+        nodes = np.ascontiguousarray(nodes, dtype=abi.BVH_NODE_DTYPE)
+        self._check(self._L.rtb_upload_scene(
+            self._h, spheres.ctypes.data if len(spheres) else None, len(spheres),
+            materials.ctypes.data if len(materials) else None, len(materials),
+            nodes.ctypes.data if len(nodes) else None, len(nodes)))
+
+    def upload(self, scene):
+        self.upload_scene(scene.spheres, scene.materials, scene.nodes)
+
+    # ---- the hot path ------------------------------------------------------------------
+    def sample_batch(self, params, buffers, cancel=None):
+        """Blocking call with HOST buffers (`HostBuffers`): H2D, megakernel, D2H."""
+        b = buffers.as_struct()
+        cancel_ptr = cancel.ctypes.data if cancel is not None else None
+        self._check(self._L.rtb_sample_batch(self._h, C.byref(params), C.byref(b), cancel_ptr))
+        return buffers
+
+    def sample_batch_device(self, params, device_buffers, stream=None):
+        """Enqueues the batch on device-resident buffers (`rtb_batch_buffers` of device pointers)."""
+        self._check(self._L.rtb_sample_batch_device(self._h, C.byref(params), C.byref(device_buffers), stream))
+
+    def register_host_buffers(self, buffers):
+        for a in buffers.arrays():
+            self._check(self._L.rtb_register_host_buffer(self._h, a.ctypes.data, a.nbytes))
+
+    def unregister_host_buffers(self, buffers):
+        for a in buffers.arrays():
+            self._check(self._L.rtb_unregister_host_buffer(self._h, a.ctypes.data))
+
+    # ---- adjacent jobs -----------------------------------------------------------------
+    def combine_device(self, width, height, color4, normal3, albedo3, out_color3, out_normal3, out_albedo3,
+                       debug_mode=False, ldr_albedo=False, stream=None):
+        def ptr(x):
+            return None if x is None else (x.data_ptr() if hasattr(x, "data_ptr") else int(x))
+        self._check(self._L.rtb_combine_device(self._h, width, height, int(debug_mode), int(ldr_albedo), ptr(color4),
+                                               ptr(normal3), ptr(albedo3), ptr(out_color3), ptr(out_normal3),
+                                               ptr(out_albedo3), stream))
+
+    def reduce_metrics_device(self, width, height, diagnostics, color4, weight, stream=None):
+        def ptr(x):
+            return None if x is None else (x.data_ptr() if hasattr(x, "data_ptr") else int(x))
+        m = abi.Metrics()
+        self._check(self._L.rtb_reduce_metrics_device(self._h, width, height, ptr(diagnostics), ptr(color4), ptr(weight),
+                                                      C.byref(m), stream))
+        return m
+
+    # ---- measurement -------------------------------------------------------------------
+    def set_option(self, option, value):
+        self._check(self._L.rtb_set_option(self._h, option, value))
+
+    def counters(self):
+        c = abi.Counters()
+        self._check(self._L.rtb_get_counters(self._h, C.byref(c)))
+        return {name: getattr(c, name) for name, _ in abi.Counters._fields_}
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        self._check(self._L.rtb_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
