@@ -3,7 +3,8 @@ renaudbedard/raytracing-in-one-weekend (Runtime/Jobs/SampleBatchJob.cs).
 
   host      stand-in for the C# host: scenes, BVH build, View (librtb_host.so, CPU only)
   plugin    ctypes binding of the C ABI (include/rtb.h) of librtb.so — the sm_100a kernels
-  job       SampleBatchJob / CombineJob / ReduceMetricsJob mirrors with the reference's field names
+  job       SampleBatchJob mirror with the reference's field names + the ScheduleSample batch loop
+  sharding  row-tile partition of a frame across GPUs + the one NCCL gather per frame (imported lazily: needs torch)
 
 The directory name is not a Python identifier; import it with
     rtb = importlib.import_module("raytracing-in-one-weekend_b200")

@@ -1,0 +1,66 @@
+"""Host-side logic: interlacing series, row activation, sharding partition, job mirror."""
+import numpy as np
+import pytest
+
+
+def test_space_filling_series(rtb):
+    # Tools.SpaceFillingSeries (Tools.cs:101-124): a permutation of 0..n-1 starting at 0 that halves gaps
+    assert rtb.host.space_filling_series(1) == [0]
+    assert rtb.host.space_filling_series(2) == [0, 1]
+    assert rtb.host.space_filling_series(4) == [0, 2, 1, 3]
+    assert rtb.host.space_filling_series(8) == [0, 4, 2, 6, 1, 3, 5, 7]
+    for n in (3, 8, 16, 32):
+        s = rtb.host.space_filling_series(n)
+        assert sorted(s) == list(range(n)) and s[0] == 0
+    # literal restatement, quirk included: for some non-power-of-two lengths i * increment overshoots
+    assert rtb.host.space_filling_series(5) == [0, 3, 2, 4, 6]
+
+
+def test_view_basis_is_orthonormal_and_left_handed(rtb):
+    v = rtb.host.make_view((0, 0, -2.25), (0, 0, 0), (0, 1, 0), 60.0, 16 / 9, 0.2, 3.0)
+    f, u, r = (np.array(tuple(x)) for x in (v.forward, v.up, v.right))
+    assert np.allclose([f @ u, f @ r, u @ r], 0, atol=1e-6)
+    assert np.allclose([np.linalg.norm(f), np.linalg.norm(u), np.linalg.norm(r)], 1, atol=1e-6)
+    assert np.allclose(f, (0, 0, -1)) and np.allclose(r, (1, 0, 0))    # Forward = normalize(origin - lookAt), View.cs:24
+    assert abs(v.lens_radius - 0.1) < 1e-7
+    assert np.allclose(np.linalg.norm(tuple(v.vertical)), 2 * np.tan(np.radians(30)) * 3.0, rtol=1e-5)
+
+
+def test_make_params_mirrors_schedule_sample(rtb):
+    scene = rtb.host.make_scene("three_spheres")
+    p = rtb.host.make_params(scene, 400, 225, 4, 8)
+    assert (p.size[0], p.size[1]) == (400.0, 225.0)
+    assert (p.slice_offset, p.slice_divider, p.seed) == (0, 1, 1)
+    assert tuple(p.sample_count_range) == (4, 4) and p.trace_depth == 8 and p.sub_pixel_jitter == 1
+    assert p.environment.sky_type == rtb.abi.SKY_GRADIENT
+
+
+def test_job_mirror_builds_the_same_params(rtb):
+    from importlib import import_module
+
+    job = import_module("raytracing-in-one-weekend_b200.job")
+    scene = rtb.host.make_scene("three_spheres")
+    view, _ = rtb.host.view_for(scene, 64, 36)
+    j = job.SampleBatchJob(Size=(64, 36), SliceOffset=1, SliceDivider=2, Seed=7, View=view, Environment=scene.environment,
+                           SampleCountRange=(2, 5), TraceDepth=9, SubPixelJitter=False, SampleCountWeightExtrema=(0.5, 2.0))
+    p = j.params()
+    assert (p.size[0], p.size[1], p.slice_offset, p.slice_divider, p.seed) == (64.0, 36.0, 1, 2, 7)
+    assert tuple(p.sample_count_range) == (2, 5) and p.trace_depth == 9 and p.sub_pixel_jitter == 0
+    assert tuple(p.sample_count_weight_extrema) == (0.5, 2.0)
+    assert bytes(p.view) == bytes(view)
+
+
+def test_row_tiles_partition(rtb):
+    from importlib import import_module
+
+    sh = import_module("raytracing-in-one-weekend_b200.sharding")
+    for h, w in [(1080, 8), (1080, 7), (225, 2), (5, 4), (2160, 8)]:
+        tiles = sh.row_tiles(h, w)
+        assert tiles[0][0] == 0 and tiles[-1][1] == h
+        assert all(tiles[i][1] == tiles[i + 1][0] for i in range(w - 1))
+        assert max(e - b for b, e in tiles) - min(e - b for b, e in tiles) <= 1
+    cost = np.concatenate([np.full(100, 1.0), np.full(100, 9.0)])
+    tiles = sh.balanced_row_tiles(cost, 4)
+    assert tiles[0][0] == 0 and tiles[-1][1] == 200 and all(e > b for b, e in tiles)
+    sums = [cost[b:e].sum() for b, e in tiles]
+    assert max(sums) / min(sums) < 1.15
