@@ -255,6 +255,10 @@ RTB_API int rtb_set_option(rtb_ctx* ctx, int option, int64_t value);
 /* Milliseconds of the last kernel launch sequence on the context stream (CUDA events; the
  * same bracket as the two RecordTimeJobs, Raytracer.cs:729-738).  Valid after a synchronising call. */
 RTB_API int rtb_last_kernel_ms(rtb_ctx* ctx, float* out_ms);
+/* Roofline denominator for this path (MEASURED_PEAKS.json has no FP32-pipe figure):
+ * runs an all-SM microbenchmark of independent FP32 FMA chains and returns the best of
+ * `repeats` timings in TFLOP/s (FMA = 2 flop).  Not part of the reference's interface. */
+RTB_API int rtb_measure_fp32_peak(rtb_ctx* ctx, int repeats, double* out_tflops);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ MATERIAL_STANDARD, MATERIAL_DIELECTRIC, MATERIAL_PROBABILISTIC_VOLUME = 0, 1, 2
 SKY_NONE, SKY_GRADIENT, SKY_CUBEMAP = 0, 1, 2
 SCENE_THREE_SPHERES, SCENE_FINAL, SCENE_STRESS = 0, 1, 2
 
+ABI_VERSION = 1
 RTB_OK = 0
 RTB_ERR_INVALID_ARGUMENT = 1
 RTB_ERR_NO_SCENE = 2

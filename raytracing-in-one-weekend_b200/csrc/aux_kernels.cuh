@@ -94,4 +94,19 @@ __global__ void reduce_metrics_kernel(int n, const rtb_diagnostics* __restrict__
   }
 }
 
+// FP32-pipe roofline microbenchmark: 16 independent FMA chains per thread, register operands.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float b, float c) {
+  float a[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = (float)(threadIdx.x + k) * 1e-3f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = __fmaf_rn(a[k], b, c);
+  }
+  float s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += a[k];
+  if (s == 123456.789f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the chains alive
+}
+
 }  // namespace rtbk

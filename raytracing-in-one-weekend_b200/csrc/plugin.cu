@@ -633,6 +633,30 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
   return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "unknown option %d", option);
 }
 
+int rtb_measure_fp32_peak(rtb_ctx* ctx, int repeats, double* out_tflops) {
+  if (!ctx || !out_tflops || repeats < 1) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_measure_fp32_peak: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  DeviceGuard g(ctx->device);
+  const int iters = 1 << 14, blocks = ctx->sm_count * 8, threads = 256;
+  float* d_out = nullptr;
+  RTB_CUDA(ctx, cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(float)));
+  double best = 0.0;
+  for (int r = 0; r < repeats + 1; r++) {   // first launch is a warm-up
+    cudaEventRecord(ctx->ev_start, ctx->stream);
+    fp32_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0000001f, 1e-7f);
+    cudaEventRecord(ctx->ev_stop, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_out); return fail(ctx, RTB_ERR_CUDA + (int)e, "fp32 peak kernel: %s", cudaGetErrorString(e)); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+    const double tf = (double)blocks * threads * iters * 16.0 * 2.0 / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaFree(d_out);
+  *out_tflops = best;
+  return RTB_OK;
+}
+
 int rtb_last_kernel_ms(rtb_ctx* ctx, float* out_ms) {
   if (!ctx || !out_ms) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_last_kernel_ms: bad argument");
   *out_ms = ctx->last_ms;

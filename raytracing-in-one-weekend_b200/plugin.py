@@ -18,7 +18,7 @@ EXPORTS = [
     "rtb_upload_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_reduce_metrics_device",
-    "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms",
+    "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_measure_fp32_peak",
 ]
 
 _lib = None
@@ -58,6 +58,7 @@ def lib():
         L.rtb_get_counters.argtypes = [vp, C.POINTER(abi.Counters)]
         L.rtb_set_option.argtypes = [vp, C.c_int, C.c_int64]
         L.rtb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.rtb_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
         for name in EXPORTS:
             if name != "rtb_last_error":
                 getattr(L, name).restype = C.c_int
@@ -222,6 +223,12 @@ class Context:
         c = abi.Counters()
         self._check(self._L.rtb_get_counters(self._h, C.byref(c)))
         return {name: getattr(c, name) for name, _ in abi.Counters._fields_}
+
+    def measure_fp32_peak(self, repeats=5):
+        """Measured FP32 FMA peak of this device in TFLOP/s (the roofline that bounds this path)."""
+        tf = C.c_double(0)
+        self._check(self._L.rtb_measure_fp32_peak(self._h, repeats, C.byref(tf)))
+        return tf.value
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

@@ -1,0 +1,26 @@
+"""One device-resident step of BASELINE config 3 (or --config) for ncu captures."""
+import argparse
+import importlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+sys.argv = [sys.argv[0]] + sys.argv[1:]
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="c3")
+ap.add_argument("--steps", type=int, default=1)
+args = ap.parse_args()
+bench = importlib.import_module("bench")
+rtb = importlib.import_module("raytracing-in-one-weekend_b200")
+renderer = importlib.import_module("raytracing-in-one-weekend_b200.renderer")
+name, depth, W, H, spp, td, aperture = bench.CONFIGS[args.config]
+scene = rtb.host.make_scene(name, max_bvh_depth=depth)
+p = rtb.host.make_params(scene, W, H, spp, td, aperture=aperture)
+fr = renderer.FrameRenderer(scene, W, H, 0)
+for _ in range(args.steps):
+    fr.render_device(p)
+torch.cuda.synchronize()
+print("rendered", args.config, float(fr.out["color"][:, :3].sum().item()))
