@@ -274,7 +274,7 @@ def run_ours(args):
 
     if rank == 0:
         traffic = None
-        summary = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        summary = os.path.join(ROOT, "profiles", "ncu_summary_latest.json")
         if os.path.exists(summary):
             try:
                 traffic = json.load(open(summary)).get("dram_bytes_per_launch")

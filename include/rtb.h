@@ -197,7 +197,7 @@ RTB_API int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params,
                              const volatile uint8_t* cancel);
 
 /* Same batch on DEVICE-resident buffers, enqueued on `cuda_stream` (a cudaStream_t passed as
- * void*; NULL = the context's own stream) without synchronising: the caller owns the
+ * void*; NULL = the CUDA default stream) without synchronising: the caller owns the
  * buffers and the stream (used for multi-batch accumulation that never leaves HBM, and for
  * row-tile sharding where each rank renders into its slice of a gather buffer). */
 RTB_API int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params,

@@ -466,7 +466,7 @@ int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params, const 
       !dev->out_sample_count_weight || !dev->out_normal || !dev->out_albedo)
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "a batch buffer pointer is NULL");
   DeviceGuard g(ctx->device);
-  cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;   // NULL = the CUDA default stream, as in every CUDA API
   return launch_batch(ctx, *params, *dev, width, height, active_rows(*params, height, 0, 0), stream);
 }
 
@@ -563,7 +563,7 @@ int rtb_combine_device(rtb_ctx* ctx, int width, int height, int debug_mode, int 
   if (width < 1 || height < 1 || !color4) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_combine_device: bad argument");
   if ((out_normal3 && !normal3) || (out_albedo3 && !albedo3)) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_combine_device: missing input");
   DeviceGuard g(ctx->device);
-  cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
   const int n = width * height;
   const int grid = std::min((n + 255) / 256, ctx->sm_count * 8);
   combine_kernel<<<grid, 256, 0, stream>>>(width, height, debug_mode, ldr_albedo, reinterpret_cast<const float4*>(color4),
@@ -579,7 +579,7 @@ int rtb_reduce_metrics_device(rtb_ctx* ctx, int width, int height, const rtb_dia
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_reduce_metrics_device: bad argument");
   std::lock_guard<std::mutex> lock(ctx->mu);
   DeviceGuard g(ctx->device);
-  cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
   const int n = width * height;
   const int grid = std::max(1, std::min({(n + 255) / 256, ctx->sm_count * 4, 1024}));
   reduce_metrics_kernel<<<grid, 256, 0, stream>>>(n, diagnostics, reinterpret_cast<const float4*>(color4), sample_count_weight,

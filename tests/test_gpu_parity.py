@@ -130,7 +130,7 @@ def test_row_tiles_compose_to_the_full_frame_bitwise(rtb, ctx):
         pt = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1, row_begin=b, row_end=e)
         ctx.sample_batch(pt, tiled)
     for a, b_ in zip(full.arrays(), tiled.arrays()):
-        assert np.array_equal(a, b_) or np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b_.view(np.uint32) if b_.dtype == np.float32 else b_)
+        assert a.tobytes() == b_.tobytes()        # bytes: sample_count_weight diagnostics are NaN on a fresh buffer
 
 
 def test_progressive_accumulation_two_batches(rtb, oracle, ctx):
