@@ -85,6 +85,17 @@ def build_plugin(force=False, verbose=False, extra_flags=()):
     return out
 
 
+def build_variant(tag, defines, verbose=False):
+    """Experiment builds: lib/variants/librtb_<tag>.so with extra -D flags (selected at run time through
+    the RTB_PLUGIN_LIB environment variable, see plugin.lib())."""
+    d = os.path.join(LIB, "variants")
+    os.makedirs(d, exist_ok=True)
+    out = os.path.join(d, f"librtb_{tag}.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    _run([nvcc] + NVCC_FLAGS + [f"-D{x}" for x in defines] + ["-o", out] + CUDA_SOURCES, verbose)
+    return out
+
+
 def build_all(force=False, verbose=False):
     return build_host(force, verbose), build_plugin(force, verbose)
 

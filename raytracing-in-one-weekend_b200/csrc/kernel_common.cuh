@@ -36,24 +36,32 @@ using um::f3;
 //   spheres      : n_spheres * 16 B  float4 (center.xyz, radius), BVH leaf order
 //   leaf_count   : n_spheres * 4 B   entity count of the leaf that STARTS at this sphere
 //   mat_index    : n_spheres * 4 B   material index of the sphere
-//   materials    : n_materials * 48 B  DevMaterial
+// Materials (n_materials * 64 B DevMaterial) stay in HBM behind the read-only path: they are
+// read once per bounce, not once per node.
 // ---------------------------------------------------------------------------------------
-struct DevMaterial {            // 48 bytes = 3 x float4
+struct DevMaterial {            // 64 bytes = 4 x float4; lives in HBM (read-only path), one read per bounce
   float albedo[3];
   uint32_t type;                // rtb_material_type
   float emission[3];
   float glossiness;
   float metallic;
-  float ior;
-  uint32_t perfect_specular;    // Material.IsPerfectSpecular (Material.cs:181-196), precomputed on upload
+  float ior;                    // Standard: lerp(PlasticIor, MetalIor, metallic) (Material.cs:86); Dielectric: IndexOfRefraction
+  uint32_t perfect_specular;    // Material.IsPerfectSpecular (Material.cs:181-196)
+  float roughness;              // Standard: pow(1 - glossiness, 2) (:82); Dielectric: 1 - glossiness (:123)
+  // Per-material constants of Scatter, evaluated ON THE DEVICE at upload by the same functions the
+  // per-hit code would call (derive_materials_kernel), so hoisting them changes no bits.
+  float alpha;                  // Microfacet.RoughnessToAlpha(roughness) (Standard)
+  float r0;                     // Schlick: ((1 - ior) / (1 + ior))^2
+  float one_minus_r0;
   uint32_t pad;
 };
-static_assert(sizeof(DevMaterial) == 48, "DevMaterial layout");
+static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
 
 struct SceneDesc {
   const unsigned char* blob;    // device pointer
   uint32_t blob_bytes;          // multiple of 16
-  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, material_off;
+  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off;
+  const DevMaterial* materials; // device pointer
   uint32_t n_inner, n_spheres, n_materials;
   int32_t root_ref;             // as child refs; meaningful when has_root
   uint32_t has_root;            // 0: empty world (node_count == 0)
@@ -142,14 +150,12 @@ struct SceneView {
   const float4* spheres;
   const uint32_t* leaf_count;
   const uint32_t* mat_index;
-  const float4* materials;
 
   __device__ __forceinline__ void bind(const unsigned char* base, const SceneDesc& s) {
     inner = reinterpret_cast<const float4*>(base + s.inner_off);
     spheres = reinterpret_cast<const float4*>(base + s.sphere_off);
     leaf_count = reinterpret_cast<const uint32_t*>(base + s.leaf_count_off);
     mat_index = reinterpret_cast<const uint32_t*>(base + s.mat_index_off);
-    materials = reinterpret_cast<const float4*>(base + s.material_off);
   }
   __device__ __forceinline__ float4 ld4(const float4* p) const {
     if (SMEM) return *p;
@@ -209,6 +215,11 @@ __device__ __forceinline__ void sphere_hit(float4 s, int idx, f3 o, f3 d, float 
 // far larger than the rounding error of either distance), so it returns the same nearest
 // record while testing a fraction of the nodes.
 constexpr float kPruneMargin = 1.0005f;
+constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
+
+#ifndef RTB_TRAVERSAL
+#define RTB_TRAVERSAL 0   // 0: one node (inner or leaf) per loop trip (measured fastest on B200); 1: while-while (inner run, then leaf run)
+#endif
 
 template <bool SMEM, bool COUNTERS>
 __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
@@ -226,8 +237,45 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   if (!aabb_hit(v3(sd.root_min), v3(sd.root_max), o, inv, &t_enter)) return;
 
   int stack[kStackMax];
-  int sp = 0;
+  stack[0] = kTraversalDone;
+  int sp = 1;
   int cur = sd.root_ref;
+#if RTB_TRAVERSAL == 1
+  while (cur != kTraversalDone) {
+    // inner nodes until this lane holds a leaf (or is done); the warp reconverges after the loop,
+    // so the sphere tests below run with every lane that found a leaf
+    while (cur >= 0) {
+      const float4* n = sv.inner + 4 * cur;
+      const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+      float tl, tr;
+      bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
+      bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
+      if (COUNTERS) wc.node_tests += 2;
+      const float limit = best_t * kPruneMargin;
+      hl = hl && tl < limit;
+      hr = hr && tr < limit;
+      const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+      if (hl && hr) {
+        const bool left_first = tl <= tr;
+        stack[sp++] = left_first ? right : left;
+        cur = left_first ? left : right;
+      } else if (hl || hr) {
+        cur = hl ? left : right;
+      } else {
+        cur = stack[--sp];
+      }
+    }
+    if (cur != kTraversalDone) {
+      const int first = ~cur;
+      const int count = (int)sv.ld1(sv.leaf_count + first);
+      for (int i = 0; i < count; i++) {
+        sphere_hit(sv.ld4(sv.spheres + first + i), first + i, o, d, a, best_t, best_idx);
+      }
+      if (COUNTERS) wc.sphere_tests += count;
+      cur = stack[--sp];
+    }
+  }
+#else
   for (;;) {
     if (cur >= 0) {
       const float4* n = sv.inner + 4 * cur;
@@ -256,9 +304,10 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       }
       if (COUNTERS) wc.sphere_tests += count;
     }
-    if (sp == 0) break;
     cur = stack[--sp];
+    if (cur == kTraversalDone) break;
   }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -272,30 +321,31 @@ __device__ __forceinline__ f3 tangent_to_world(f3 v, f3 normal) {
   f3 bitangent = um::mk(b, s + normal.y * normal.y * a, -normal.y);
   return um::normalize(um::mul_cols(tangent, normal, bitangent, v));
 }
-// RandomSource.OnCosineWeightedHemisphere (RandomSource.cs:63-89)
-__device__ __forceinline__ f3 cosine_hemisphere(f3 normal, float ux, float uy) {
+// The three sampling transforms take the angle as u * 2 * PI (RandomSource.cs:70), u * PI * 2
+// (:125) and u * (2 * PI) (:46): doubling is exact, so all three are the same float and one
+// sincos serves whichever transform a lane needs.
+__device__ __forceinline__ void unit_angle_sincos(float u, float* s, float* c) { um::sincos(u * 2 * um::PI, s, c); }
+// RandomSource.OnCosineWeightedHemisphere (RandomSource.cs:63-89); (s, c) = sincos(uy * 2 * PI)
+__device__ __forceinline__ f3 cosine_hemisphere(f3 normal, float ux, float s, float c) {
   float radius = um::sqrt(ux);
-  float theta = uy * 2 * um::PI;
-  float s, c;
-  um::sincos(theta, &s, &c);
   f3 tangent_space = um::mk(radius * c, um::sqrt(1 - ux), radius * s);
   return tangent_to_world(tangent_space, normal);
 }
-// RandomSource.NextFloat3Direction (RandomSource.cs:113-128)
-__device__ __forceinline__ f3 random_direction(float rx, float ry) {
+// RandomSource.NextFloat3Direction (RandomSource.cs:113-128); (s, c) = sincos(ry * PI * 2)
+__device__ __forceinline__ f3 random_direction(float rx, float s, float c) {
   float z = rx * 2.0f - 1.0f;
   float r = um::sqrt(um::max(1.0f - z * z, 0.0f));
-  float angle = ry * um::PI * 2.0f;
-  float s, c;
-  um::sincos(angle, &s, &c);
   return um::mk(c * r, s * r, z);
 }
 
-// Material.cs:212-217
-__device__ __forceinline__ float schlick(float cosine, float ior) {
+// Material.cs:212-217, split at the per-material constant
+__device__ __forceinline__ float schlick_r0(float ior) {
   float r0 = um::div(1 - ior, 1 + ior);
   r0 *= r0;
-  return r0 + (1 - r0) * um::pow5(1 - cosine);
+  return r0;
+}
+__device__ __forceinline__ float schlick(float cosine, float r0, float one_minus_r0) {
+  return r0 + one_minus_r0 * um::pow5(1 - cosine);
 }
 // Microfacet.cs:71-80
 __device__ __forceinline__ float roughness_to_alpha(float roughness) {
@@ -303,8 +353,8 @@ __device__ __forceinline__ float roughness_to_alpha(float roughness) {
   float x = um::log(roughness);
   return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
-// Microfacet.cs:9-12,53-69
-__device__ __forceinline__ float smith_masking_shadowing(f3 w, f3 normal, float roughness) {
+// Microfacet.cs:9-12,53-69; alpha = RoughnessToAlpha(roughness) hoisted to the material record
+__device__ __forceinline__ float smith_masking_shadowing(f3 w, f3 normal, float alpha) {
   float cos_theta = um::dot(normal, w);
   float sq_cos = cos_theta * cos_theta;
   float sq_sin = um::max(0.0f, 1 - sq_cos);
@@ -315,7 +365,6 @@ __device__ __forceinline__ float smith_masking_shadowing(f3 w, f3 normal, float 
   if (um::isinf(abs_tan)) {
     lambda = 0;
   } else {
-    float alpha = roughness_to_alpha(roughness);
     float a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
     lambda = um::div(-1 + um::sqrt(1 + a2t2), 2.0f);
   }
@@ -342,7 +391,7 @@ __device__ __forceinline__ PathRay camera_ray(const rtb_batch_params& p, int cx,
       float theta = u2f(r.z) * (2 * um::PI - 0) + 0;
       float radius = um::sqrt(u2f(r.w));
       float s, c;
-      um::sincos(theta, &s, &c);
+      um::sincos(theta, &s, &c);   // theta == u * 2 * PI bit for bit (see unit_angle_sincos)
       rdx = v.lens_radius * (radius * c);
       rdy = v.lens_radius * (radius * s);
     }
@@ -363,39 +412,54 @@ struct ScatterResult {
 };
 
 // Material.Scatter (Material.cs:67-173) for constant textures (Texture.cs:50-59,101-108).
-// m0 = (albedo.xyz, type), m1 = (emission.xyz, glossiness), m2 = (metallic, ior, perfect_specular, -)
-__device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2, f3 D, f3 N,
+// m0 = (albedo.xyz, type), m1 = (emission.xyz, glossiness), m2 = (metallic, ior, perfect_specular, roughness),
+// m3 = (alpha, r0, 1 - r0, -).
+//
+// Layout for SIMT efficiency: a warp almost always holds Lambertian, metal and glass hits at once, so
+// the pieces every material needs are executed ONCE, converged, with per-lane operands — one Philox
+// block (its index is the only per-material difference), one sincos, one cosine-hemisphere sample —
+// and only the short material-specific tails diverge.
+__device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N,
                                                  uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
   ScatterResult out;
   out.reflectance = um::mk(m0.x, m0.y, m0.z);
-  const uint32_t type = __float_as_uint(m0.w);
-  if (type == RTB_MATERIAL_STANDARD) {
-    const float metallic = m2.x, glossiness = m1.w;
-    const float roughness = um::pow2(1 - glossiness);
+  const bool standard = __float_as_uint(m0.w) == RTB_MATERIAL_STANDARD;   // else Dielectric (upload rejects the rest)
+  const float glossiness = m1.w, metallic = m2.x, roughness = m2.w;
+  // With glossiness == 0 the reflection chance saturate(fresnel * 0 * G) is exactly 0 and with
+  // metallic == 0 the rough normal has no other consumer: the first draw pair (slots 0,1) is skipped
+  // and the diffuse draw (block 1) is the only one — same result as evaluating Material.cs:83-89.
+  const bool pure_diffuse = standard && glossiness == 0.0f && metallic == 0.0f;
+  const uint4 r = philox4x32_10(pixel, sample, bounce, pure_diffuse ? 1u : 0u, seed, kPhiloxKey1);
+  const float ux = u2f(r.x), uy = u2f(r.y);
+  // Dielectric with roughness 0: normalize(N + 0 * randomDirection) == normalize(N); the direction is not evaluated.
+  const bool need_angle = standard ? (pure_diffuse || roughness > 0) : (roughness > 0);
+  float sn = 0, cs = 1;
+  if (need_angle) unit_angle_sincos(uy, &sn, &cs);
+  f3 hemi = N;
+  if (standard && need_angle) hemi = cosine_hemisphere(N, ux, sn, cs);
+
+  if (standard) {
     float chance = 0.0f;
     f3 rough_normal = N;
-    uint4 r0 = make_uint4(0, 0, 0, 0);
-    // With glossiness == 0 the reflection chance saturate(fresnel * 0 * G) is exactly 0
-    // and with metallic == 0 the rough normal has no other consumer: skip both (and the
-    // Philox block behind them).  Same result as evaluating Material.cs:83-89.
-    const bool pure_diffuse = glossiness == 0.0f && metallic == 0.0f;
     if (!pure_diffuse) {
-      r0 = philox4x32_10(pixel, sample, bounce, 0, seed, kPhiloxKey1);
-      if (roughness > 0) rough_normal = um::normalize(um::lerp(N, cosine_hemisphere(N, u2f(r0.x), u2f(r0.y)), roughness));
-      float incident_cosine = -um::dot(D, rough_normal);
-      float ior = um::lerp(1.5f, 1.1f, metallic);
-      float fresnel = schlick(incident_cosine, ior);
-      float g = smith_masking_shadowing(D, N, roughness);
+      if (roughness > 0) rough_normal = um::normalize(um::lerp(N, hemi, roughness));
+      const float incident_cosine = -um::dot(D, rough_normal);
+      const float fresnel = schlick(incident_cosine, m3.y, m3.z);
+      const float g = smith_masking_shadowing(D, N, m3.x);
       chance = um::saturate(fresnel * glossiness * g);
     }
-    if (chance > 0 && u2f(r0.z) < chance) {
+    if (pure_diffuse) {
+      out.dir = hemi;
+    } else if (chance > 0 && u2f(r.z) < chance) {
       out.dir = um::reflect(D, rough_normal);
       out.reflectance = um::mk(1.0f);
-    } else if (metallic > 0 && u2f(r0.w) < metallic) {
+    } else if (metallic > 0 && u2f(r.w) < metallic) {
       out.dir = um::reflect(D, rough_normal);
-    } else {
-      uint4 r1 = philox4x32_10(pixel, sample, bounce, 1, seed, kPhiloxKey1);
-      out.dir = cosine_hemisphere(N, u2f(r1.x), u2f(r1.y));
+    } else {   // a glossy or part-metallic material falling through to its diffuse lobe: second block
+      const uint4 r1 = philox4x32_10(pixel, sample, bounce, 1, seed, kPhiloxKey1);
+      float s1, c1;
+      unit_angle_sincos(u2f(r1.y), &s1, &c1);
+      out.dir = cosine_hemisphere(N, u2f(r1.x), s1, c1);
     }
     float ev = 0;
     if (chance > 0 && chance < 1) ev++;
@@ -403,14 +467,12 @@ __device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2
     ev += roughness * (chance + (1 - chance) * metallic);
     ev += (1 - chance) * (1 - metallic);
     out.random_events = ev;
-  } else {  // RTB_MATERIAL_DIELECTRIC (upload rejects anything else)
+  } else {
     const float ior = m2.y;
-    const float roughness = 1 - m1.w;
-    uint4 r0 = philox4x32_10(pixel, sample, bounce, 0, seed, kPhiloxKey1);
-    f3 rough_normal = um::normalize(N + roughness * random_direction(u2f(r0.x), u2f(r0.y)));
+    f3 rough_normal = roughness > 0 ? um::normalize(N + roughness * random_direction(ux, sn, cs)) : um::normalize(N);
     float ni_over_nt, cosine;
     f3 outward;
-    float ddn = um::dot(D, rough_normal);
+    const float ddn = um::dot(D, rough_normal);
     if (ddn > 0) {
       outward = -rough_normal;
       ni_over_nt = ior;
@@ -421,11 +483,11 @@ __device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2
       cosine = -ddn;
     }
     // Material.Refract (Material.cs:198-210)
-    float dt = um::dot(D, outward);
-    float disc = 1 - ni_over_nt * ni_over_nt * (1 - dt * dt);
+    const float dt = um::dot(D, outward);
+    const float disc = 1 - ni_over_nt * ni_over_nt * (1 - dt * dt);
     bool refracted = false;
     if (disc > 0) {
-      if (u2f(r0.z) > schlick(cosine, ior)) {
+      if (u2f(r.z) > schlick(cosine, m3.y, m3.z)) {
         out.dir = ni_over_nt * (D - outward * dt) - outward * um::sqrt(disc);
         refracted = true;
       }
@@ -440,6 +502,24 @@ __device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2
     out.random_events = ev;
   }
   return out;
+}
+
+// Fills DevMaterial's derived constants on the device (one thread per material, at upload).
+__global__ void derive_materials_kernel(DevMaterial* m, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DevMaterial x = m[i];
+  if (x.type == RTB_MATERIAL_STANDARD) {
+    x.roughness = um::pow2(1 - x.glossiness);
+    x.ior = um::lerp(1.5f, 1.1f, x.metallic);        // PlasticIor, MetalIor (Material.cs:18-19)
+    x.alpha = roughness_to_alpha(x.roughness);
+  } else {
+    x.roughness = 1 - x.glossiness;
+    x.alpha = 0;
+  }
+  x.r0 = schlick_r0(x.ior);
+  x.one_minus_r0 = 1 - x.r0;
+  m[i] = x;
 }
 
 // Sky (SampleBatchJob.cs:348-374; Environment.cs)

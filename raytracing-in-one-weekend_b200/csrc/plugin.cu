@@ -47,6 +47,7 @@ struct rtb_ctx {
 
   // scene
   unsigned char* d_blob = nullptr;
+  DevMaterial* d_materials = nullptr;
   SceneDesc scene{};
   bool has_scene = false;
 
@@ -93,6 +94,7 @@ int fail(rtb_ctx* ctx, int code, const char* fmt, ...) {
 // ---- scene flattening: rtb_bvh_node[] (reference order, root = 0) -> device blob ----------
 struct HostBlob {
   std::vector<unsigned char> bytes;
+  std::vector<DevMaterial> materials;
   SceneDesc desc{};
 };
 
@@ -181,7 +183,6 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
   d.sphere_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 16);
   d.leaf_count_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 4);   // +1: the empty-leaf sentinel
   d.mat_index_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 4);
-  d.material_off = (uint32_t)off; off = align16(off + material_count * sizeof(DevMaterial));
   if (off == 0) off = 16;
   d.blob_bytes = (uint32_t)off;
   out->bytes.assign(off, 0);
@@ -193,6 +194,7 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
     memcpy(b + d.leaf_count_off + i * 4, &f.leaf_count[i], 4);
     memcpy(b + d.mat_index_off + i * 4, &spheres[i].material, 4);
   }
+  out->materials.resize(std::max<size_t>(material_count, 1));
   for (size_t i = 0; i < material_count; i++) {
     DevMaterial m{};
     const rtb_material& s = materials[i];
@@ -200,10 +202,10 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
     m.type = s.type;
     m.glossiness = s.glossiness;
     m.metallic = s.metallic;
-    m.ior = s.index_of_refraction;
+    m.ior = s.index_of_refraction;      // Standard: replaced on the device by lerp(1.5, 1.1, metallic)
     // Material.IsPerfectSpecular (Material.cs:181-196)
     m.perfect_specular = s.type == RTB_MATERIAL_DIELECTRIC || (almost_equals_1(s.metallic) && almost_equals_1(s.glossiness));
-    memcpy(b + d.material_off + i * sizeof(DevMaterial), &m, sizeof m);
+    out->materials[i] = m;              // roughness / alpha / r0 are filled by derive_materials_kernel
   }
   *status = RTB_OK;
   return nullptr;
@@ -413,7 +415,7 @@ int rtb_destroy(rtb_ctx* ctx) {
     for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
     DeviceBuffers& b = ctx->buf;
     void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
-                    b.diagnostics, ctx->d_blob, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+                    b.diagnostics, ctx->d_blob, ctx->d_materials, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -446,12 +448,22 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_sphere* spheres, size_t sphere_coun
   DeviceGuard g(ctx->device);
   RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->d_blob) cudaFree(ctx->d_blob);
+  if (ctx->d_materials) cudaFree(ctx->d_materials);
   ctx->d_blob = nullptr;
+  ctx->d_materials = nullptr;
   ctx->has_scene = false;
   RTB_CUDA(ctx, cudaMalloc(&ctx->d_blob, hb.bytes.size()));
   RTB_CUDA(ctx, cudaMemcpy(ctx->d_blob, hb.bytes.data(), hb.bytes.size(), cudaMemcpyHostToDevice));
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_materials, hb.materials.size() * sizeof(DevMaterial)));
+  RTB_CUDA(ctx, cudaMemcpy(ctx->d_materials, hb.materials.data(), hb.materials.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice));
+  if (material_count) {
+    derive_materials_kernel<<<(unsigned)((material_count + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_materials, (uint32_t)material_count);
+    RTB_CUDA(ctx, cudaGetLastError());
+    RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   ctx->scene = hb.desc;
   ctx->scene.blob = ctx->d_blob;
+  ctx->scene.materials = ctx->d_materials;
   ctx->has_scene = true;
   return RTB_OK;
 }

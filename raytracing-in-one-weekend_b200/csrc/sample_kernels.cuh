@@ -15,17 +15,29 @@
 
 namespace rtbk {
 
-constexpr int kMegaBlock = 256;          // threads per CTA (8 warps)
+#ifndef RTB_MEGA_BLOCK
+#define RTB_MEGA_BLOCK 1024           // threads per CTA; one persistent CTA per SM shares one staged world (64 regs/thread, no spills)
+#endif
+#ifndef RTB_MEGA_MIN_BLOCKS
+#define RTB_MEGA_MIN_BLOCKS 1
+#endif
+constexpr int kMegaBlock = RTB_MEGA_BLOCK;
 constexpr int kMegaWarps = kMegaBlock / 32;
 constexpr float kFixedScale = 4294967296.0f;            // 2^32
 constexpr float kFixedInvScale = 2.3283064365386963e-10f;  // 2^-32
 constexpr int kAccValues = 10;           // color.xyz, normal.xyz, albedo.xyz, sampleCountWeight
 
-// Shared-memory state of one warp's tile.  Accumulators are 64-bit fixed point (2^-32)
-// split into two 32-bit words so that native 32-bit shared atomics can be used: the sum of
-// a pixel's samples does not depend on the order in which its paths finish, which makes
-// the image deterministic although lanes retire paths in data-dependent order.
+// Shared-memory state of one warp's tile.  Sums are 64-bit fixed point (2^-32): integer addition
+// is associative, so a pixel's sum does not depend on the order in which its paths retire nor on
+// how the frame is tiled or sharded — the image is bit-reproducible for any GPU count.
+//   lane_*  : each lane's private partial sums for the pixel slot it is currently feeding
+//             (plain LDS/STS, conflict-free [value][lane] layout, no atomics in the bounce loop)
+//   acc_*   : per-pixel totals; a lane flushes its partials here (native 32-bit shared atomics,
+//             carry propagated by hand) only when it moves to another pixel or the tile retires
 struct WarpTile {
+  uint2 lane_acc[kAccValues][32];
+  uint32_t lane_counts[32];              // successes << 20 | rays (per flush interval)
+  float aov[6][32];                      // the live path's sampleNormal / sampleAlbedo (written <= 2x per path, read once)
   uint32_t acc_lo[kTilePixelsMax][kAccValues];
   uint32_t acc_hi[kTilePixelsMax][kAccValues];
   uint32_t successes[kTilePixelsMax];
@@ -37,12 +49,31 @@ struct WarpTile {
   uint32_t prefix[kTilePixelsMax + 1];   // exclusive prefix of per-pixel sample counts
 };
 
-__device__ __forceinline__ void fixed_add(WarpTile& t, int slot, int v, float x) {
-  long long q = __float2ll_rn(x * kFixedScale);
-  uint32_t lo = (uint32_t)q, hi = (uint32_t)((unsigned long long)q >> 32);
-  uint32_t old = atomicAdd(&t.acc_lo[slot][v], lo);
-  uint32_t carry = (old + lo) < old ? 1u : 0u;
-  if (hi + carry) atomicAdd(&t.acc_hi[slot][v], hi + carry);
+// lane-private += x (exact: x * 2^32 is an integer for |x| >= 2^-9, rounded to 2^-32 below that)
+__device__ __forceinline__ void lane_add(WarpTile& t, int lane, int v, float x) {
+  const unsigned long long q = (unsigned long long)__float2ll_rn(x * kFixedScale);
+  uint2 cur = t.lane_acc[v][lane];
+  const unsigned long long sum = (((unsigned long long)cur.y << 32) | cur.x) + q;
+  t.lane_acc[v][lane] = make_uint2((uint32_t)sum, (uint32_t)(sum >> 32));
+}
+// tile totals += this lane's partials; partials := 0
+__device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
+#pragma unroll
+  for (int v = 0; v < kAccValues; v++) {
+    const uint2 cur = t.lane_acc[v][lane];
+    if (cur.x | cur.y) {
+      const uint32_t old = atomicAdd(&t.acc_lo[slot][v], cur.x);
+      const uint32_t hi = cur.y + ((old + cur.x) < old ? 1u : 0u);
+      if (hi) atomicAdd(&t.acc_hi[slot][v], hi);
+      t.lane_acc[v][lane] = make_uint2(0u, 0u);
+    }
+  }
+  const uint32_t c = t.lane_counts[lane];
+  if (c) {
+    if (c >> 20) atomicAdd(&t.successes[slot], c >> 20);
+    atomicAdd(&t.rays[slot], c & 0xfffffu);
+    t.lane_counts[lane] = 0;
+  }
 }
 __device__ __forceinline__ float fixed_read(const WarpTile& t, int slot, int v) {
   long long q = (long long)(((unsigned long long)t.acc_hi[slot][v] << 32) | t.acc_lo[slot][v]);
@@ -65,7 +96,7 @@ __device__ __forceinline__ void active_pixel(const BatchArgs& a, uint32_t k, int
 }
 
 template <bool SMEM, bool COUNTERS>
-__global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* blob_smem = smem + 16;
@@ -104,10 +135,15 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
   bool first_non_specular = false;
   PathRay ray{um::mk(0.0f), um::mk(0.0f)};
   f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
-  f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
-  float events_acc = 0, pow2depth = 1;
+  float events_acc = 0, inv_pow2depth = 1;
+  auto set_normal = [&](f3 n) { tile.aov[0][lane] = n.x; tile.aov[1][lane] = n.y; tile.aov[2][lane] = n.z; };
+  auto set_albedo = [&](f3 c) { tile.aov[3][lane] = c.x; tile.aov[4][lane] = c.y; tile.aov[5][lane] = c.z; };
   uint32_t path_rays = 0;
+  int acc_slot = -1;          // pixel slot this lane's private partial sums belong to
   WorkCounters wc;
+#pragma unroll
+  for (int k = 0; k < kAccValues; k++) tile.lane_acc[k][lane] = make_uint2(0u, 0u);
+  tile.lane_counts[lane] = 0;
 
   // ---- warp-uniform tile state ----
   uint32_t tile_base = 0, next_item = 0, total_items = 0;
@@ -135,10 +171,10 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
         first_non_specular = false;
         throughput = um::mk(1.0f);
         radiance = um::mk(0.0f);
-        s_normal = um::mk(0.0f);
-        s_albedo = um::mk(0.0f);
+        set_normal(um::mk(0.0f));
+        set_albedo(um::mk(0.0f));
         events_acc = 0;
-        pow2depth = 1;
+        inv_pow2depth = 1;
         path_rays = 0;
       }
       next_item = min(next_item + (uint32_t)__popc(need), total_items);
@@ -146,6 +182,8 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
 
     // (2) nothing in flight and nothing left in the tile: retire it, fetch the next one
     if (__ballot_sync(0xffffffffu, alive) == 0) {
+      if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
+      acc_slot = -1;
       __syncwarp();
       if (tile_n > 0 && lane < tile_n) {
         int cx, cy;
@@ -234,22 +272,23 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
       if (hit_idx >= 0) {
         const float4 s = sv.ld4(sv.spheres + hit_idx);
         const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
-        const float4 m0 = sv.ld4(sv.materials + 3 * mi), m1 = sv.ld4(sv.materials + 3 * mi + 1),
-                     m2 = sv.ld4(sv.materials + 3 * mi + 2);
+        const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
+        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
         const f3 oc = ray.o + um::mk(-s.x, -s.y, -s.z);
         const f3 N = um::normalize(um::mad(ray.d, t_hit, oc) / s.w);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
-        const ScatterResult sc = scatter(m0, m1, m2, ray.d, N, pixel, sample, (uint32_t)depth, p.seed);
+        const ScatterResult sc = scatter(m0, m1, m2, m3, ray.d, N, pixel, sample, (uint32_t)depth, p.seed);
         if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
         const f3 emission = um::mk(m1.x, m1.y, m1.z);
         if (depth == 0) {
-          s_normal = N;
+          set_normal(N);
           if (sample == 0) { tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z; }
         }
         if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
-          s_albedo = emission + sc.reflectance;
-          s_normal = N;
+          const f3 s_albedo = emission + sc.reflectance;
+          set_albedo(s_albedo);
+          set_normal(N);
           first_non_specular = true;
           if (sample == 0) {
             tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z;
@@ -259,20 +298,22 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
         // forward form of the emission/attenuation unstack (SampleBatchJob.cs:383-396)
         radiance = um::mad(throughput, emission, radiance);
         throughput = throughput * sc.reflectance;
-        events_acc += um::div(sc.random_events, pow2depth);
+        // RandomEvents / pow(2, depth) (SampleBatchJob.cs:332): dividing by a power of two == multiplying by its inverse, exactly
+        events_acc += sc.random_events * inv_pow2depth;
         // next ray (SampleBatchJob.cs:335-336, Ray.cs:18)
         const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
         ray.o = um::mad(off_n, 0.001f, P);
         ray.d = sc.dir;
         depth++;
-        pow2depth *= 2.0f;
+        inv_pow2depth *= 0.5f;
         if (depth == p.trace_depth) finished = true;   // failed sample (:379-381)
       } else {
         const f3 sky = sky_color(p.environment, ray.d);
         radiance = um::mad(throughput, sky, radiance);
         if (!first_non_specular) {
-          s_albedo = sky;
-          s_normal = -ray.d;
+          const f3 s_normal = -ray.d;
+          set_albedo(sky);
+          set_normal(s_normal);
           if (sample == 0) {
             tile.fallback[slot][0] = s_normal.x; tile.fallback[slot][1] = s_normal.y; tile.fallback[slot][2] = s_normal.z;
             tile.fallback[slot][3] = sky.x; tile.fallback[slot][4] = sky.y; tile.fallback[slot][5] = sky.z;
@@ -283,7 +324,10 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
       }
       if (finished) {
         alive = false;
-        atomicAdd(&tile.rays[slot], path_rays);
+        if (acc_slot != slot) {
+          if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
+          acc_slot = slot;
+        }
         if (COUNTERS) {
           atomicAdd(&tile.node_tests[slot], wc.node_tests);
           atomicAdd(&tile.sphere_tests[slot], wc.sphere_tests);
@@ -293,20 +337,24 @@ __global__ void __launch_bounds__(kMegaBlock, 2) sample_megakernel(const __grid_
           }
           wc = WorkCounters();
         }
+        uint32_t counts = tile.lane_counts[lane] + path_rays;
         if (success) {
-          const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, s_normal.x, s_normal.y, s_normal.z,
-                                          s_albedo.x, s_albedo.y, s_albedo.z, events_acc};
+          const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, tile.aov[0][lane], tile.aov[1][lane], tile.aov[2][lane],
+                                          tile.aov[3][lane], tile.aov[4][lane], tile.aov[5][lane], events_acc};
           bool finite = true;
 #pragma unroll
           for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
           if (finite) {
 #pragma unroll
-            for (int k = 0; k < kAccValues; k++) fixed_add(tile, slot, k, vals[k]);
+            for (int k = 0; k < kAccValues; k++) lane_add(tile, lane, k, vals[k]);
           } else {
             tile.non_finite[slot] = 1;
           }
-          atomicAdd(&tile.successes[slot], 1u);
+          counts += 1u << 20;
         }
+        tile.lane_counts[lane] = counts;
+        // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps
+        if ((counts >> 20) >= 2048u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
       }
     }
     __syncwarp();
@@ -394,12 +442,12 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
       if (hit_idx >= 0) {
         const float4 sp = sv.ld4(sv.spheres + hit_idx);
         const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
-        const float4 m0 = sv.ld4(sv.materials + 3 * mi), m1 = sv.ld4(sv.materials + 3 * mi + 1),
-                     m2 = sv.ld4(sv.materials + 3 * mi + 2);
+        const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
+        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
         const f3 oc = ray.o + um::mk(-sp.x, -sp.y, -sp.z);
         const f3 N = um::normalize(um::mad(ray.d, t_hit, oc) / sp.w);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
-        const ScatterResult sc = scatter(m0, m1, m2, ray.d, N, index, s, (uint32_t)depth, p.seed);
+        const ScatterResult sc = scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed);
         if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
         const f3 emission = um::mk(m1.x, m1.y, m1.z);
         if (depth == 0) s_normal = N;

@@ -34,7 +34,7 @@ def lib():
     """Loads lib/librtb.so (never builds it implicitly on a GPU box: the .so ships in-tree)."""
     global _lib
     if _lib is None:
-        path = _build.plugin_lib_path()
+        path = os.environ.get("RTB_PLUGIN_LIB") or _build.plugin_lib_path()   # override: experiment builds only
         if not os.path.exists(path):
             raise ImportError(
                 f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
