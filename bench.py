@@ -145,7 +145,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -179,15 +179,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- load-balanced row tiles from a cheap probe batch (Diagnostics.RayCount per row) -------
+    # ---- load-balanced row tiles ----------------------------------------------------------------
+    # (1) cost model from a cheap instrumented probe batch: per-row executed box tests, sphere tests and
+    #     rays (the reference's FULL_DIAGNOSTICS counters, Raytracer.cs:56-60) weighted by their
+    #     instruction cost; (2) feedback from measured per-rank kernel times during the warm-up steps.
     tiles_kind = "equal"
+    row_cost = None
     if world > 1 and not args.equal_tiles:
         probe = rtb.host.make_params(scene, W, H, max(1, min(8, spp)), td, aperture=ap, seed=12345)
+        fr.ctx.set_option(abi.OPT_COUNTERS, 1)
         fr.render_device(probe)
+        fr.ctx.set_option(abi.OPT_COUNTERS, 0)
         torch.cuda.synchronize()
-        row_cost = fr.diag[:, 0].view(H, W).sum(dim=1).double().cpu().numpy()
+        d = fr.diag.view(H, W, 4).double()
+        row_cost = (450.0 * d[:, :, 0] + 35.0 * d[:, :, 1] + 40.0 * d[:, :, 2]).sum(dim=1).cpu().numpy()
         fr.set_tiles(sharding.balanced_row_tiles(row_cost, world))
-        tiles_kind = "ray-count balanced"
+        tiles_kind = "cost-model balanced + kernel-time feedback"
+
+    def rebalance_from_times():
+        """Scale each tile's rows by measured time / modelled cost and re-partition (all ranks compute the same tiles)."""
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = last_kernel_ms[0]
+        dist.all_reduce(t)
+        times = t.cpu().numpy()
+        cost = row_cost.copy()
+        for g, (b, e) in enumerate(fr.tiles):
+            c = cost[b:e].sum()
+            if c > 0 and times[g] > 0:
+                cost[b:e] *= times[g] / c
+        row_cost[:] = cost
+        fr.set_tiles(sharding.balanced_row_tiles(cost, world))
 
     # ---- work counters of one step (instrumented kernel, untimed) for the roofline numerator ---
     fr.ctx.set_option(abi.OPT_COUNTERS, 1)
@@ -202,8 +223,17 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     # ---- device-resident throughput ---------------------------------------------------------
+    last_kernel_ms = [0.0]
+    wev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     for _ in range(args.warmup):
-        fr.render_device(params)
+        wev[0].record()
+        fr.render_device(params, gather=False)
+        wev[1].record()
+        fr.gather()
+        torch.cuda.synchronize()
+        last_kernel_ms[0] = wev[0].elapsed_time(wev[1])
+        if row_cost is not None:
+            rebalance_from_times()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.25 if sampler else 0)
@@ -313,7 +343,7 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     fr.close()
     if world > 1:
         dist.destroy_process_group()
@@ -326,7 +356,19 @@ def _hbm_peak():
         return 6650.0     # B200_PROFILING.md fallback
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # NCCL / torchrun banners must not pollute the one-line contract
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
