@@ -186,6 +186,23 @@ RTB_API int rtb_upload_scene(rtb_ctx* ctx,
                              const rtb_material* materials, size_t material_count,
                              const rtb_bvh_node* nodes, size_t node_count);
 
+/* How rtb_upload_scene would lay this world out on the device (no device needed; for tests and
+ * tuning).  `leaf_spheres` as RTB_OPT_LEAF_SPHERES. */
+typedef struct rtb_scene_layout {
+  uint32_t inner_nodes;         /* device inner nodes (two child boxes each) */
+  uint32_t leaves;              /* device leaves */
+  uint32_t device_spheres;      /* sphere slots in depth-first leaf order (= spheres referenced by the BVH) */
+  uint32_t max_leaf_spheres;
+  uint32_t max_depth;           /* deepest root-to-leaf path of the device tree */
+  uint32_t blob_bytes;          /* bytes staged to shared memory per CTA */
+  uint32_t chain_boxes;         /* host boxes kept for exact re-testing of collapsed leaves */
+  uint32_t collapsed;           /* 1 when some device leaf is a collapsed host subtree */
+} rtb_scene_layout;
+RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
+                               const rtb_material* materials, size_t material_count,
+                               const rtb_bvh_node* nodes, size_t node_count,
+                               int leaf_spheres, rtb_scene_layout* out);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* Replaces `sampleBatchJob.Schedule(W*H, 1, dep).Complete()` (Raytracer.cs:730-736) with HOST
  * buffers: uploads the four input accumulators, runs the megakernel, downloads the four
@@ -249,7 +266,12 @@ RTB_API int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out);
 typedef enum rtb_option {
   RTB_OPT_COUNTERS = 1,         /* 0/1: run the instrumented kernel (slower) */
   RTB_OPT_KERNEL = 2,           /* 0 = auto, 1 = simple (thread per pixel), 2 = persistent megakernel */
-  RTB_OPT_CANCEL_CHUNK_ROWS = 3 /* rows per launch when a cancel token is passed (0 = auto) */
+  RTB_OPT_CANCEL_CHUNK_ROWS = 3,/* rows per launch when a cancel token is passed (0 = auto) */
+  RTB_OPT_LEAF_SPHERES = 4,     /* 1..15 (default 8): subtrees of the host's BVH holding at most this many spheres are
+                                 * walked as one leaf on the device (results are identical for every value; takes effect
+                                 * at the next rtb_upload_scene) */
+  RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
+                                 * instead of only when the hit geometry does not already prove them (same results, slower) */
 } rtb_option;
 RTB_API int rtb_set_option(rtb_ctx* ctx, int option, int64_t value);
 /* Milliseconds of the last kernel launch sequence on the context stream (CUDA events; the

@@ -53,7 +53,7 @@ RTB_ERR_UNSUPPORTED = 4
 RTB_ERR_OUT_OF_MEMORY = 5
 RTB_ERR_CUDA = 100
 
-OPT_COUNTERS, OPT_KERNEL, OPT_CANCEL_CHUNK_ROWS = 1, 2, 3
+OPT_COUNTERS, OPT_KERNEL, OPT_CANCEL_CHUNK_ROWS, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS = 1, 2, 3, 4, 5
 KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA = 0, 1, 2
 
 f32 = C.c_float
@@ -133,6 +133,11 @@ class Counters(C.Structure):  # rtb_counters
     ]
 
 
+class SceneLayout(C.Structure):  # rtb_scene_layout
+    _fields_ = [(n, C.c_uint32) for n in ("inner_nodes", "leaves", "device_spheres", "max_leaf_spheres", "max_depth",
+                                          "blob_bytes", "chain_boxes", "collapsed")]
+
+
 class Camera(C.Structure):  # rtbh_camera
     _fields_ = [("position", f32x3), ("target", f32x3), ("aperture", f32), ("vertical_fov", f32)]
 
@@ -165,6 +170,7 @@ STRUCT_SIZES = {  # name in the headers -> python mirror; checked against sizeof
     "rtb_batch_buffers": C.sizeof(BatchBuffers),
     "rtb_metrics": C.sizeof(Metrics),
     "rtb_counters": C.sizeof(Counters),
+    "rtb_scene_layout": C.sizeof(SceneLayout),
     "rtbh_camera": C.sizeof(Camera),
     "rtbh_scene_info": C.sizeof(SceneInfo),
 }

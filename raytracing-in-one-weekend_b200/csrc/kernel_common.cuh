@@ -32,10 +32,13 @@ using um::f3;
 //                    q1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
 //                    q2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)
 //                    q3 = (left_ref, right_ref, -, -) as int32
-//                  ref >= 0: inner node index; ref < 0: leaf, first sphere = ~ref
-//   spheres      : n_spheres * 16 B  float4 (center.xyz, radius), BVH leaf order
-//   leaf_count   : n_spheres * 4 B   entity count of the leaf that STARTS at this sphere
+//                  ref >= 0: inner node index; ref < 0: leaf, ~ref = first sphere << 4 | (count - 1)
+//                  (count - 1 == 15: the count is leaf_count[first])
+//   spheres      : n_spheres * 16 B  float4 (center.xyz, radius), depth-first leaf order
+//   leaf_count   : n_spheres * 4 B   sphere count of the leaf that STARTS at this sphere
 //   mat_index    : n_spheres * 4 B   material index of the sphere
+// A device leaf is a subtree of the host's BVH with at most RTB_OPT_LEAF_SPHERES spheres
+// (plugin.cu: Flattener); the host boxes it no longer walks are in chain_ref / chain_boxes (HBM).
 // Materials (n_materials * 64 B DevMaterial) stay in HBM behind the read-only path: they are
 // read once per bounce, not once per node.
 // ---------------------------------------------------------------------------------------
@@ -67,7 +70,14 @@ struct SceneDesc {
   uint32_t has_root;            // 0: empty world (node_count == 0)
   float root_min[3], root_max[3];
   uint32_t max_depth;           // deepest root-to-leaf path (stack bound)
+  uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
+  const uint32_t* chain_ref;    // per sphere: first chain box | box count << 24
+  const float4* chain_boxes;    // 2 x float4 per box (min.xyz, max.xyz), tightest first
 };
+
+constexpr int kDefaultCollapse = 8;
+// Geometry of the guard that stands in for the skipped boxes (see chain_guard).
+constexpr float kChainShrink = 1.0e-3f;   // upload checks: every skipped box contains its sphere shrunk by this
 
 constexpr int kStackMax = 64;   // traversal stack entries (BVH depth bound; upload rejects deeper trees)
 constexpr int kTilePixelsMax = 16;
@@ -185,22 +195,52 @@ __device__ __forceinline__ bool aabb_hit(f3 mn, f3 mx, f3 o, f3 inv, float* t_en
   return tmin < tmax;
 }
 
+// The host boxes between a collapsed device leaf and sphere `idx`, applied exactly as the reference
+// would (FindHitCandidates reaches a sphere only through a chain of hit boxes, SampleBatchJob.cs:420-447).
+__device__ __noinline__ bool chain_boxes_hit(const SceneDesc& sd, int idx, f3 o, f3 inv) {
+  const uint32_t ref = __ldg(sd.chain_ref + idx);
+  const float4* b = sd.chain_boxes + 2 * (size_t)(ref & 0xffffffu);
+  for (uint32_t k = ref >> 24; k > 0; k--, b += 2) {
+    const float4 mn = __ldg(b), mx = __ldg(b + 1);
+    float t;
+    if (!aabb_hit(um::mk(mn.x, mn.y, mn.z), um::mk(mx.x, mx.y, mx.z), o, inv, &t)) return false;
+  }
+  return true;
+}
+
+// When does an accepted sphere hit PROVE that every skipped box test passes?  Every skipped box
+// contains the sphere shrunk by kChainShrink (checked at upload).  If the ray passes the centre at a
+// distance <= (1 - 2 kChainShrink) |r|, the chord midpoint (t_m = -b/a >= 0) lies at least
+// kChainShrink |r| inside every face of every such box, so each slab interval contains
+// t_m -/+ kChainShrink |r| / |d|; the slab arithmetic (one subtraction, one reciprocal, one product:
+// relative error < 2^-22 per bound) cannot close an interval that wide while t_m |d| < 2^10 |r|.
+// In terms of the rounded values the sphere test already has: disc / a = r^2 - dist^2, computed with an
+// absolute error below 2^-20 a (|oc|^2 + r^2).  Hits that fail the guard (grazing, very distant, or
+// leaving a sphere the ray started in) take chain_boxes_hit.
+__device__ __forceinline__ bool chain_guard(float a, float b, float oc2, float r2, float disc) {
+  return b <= 0.0f && disc >= a * (8.0e-3f * r2 + 2.0e-6f * (oc2 + r2)) && b * b <= 1.0e6f * (a * r2);
+}
+
 // HitTests.Hit(this Sphere) (HitTests.cs:23-60) behind Entity.HitInternal (Entity.cs:74-103)
 // for a static, unrotated entity: entity-space origin = o + (-center), direction unchanged.
 // `a` = dot(d, d) is hoisted out by the caller.  Updates (best_t, best_idx) when this sphere
 // is hit nearer than best_t: the same record FindHits' sort would put first
 // (SampleBatchJob.cs:450-475) — a root is accepted iff 0 < t < +inf there, and the
 // second root is never nearer than the first, so clipping at best_t changes nothing.
-__device__ __forceinline__ void sphere_hit(float4 s, int idx, f3 o, f3 d, float a, float& best_t, int& best_idx) {
+__device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a,
+                                           float& best_t, int& best_idx) {
   f3 oc = o + um::mk(-s.x, -s.y, -s.z);
   float b = um::dot(oc, d);
-  float c = um::dot(oc, oc) - s.w * s.w;
+  float oc2 = um::dot(oc, oc);
+  float r2 = s.w * s.w;
+  float c = oc2 - r2;
   float disc = um::fma(b, b, -(a * c));
   if (disc > 0.0f) {
     float sq = um::sqrt(disc);
     float t = um::div(-b - sq, a);
     if (!(t < best_t && t > 0.0f)) t = um::div(-b + sq, a);
     if (t < best_t && t > 0.0f) {
+      if (sd.has_chains && (sd.has_chains == 2u || !chain_guard(a, b, oc2, r2, disc)) && !chain_boxes_hit(sd, idx, o, inv)) return;
       best_t = t;
       best_idx = idx;
     }
@@ -266,10 +306,12 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       }
     }
     if (cur != kTraversalDone) {
-      const int first = ~cur;
-      const int count = (int)sv.ld1(sv.leaf_count + first);
+      const uint32_t code = (uint32_t)~cur;
+      const int first = (int)(code >> 4);
+      int count = (int)(code & 15u) + 1;
+      if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
       for (int i = 0; i < count; i++) {
-        sphere_hit(sv.ld4(sv.spheres + first + i), first + i, o, d, a, best_t, best_idx);
+        sphere_hit(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
       }
       if (COUNTERS) wc.sphere_tests += count;
       cur = stack[--sp];
@@ -297,10 +339,12 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       if (hl) { cur = left; continue; }
       if (hr) { cur = right; continue; }
     } else {
-      const int first = ~cur;
-      const int count = (int)sv.ld1(sv.leaf_count + first);
+      const uint32_t code = (uint32_t)~cur;
+      const int first = (int)(code >> 4);
+      int count = (int)(code & 15u) + 1;
+      if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
       for (int i = 0; i < count; i++) {
-        sphere_hit(sv.ld4(sv.spheres + first + i), first + i, o, d, a, best_t, best_idx);
+        sphere_hit(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
       }
       if (COUNTERS) wc.sphere_tests += count;
     }

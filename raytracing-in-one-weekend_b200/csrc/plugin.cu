@@ -11,7 +11,9 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <string>
@@ -48,6 +50,8 @@ struct rtb_ctx {
   // scene
   unsigned char* d_blob = nullptr;
   DevMaterial* d_materials = nullptr;
+  uint32_t* d_chain_ref = nullptr;
+  float4* d_chain_boxes = nullptr;
   SceneDesc scene{};
   bool has_scene = false;
 
@@ -55,7 +59,7 @@ struct rtb_ctx {
   uint32_t* d_tile_counter = nullptr;
   unsigned long long* d_counters = nullptr;
   rtb_counters counters{};
-  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0;
+  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0;
   float last_ms = 0.0f;
   bool smem_attr_set[2][2] = {{false, false}, {false, false}};
 
@@ -92,42 +96,152 @@ int fail(rtb_ctx* ctx, int code, const char* fmt, ...) {
   } while (0)
 
 // ---- scene flattening: rtb_bvh_node[] (reference order, root = 0) -> device blob ----------
+//
+// The device tree is the reference tree with its bottom COLLAPSED: a subtree that holds at most
+// `collapse_k` spheres becomes one leaf whose spheres are tested directly.  Spheres are re-laid
+// out in depth-first leaf order, so every subtree owns a contiguous range.  The reference accepts
+// a sphere hit only if the box of every node on the path root -> leaf is hit
+// (SampleBatchJob.cs:403-448); the boxes a collapsed leaf no longer tests are kept per sphere in
+// the "chain" arrays, and the kernel re-applies them, exactly, to the rare accepted hit whose
+// geometry does not already prove they pass (kernel_common.cuh: chain_guard).
 struct HostBlob {
   std::vector<unsigned char> bytes;
   std::vector<DevMaterial> materials;
+  std::vector<uint32_t> chain_ref;     // per device sphere: first chain box | count << 24
+  std::vector<float> chain_boxes;      // 8 floats per box: min.xyz, -, max.xyz, -
   SceneDesc desc{};
 };
 
 struct Flattener {
   const rtb_bvh_node* nodes;
   size_t node_count, sphere_count;
+  const rtb_sphere* spheres;
+  uint32_t collapse_k;
   std::vector<uint8_t> visited;
-  std::vector<float> inner;          // 16 floats per inner node
-  std::vector<uint32_t> leaf_count;
+  std::vector<uint32_t> subtree_spheres;   // per reference node
+  std::vector<float> inner;                // 16 floats per device inner node
+  std::vector<uint32_t> order;             // device sphere -> host sphere
+  std::vector<uint32_t> leaf_count;        // per device sphere: count of the device leaf starting here
+  std::vector<uint32_t> chain_ref;
+  std::vector<float> chain_boxes;
+  std::vector<int32_t> path;               // reference nodes below the current collapse root
   uint32_t max_depth = 0;
+  bool collapsed_any = false;
   const char* error = nullptr;
 
-  int32_t ref_of(int32_t n, uint32_t depth) {
+  // pass 1: validate (tree-ness, ranges) and count spheres per subtree
+  uint32_t count_pass(int32_t n, uint32_t depth) {
     if (error) return 0;
     if (n < 0 || (size_t)n >= node_count) { error = "BVH child index out of range"; return 0; }
     if (visited[n]) { error = "BVH is not a tree (node reachable twice)"; return 0; }
+    if (depth > 4096) { error = "BVH deeper than 4096 levels"; return 0; }
     visited[n] = 1;
-    max_depth = std::max(max_depth, depth);
     const rtb_bvh_node& nd = nodes[n];
+    uint32_t c;
     if (nd.first_entity >= 0) {
       if (nd.entity_count < 0 || (size_t)nd.first_entity + (size_t)nd.entity_count > sphere_count) {
         error = "BVH leaf range outside the sphere array";
         return 0;
       }
-      if (nd.entity_count == 0) return ~(int32_t)sphere_count;  // sentinel slot: leaf_count == 0
-      leaf_count[nd.first_entity] = (uint32_t)nd.entity_count;
-      return ~nd.first_entity;
+      c = (uint32_t)nd.entity_count;
+    } else {
+      if (nd.left < 0 || nd.right < 0) { error = "BVH inner node without two children"; return 0; }
+      c = count_pass(nd.left, depth + 1) + count_pass(nd.right, depth + 1);
+    }
+    subtree_spheres[n] = c;
+    return c;
+  }
+
+  // The guard in the kernel certifies the skipped boxes from the sphere's geometry; that needs every
+  // skipped box to contain the sphere shrunk by kChainShrink (true for any BVH built from the spheres'
+  // bounds, Sphere.cs:16-23; a host could pass anything).  Otherwise the subtree is not collapsed.
+  bool box_contains(const rtb_bvh_node& nd, const rtb_sphere& s) const {
+    const float r = std::fabs(s.radius) * (1.0f - kChainShrink);
+    for (int k = 0; k < 3; k++)
+      if (!(nd.bounds_min[k] <= s.center[k] - r && nd.bounds_max[k] >= s.center[k] + r)) return false;
+    return true;
+  }
+  // every box strictly below `root` contains every sphere below it
+  bool collapsible(int32_t n, bool is_root) {
+    const rtb_bvh_node& nd = nodes[n];
+    if (nd.first_entity >= 0) {
+      if (!is_root)
+        for (int i = 0; i < nd.entity_count; i++)
+          if (!box_contains(nd, spheres[nd.first_entity + i])) return false;
+      return true;
+    }
+    if (!collapsible(nd.left, false) || !collapsible(nd.right, false)) return false;
+    if (!is_root) {
+      // inner boxes enclose their children's boxes in any sane tree; check against the spheres directly
+      std::vector<int32_t> st{n};
+      while (!st.empty()) {
+        const rtb_bvh_node& x = nodes[st.back()];
+        st.pop_back();
+        if (x.first_entity >= 0) {
+          for (int i = 0; i < x.entity_count; i++)
+            if (!box_contains(nd, spheres[x.first_entity + i])) return false;
+        } else {
+          st.push_back(x.left);
+          st.push_back(x.right);
+        }
+      }
+    }
+    return true;
+  }
+
+  // emits the spheres of reference subtree n in depth-first order with their chains
+  void emit_spheres(int32_t n, bool is_root) {
+    const rtb_bvh_node& nd = nodes[n];
+    if (!is_root) path.push_back(n);
+    if (nd.first_entity >= 0) {
+      for (int i = 0; i < nd.entity_count; i++) {
+        order.push_back((uint32_t)(nd.first_entity + i));
+        leaf_count.push_back(0);
+        const uint32_t first_box = (uint32_t)(chain_boxes.size() / 8);
+        for (size_t k = path.size(); k-- > 0;) {       // nearest (tightest) box first
+          const rtb_bvh_node& b = nodes[path[k]];
+          const float q[8] = {b.bounds_min[0], b.bounds_min[1], b.bounds_min[2], 0.0f, b.bounds_max[0], b.bounds_max[1], b.bounds_max[2], 0.0f};
+          chain_boxes.insert(chain_boxes.end(), q, q + 8);
+        }
+        chain_ref.push_back(first_box | ((uint32_t)path.size() << 24));
+      }
+    } else {
+      emit_spheres(nd.left, false);
+      emit_spheres(nd.right, false);
+    }
+    if (!is_root) path.pop_back();
+  }
+
+  static int32_t leaf_ref(uint32_t first, uint32_t count) {
+    const uint32_t code = (first << 4) | (count >= 1 && count <= 15 ? count - 1 : 15u);   // 15: count in leaf_count[first]
+    return ~(int32_t)code;
+  }
+
+  // pass 2: device nodes
+  int32_t ref_of(int32_t n, uint32_t depth) {
+    if (error) return 0;
+    max_depth = std::max(max_depth, depth);
+    const rtb_bvh_node& nd = nodes[n];
+    const uint32_t c = subtree_spheres[n];
+    const bool is_leaf = nd.first_entity >= 0;
+    if (is_leaf || (c <= collapse_k && c <= 15 && path_len_ok(n) && collapsible(n, true))) {
+      if (!is_leaf) collapsed_any = true;
+      const uint32_t first = (uint32_t)order.size();
+      if (first + c >= (1u << 27)) { error = "scene too large"; return 0; }
+      if (c == 0) {                       // empty leaf: a slot whose leaf_count is 0
+        order.push_back(0xFFFFFFFFu);
+        leaf_count.push_back(0);
+        chain_ref.push_back(0);
+        return leaf_ref(first, 0);
+      }
+      emit_spheres(n, true);
+      leaf_count[first] = c;
+      return leaf_ref(first, c);
     }
     const int32_t self = (int32_t)(inner.size() / 16);
     inner.resize(inner.size() + 16, 0.0f);
-    if (nd.left < 0 || nd.right < 0) { error = "BVH inner node without two children"; return 0; }
-    const rtb_bvh_node& l = nodes[std::min<size_t>((size_t)nd.left, node_count - 1)];
-    const rtb_bvh_node& r = nodes[std::min<size_t>((size_t)nd.right, node_count - 1)];
+    const rtb_bvh_node& l = nodes[nd.left];
+    const rtb_bvh_node& r = nodes[nd.right];
     const int32_t lref = ref_of(nd.left, depth + 1);
     const int32_t rref = ref_of(nd.right, depth + 1);
     if (error) return 0;
@@ -139,13 +253,25 @@ struct Flattener {
     memcpy(&q[13], &rref, 4);
     return self;
   }
+  // a chain holds at most 255 boxes
+  bool path_len_ok(int32_t n) const {
+    uint32_t d = 0;
+    std::vector<std::pair<int32_t, uint32_t>> st{{n, 0}};
+    while (!st.empty()) {
+      auto [x, dx] = st.back();
+      st.pop_back();
+      d = std::max(d, dx);
+      if (nodes[x].first_entity < 0) { st.push_back({nodes[x].left, dx + 1}); st.push_back({nodes[x].right, dx + 1}); }
+    }
+    return d < 200;
+  }
 };
 
 bool almost_equals_1(float v) { return std::fabs(1.0f - v) < 1e-6f; }  // MathExtensions.cs:23-27
 
 const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials,
-                       size_t material_count, const rtb_bvh_node* nodes, size_t node_count, HostBlob* out,
-                       int* status) {
+                       size_t material_count, const rtb_bvh_node* nodes, size_t node_count, uint32_t collapse_k,
+                       HostBlob* out, int* status) {
   *status = RTB_ERR_INVALID_ARGUMENT;
   for (size_t i = 0; i < material_count; i++) {
     if (materials[i].type > RTB_MATERIAL_DIELECTRIC) {
@@ -156,12 +282,17 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
   for (size_t i = 0; i < sphere_count; i++)
     if (spheres[i].material >= material_count) return "sphere material index out of range";
 
-  Flattener f{nodes, node_count, sphere_count, std::vector<uint8_t>(node_count, 0), {}, std::vector<uint32_t>(sphere_count + 1, 0)};
+  Flattener f{};
+  f.nodes = nodes; f.node_count = node_count; f.sphere_count = sphere_count; f.spheres = spheres;
+  f.collapse_k = std::max<uint32_t>(1, std::min<uint32_t>(collapse_k, 15));
+  f.visited.assign(node_count, 0);
+  f.subtree_spheres.assign(node_count, 0);
   SceneDesc& d = out->desc;
   d = SceneDesc{};
   if (node_count > 0) {
-    d.has_root = 1;
-    if (nodes[0].first_entity >= 0 && nodes[0].entity_count == 0) d.has_root = 0;  // empty world
+    f.count_pass(0, 1);
+    if (f.error) return f.error;
+    d.has_root = f.subtree_spheres[0] > 0 ? 1 : 0;   // empty world
     if (d.has_root) {
       d.root_ref = f.ref_of(0, 1);
       if (f.error) return f.error;
@@ -174,26 +305,36 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
   }
   d.max_depth = f.max_depth;
   d.n_inner = (uint32_t)(f.inner.size() / 16);
-  d.n_spheres = (uint32_t)sphere_count;
+  const size_t n_dev = f.order.size();
+  d.n_spheres = (uint32_t)n_dev;
   d.n_materials = (uint32_t)material_count;
+  d.has_chains = f.collapsed_any ? 1 : 0;
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t off = 0;
   d.inner_off = (uint32_t)off; off = align16(off + (size_t)d.n_inner * 64);
-  d.sphere_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 16);
-  d.leaf_count_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 4);   // +1: the empty-leaf sentinel
-  d.mat_index_off = (uint32_t)off; off = align16(off + (sphere_count + 1) * 4);
+  d.sphere_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 16);
+  d.leaf_count_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
+  d.mat_index_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
   if (off == 0) off = 16;
   d.blob_bytes = (uint32_t)off;
   out->bytes.assign(off, 0);
   unsigned char* b = out->bytes.data();
   if (d.n_inner) memcpy(b + d.inner_off, f.inner.data(), (size_t)d.n_inner * 64);
-  for (size_t i = 0; i < sphere_count; i++) {
-    float s[4] = {spheres[i].center[0], spheres[i].center[1], spheres[i].center[2], spheres[i].radius};
+  for (size_t i = 0; i < n_dev; i++) {
+    const uint32_t h = f.order[i];
+    float s[4] = {0, 0, 0, 0};
+    uint32_t mat = 0;
+    if (h != 0xFFFFFFFFu) {
+      s[0] = spheres[h].center[0]; s[1] = spheres[h].center[1]; s[2] = spheres[h].center[2]; s[3] = spheres[h].radius;
+      mat = spheres[h].material;
+    }
     memcpy(b + d.sphere_off + i * 16, s, 16);
     memcpy(b + d.leaf_count_off + i * 4, &f.leaf_count[i], 4);
-    memcpy(b + d.mat_index_off + i * 4, &spheres[i].material, 4);
+    memcpy(b + d.mat_index_off + i * 4, &mat, 4);
   }
+  out->chain_ref = std::move(f.chain_ref);
+  out->chain_boxes = std::move(f.chain_boxes);
   out->materials.resize(std::max<size_t>(material_count, 1));
   for (size_t i = 0; i < material_count; i++) {
     DevMaterial m{};
@@ -391,6 +532,10 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (const char* k = getenv("RTB_LEAF_SPHERES")) {   // experiment knob; RTB_OPT_LEAF_SPHERES is the API
+    const long v = strtol(k, nullptr, 10);
+    if (v >= 1 && v <= 15) ctx->opt_collapse = v;
+  }
   DeviceGuard g(device);
   auto bail = [&](cudaError_t err, const char* what) {
     int rc = fail(nullptr, RTB_ERR_CUDA + (int)err, "%s: %s", what, cudaGetErrorString(err));
@@ -415,7 +560,7 @@ int rtb_destroy(rtb_ctx* ctx) {
     for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
     DeviceBuffers& b = ctx->buf;
     void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
-                    b.diagnostics, ctx->d_blob, ctx->d_materials, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+                    b.diagnostics, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -443,19 +588,30 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_sphere* spheres, size_t sphere_coun
   std::lock_guard<std::mutex> lock(ctx->mu);
   HostBlob hb;
   int status;
-  const char* err = build_blob(spheres, sphere_count, materials, material_count, nodes, node_count, &hb, &status);
+  const char* err = build_blob(spheres, sphere_count, materials, material_count, nodes, node_count,
+                               (uint32_t)ctx->opt_collapse, &hb, &status);
   if (err) return fail(ctx, status, "rtb_upload_scene: %s", err);
   DeviceGuard g(ctx->device);
   RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->d_blob) cudaFree(ctx->d_blob);
   if (ctx->d_materials) cudaFree(ctx->d_materials);
+  if (ctx->d_chain_ref) cudaFree(ctx->d_chain_ref);
+  if (ctx->d_chain_boxes) cudaFree(ctx->d_chain_boxes);
   ctx->d_blob = nullptr;
   ctx->d_materials = nullptr;
+  ctx->d_chain_ref = nullptr;
+  ctx->d_chain_boxes = nullptr;
   ctx->has_scene = false;
   RTB_CUDA(ctx, cudaMalloc(&ctx->d_blob, hb.bytes.size()));
   RTB_CUDA(ctx, cudaMemcpy(ctx->d_blob, hb.bytes.data(), hb.bytes.size(), cudaMemcpyHostToDevice));
   RTB_CUDA(ctx, cudaMalloc(&ctx->d_materials, hb.materials.size() * sizeof(DevMaterial)));
   RTB_CUDA(ctx, cudaMemcpy(ctx->d_materials, hb.materials.data(), hb.materials.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice));
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_chain_ref, std::max<size_t>(hb.chain_ref.size(), 1) * sizeof(uint32_t)));
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_chain_boxes, std::max<size_t>(hb.chain_boxes.size(), 8) * sizeof(float)));
+  if (!hb.chain_ref.empty())
+    RTB_CUDA(ctx, cudaMemcpy(ctx->d_chain_ref, hb.chain_ref.data(), hb.chain_ref.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (!hb.chain_boxes.empty())
+    RTB_CUDA(ctx, cudaMemcpy(ctx->d_chain_boxes, hb.chain_boxes.data(), hb.chain_boxes.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (material_count) {
     derive_materials_kernel<<<(unsigned)((material_count + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_materials, (uint32_t)material_count);
     RTB_CUDA(ctx, cudaGetLastError());
@@ -464,7 +620,34 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_sphere* spheres, size_t sphere_coun
   ctx->scene = hb.desc;
   ctx->scene.blob = ctx->d_blob;
   ctx->scene.materials = ctx->d_materials;
+  ctx->scene.chain_ref = ctx->d_chain_ref;
+  ctx->scene.chain_boxes = ctx->d_chain_boxes;
+  if (ctx->scene.has_chains && ctx->opt_walk_chains) ctx->scene.has_chains = 2u;
   ctx->has_scene = true;
+  return RTB_OK;
+}
+
+int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials, size_t material_count,
+                       const rtb_bvh_node* nodes, size_t node_count, int leaf_spheres, rtb_scene_layout* out) {
+  if (!out) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "out is NULL");
+  if ((sphere_count && !spheres) || (material_count && !materials) || (node_count && !nodes))
+    return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "NULL array with a non-zero count");
+  if (leaf_spheres < 1 || leaf_spheres > 15) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "leaf_spheres must be 1..15");
+  HostBlob hb;
+  int status;
+  const char* err = build_blob(spheres, sphere_count, materials, material_count, nodes, node_count, (uint32_t)leaf_spheres, &hb, &status);
+  if (err) return fail(nullptr, status, "rtb_describe_scene: %s", err);
+  *out = rtb_scene_layout{};
+  out->inner_nodes = hb.desc.n_inner;
+  out->device_spheres = hb.desc.n_spheres;
+  out->max_depth = hb.desc.max_depth;
+  out->blob_bytes = hb.desc.blob_bytes;
+  out->chain_boxes = (uint32_t)(hb.chain_boxes.size() / 8);
+  out->collapsed = hb.desc.has_chains;
+  const uint32_t* lc = reinterpret_cast<const uint32_t*>(hb.bytes.data() + hb.desc.leaf_count_off);
+  for (uint32_t i = 0; i < hb.desc.n_spheres; i++) {
+    if (lc[i]) { out->leaves++; out->max_leaf_spheres = std::max(out->max_leaf_spheres, lc[i]); }
+  }
   return RTB_OK;
 }
 
@@ -636,6 +819,14 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
     case RTB_OPT_KERNEL:
       if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_KERNEL must be 0, 1 or 2");
       ctx->opt_kernel = value;
+      return RTB_OK;
+    case RTB_OPT_LEAF_SPHERES:
+      if (value < 1 || value > 15) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_LEAF_SPHERES must be 1..15");
+      ctx->opt_collapse = value;
+      return RTB_OK;
+    case RTB_OPT_ALWAYS_WALK_CHAINS:
+      ctx->opt_walk_chains = value ? 1 : 0;
+      if (ctx->has_scene && ctx->scene.has_chains) ctx->scene.has_chains = value ? 2u : 1u;
       return RTB_OK;
     case RTB_OPT_CANCEL_CHUNK_ROWS:
       if (value < 0) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_CANCEL_CHUNK_ROWS must be >= 0");

@@ -15,7 +15,7 @@ from . import build as _build
 
 EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
-    "rtb_upload_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_upload_scene", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_measure_fp32_peak",
@@ -49,6 +49,7 @@ def lib():
         L.rtb_last_error.restype = C.c_char_p
         L.rtb_set_log_callback.argtypes = [vp, vp, vp]
         L.rtb_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+        L.rtb_describe_scene.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.POINTER(abi.SceneLayout)]
         L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
         L.rtb_sample_batch_device.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
         L.rtb_register_host_buffer.argtypes = [vp, vp, sz]
@@ -131,6 +132,21 @@ def device_buffers_struct(in_color, in_weight, in_normal, in_albedo, out_color, 
     b.out_color, b.out_sample_count_weight, b.out_normal, b.out_albedo = ptr(out_color), ptr(out_weight), ptr(out_normal), ptr(out_albedo)
     b.out_diagnostics = ptr(diagnostics)
     return b
+
+
+def describe_scene(scene, leaf_spheres=8):
+    """rtb_describe_scene: how the device would lay `scene` out (host-side only, no GPU needed)."""
+    spheres = np.ascontiguousarray(scene.spheres, dtype=abi.SPHERE_DTYPE)
+    materials = np.ascontiguousarray(scene.materials, dtype=abi.MATERIAL_DTYPE)
+    nodes = np.ascontiguousarray(scene.nodes, dtype=abi.BVH_NODE_DTYPE)
+    out = abi.SceneLayout()
+    L = lib()
+    rc = L.rtb_describe_scene(spheres.ctypes.data if len(spheres) else None, len(spheres),
+                              materials.ctypes.data if len(materials) else None, len(materials),
+                              nodes.ctypes.data if len(nodes) else None, len(nodes), int(leaf_spheres), C.byref(out))
+    if rc != 0:
+        raise RtbError(rc, (L.rtb_last_error(None) or b"").decode())
+    return {name: getattr(out, name) for name, _ in abi.SceneLayout._fields_}
 
 
 class Context:

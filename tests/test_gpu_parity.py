@@ -96,6 +96,42 @@ def test_gpu_matches_golden_fixtures(rtb, ctx, case):
     assert np.abs(mega.out_color[:, :3] / n - g["color"][:, :3] / n).max() <= RGB_TOL
 
 
+@pytest.mark.parametrize("name,depth,td,ap", [("final", 16, 50, 0.1), ("final", 32, 50, 0.0), ("three_spheres", 2, 50, 0.2)])
+def test_image_does_not_depend_on_the_device_tree(rtb, oracle, ctx, name, depth, td, ap):
+    """RTB_OPT_LEAF_SPHERES: collapsing subtrees of the host's BVH into device leaves changes what the
+    walk executes (bounds_hit_count / candidate_count) and nothing else — every output is bitwise
+    identical for every setting, and equal to the oracle's decisions."""
+    W, H, spp = 96, 54, 24
+    scene = rtb.host.make_scene(name, max_bvh_depth=depth)
+    p = rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    base = None
+    try:
+        for k in (1, 2, 5, 8, 15):
+            ctx.set_option(rtb.abi.OPT_LEAF_SPHERES, k)
+            got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+            assert_parity(ref, got, exact=False)
+            simple = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE)
+            assert_parity(ref, simple, exact=True)
+            if base is None:
+                base = got
+            else:
+                for x, y in ((base.out_color, got.out_color), (base.out_normal, got.out_normal), (base.out_albedo, got.out_albedo),
+                             (base.out_weight, got.out_weight), (base.diagnostics["ray_count"], got.diagnostics["ray_count"])):
+                    assert x.tobytes() == y.tobytes()
+                assert got.diagnostics["bounds_hit_count"].sum() < base.diagnostics["bounds_hit_count"].sum()
+        # the exact re-test of the skipped host boxes, forced for every accepted hit: same image
+        ctx.set_option(rtb.abi.OPT_LEAF_SPHERES, 8)
+        ctx.set_option(rtb.abi.OPT_ALWAYS_WALK_CHAINS, 1)
+        walked = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+        assert walked.out_color.tobytes() == base.out_color.tobytes()
+        assert walked.diagnostics["ray_count"].tobytes() == base.diagnostics["ray_count"].tobytes()
+    finally:
+        ctx.set_option(rtb.abi.OPT_LEAF_SPHERES, 8)
+        ctx.set_option(rtb.abi.OPT_ALWAYS_WALK_CHAINS, 0)
+
+
 def test_interlaced_rows_and_carry_over(rtb, oracle, ctx):
     """SliceOffset/SliceDivider (SampleBatchJob.cs:69): skipped rows keep whatever the host put in out_*."""
     W, H, spp = 48, 30, 4
@@ -328,7 +364,7 @@ def test_combine_and_reduce_metrics_device(rtb, ctx):
     assert abs(m.sample_count_weight_min - np.nanmin(w)) < 1e-6 and abs(m.sample_count_weight_max - np.nanmax(w)) < 1e-6
 
 
-def test_full_size_properties_config3(rtb, ctx):
+def test_full_size_properties_config3(rtb, oracle, ctx):
     """BASELINE config 3 at full size (1920x1080, 256 spp, depth 50, BVH + defocus): properties that do
     not need the oracle — every sample accounted for, determinism, shard-invariance on a band, and the
     downsampled image agreeing with an independent 256-spp oracle render statistically."""
@@ -337,7 +373,17 @@ def test_full_size_properties_config3(rtb, ctx):
     p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
     a = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
     cnt = a.out_color[:, 3]
-    assert cnt.max() == spp and cnt.min() >= spp - 8           # failures are rare glass paths
+    # failed samples (depth == TraceDepth, SampleBatchJob.cs:379-381) are rare glass paths
+    assert cnt.max() == spp and cnt.min() >= spp // 2 and (W * H * spp - cnt.astype(np.int64).sum()) < 1e-3 * W * H * spp
+    # the row holding the pixel with the most failed samples, against the oracle: counts and ray counts exact
+    worst = int(np.argmin(cnt)) // W
+    pr = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1, row_begin=worst, row_end=worst + 1)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, pr, ref)
+    rs = slice(worst * W, (worst + 1) * W)
+    assert np.array_equal(ref.out_color[rs, 3], a.out_color[rs, 3])
+    assert np.array_equal(ref.diagnostics["ray_count"][rs], a.diagnostics["ray_count"][rs])
+    assert np.abs(ref.rgb()[worst] - a.rgb()[worst]).max() <= RGB_TOL
     assert np.isfinite(a.out_color).all()
     rays = a.diagnostics["ray_count"].astype(np.int64)
     assert rays.min() >= spp and rays.sum() > 2 * W * H * spp

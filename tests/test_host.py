@@ -64,3 +64,28 @@ def test_row_tiles_partition(rtb):
     assert tiles[0][0] == 0 and tiles[-1][1] == 200 and all(e > b for b, e in tiles)
     sums = [cost[b:e].sum() for b, e in tiles]
     assert max(sums) / min(sums) < 1.15
+
+
+@pytest.mark.parametrize("name,depth", [("final", 16), ("final", 0), ("final", 3), ("three_spheres", 2), ("three_spheres", 0)])
+def test_device_layout_collapses_small_subtrees(rtb, name, depth):
+    """rtb_describe_scene (host-side half of rtb_upload_scene): the device tree is the host's BVH with
+    subtrees of <= leaf_spheres spheres collapsed into one leaf; every sphere the BVH references
+    lands in exactly one leaf slot for every setting."""
+    scene = rtb.host.make_scene(name, max_bvh_depth=depth)
+    nodes = scene.nodes
+    n_ref_spheres = int(nodes["entity_count"][nodes["first_entity"] >= 0].sum())
+    n_ref_inner = int((nodes["first_entity"] < 0).sum())
+    one = rtb.plugin.describe_scene(scene, 1)
+    assert one["device_spheres"] == n_ref_spheres and one["inner_nodes"] == n_ref_inner
+    assert one["collapsed"] == 0 and one["chain_boxes"] == 0
+    prev = one["inner_nodes"]
+    for k in (2, 4, 8, 15):
+        lay = rtb.plugin.describe_scene(scene, k)
+        assert lay["device_spheres"] == n_ref_spheres
+        assert lay["inner_nodes"] <= prev and lay["max_depth"] <= one["max_depth"]
+        assert lay["leaves"] == lay["inner_nodes"] + 1
+        prev = lay["inner_nodes"]
+        if lay["collapsed"]:
+            assert lay["chain_boxes"] > 0 and lay["max_leaf_spheres"] <= max(k, one["max_leaf_spheres"])
+    if name == "final" and depth == 16:
+        assert rtb.plugin.describe_scene(scene, 8)["inner_nodes"] < n_ref_inner // 3

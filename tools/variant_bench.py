@@ -41,6 +41,7 @@ print("RESULT " + json.dumps(res))
 
 def main():
     tags = [a for a in sys.argv[1:] if not a.startswith("--")]
+    sweep = [a[len("--env="):] for a in sys.argv[1:] if a.startswith("--env=")]   # --env=NAME=v1,v2: default build per value
     cfgs = ["c3", "c2"] if "--c2" in sys.argv else ["c3"]
     vdir = os.path.join(ROOT, "raytracing-in-one-weekend_b200", "lib", "variants")
     libs = {"default": None}
@@ -49,8 +50,14 @@ def main():
     if tags:
         libs = {t: libs[t] for t in tags}
     out = []
-    for tag, path in libs.items():
+    runs = [(tag, path, {}) for tag, path in libs.items()]
+    for sw in sweep:
+        name, vals = sw.split("=", 1)
+        base = libs.get(tags[0]) if tags else None
+        runs += [(f"{tags[0] if tags else 'default'}:{name}={v}", base, {name: v}) for v in vals.split(",")]
+    for tag, path, extra in runs:
         env = dict(os.environ)
+        env.update(extra)
         if path:
             env["RTB_PLUGIN_LIB"] = path
         r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "tag": tag, "cfgs": cfgs}], env=env, capture_output=True, text=True, timeout=900)
