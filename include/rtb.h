@@ -265,9 +265,9 @@ RTB_API int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out);
 
 typedef enum rtb_option {
   RTB_OPT_COUNTERS = 1,         /* 0/1: run the instrumented kernel (slower) */
-  RTB_OPT_KERNEL = 2,           /* 0 = auto, 1 = simple (thread per pixel), 2 = persistent megakernel */
+  RTB_OPT_KERNEL = 2,           /* 0 = auto, 1 = simple (thread per pixel), 2 = persistent megakernel, 3 = warp-pool wavefront kernel */
   RTB_OPT_CANCEL_CHUNK_ROWS = 3,/* rows per launch when a cancel token is passed (0 = auto) */
-  RTB_OPT_LEAF_SPHERES = 4,     /* 1..15 (default 8): subtrees of the host's BVH holding at most this many spheres are
+  RTB_OPT_LEAF_SPHERES = 4,     /* 1..15 (default 1): subtrees of the host's BVH holding at most this many spheres are
                                  * walked as one leaf on the device (results are identical for every value; takes effect
                                  * at the next rtb_upload_scene) */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit

@@ -54,7 +54,7 @@ RTB_ERR_OUT_OF_MEMORY = 5
 RTB_ERR_CUDA = 100
 
 OPT_COUNTERS, OPT_KERNEL, OPT_CANCEL_CHUNK_ROWS, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS = 1, 2, 3, 4, 5
-KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA = 0, 1, 2
+KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA, KERNEL_POOL = 0, 1, 2, 3
 
 f32 = C.c_float
 f32x2 = C.c_float * 2

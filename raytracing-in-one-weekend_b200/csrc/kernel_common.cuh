@@ -75,7 +75,7 @@ struct SceneDesc {
   const float4* chain_boxes;    // 2 x float4 per box (min.xyz, max.xyz), tightest first
 };
 
-constexpr int kDefaultCollapse = 8;
+constexpr int kDefaultCollapse = 1;   // measured on B200 (profiles/README.md): single-sphere leaves are fastest for the staged-in-smem walk
 // Geometry of the guard that stands in for the skipped boxes (see chain_guard).
 constexpr float kChainShrink = 1.0e-3f;   // upload checks: every skipped box contains its sphere shrunk by this
 
@@ -227,6 +227,7 @@ __device__ __forceinline__ bool chain_guard(float a, float b, float oc2, float r
 // is hit nearer than best_t: the same record FindHits' sort would put first
 // (SampleBatchJob.cs:450-475) — a root is accepted iff 0 < t < +inf there, and the
 // second root is never nearer than the first, so clipping at best_t changes nothing.
+template <bool CHAINS>
 __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a,
                                            float& best_t, int& best_idx) {
   f3 oc = o + um::mk(-s.x, -s.y, -s.z);
@@ -240,7 +241,7 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
     float t = um::div(-b - sq, a);
     if (!(t < best_t && t > 0.0f)) t = um::div(-b + sq, a);
     if (t < best_t && t > 0.0f) {
-      if (sd.has_chains && (sd.has_chains == 2u || !chain_guard(a, b, oc2, r2, disc)) && !chain_boxes_hit(sd, idx, o, inv)) return;
+      if (CHAINS && sd.has_chains && (sd.has_chains == 2u || !chain_guard(a, b, oc2, r2, disc)) && !chain_boxes_hit(sd, idx, o, inv)) return;
       best_t = t;
       best_idx = idx;
     }
@@ -261,7 +262,8 @@ constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an 
 #define RTB_TRAVERSAL 0   // 0: one node (inner or leaf) per loop trip (measured fastest on B200); 1: while-while (inner run, then leaf run)
 #endif
 
-template <bool SMEM, bool COUNTERS>
+// CHAINS = false: the build for scenes uploaded without collapsed leaves (the accepted-hit path carries no guard).
+template <bool SMEM, bool COUNTERS, bool CHAINS>
 __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
                                             float& best_t, int& best_idx, WorkCounters& wc) {
   best_t = um::INF;
@@ -280,7 +282,55 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   stack[0] = kTraversalDone;
   int sp = 1;
   int cur = sd.root_ref;
-#if RTB_TRAVERSAL == 1
+#if RTB_TRAVERSAL == 2
+  // Speculative while-while (Aila & Laine, HPG 2009), one step per trip with warp votes: a lane that
+  // reaches a leaf parks it in `leaf` and keeps walking inner nodes for as long as ANY lane of the warp
+  // is still looking for its first leaf; when nobody is, every lane tests the spheres of its parked
+  // leaf in the same trips.  Sphere tests therefore run with most of the warp instead of the one or
+  // two lanes that happen to sit on a leaf.  (Walking on with an untested leaf only delays pruning.)
+  const unsigned mask = __activemask();
+  int leaf = 0;                                   // parked leaf ref (negative) or 0
+  auto is_leaf = [](int r) { return r < 0 && r != kTraversalDone; };
+  for (;;) {
+    if (leaf == 0 && is_leaf(cur)) { leaf = cur; cur = stack[--sp]; }
+    if (__any_sync(mask, cur >= 0 && leaf == 0)) {
+      if (cur >= 0) {
+        const float4* n = sv.inner + 4 * cur;
+        const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+        float tl, tr;
+        bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
+        bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
+        if (COUNTERS) wc.node_tests += 2;
+        const float limit = best_t * kPruneMargin;
+        hl = hl && tl < limit;
+        hr = hr && tr < limit;
+        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+        if (hl && hr) {
+          const bool left_first = tl <= tr;
+          stack[sp++] = left_first ? right : left;
+          cur = left_first ? left : right;
+        } else if (hl || hr) {
+          cur = hl ? left : right;
+        } else {
+          cur = stack[--sp];
+        }
+      }
+      continue;
+    }
+    if (!__any_sync(mask, leaf != 0)) break;      // nobody searching, nobody holding a leaf: every lane is done
+    if (leaf != 0) {
+      const uint32_t code = (uint32_t)~leaf;
+      const int first = (int)(code >> 4);
+      int count = (int)(code & 15u) + 1;
+      if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
+      for (int i = 0; i < count; i++) {
+        sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
+      }
+      if (COUNTERS) wc.sphere_tests += count;
+      leaf = 0;
+    }
+  }
+#elif RTB_TRAVERSAL == 1
   while (cur != kTraversalDone) {
     // inner nodes until this lane holds a leaf (or is done); the warp reconverges after the loop,
     // so the sphere tests below run with every lane that found a leaf
@@ -311,7 +361,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       int count = (int)(code & 15u) + 1;
       if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
       for (int i = 0; i < count; i++) {
-        sphere_hit(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
+        sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
       }
       if (COUNTERS) wc.sphere_tests += count;
       cur = stack[--sp];
@@ -344,7 +394,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       int count = (int)(code & 15u) + 1;
       if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
       for (int i = 0; i < count; i++) {
-        sphere_hit(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
+        sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
       }
       if (COUNTERS) wc.sphere_tests += count;
     }

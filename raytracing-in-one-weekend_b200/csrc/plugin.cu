@@ -21,6 +21,7 @@
 
 #include "aux_kernels.cuh"
 #include "sample_kernels.cuh"
+#include "pool_kernel.cuh"
 
 using namespace rtbk;
 
@@ -59,9 +60,11 @@ struct rtb_ctx {
   uint32_t* d_tile_counter = nullptr;
   unsigned long long* d_counters = nullptr;
   rtb_counters counters{};
+  int default_kernel = 2;
   int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0;
   float last_ms = 0.0f;
-  bool smem_attr_set[2][2] = {{false, false}, {false, false}};
+  bool smem_attr_set[2][4] = {};
+  bool pool_attr_set[2][2] = {{false, false}, {false, false}};
 
   DeviceBuffers buf;
   MetricsAcc* d_metrics_partial = nullptr;
@@ -388,29 +391,55 @@ int validate_params(rtb_ctx* ctx, const rtb_batch_params* p, int* width, int* he
   return RTB_OK;
 }
 
-template <bool SMEM, bool COUNTERS>
+void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp);
+
+template <bool SMEM, bool COUNTERS, bool CHAINS>
 int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_spp) {
   const size_t smem = mega_smem_bytes(a.scene.blob_bytes, SMEM);
-  auto kernel = sample_megakernel<SMEM, COUNTERS>;
-  if (!ctx->smem_attr_set[SMEM][COUNTERS]) {
+  auto kernel = sample_megakernel<SMEM, COUNTERS, CHAINS>;
+  if (!ctx->smem_attr_set[SMEM][COUNTERS + 2 * CHAINS]) {
     RTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    ctx->smem_attr_set[SMEM][COUNTERS] = true;
+    ctx->smem_attr_set[SMEM][COUNTERS + 2 * CHAINS] = true;
   }
   int blocks_per_sm = 0;
   RTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kMegaBlock, smem));
   if (blocks_per_sm < 1) return fail(ctx, RTB_ERR_CUDA, "megakernel does not fit on an SM (smem %zu B)", smem);
   const uint32_t n_warps_full = (uint32_t)(ctx->sm_count * blocks_per_sm * kMegaWarps);
 
-  // tile size: ~4096 samples per warp tile, at least ~6 tiles per resident warp when the
-  // image is small, never fewer than 1024 samples per tile unless the pixel count forces it
-  int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (4096 + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
-  while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
-  a.tile_pixels = tp;
-  a.n_tiles = (a.n_active_pixels + (uint32_t)tp - 1) / (uint32_t)tp;
+  choose_tiles(a, n_warps_full, max_spp);
   const uint32_t ctas_needed = (a.n_tiles + kMegaWarps - 1) / kMegaWarps;
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
   RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
   kernel<<<grid, kMegaBlock, smem, stream>>>(a);
+  RTB_CUDA(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
+// Tile size shared by the two persistent kernels: ~4096 samples per warp tile, at least ~6 tiles per
+// resident warp when the image is small, never fewer than 1024 samples per tile unless the pixel count forces it.
+void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
+  int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (4096 + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
+  while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
+  a.tile_pixels = tp;
+  a.n_tiles = (a.n_active_pixels + (uint32_t)tp - 1) / (uint32_t)tp;
+}
+
+template <bool SMEM, bool COUNTERS>
+int launch_pool_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_spp) {
+  const size_t smem = pool_smem_bytes(a.scene.blob_bytes, SMEM);
+  auto kernel = sample_poolkernel<SMEM, COUNTERS>;
+  if (!ctx->pool_attr_set[SMEM][COUNTERS]) {
+    RTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    ctx->pool_attr_set[SMEM][COUNTERS] = true;
+  }
+  int blocks_per_sm = 0;
+  RTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kPoolBlock, smem));
+  if (blocks_per_sm < 1) return fail(ctx, RTB_ERR_CUDA, "pool kernel does not fit on an SM (smem %zu B)", smem);
+  choose_tiles(a, (uint32_t)(ctx->sm_count * blocks_per_sm * kPoolWarps), max_spp);
+  const uint32_t ctas_needed = (a.n_tiles + kPoolWarps - 1) / kPoolWarps;
+  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
+  RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
+  kernel<<<grid, kPoolBlock, smem, stream>>>(a);
   RTB_CUDA(ctx, cudaGetLastError());
   return RTB_OK;
 }
@@ -451,18 +480,28 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   (void)user_diag;
 
   int kernel_kind = (int)ctx->opt_kernel;
-  if (kernel_kind == 0) kernel_kind = 2;
+  if (kernel_kind == 0) kernel_kind = ctx->default_kernel;
   if (kernel_kind == 1) {
     const uint32_t grid = (a.n_active_pixels + 127) / 128;
     if (counters) sample_simple<true><<<grid, 128, 0, stream>>>(a);
     else sample_simple<false><<<grid, 128, 0, stream>>>(a);
     RTB_CUDA(ctx, cudaGetLastError());
+  } else if (kernel_kind == 3) {
+    const bool fits = pool_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
+                      ctx->scene.blob_bytes < (1u << 20);
+    int rc;
+    if (fits) rc = counters ? launch_pool_t<true, true>(ctx, a, stream, max_spp) : launch_pool_t<true, false>(ctx, a, stream, max_spp);
+    else rc = counters ? launch_pool_t<false, true>(ctx, a, stream, max_spp) : launch_pool_t<false, false>(ctx, a, stream, max_spp);
+    if (rc != RTB_OK) return rc;
   } else {
     const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
-    if (fits) rc = counters ? launch_mega_t<true, true>(ctx, a, stream, max_spp) : launch_mega_t<true, false>(ctx, a, stream, max_spp);
-    else rc = counters ? launch_mega_t<false, true>(ctx, a, stream, max_spp) : launch_mega_t<false, false>(ctx, a, stream, max_spp);
+    const bool chains = ctx->scene.has_chains != 0;
+    if (fits) rc = counters ? launch_mega_t<true, true, true>(ctx, a, stream, max_spp)
+                   : chains ? launch_mega_t<true, false, true>(ctx, a, stream, max_spp) : launch_mega_t<true, false, false>(ctx, a, stream, max_spp);
+    else rc = counters ? launch_mega_t<false, true, true>(ctx, a, stream, max_spp)
+              : chains ? launch_mega_t<false, false, true>(ctx, a, stream, max_spp) : launch_mega_t<false, false, false>(ctx, a, stream, max_spp);
     if (rc != RTB_OK) return rc;
   }
   if (counters) {
@@ -532,6 +571,10 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (const char* k = getenv("RTB_KERNEL")) {         // experiment knob; RTB_OPT_KERNEL is the API
+    const long v = strtol(k, nullptr, 10);
+    if (v >= 1 && v <= 3) ctx->default_kernel = (int)v;
+  }
   if (const char* k = getenv("RTB_LEAF_SPHERES")) {   // experiment knob; RTB_OPT_LEAF_SPHERES is the API
     const long v = strtol(k, nullptr, 10);
     if (v >= 1 && v <= 15) ctx->opt_collapse = v;
@@ -817,7 +860,7 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
   switch (option) {
     case RTB_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; return RTB_OK;
     case RTB_OPT_KERNEL:
-      if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_KERNEL must be 0, 1 or 2");
+      if (value < 0 || value > 3) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_KERNEL must be 0..3");
       ctx->opt_kernel = value;
       return RTB_OK;
     case RTB_OPT_LEAF_SPHERES:

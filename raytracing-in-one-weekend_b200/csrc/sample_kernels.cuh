@@ -95,7 +95,7 @@ __device__ __forceinline__ void active_pixel(const BatchArgs& a, uint32_t k, int
   *index = (uint32_t)*cy * (uint32_t)a.width + (uint32_t)*cx;
 }
 
-template <bool SMEM, bool COUNTERS>
+template <bool SMEM, bool COUNTERS, bool CHAINS>
 __global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megake
     if (alive) {
       float t_hit;
       int hit_idx;
-      closest_hit<SMEM, COUNTERS>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      closest_hit<SMEM, COUNTERS, CHAINS>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
       path_rays++;
       bool finished = false, success = false;
       if (hit_idx >= 0) {
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
     for (; depth < p.trace_depth; depth++) {
       float t_hit;
       int hit_idx;
-      closest_hit<false, COUNTERS>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      closest_hit<false, COUNTERS, true>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
       rays++;
       if (hit_idx >= 0) {
         const float4 sp = sv.ld4(sv.spheres + hit_idx);

@@ -134,7 +134,7 @@ def device_buffers_struct(in_color, in_weight, in_normal, in_albedo, out_color, 
     return b
 
 
-def describe_scene(scene, leaf_spheres=8):
+def describe_scene(scene, leaf_spheres=1):
     """rtb_describe_scene: how the device would lay `scene` out (host-side only, no GPU needed)."""
     spheres = np.ascontiguousarray(scene.spheres, dtype=abi.SPHERE_DTYPE)
     materials = np.ascontiguousarray(scene.materials, dtype=abi.MATERIAL_DTYPE)

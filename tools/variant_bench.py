@@ -50,11 +50,13 @@ def main():
     if tags:
         libs = {t: libs[t] for t in tags}
     out = []
-    runs = [(tag, path, {}) for tag, path in libs.items()]
-    for sw in sweep:
-        name, vals = sw.split("=", 1)
-        base = libs.get(tags[0]) if tags else None
-        runs += [(f"{tags[0] if tags else 'default'}:{name}={v}", base, {name: v}) for v in vals.split(",")]
+    runs = []
+    for tag, path in libs.items():
+        if not sweep:
+            runs.append((tag, path, {}))
+        for sw in sweep:
+            name, vals = sw.split("=", 1)
+            runs += [(f"{tag}:{name}={v}", path, {name: v}) for v in vals.split(",")]
     for tag, path, extra in runs:
         env = dict(os.environ)
         env.update(extra)
