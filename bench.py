@@ -39,12 +39,23 @@ CONFIGS = {
     "c2": ("final", 0, 1280, 720, 64, 50, None),
     "c3": ("final", 16, 1920, 1080, 256, 50, 0.1),
     "c4": ("final", 16, 3840, 2160, 1024, 50, 0.1),
+    "c5": ("stress", 16, 4096, 4096, 2048, 50, 0.1),
+    "c5s": ("stress", 16, 1920, 1080, 64, 50, 0.1),     # config 5's world at a single-GPU size
 }
+STRESS_SPHERES = 10000
+
+
+def make_scene(host, cfg):
+    name, depth = CONFIGS[cfg][0], CONFIGS[cfg][1]
+    return host.make_scene(name, max_bvh_depth=depth, target_count=STRESS_SPHERES if name == "stress" else 0)
+
 WORKLOADS = {
     "c1": "three-sphere scene 400x225x4spp depth 8 (linear list)",
     "c2": "book-1 final scene (482 spheres, linear hit list) 1280x720x64spp depth 50",
     "c3": "book-1 final scene (482 spheres) BVH(maxDepth 16) + defocus(aperture 0.1) 1920x1080x256spp depth 50",
     "c4": "book-1 final scene BVH + defocus 3840x2160x1024spp depth 50",
+    "c5": "10k-sphere synthetic stress scene BVH(maxDepth 16) + defocus 4096x4096x2048spp depth 50",
+    "c5s": "10k-sphere synthetic stress scene BVH(maxDepth 16) + defocus 1920x1080x64spp depth 50",
 }
 
 
@@ -100,7 +111,7 @@ def cpu_reference(cfg, threads, target_seconds=12.0, steps=1, warmup=0):
     import oracle_lib as O
 
     name, depth, W, H, spp, td, ap = CONFIGS[cfg]
-    scene = O.rtb.host.make_scene(name, max_bvh_depth=depth)
+    scene = make_scene(O.rtb.host, cfg)
     # calibrate on 2 rows, then pick the row stride for ~target_seconds
     p = O.rtb.host.make_params(scene, W, H, spp, td, aperture=ap, slice_offset=H // 2 % max(H // 2, 1), slice_divider=max(H // 2, 1))
     buf = O.Buffers(W, H, diagnostics=True)
@@ -169,7 +180,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     name, depth, W, H, spp, td, ap = CONFIGS[args.config]
-    scene = rtb.host.make_scene(name, max_bvh_depth=depth)
+    scene = make_scene(rtb.host, args.config)
     params = rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
     fr = renderer_mod.FrameRenderer(scene, W, H, device_index=local_rank)
     samples_per_step = W * H * spp

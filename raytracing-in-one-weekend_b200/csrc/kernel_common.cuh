@@ -236,10 +236,28 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
   float r2 = s.w * s.w;
   float c = oc2 - r2;
   float disc = um::fma(b, b, -(a * c));
+  // HitTests.cs:33-55 takes the first of t1 = (-b - sqrt(disc)) / a, t2 = (-b + sqrt(disc)) / a that lies in (0, best_t).
+  // Cases decided without evaluating a root, with the SAME outcome as evaluating both (a > 0; rounding is monotonic,
+  // and sqrt(fl(b*b)) == |b|, so c > 0 gives disc <= fl(b*b) and sqrt(disc) <= |b|):
+  //   c > 0, b >= 0 (outside, moving away):  -b - sq <= 0 and -b + sq <= 0: neither root is > 0            -> no hit
+  //   c <= 0 (inside or on the sphere):      sq >= |b| so t1 <= 0: only t2 can be accepted
+  //   c > 0, b < 0:                          0 <= t1 <= t2: if t1 > 0 it alone decides (t1 >= best_t implies t2 >= best_t)
+#if !defined(RTB_NO_ROOT_SHORTCUTS)
+  if (disc > 0.0f && !(c > 0.0f && b >= 0.0f)) {
+    const float sq = um::sqrt(disc);
+    float t;
+    if (c > 0.0f) {
+      t = um::div(-b - sq, a);
+      if (!(t > 0.0f)) t = um::div(-b + sq, a);      // t1 rounded to 0: the reference moves on to t2
+    } else {
+      t = um::div(-b + sq, a);
+    }
+#else
   if (disc > 0.0f) {
     float sq = um::sqrt(disc);
     float t = um::div(-b - sq, a);
     if (!(t < best_t && t > 0.0f)) t = um::div(-b + sq, a);
+#endif
     if (t < best_t && t > 0.0f) {
       if (CHAINS && sd.has_chains && (sd.has_chains == 2u || !chain_guard(a, b, oc2, r2, disc)) && !chain_boxes_hit(sd, idx, o, inv)) return;
       best_t = t;
@@ -282,6 +300,16 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   stack[0] = kTraversalDone;
   int sp = 1;
   int cur = sd.root_ref;
+  auto test_leaf = [&](int ref) {
+    const uint32_t code = (uint32_t)~ref;
+    const int first = (int)(code >> 4);
+    int count = (int)(code & 15u) + 1;
+    if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
+    for (int i = 0; i < count; i++) {
+      sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
+    }
+    if (COUNTERS) wc.sphere_tests += count;
+  };
 #if RTB_TRAVERSAL == 2
   // Speculative while-while (Aila & Laine, HPG 2009), one step per trip with warp votes: a lane that
   // reaches a leaf parks it in `leaf` and keeps walking inner nodes for as long as ANY lane of the warp
@@ -293,7 +321,8 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   auto is_leaf = [](int r) { return r < 0 && r != kTraversalDone; };
   for (;;) {
     if (leaf == 0 && is_leaf(cur)) { leaf = cur; cur = stack[--sp]; }
-    if (__any_sync(mask, cur >= 0 && leaf == 0)) {
+    const bool keep_walking = __any_sync(mask, cur >= 0 && leaf == 0);
+    if (keep_walking) {
       if (cur >= 0) {
         const float4* n = sv.inner + 4 * cur;
         const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
@@ -319,14 +348,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     }
     if (!__any_sync(mask, leaf != 0)) break;      // nobody searching, nobody holding a leaf: every lane is done
     if (leaf != 0) {
-      const uint32_t code = (uint32_t)~leaf;
-      const int first = (int)(code >> 4);
-      int count = (int)(code & 15u) + 1;
-      if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
-      for (int i = 0; i < count; i++) {
-        sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
-      }
-      if (COUNTERS) wc.sphere_tests += count;
+      test_leaf(leaf);
       leaf = 0;
     }
   }
@@ -356,14 +378,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       }
     }
     if (cur != kTraversalDone) {
-      const uint32_t code = (uint32_t)~cur;
-      const int first = (int)(code >> 4);
-      int count = (int)(code & 15u) + 1;
-      if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
-      for (int i = 0; i < count; i++) {
-        sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
-      }
-      if (COUNTERS) wc.sphere_tests += count;
+      test_leaf(cur);
       cur = stack[--sp];
     }
   }
@@ -389,14 +404,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       if (hl) { cur = left; continue; }
       if (hr) { cur = right; continue; }
     } else {
-      const uint32_t code = (uint32_t)~cur;
-      const int first = (int)(code >> 4);
-      int count = (int)(code & 15u) + 1;
-      if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
-      for (int i = 0; i < count; i++) {
-        sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
-      }
-      if (COUNTERS) wc.sphere_tests += count;
+      test_leaf(cur);
     }
     cur = stack[--sp];
     if (cur == kTraversalDone) break;

@@ -136,6 +136,22 @@ def test_image_does_not_depend_on_the_device_tree(rtb, oracle, ctx, name, depth,
         ctx.set_option(rtb.abi.OPT_ALWAYS_WALK_CHAINS, 0)
 
 
+@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+def test_stress_scene_walks_the_world_in_hbm(rtb, oracle, ctx, kernel):
+    """BASELINE config 5's world (10 000 dart-thrown spheres, BVH depth 16): the flattened world (~0.9 MB) does
+    not fit shared memory, so the kernels read it in place through the read-only path — same decisions."""
+    W, H, spp = 96, 54, 4
+    scene = rtb.host.make_scene("stress", max_bvh_depth=16, target_count=10000)
+    assert len(scene.spheres) == 10004
+    assert rtb.plugin.describe_scene(scene, 1)["blob_bytes"] > 232448
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    got = render_gpu(rtb, ctx, scene, p, W, H, k)
+    assert_parity(ref, got, exact=(kernel == "simple"))
+
+
 def test_interlaced_rows_and_carry_over(rtb, oracle, ctx):
     """SliceOffset/SliceDivider (SampleBatchJob.cs:69): skipped rows keep whatever the host put in out_*."""
     W, H, spp = 48, 30, 4

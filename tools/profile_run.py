@@ -17,7 +17,7 @@ bench = importlib.import_module("bench")
 rtb = importlib.import_module("raytracing-in-one-weekend_b200")
 renderer = importlib.import_module("raytracing-in-one-weekend_b200.renderer")
 name, depth, W, H, spp, td, aperture = bench.CONFIGS[args.config]
-scene = rtb.host.make_scene(name, max_bvh_depth=depth)
+scene = bench.make_scene(rtb.host, args.config)
 p = rtb.host.make_params(scene, W, H, spp, td, aperture=aperture)
 fr = renderer.FrameRenderer(scene, W, H, 0)
 for _ in range(args.steps):
