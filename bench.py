@@ -299,6 +299,7 @@ def run_ours(args):
         h2d, d2h = e2e_step()
     barrier()
     e2e_s = sharding.max_over_ranks(time.perf_counter() - t, dev)
+    in_place = world == 1 and fr.ctx.last_batch_in_place()
     e2e_value = samples_per_step * args.steps / e2e_s / 1e6
     if world > 1:
         bt = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
@@ -333,7 +334,7 @@ def run_ours(args):
                 "outputs": "color + normal + albedo + sampleCountWeight + diagnostics (full job contract)",
             },
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "rtb_sample_batch (C ABI, pinned host buffers)" if world == 1 else "FrameRenderer.render_host (H2D own rows, rtb_sample_batch_device, NCCL gather, D2H on rank 0)",
+                    "api": ("rtb_sample_batch (C ABI, pinned host buffers" + (", read and written in place by the kernel over PCIe)" if in_place else ", staged H2D/D2H copies)")) if world == 1 else "FrameRenderer.render_host (H2D own rows, rtb_sample_batch_device, NCCL gather, D2H on rank 0)",
                     "out_color_checksum": checksum},
             "gpu_launches": args.steps * world,
             "kernel_ms_rank0": kernel_ms, "kernel_ms_max_rank": kernel_ms_max,

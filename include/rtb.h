@@ -221,9 +221,10 @@ RTB_API int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params
                                     const rtb_batch_buffers* device_buffers,
                                     void* cuda_stream);
 
-/* Optional: pin (cudaHostRegister) the host's pooled accumulation arrays so that
- * rtb_sample_batch copies at full PCIe rate; the same 8 pointers recur every batch
- * (Raytracer.cs:279-303 pools). */
+/* Optional: pin (cudaHostRegister) the host's pooled accumulation arrays; the same 8 pointers
+ * recur every batch (Raytracer.cs:279-303 pools).  When every array of a batch is pinned,
+ * rtb_sample_batch runs the kernel directly on them (no staging copies, see RTB_OPT_HOST_ACCESS);
+ * otherwise pinned arrays still copy at full PCIe rate. */
 RTB_API int rtb_register_host_buffer(rtb_ctx* ctx, void* ptr, size_t bytes);
 RTB_API int rtb_unregister_host_buffer(rtb_ctx* ctx, void* ptr);
 
@@ -270,10 +271,14 @@ typedef enum rtb_option {
   RTB_OPT_LEAF_SPHERES = 4,     /* 1..15 (default 1): subtrees of the host's BVH holding at most this many spheres are
                                  * walked as one leaf on the device (results are identical for every value; takes effect
                                  * at the next rtb_upload_scene) */
+  RTB_OPT_HOST_ACCESS = 6,      /* 1 (default): rtb_sample_batch lets the kernel read/write PINNED host arrays in place over PCIe
+                                 * (rtb_register_host_buffer or cudaHostAlloc memory); 0: always stage through device copies */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
                                  * instead of only when the hit geometry does not already prove them (same results, slower) */
 } rtb_option;
 RTB_API int rtb_set_option(rtb_ctx* ctx, int option, int64_t value);
+/* 1 when the last rtb_sample_batch ran on the host arrays in place (all of them pinned), 0 when it staged copies. */
+RTB_API int rtb_last_batch_in_place(rtb_ctx* ctx, int* out_in_place);
 /* Milliseconds of the last kernel launch sequence on the context stream (CUDA events; the
  * same bracket as the two RecordTimeJobs, Raytracer.cs:729-738).  Valid after a synchronising call. */
 RTB_API int rtb_last_kernel_ms(rtb_ctx* ctx, float* out_ms);

@@ -61,7 +61,8 @@ struct rtb_ctx {
   unsigned long long* d_counters = nullptr;
   rtb_counters counters{};
   int default_kernel = 2;
-  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0;
+  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1;
+  bool last_in_place = false;
   float last_ms = 0.0f;
   bool smem_attr_set[2][4] = {};
   bool pool_attr_set[2][2] = {{false, false}, {false, false}};
@@ -721,21 +722,49 @@ int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_bat
   std::lock_guard<std::mutex> lock(ctx->mu);
   DeviceGuard g(ctx->device);
   const size_t pixels = (size_t)width * height;
-  if ((rc = ensure_buffers(ctx, pixels)) != RTB_OK) return rc;
-  DeviceBuffers& d = ctx->buf;
   cudaStream_t s = ctx->stream;
   const ActiveRows all = active_rows(*params, height, 0, 0);
   if (all.n_rows <= 0) return RTB_OK;
 
-  RTB_CUDA(ctx, copy_rows(d.in_color, host->in_color, 16, width, all, cudaMemcpyHostToDevice, s));
-  RTB_CUDA(ctx, copy_rows(d.in_weight, host->in_sample_count_weight, 4, width, all, cudaMemcpyHostToDevice, s));
-  RTB_CUDA(ctx, copy_rows(d.in_normal, host->in_normal, 12, width, all, cudaMemcpyHostToDevice, s));
-  RTB_CUDA(ctx, copy_rows(d.in_albedo, host->in_albedo, 12, width, all, cudaMemcpyHostToDevice, s));
-
+  // Pinned host arrays (rtb_register_host_buffer, or any cudaHostAlloc'd memory) are read and written IN PLACE by the
+  // kernel over PCIe: each accumulator crosses the bus once, inside the kernel, overlapped with tracing, instead of in
+  // eight staged copies around it.  Pageable arrays take the staged path.
   rtb_batch_buffers dev{};
-  dev.in_color = d.in_color; dev.in_sample_count_weight = d.in_weight; dev.in_normal = d.in_normal; dev.in_albedo = d.in_albedo;
-  dev.out_color = d.out_color; dev.out_sample_count_weight = d.out_weight; dev.out_normal = d.out_normal; dev.out_albedo = d.out_albedo;
-  dev.out_diagnostics = host->out_diagnostics ? d.diagnostics : nullptr;
+  bool in_place = ctx->opt_host_access != 0;
+  if (in_place) {
+    const void* hp[9] = {host->in_color, host->in_sample_count_weight, host->in_normal, host->in_albedo, host->out_color,
+                         host->out_sample_count_weight, host->out_normal, host->out_albedo, host->out_diagnostics};
+    void* dp[9] = {};
+    for (int i = 0; i < 9 && in_place; i++) {
+      if (!hp[i]) continue;             // diagnostics may be NULL
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        in_place = false;
+      } else {
+        dp[i] = at.devicePointer;
+      }
+    }
+    if (in_place) {
+      dev.in_color = (const float*)dp[0]; dev.in_sample_count_weight = (const float*)dp[1];
+      dev.in_normal = (const float*)dp[2]; dev.in_albedo = (const float*)dp[3];
+      dev.out_color = (float*)dp[4]; dev.out_sample_count_weight = (float*)dp[5];
+      dev.out_normal = (float*)dp[6]; dev.out_albedo = (float*)dp[7];
+      dev.out_diagnostics = (rtb_diagnostics*)dp[8];
+    }
+  }
+  ctx->last_in_place = in_place;
+  if (!in_place) {
+    if ((rc = ensure_buffers(ctx, pixels)) != RTB_OK) return rc;
+    DeviceBuffers& d = ctx->buf;
+    RTB_CUDA(ctx, copy_rows(d.in_color, host->in_color, 16, width, all, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(ctx, copy_rows(d.in_weight, host->in_sample_count_weight, 4, width, all, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(ctx, copy_rows(d.in_normal, host->in_normal, 12, width, all, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(ctx, copy_rows(d.in_albedo, host->in_albedo, 12, width, all, cudaMemcpyHostToDevice, s));
+    dev.in_color = d.in_color; dev.in_sample_count_weight = d.in_weight; dev.in_normal = d.in_normal; dev.in_albedo = d.in_albedo;
+    dev.out_color = d.out_color; dev.out_sample_count_weight = d.out_weight; dev.out_normal = d.out_normal; dev.out_albedo = d.out_albedo;
+    dev.out_diagnostics = host->out_diagnostics ? d.diagnostics : nullptr;
+  }
 
   RTB_CUDA(ctx, cudaEventRecord(ctx->ev_start, s));
   if (!cancel) {
@@ -759,12 +788,15 @@ int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_bat
   }
   RTB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, s));
 
-  RTB_CUDA(ctx, copy_rows(host->out_color, d.out_color, 16, width, all, cudaMemcpyDeviceToHost, s));
-  RTB_CUDA(ctx, copy_rows(host->out_sample_count_weight, d.out_weight, 4, width, all, cudaMemcpyDeviceToHost, s));
-  RTB_CUDA(ctx, copy_rows(host->out_normal, d.out_normal, 12, width, all, cudaMemcpyDeviceToHost, s));
-  RTB_CUDA(ctx, copy_rows(host->out_albedo, d.out_albedo, 12, width, all, cudaMemcpyDeviceToHost, s));
-  if (host->out_diagnostics)
-    RTB_CUDA(ctx, copy_rows(host->out_diagnostics, d.diagnostics, sizeof(rtb_diagnostics), width, all, cudaMemcpyDeviceToHost, s));
+  if (!in_place) {
+    DeviceBuffers& d = ctx->buf;
+    RTB_CUDA(ctx, copy_rows(host->out_color, d.out_color, 16, width, all, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, copy_rows(host->out_sample_count_weight, d.out_weight, 4, width, all, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, copy_rows(host->out_normal, d.out_normal, 12, width, all, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, copy_rows(host->out_albedo, d.out_albedo, 12, width, all, cudaMemcpyDeviceToHost, s));
+    if (host->out_diagnostics)
+      RTB_CUDA(ctx, copy_rows(host->out_diagnostics, d.diagnostics, sizeof(rtb_diagnostics), width, all, cudaMemcpyDeviceToHost, s));
+  }
   if (ctx->opt_counters)
     RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
   RTB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -778,7 +810,7 @@ int rtb_register_host_buffer(rtb_ctx* ctx, void* ptr, size_t bytes) {
   std::lock_guard<std::mutex> lock(ctx->mu);
   if (ctx->registered.count(ptr)) return RTB_OK;
   DeviceGuard g(ctx->device);
-  RTB_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  RTB_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   ctx->registered[ptr] = bytes;
   return RTB_OK;
 }
@@ -867,6 +899,9 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
       if (value < 1 || value > 15) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_LEAF_SPHERES must be 1..15");
       ctx->opt_collapse = value;
       return RTB_OK;
+    case RTB_OPT_HOST_ACCESS:
+      ctx->opt_host_access = value ? 1 : 0;
+      return RTB_OK;
     case RTB_OPT_ALWAYS_WALK_CHAINS:
       ctx->opt_walk_chains = value ? 1 : 0;
       if (ctx->has_scene && ctx->scene.has_chains) ctx->scene.has_chains = value ? 2u : 1u;
@@ -900,6 +935,12 @@ int rtb_measure_fp32_peak(rtb_ctx* ctx, int repeats, double* out_tflops) {
   }
   cudaFree(d_out);
   *out_tflops = best;
+  return RTB_OK;
+}
+
+int rtb_last_batch_in_place(rtb_ctx* ctx, int* out_in_place) {
+  if (!ctx || !out_in_place) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_last_batch_in_place: bad argument");
+  *out_in_place = ctx->last_in_place ? 1 : 0;
   return RTB_OK;
 }
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "rtb_upload_scene", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_reduce_metrics_device",
-    "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_measure_fp32_peak",
+    "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
 ]
 
 _lib = None
@@ -59,6 +59,7 @@ def lib():
         L.rtb_get_counters.argtypes = [vp, C.POINTER(abi.Counters)]
         L.rtb_set_option.argtypes = [vp, C.c_int, C.c_int64]
         L.rtb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.rtb_last_batch_in_place.argtypes = [vp, C.POINTER(C.c_int)]
         L.rtb_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
         for name in EXPORTS:
             if name != "rtb_last_error":
@@ -245,6 +246,12 @@ class Context:
         tf = C.c_double(0)
         self._check(self._L.rtb_measure_fp32_peak(self._h, repeats, C.byref(tf)))
         return tf.value
+
+    def last_batch_in_place(self):
+        """True when the last sample_batch ran on the (pinned) host arrays in place."""
+        v = C.c_int(0)
+        self._check(self._L.rtb_last_batch_in_place(self._h, C.byref(v)))
+        return bool(v.value)
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

@@ -152,6 +152,44 @@ def test_stress_scene_walks_the_world_in_hbm(rtb, oracle, ctx, kernel):
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
+def test_pinned_host_arrays_are_used_in_place(rtb, ctx):
+    """rtb_sample_batch on registered (pinned) host arrays runs the kernel on them in place; pageable arrays are
+    staged through device copies.  Same bytes either way, also with interlaced rows and a previous accumulation."""
+    W, H, spp = 160, 90, 8
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    ctx.upload(scene)
+    ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_MEGA)
+    rng = np.random.default_rng(5)
+    for divider, offset in ((1, 0), (3, 1)):
+        p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1, slice_offset=offset, slice_divider=divider)
+        staged, pinned = rtb.plugin.HostBuffers(W, H), rtb.plugin.HostBuffers(W, H)
+        prev = rng.random((W * H, 4)).astype(np.float32)
+        prev[:, 3] = 3
+        for b in (staged, pinned):
+            b.in_color[:] = prev
+            b.in_weight[:] = 1.5
+            b.out_color[:] = -7.0              # rows the batch skips must keep this
+        ctx.sample_batch(p, staged)
+        assert not ctx.last_batch_in_place()
+        ctx.register_host_buffers(pinned)
+        try:
+            ctx.sample_batch(p, pinned)
+            assert ctx.last_batch_in_place()
+            ctx.set_option(rtb.abi.OPT_HOST_ACCESS, 0)
+            again = rtb.plugin.HostBuffers(W, H)
+            again.in_color[:] = prev
+            again.in_weight[:] = 1.5
+            again.out_color[:] = -7.0
+            ctx.sample_batch(p, again)
+            assert not ctx.last_batch_in_place()
+        finally:
+            ctx.set_option(rtb.abi.OPT_HOST_ACCESS, 1)
+            ctx.unregister_host_buffers(pinned)
+        for x, y in zip(staged.arrays()[4:], pinned.arrays()[4:]):
+            assert x.tobytes() == y.tobytes()
+        assert staged.out_color.tobytes() == again.out_color.tobytes()
+
+
 def test_interlaced_rows_and_carry_over(rtb, oracle, ctx):
     """SliceOffset/SliceDivider (SampleBatchJob.cs:69): skipped rows keep whatever the host put in out_*."""
     W, H, spp = 48, 30, 4
