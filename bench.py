@@ -9,7 +9,7 @@ defocus, 1920x1080, 256 spp, depth 50), one process per GPU.
 
 A "step" is one full sample batch of the frame (W*H*spp camera paths).  N > 1: the frame is
 sharded by row tiles (total work fixed -> "strong" scaling) and each step ends with the NCCL
-gather of the tiles; time = max over ranks, CUDA events on the launching stream.
+gather of the tiles to rank 0; time = max over ranks, CUDA events on the launching stream.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -199,7 +199,7 @@ def run_ours(args):
     if world > 1 and not args.equal_tiles:
         probe = rtb.host.make_params(scene, W, H, max(1, min(8, spp)), td, aperture=ap, seed=12345)
         fr.ctx.set_option(abi.OPT_COUNTERS, 1)
-        fr.render_device(probe)
+        fr.render_device(probe, all_ranks=True)          # every rank derives the same tiles from the same diagnostics
         fr.ctx.set_option(abi.OPT_COUNTERS, 0)
         torch.cuda.synchronize()
         d = fr.diag.view(H, W, 4).double()
@@ -265,6 +265,11 @@ def run_ours(args):
     total_ms = sharding.max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     kernel_ms_max = sharding.max_over_ranks(kernel_ms, dev)
+    per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+    per_rank[rank] = kernel_ms
+    if world > 1:
+        dist.all_reduce(per_rank)
+    kernel_ms_per_rank = [round(float(x), 3) for x in per_rank.cpu()]
     clocks = sampler.stop(t0, t1) if sampler else None
     value = samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
 
@@ -329,7 +334,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": WORKLOADS[args.config], "seed": 1, "rng": "Philox4x32-10 keyed (pixel, sample, bounce)",
-                "parallelism": f"row tiles x{world} ({tiles_kind}) + NCCL all-gather per frame" if world > 1 else "single GPU",
+                "parallelism": f"row tiles x{world} ({tiles_kind}) + one batched NCCL gather of all tile buffers to rank 0 per frame" if world > 1 else "single GPU",
                 "l2": "256 MB buffer written between timed iterations (inside the bracket, ~0.05 ms) and 191 MB of accumulators per step > 126 MB L2",
                 "outputs": "color + normal + albedo + sampleCountWeight + diagnostics (full job contract)",
             },
@@ -337,7 +342,8 @@ def run_ours(args):
                     "api": ("rtb_sample_batch (C ABI, pinned host buffers" + (", read and written in place by the kernel over PCIe)" if in_place else ", staged H2D/D2H copies)")) if world == 1 else "FrameRenderer.render_host (H2D own rows, rtb_sample_batch_device, NCCL gather, D2H on rank 0)",
                     "out_color_checksum": checksum},
             "gpu_launches": args.steps * world,
-            "kernel_ms_rank0": kernel_ms, "kernel_ms_max_rank": kernel_ms_max,
+            "kernel_ms_rank0": kernel_ms, "kernel_ms_max_rank": kernel_ms_max, "kernel_ms_per_rank": kernel_ms_per_rank,
+            "row_tiles": [list(map(int, t)) for t in fr.tiles],
             "mrays_per_s": cnt["rays"] * (world if world > 1 else 1) / (kernel_ms_max * 1e-3) / 1e6 if world == 1 else None,
             "failed_sample_fraction": cnt["failed_samples"] / max(cnt["samples"], 1),
             "roofline": {

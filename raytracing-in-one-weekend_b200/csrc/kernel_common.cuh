@@ -92,11 +92,24 @@ struct BatchArgs {
   int width, height;
   int first_row, row_step, n_rows;   // active rows: first_row + j * row_step, j < n_rows
   uint32_t n_active_pixels;          // n_rows * width
-  int tile_pixels;                   // pixels per warp tile (<= kTilePixelsMax)
+  // Work tiles, claimed in order from tile_counter.  Three phases of shrinking tile size (guided
+  // self-scheduling): phase k covers active pixels [phase_pixel[k], phase_pixel[k+1]) in tiles of
+  // phase_size[k] pixels (<= kTilePixelsMax), starting at tile id phase_tile[k].  Big tiles amortise the
+  // per-tile drain; the small ones at the end keep the kernel's tail (warps finishing their last tile
+  // at different times) short.
+  uint32_t phase_tile[4], phase_pixel[4];
+  int phase_size[3];
   uint32_t n_tiles;
   uint32_t* tile_counter;            // global work counter (zeroed before launch)
   unsigned long long* counters;      // rtb_counters as 8 x u64, or nullptr
 };
+
+__device__ __forceinline__ void tile_range(const BatchArgs& a, uint32_t t, uint32_t* base, int* n) {
+  const int k = t >= a.phase_tile[2] ? 2 : (t >= a.phase_tile[1] ? 1 : 0);
+  const uint32_t b = a.phase_pixel[k] + (t - a.phase_tile[k]) * (uint32_t)a.phase_size[k];
+  *base = b;
+  *n = (int)min((uint32_t)a.phase_size[k], a.phase_pixel[k + 1] - b);
+}
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter = (pixel, sample, bounce, block),

@@ -421,8 +421,32 @@ int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_
 void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
   int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (4096 + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
   while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
-  a.tile_pixels = tp;
-  a.n_tiles = (a.n_active_pixels + (uint32_t)tp - 1) / (uint32_t)tp;
+  // guided self-scheduling: the last ~8 tiles per resident warp are a quarter of the size, the last ~8 after
+  // those a sixteenth (never fewer than ~256 samples per tile: below that the per-tile drain costs more than the tail)
+  auto shrink = [&](int t, int by) {
+    int r = std::max(1, t / by);
+    while (r < t && (uint64_t)r * max_spp < 256) r *= 2;
+    return std::min(r, t);
+  };
+  const int size[3] = {tp, shrink(tp, 4), shrink(tp, 16)};
+  const uint32_t P = a.n_active_pixels;
+  static const int per_warp = [] { const char* e = getenv("RTB_TAIL_TILES"); return e ? std::max(0, atoi(e)) : 8; }();
+  uint32_t tail2 = std::min<uint64_t>(P, (uint64_t)per_warp * n_warps_full * size[2]);
+  uint32_t tail1 = std::min<uint64_t>(P - tail2, (uint64_t)per_warp * n_warps_full * size[1]);
+  if (size[2] == size[1]) { tail1 += tail2; tail2 = 0; }
+  if (size[1] == size[0]) { tail1 = 0; if (size[2] == size[0]) tail2 = 0; }
+  uint32_t begin[4] = {0, P - tail1 - tail2, P - tail2, P};
+  // phase boundaries on multiples of the phase's tile size so only the last tile of a phase is ragged
+  uint32_t tile = 0;
+  for (int k = 0; k < 3; k++) {
+    a.phase_size[k] = size[k];
+    a.phase_pixel[k] = begin[k];
+    a.phase_tile[k] = tile;
+    tile += (begin[k + 1] - begin[k] + (uint32_t)size[k] - 1) / (uint32_t)size[k];
+  }
+  a.phase_pixel[3] = P;
+  a.phase_tile[3] = tile;
+  a.n_tiles = tile;
 }
 
 template <bool SMEM, bool COUNTERS>

@@ -183,8 +183,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
       if (lane == 0) tnext = atomicAdd(a.tile_counter, 1u);
       tnext = __shfl_sync(FULL, tnext, 0);
       if (tnext >= a.n_tiles) break;
-      tile_base = tnext * (uint32_t)a.tile_pixels;
-      tile_n = (int)min((uint32_t)a.tile_pixels, a.n_active_pixels - tile_base);
+      tile_range(a, tnext, &tile_base, &tile_n);
       uint32_t n_samples = 0;
       if (lane < tile_n) {
         int cx, cy;

@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megake
       if (lane == 0) t = atomicAdd(a.tile_counter, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= a.n_tiles) break;
-      tile_base = t * (uint32_t)a.tile_pixels;
-      tile_n = (int)min((uint32_t)a.tile_pixels, a.n_active_pixels - tile_base);
+      tile_range(a, t, &tile_base, &tile_n);
       uint32_t n_samples = 0;
       if (lane < tile_n) {
         int cx, cy;

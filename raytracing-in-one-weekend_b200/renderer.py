@@ -64,23 +64,29 @@ class FrameRenderer:
         p.row_begin, p.row_end = self.my_rows
         return p
 
-    def render_device(self, params, gather=True, gather_aovs=True):
+    def render_device(self, params, gather=True, gather_aovs=True, all_ranks=False):
         """Enqueue one batch for this rank's row tile on torch's current stream, then the frame gather."""
         b, e = self.my_rows
         if e > b:
             self.ctx.sample_batch_device(self._tile_params(params), self.buffers, torch.cuda.current_stream().cuda_stream)
         if gather:
-            self.gather(gather_aovs)
+            self.gather(gather_aovs, all_ranks)
 
-    def gather(self, aovs=True):
-        """The one exchange per frame: in-place all-gather of the row tiles of the output buffers."""
+    def gather(self, aovs=True, all_ranks=False):
+        """The one exchange per frame.  Default: every buffer's row tiles to rank 0 in ONE batched NCCL
+        send/recv group (the host reads the frame on one rank).  all_ranks=True: in-place all-gather
+        of each buffer instead, for consumers that need the frame everywhere."""
         if self.world == 1:
             return
         keys = ("color", "weight", "normal", "albedo") if aovs else ("color",)
-        for k in keys:
-            _sharding.gather_frame(self.out[k], self.tiles, self.group)
+        frames = [self.out[k] for k in keys]
         if self.diag is not None and aovs:
-            _sharding.gather_frame(self.diag, self.tiles, self.group)
+            frames.append(self.diag)
+        if all_ranks:
+            for f in frames:
+                _sharding.gather_frame(f, self.tiles, self.group)
+        else:
+            _sharding.gather_frames_to_root(frames, self.tiles, 0, self.group)
 
     def render_host(self, params, host, fetch_all_ranks=False):
         """End-to-end batch with (pinned) HOST accumulators `host` (dict of torch CPU tensors with the
@@ -93,7 +99,7 @@ class FrameRenderer:
             src = host["in_" + k].view(self.height * w, -1)[b * w:e * w]
             self.inp[k][b * w:e * w].copy_(src, non_blocking=True)
             h2d += src.numel() * 4
-        self.render_device(params)
+        self.render_device(params, all_ranks=fetch_all_ranks)
         if self.rank == 0 or fetch_all_ranks:
             for k in ("color", "weight", "normal", "albedo"):
                 host["out_" + k].view(self.height * w, -1).copy_(self.out[k], non_blocking=True)

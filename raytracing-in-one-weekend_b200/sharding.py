@@ -5,7 +5,9 @@ element `index`) and the Philox stream is keyed by the GLOBAL pixel index, so an
 the rows renders the same image bit for bit.  Rank g renders rows [begin_g, end_g) straight
 into its slice of a full-frame device buffer (rtb_batch_params.row_begin/row_end), and ONE
 collective per frame — an in-place all-gather of the row tiles over NCCL/NVLink — assembles
-the frame on every rank.  No other data-path communication exists.
+the frame on every rank (`gather_frame`), or — what a host that reads the frame on one rank needs,
+and what `bench.py` times — one batched gather of every buffer's tiles to rank 0
+(`gather_frames_to_root`).  No other data-path communication exists.
 
 The reference's own row mechanism (SliceOffset/SliceDivider, SampleBatchJob.cs:69) shards rows
 in time; `interlaced_rows` exposes the same rule for callers that prefer row % N == g.
@@ -69,6 +71,37 @@ def gather_frame(frame, tiles, group=None):
     for w in works:
         w.wait()
     return frame
+
+
+def gather_frames_to_root(frames, tiles, root=0, group=None):
+    """THE frame-end exchange: rank g sends its row tile of every buffer in `frames` (a list of
+    [H*W, C] / [H, W, C] tensors) to `root`, as ONE batched group of point-to-point operations
+    (a single ncclGroup: one launch whatever the number of buffers and ranks, equal tiles or not).
+    On return `root` holds the whole frame in every buffer; other ranks are unchanged."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return frames
+    height = tiles[-1][1]
+
+    def glob(r):
+        return dist.get_global_rank(group, r) if group is not None else r
+
+    ops = []
+    for f in frames:
+        rows = f.reshape(height, -1)
+        if rank == root:
+            for g, (b, e) in enumerate(tiles):
+                if g != root and e > b:
+                    ops.append(dist.P2POp(dist.irecv, rows[b:e], glob(g), group))
+        else:
+            b, e = tiles[rank]
+            if e > b:
+                ops.append(dist.P2POp(dist.isend, rows[b:e], glob(root), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return frames
 
 
 def max_over_ranks(value, device, group=None):

@@ -46,6 +46,15 @@ def _worker(rank, world, port, mode, out_dir):
         frame = torch.from_numpy(buf.out_color).reshape(H, W, 4)
         inside = frame[b:e].clone()
         assert float(frame[:b].abs().sum()) == 0.0 and float(frame[e:].abs().sum()) == 0.0   # only own rows written
+        # the batched gather to rank 0 of several buffers at once (what bench.py times) ...
+        extra = torch.from_numpy(buf.out_normal).reshape(H, W, 3).clone()
+        to_root = [frame.clone(), extra]
+        sh.gather_frames_to_root(to_root, tiles, root=0)
+        if rank != 0:
+            assert float(to_root[0][:b].abs().sum()) == 0.0 and float(to_root[0][e:].abs().sum()) == 0.0   # untouched off-root
+        np.save(os.path.join(out_dir, f"root_{mode}_{rank}.npy"), to_root[0].numpy())
+        np.save(os.path.join(out_dir, f"rootn_{mode}_{rank}.npy"), to_root[1].numpy())
+        # ... and the all-gather form
         sh.gather_frame(frame, tiles)
         assert torch.equal(frame[b:e], inside)
         t = sh.max_over_ranks(float(rank + 1), "cpu")
@@ -68,3 +77,5 @@ def test_row_tile_shard_and_gather_world2(tmp_path, oracle, rtb, mode):
     for r in range(world):
         got = np.load(tmp_path / f"frame_{mode}_{r}.npy")
         assert np.array_equal(got, want)
+    assert np.array_equal(np.load(tmp_path / f"root_{mode}_0.npy"), want)
+    assert np.array_equal(np.load(tmp_path / f"rootn_{mode}_0.npy"), full.out_normal.reshape(H, W, 3))
