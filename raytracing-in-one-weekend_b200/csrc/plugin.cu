@@ -416,10 +416,11 @@ int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_
   return RTB_OK;
 }
 
-// Tile size shared by the two persistent kernels: ~4096 samples per warp tile, at least ~6 tiles per
+// Tile size shared by the two persistent kernels: ~2048 samples per warp tile (measured best on B200, profiles/README.md), at least ~6 tiles per
 // resident warp when the image is small, never fewer than 1024 samples per tile unless the pixel count forces it.
 void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
-  int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (4096 + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
+  static const uint32_t target = [] { const char* e = getenv("RTB_TILE_SAMPLES"); return e ? (uint32_t)std::max(32, atoi(e)) : 2048u; }();
+  int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (target + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
   while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
   // guided self-scheduling: the last ~8 tiles per resident warp are a quarter of the size, the last ~8 after
   // those a sixteenth (never fewer than ~256 samples per tile: below that the per-tile drain costs more than the tail)
