@@ -134,6 +134,12 @@ def cpu_reference(cfg, threads, target_seconds=12.0, steps=1, warmup=0):
             vals.append(W * rows * spp / dt / 1e6)
     desc = (f"rows r % {divider} == {offset} of the {W}x{H} frame ({rows} rows = {W * rows * spp / 1e6:.1f} Msamples at {spp} spp), "
             f"{threads} threads, 1 pixel per work item")
+    # what the reference's collect-all traversal executes per ray on this sample (its FULL_DIAGNOSTICS counters,
+    # Raytracer.cs:56-60; SampleBatchJob.cs:203,428,439), to set beside the pruned walk's executed counts
+    d = buf.diagnostics
+    rays = float(d["ray_count"].astype("float64").sum())
+    cpu_reference.work = {"rays": rays, "box_tests_per_ray": float(d["bounds_hit_count"].astype("float64").sum()) / max(rays, 1.0),
+                          "sphere_tests_per_ray": float(d["candidate_count"].astype("float64").sum()) / max(rays, 1.0)}
     return vals, desc
 
 
@@ -152,7 +158,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * (W * H * spp / 1e6) / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config], "note": "ms_per_step extrapolated from the sample to the full frame"},
-        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": desc,
+                         "reference_traversal_per_ray": getattr(cpu_reference, "work", None)},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -317,7 +324,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         vals, desc = cpu_reference(args.config, threads, target_seconds=12.0)
-        cpu = {"value": vals[0], "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": desc}
+        cpu = {"value": vals[0], "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": desc,
+               "reference_traversal_per_ray": getattr(cpu_reference, "work", None)}
 
     if rank == 0:
         traffic = None
@@ -351,6 +359,7 @@ def run_ours(args):
                 "traffic": traffic,
                 "note": "path is FP32-ALU/latency bound (SURVEY §8d): executed algorithmic flops of rank 0's tile (kernel counters x per-unit constants) / rank 0 kernel time; peak = FP32 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32-pipe figure)",
                 "counters_rank0": cnt,
+                "executed_per_ray": {"box_tests": cnt["node_tests"] / max(cnt["rays"], 1), "sphere_tests": cnt["sphere_tests"] / max(cnt["rays"], 1)},
             },
             "roofline_hbm": {
                 "bound": "hbm", "achieved": BYTES_PER_PIXEL * n / world / (kernel_ms * 1e-3) / 1e9, "peak": _hbm_peak(), "unit": "GB/s",

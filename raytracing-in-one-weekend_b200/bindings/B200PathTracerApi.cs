@@ -54,6 +54,10 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern RtbStatus rtb_sample_batch(IntPtr ctx, RtbBatchParams* p, RtbBatchBuffers* hostBuffers, bool* cancel);
 		[DllImport(Lib)] public static extern RtbStatus rtb_register_host_buffer(IntPtr ctx, void* ptr, UIntPtr bytes);
 		[DllImport(Lib)] public static extern RtbStatus rtb_unregister_host_buffer(IntPtr ctx, void* ptr);
+		// rtb_option (include/rtb.h): Counters = 1, Kernel = 2, CancelChunkRows = 3, LeafSpheres = 4, AlwaysWalkChains = 5, HostAccess = 6
+		[DllImport(Lib)] public static extern RtbStatus rtb_set_option(IntPtr ctx, int option, long value);
+		[DllImport(Lib)] public static extern RtbStatus rtb_last_kernel_ms(IntPtr ctx, out float ms);
+		[DllImport(Lib)] public static extern RtbStatus rtb_last_batch_in_place(IntPtr ctx, out int inPlace);
 		public static string LastError(IntPtr ctx) => Marshal.PtrToStringAnsi(rtb_last_error(ctx));
 	}
 
