@@ -64,6 +64,33 @@ typedef struct rtb_sphere {
   uint32_t reserved[3];
 } rtb_sphere;                   /* 32 bytes */
 
+/* Entity of EntityType.Triangle (Entity.cs:13-20, EntityTypes/Triangle.cs:8-29): what the host's mesh
+ * ingestion produces (AddMeshRuntimeEntitiesJob.cs; Raytracer.cs:1185-1304).  Triangles are always in
+ * world space (Entity.cs:92-93), so there is no transform.  Fields are the reference's: Data columns
+ * (v2 - v0, v1 - v0, v0) and the three (already normalised) vertex normals. */
+typedef struct rtb_triangle {
+  float edge2[3];               /* Triangle.Data[0] = v2 - v0 */
+  float edge1[3];               /* Triangle.Data[1] = v1 - v0 */
+  float v0[3];                  /* Triangle.Data[2] */
+  float normals[3][3];          /* Triangle.Normals columns: n0, n1, n2 */
+  uint32_t material;
+  uint32_t reserved;
+} rtb_triangle;                 /* 80 bytes */
+
+typedef enum rtb_entity_type {  /* Entity.cs:13-20 */
+  RTB_ENTITY_SPHERE = 1,
+  RTB_ENTITY_RECT = 2,          /* not on the hot path: RTB_ERR_UNSUPPORTED */
+  RTB_ENTITY_BOX = 3,           /* not on the hot path: RTB_ERR_UNSUPPORTED */
+  RTB_ENTITY_TRIANGLE = 4
+} rtb_entity_type;
+
+/* One element of the BVH-ordered entity list the leaves point into (bvhEntities, BvhNodeData.cs:157-160):
+ * the entity's type and its index in the sphere / triangle array (Entity.Content). */
+typedef struct rtb_entity {
+  uint32_t type;                /* rtb_entity_type */
+  uint32_t index;
+} rtb_entity;
+
 typedef enum rtb_material_type {     /* Material.cs:9-14 */
   RTB_MATERIAL_STANDARD = 0,
   RTB_MATERIAL_DIELECTRIC = 1,
@@ -183,6 +210,15 @@ RTB_API int rtb_set_log_callback(rtb_ctx* ctx, rtb_log_fn fn, void* user);
  * SampleBatchJob.cs:34).  The host may free its arrays on return. */
 RTB_API int rtb_upload_scene(rtb_ctx* ctx,
                              const rtb_sphere* spheres, size_t sphere_count,
+                             const rtb_material* materials, size_t material_count,
+                             const rtb_bvh_node* nodes, size_t node_count);
+
+/* The general form: leaves of `nodes` index into `entities`, each of which names a sphere or a triangle.
+ * rtb_upload_scene(spheres, ...) is the same call with entities[i] = {SPHERE, i}. */
+RTB_API int rtb_upload_world(rtb_ctx* ctx,
+                             const rtb_entity* entities, size_t entity_count,
+                             const rtb_sphere* spheres, size_t sphere_count,
+                             const rtb_triangle* triangles, size_t triangle_count,
                              const rtb_material* materials, size_t material_count,
                              const rtb_bvh_node* nodes, size_t node_count);
 

@@ -70,6 +70,21 @@ RTB_API int rtbh_build_bvh(const rtb_sphere* spheres, size_t sphere_count, int m
                            rtb_sphere* out_spheres, size_t out_sphere_capacity,
                            rtb_bvh_node* out_nodes, size_t node_capacity, size_t* out_node_count);
 
+/* The same builder over precomputed world bounds (6 floats per entity: min.xyz, max.xyz), for worlds
+ * that mix entity types (CreateBvhBuildingEntitiesJob computes exactly these, BvhNodeData.cs:94-107).
+ * out_order[i] = input index of the i-th entity of the BVH-ordered list (bvhEntities). */
+RTB_API int rtbh_build_bvh_from_bounds(const float* bounds, size_t entity_count, int max_depth,
+                                       uint32_t* out_order, size_t order_capacity,
+                                       rtb_bvh_node* out_nodes, size_t node_capacity, size_t* out_node_count);
+/* Entity bounds as the reference computes them: Sphere.Bounds through the (identity-rotation) rigid
+ * transform (Sphere.cs:16-23, BvhNodeData.cs:41-78); Triangle.Bounds (Triangle.cs:38-49). */
+RTB_API void rtbh_sphere_bounds(const rtb_sphere* sphere, float out_bounds[6]);
+RTB_API void rtbh_triangle_bounds(const rtb_triangle* triangle, float out_bounds[6]);
+/* Triangle constructors (Triangle.cs:14-29): n1..n3 NULL = the face-normal form. */
+RTB_API void rtbh_make_triangle(const float v1[3], const float v2[3], const float v3[3],
+                                const float* n1, const float* n2, const float* n3,
+                                uint32_t material, rtb_triangle* out);
+
 /* ---- camera ----------------------------------------------------------------------------- */
 RTB_API void rtbh_make_view(const float origin[3], const float look_at[3], const float up[3],
                             float vertical_fov_degrees, float aspect, float aperture,

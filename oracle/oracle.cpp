@@ -170,6 +170,8 @@ f3 RandomSource::OnCosineWeightedHemisphere(f3 normal, int slot) {
 // Runtime structs
 // ======================================================================================
 
+f3 v3(const float* p) { return um::mk(p[0], p[1], p[2]); }
+
 struct Ray {  // Ray.cs
   f3 Origin, Direction;
   float Time;
@@ -187,7 +189,15 @@ struct Scene {
   const rtb_sphere* spheres; size_t sphere_count;
   const rtb_material* materials; size_t material_count;
   const rtb_bvh_node* nodes; size_t node_count;
-  std::vector<um::rigid> origin_transform, inverse_transform;  // Entity.OriginTransform / InverseTransform
+  std::vector<um::rigid> origin_transform, inverse_transform;  // Entity.OriginTransform / InverseTransform (per sphere)
+  // bvhEntities: what the leaves index (nullptr: entity i is sphere i); Entity.Type / Entity.Content
+  const rtb_entity* entities = nullptr; size_t entity_count = 0;
+  const rtb_triangle* triangles = nullptr; size_t triangle_count = 0;
+  uint32_t material_of(int entity) const {
+    if (!entities) return spheres[entity].material;
+    const rtb_entity& e = entities[entity];
+    return e.type == RTB_ENTITY_TRIANGLE ? triangles[e.index].material : spheres[e.index].material;
+  }
 };
 
 // HitTests.Hit(this AxisAlignedBoundingBox) (HitTests.cs:9-21)
@@ -229,14 +239,54 @@ bool SphereHit(float radius, const Ray& r, float tMin, float tMax, float* distan
   return false;
 }
 
-// Entity.Hit -> HitInternal -> HitContent (Entity.cs:57-122), static sphere entity
+// HitTests.Hit(this Triangle) (HitTests.cs:113-150): Moeller-Trumbore, both faces, vertex normals interpolated
+bool TriangleHit(const rtb_triangle& tri, const Ray& r, float tMin, float tMax, float* distance, f3* normal) {
+  *distance = 0;
+  *normal = um::mk(0.0f);
+  const f3 data0 = v3(tri.edge2), data1 = v3(tri.edge1), data2 = v3(tri.v0);
+  f3 pvec = um::cross(r.Direction, data0);
+  float det = um::dot(data1, pvec);
+  if (det == 0) return false;
+  float invDet = um::div(1.0f, det);
+  f3 tvec = r.Origin - data2;
+  float u = um::dot(tvec, pvec) * invDet;
+  if (u < 0 || u > 1) return false;
+  f3 qvec = um::cross(tvec, data1);
+  float v = um::dot(r.Direction, qvec) * invDet;
+  if (v < 0 || u + v > 1) return false;
+  float d = um::dot(data0, qvec) * invDet;
+  if (d < tMin || d > tMax) return false;
+  *distance = d;
+  f3 barycentricCoords = um::mk(1 - u - v, u, v);
+  *normal = um::mul_cols(v3(tri.normals[0]), v3(tri.normals[1]), v3(tri.normals[2]), barycentricCoords);
+  return true;
+}
+
+// Entity.Hit -> HitInternal -> HitContent (Entity.cs:57-122): static sphere entity, or world-space triangle
 bool EntityHit(const Scene& sc, int entity, const Ray& ray, float tMin, float tMax, HitRecord* rec) {
-  const um::rigid& transformAtTime = sc.origin_transform[entity];
-  const um::rigid& inverseTransform = sc.inverse_transform[entity];
+  int sphere = entity;
+  if (sc.entities) {
+    const rtb_entity& e = sc.entities[entity];
+    if (e.type == RTB_ENTITY_TRIANGLE) {
+      // "Triangles are always world-space" (Entity.cs:92-93); OriginTransform is the identity the mesh job gives
+      // every triangle entity (AddMeshRuntimeEntitiesJob.cs), so rotate(transformAtTime, n) == n
+      float distance;
+      f3 entityLocalNormal;
+      if (!TriangleHit(sc.triangles[e.index], ray, tMin, tMax, &distance, &entityLocalNormal)) return false;
+      rec->Distance = distance;
+      rec->Point = ray.GetPoint(distance);
+      rec->Normal = um::normalize(um::rotate(um::quat_identity(), entityLocalNormal));
+      rec->Entity = entity;
+      return true;
+    }
+    sphere = (int)e.index;
+  }
+  const um::rigid& transformAtTime = sc.origin_transform[sphere];
+  const um::rigid& inverseTransform = sc.inverse_transform[sphere];
   Ray entitySpaceRay{um::transform(inverseTransform, ray.Origin), um::rotate(inverseTransform.rot, ray.Direction), 0};
   float distance;
   f3 entityLocalNormal;
-  if (!SphereHit(sc.spheres[entity].radius, entitySpaceRay, tMin, tMax, &distance, &entityLocalNormal)) return false;
+  if (!SphereHit(sc.spheres[sphere].radius, entitySpaceRay, tMin, tMax, &distance, &entityLocalNormal)) return false;
   rec->Distance = distance;
   rec->Point = ray.GetPoint(distance);
   rec->Normal = um::normalize(um::rotate(transformAtTime.rot, entityLocalNormal));
@@ -365,7 +415,6 @@ void Scatter(const rtb_material& m, const Ray& ray, const HitRecord& rec, Random
 // ======================================================================================
 // View (View.cs:38-48)
 // ======================================================================================
-f3 v3(const float* p) { return um::mk(p[0], p[1], p[2]); }
 
 Ray GetRay(const rtb_view& v, float nx, float ny, RandomSource& rng) {
   float rdx = 0, rdy = 0;
@@ -459,7 +508,7 @@ bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleCo
 
     if (!w.hits.empty()) {
       const HitRecord rec = w.hits[0];
-      const rtb_material& material = sc.materials[sc.spheres[rec.Entity].material];
+      const rtb_material& material = sc.materials[sc.material_of(rec.Entity)];
       f3 albedo;
       Ray scatteredRay;
       Scatter(material, ray, rec, rng, &albedo, &scatteredRay);
@@ -589,17 +638,46 @@ extern "C" {
 // Runs one SampleBatchJob over pixel indices [index_begin, index_end) (0,0 = all) with
 // `threads` worker threads pulling one pixel at a time (== Schedule(W*H, 1, ...),
 // Raytracer.cs:730).  noise: 0 = the reference's xorshift32 white noise, 1 = Philox slots.
+ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
+                                         const rtb_entity* entities, size_t entity_count,
+                                         const rtb_sphere* spheres, size_t sphere_count,
+                                         const rtb_triangle* triangles, size_t triangle_count,
+                                         const rtb_material* materials, size_t material_count,
+                                         const rtb_bvh_node* nodes, size_t node_count,
+                                         const rtb_batch_buffers* buffers, int noise, int threads,
+                                         int64_t index_begin, int64_t index_end);
+
 ORACLE_API int oracle_sample_batch(const rtb_batch_params* params,
                                    const rtb_sphere* spheres, size_t sphere_count,
                                    const rtb_material* materials, size_t material_count,
                                    const rtb_bvh_node* nodes, size_t node_count,
                                    const rtb_batch_buffers* buffers, int noise, int threads,
                                    int64_t index_begin, int64_t index_end) {
+  return oracle_sample_batch_world(params, nullptr, 0, spheres, sphere_count, nullptr, 0, materials, material_count, nodes,
+                                   node_count, buffers, noise, threads, index_begin, index_end);
+}
+
+ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
+                                         const rtb_entity* entities, size_t entity_count,
+                                         const rtb_sphere* spheres, size_t sphere_count,
+                                         const rtb_triangle* triangles, size_t triangle_count,
+                                         const rtb_material* materials, size_t material_count,
+                                         const rtb_bvh_node* nodes, size_t node_count,
+                                         const rtb_batch_buffers* buffers, int noise, int threads,
+                                         int64_t index_begin, int64_t index_end) {
   if (!params || !buffers || params->slice_divider < 1 || params->trace_depth < 0) return RTB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < entity_count; i++) {
+    if (entities[i].type != RTB_ENTITY_SPHERE && entities[i].type != RTB_ENTITY_TRIANGLE) return RTB_ERR_UNSUPPORTED;
+    if (entities[i].index >= (entities[i].type == RTB_ENTITY_SPHERE ? sphere_count : triangle_count)) return RTB_ERR_INVALID_ARGUMENT;
+  }
   for (size_t i = 0; i < material_count; i++)
     if (materials[i].type > RTB_MATERIAL_DIELECTRIC) return RTB_ERR_UNSUPPORTED;
   if (params->environment.sky_type == RTB_SKY_CUBEMAP) return RTB_ERR_UNSUPPORTED;
   Scene sc{spheres, sphere_count, materials, material_count, nodes, node_count, {}, {}};
+  sc.entities = entity_count ? entities : nullptr;
+  sc.entity_count = entity_count;
+  sc.triangles = triangles;
+  sc.triangle_count = triangle_count;
   sc.origin_transform.resize(sphere_count);
   sc.inverse_transform.resize(sphere_count);
   for (size_t i = 0; i < sphere_count; i++) {
@@ -648,6 +726,19 @@ ORACLE_API int oracle_sphere_hit(const float center[3], float radius, const floa
   um::rigid t{um::quat_identity(), v3(center)};
   sc.origin_transform.push_back(t);
   sc.inverse_transform.push_back(um::inverse(t));
+  HitRecord rec;
+  Ray ray{v3(origin), v3(dir), 0};
+  if (!EntityHit(sc, 0, ray, 0, um::INF, &rec)) return 0;
+  *distance = rec.Distance;
+  point[0] = rec.Point.x; point[1] = rec.Point.y; point[2] = rec.Point.z;
+  normal[0] = rec.Normal.x; normal[1] = rec.Normal.y; normal[2] = rec.Normal.z;
+  return 1;
+}
+ORACLE_API int oracle_triangle_hit(const rtb_triangle* tri, const float origin[3], const float dir[3], float* distance,
+                                   float point[3], float normal[3]) {
+  rtb_entity e{RTB_ENTITY_TRIANGLE, 0};
+  Scene sc{nullptr, 0, nullptr, 0, nullptr, 0, {}, {}};
+  sc.entities = &e; sc.entity_count = 1; sc.triangles = tri; sc.triangle_count = 1;
   HitRecord rec;
   Ray ray{v3(origin), v3(dir), 0};
   if (!EntityHit(sc, 0, ray, 0, um::INF, &rec)) return 0;

@@ -38,7 +38,15 @@ DIAGNOSTICS_DTYPE = np.dtype(
     [("ray_count", "<f4"), ("bounds_hit_count", "<f4"), ("candidate_count", "<f4"), ("sample_count_weight", "<f4")]
 )  # rtb_diagnostics, 16 B
 
+TRIANGLE_DTYPE = np.dtype(
+    [("edge2", "<f4", 3), ("edge1", "<f4", 3), ("v0", "<f4", 3), ("normals", "<f4", (3, 3)), ("material", "<u4"), ("reserved", "<u4")],
+    align=False,
+)  # rtb_triangle, 80 B
+ENTITY_DTYPE = np.dtype([("type", "<u4"), ("index", "<u4")])  # rtb_entity, 8 B
+ENTITY_SPHERE, ENTITY_RECT, ENTITY_BOX, ENTITY_TRIANGLE = 1, 2, 3, 4
+
 assert SPHERE_DTYPE.itemsize == 32 and MATERIAL_DTYPE.itemsize == 48 and BVH_NODE_DTYPE.itemsize == 40
+assert TRIANGLE_DTYPE.itemsize == 80 and ENTITY_DTYPE.itemsize == 8
 
 MATERIAL_STANDARD, MATERIAL_DIELECTRIC, MATERIAL_PROBABILISTIC_VOLUME = 0, 1, 2
 SKY_NONE, SKY_GRADIENT, SKY_CUBEMAP = 0, 1, 2
@@ -163,6 +171,8 @@ STRUCT_SIZES = {  # name in the headers -> python mirror; checked against sizeof
     "rtb_sphere": SPHERE_DTYPE.itemsize,
     "rtb_material": MATERIAL_DTYPE.itemsize,
     "rtb_bvh_node": BVH_NODE_DTYPE.itemsize,
+    "rtb_triangle": TRIANGLE_DTYPE.itemsize,
+    "rtb_entity": ENTITY_DTYPE.itemsize,
     "rtb_diagnostics": DIAGNOSTICS_DTYPE.itemsize,
     "rtb_view": C.sizeof(View),
     "rtb_environment": C.sizeof(Environment),

@@ -437,6 +437,72 @@ int rtbh_build_bvh(const rtb_sphere* spheres, size_t sphere_count, int max_depth
   return RTB_OK;
 }
 
+int rtbh_build_bvh_from_bounds(const float* bounds, size_t entity_count, int max_depth, uint32_t* out_order,
+                               size_t order_capacity, rtb_bvh_node* out_nodes, size_t node_capacity, size_t* out_node_count) {
+  if ((!bounds && entity_count) || !out_nodes || !out_node_count || max_depth < 0) return RTB_ERR_INVALID_ARGUMENT;
+  if (order_capacity < entity_count || (entity_count && !out_order)) return RTB_ERR_INVALID_ARGUMENT;
+  std::vector<BuildEntity> ents(entity_count);
+  for (size_t i = 0; i < entity_count; i++) {
+    const float* b = bounds + 6 * i;
+    ents[i] = BuildEntity{(uint32_t)i, Aabb{um::mk(b[0], b[1], b[2]), um::mk(b[3], b[4], b[5])}};
+  }
+  Builder b;
+  b.spheres = nullptr;
+  b.max_depth = max_depth;
+  b.nodes.reserve(entity_count * 2 + 1);
+  b.nodes.emplace_back();
+  b.build(0, ents.data(), (int)entity_count, 0, -1);
+  if (node_capacity < b.nodes.size()) return RTB_ERR_INVALID_ARGUMENT;
+  b.next_index = (int)b.nodes.size() - 1;
+  b.flatten(0, out_nodes);
+  for (size_t i = 0; i < b.bvh_entities.size(); i++) out_order[i] = b.bvh_entities[i];
+  *out_node_count = b.nodes.size();
+  return RTB_OK;
+}
+
+void rtbh_sphere_bounds(const rtb_sphere* sphere, float out_bounds[6]) {
+  const Aabb a = sphere_world_bounds(*sphere);
+  out_bounds[0] = a.mn.x; out_bounds[1] = a.mn.y; out_bounds[2] = a.mn.z;
+  out_bounds[3] = a.mx.x; out_bounds[4] = a.mx.y; out_bounds[5] = a.mx.z;
+}
+
+void rtbh_triangle_bounds(const rtb_triangle* t, float out_bounds[6]) {
+  // Triangle.Bounds (Triangle.cs:38-49): vertices -/+ |vertex normal| * 0.001, min / max over the three
+  const f3 d0 = um::mk(t->edge2[0], t->edge2[1], t->edge2[2]), d1 = um::mk(t->edge1[0], t->edge1[1], t->edge1[2]);
+  const f3 d2 = um::mk(t->v0[0], t->v0[1], t->v0[2]);
+  const f3 vertices[3] = {d2, d1 + d2, d0 + d2};
+  f3 mn = um::mk(0.0f), mx = um::mk(0.0f);
+  for (int i = 0; i < 3; i++) {
+    const f3 n = um::mk(std::fabs(t->normals[i][0]), std::fabs(t->normals[i][1]), std::fabs(t->normals[i][2]));
+    const f3 neg = vertices[i] - n * 0.001f, pos = vertices[i] + n * 0.001f;
+    mn = i == 0 ? neg : um::min(mn, neg);
+    mx = i == 0 ? pos : um::max(mx, pos);
+  }
+  out_bounds[0] = mn.x; out_bounds[1] = mn.y; out_bounds[2] = mn.z;
+  out_bounds[3] = mx.x; out_bounds[4] = mx.y; out_bounds[5] = mx.z;
+}
+
+void rtbh_make_triangle(const float v1[3], const float v2[3], const float v3[3], const float* n1, const float* n2,
+                        const float* n3, uint32_t material, rtb_triangle* out) {
+  // Data = float3x3(v3 - v1, v2 - v1, v1) (Triangle.cs:16,25)
+  const f3 a = um::mk(v1[0], v1[1], v1[2]), b = um::mk(v2[0], v2[1], v2[2]), c = um::mk(v3[0], v3[1], v3[2]);
+  const f3 d0 = c - a, d1 = b - a;
+  f3 n[3];
+  if (n1 && n2 && n3) {
+    n[0] = um::normalize(um::mk(n1[0], n1[1], n1[2]));
+    n[1] = um::normalize(um::mk(n2[0], n2[1], n2[2]));
+    n[2] = um::normalize(um::mk(n3[0], n3[1], n3[2]));
+  } else {
+    n[0] = n[1] = n[2] = um::normalize(um::cross(d1, d0));   // faceNormal = normalize(cross(Data[1], Data[0]))
+  }
+  *out = rtb_triangle{};
+  out->edge2[0] = d0.x; out->edge2[1] = d0.y; out->edge2[2] = d0.z;
+  out->edge1[0] = d1.x; out->edge1[1] = d1.y; out->edge1[2] = d1.z;
+  out->v0[0] = a.x; out->v0[1] = a.y; out->v0[2] = a.z;
+  for (int i = 0; i < 3; i++) { out->normals[i][0] = n[i].x; out->normals[i][1] = n[i].y; out->normals[i][2] = n[i].z; }
+  out->material = material;
+}
+
 void rtbh_make_view(const float origin[3], const float look_at[3], const float up_in[3],
                     float vertical_fov_degrees, float aspect, float aperture,
                     float focus_distance, rtb_view* out) {

@@ -37,6 +37,10 @@ using um::f3;
 //   spheres      : n_spheres * 16 B  float4 (center.xyz, radius), depth-first leaf order
 //   leaf_count   : n_spheres * 4 B   sphere count of the leaf that STARTS at this sphere
 //   mat_index    : n_spheres * 4 B   material index of the sphere
+//   triangles    : n_triangles * 80 B  5 x float4 per EntityType.Triangle entity (world space):
+//                    T0 = (Data[0].xyz, Data[1].x)  T1 = (Data[1].yz, Data[2].xy)  T2 = (Data[2].z, n0.xyz)
+//                    T3 = (n1.xyz, n2.x)            T4 = (n2.yz, -, -)          (Triangle.cs:10-11)
+//                  a triangle entity's slot in `spheres` is (triangle index as bits, 0, 0, NaN): NaN radius = triangle
 // A device leaf is a subtree of the host's BVH with at most RTB_OPT_LEAF_SPHERES spheres
 // (plugin.cu: Flattener); the host boxes it no longer walks are in chain_ref / chain_boxes (HBM).
 // Materials (n_materials * 64 B DevMaterial) stay in HBM behind the read-only path: they are
@@ -63,9 +67,9 @@ static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
 struct SceneDesc {
   const unsigned char* blob;    // device pointer
   uint32_t blob_bytes;          // multiple of 16
-  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off;
+  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, tri_off;
   const DevMaterial* materials; // device pointer
-  uint32_t n_inner, n_spheres, n_materials;
+  uint32_t n_inner, n_spheres, n_materials, n_triangles;
   int32_t root_ref;             // as child refs; meaningful when has_root
   uint32_t has_root;            // 0: empty world (node_count == 0)
   float root_min[3], root_max[3];
@@ -169,25 +173,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------
 template <bool SMEM>
 struct SceneView {
-  const float4* inner;
-  const float4* spheres;
-  const uint32_t* leaf_count;
-  const uint32_t* mat_index;
+  // SMEM: `s` is the blob's address in the shared window, kept as a 32-bit register so that every access is a
+  // plain LDS [reg + imm] (a generic pointer makes the compiler rebuild the window base around each load);
+  // else `g` is the blob in HBM.
+  const unsigned char* g;
+  uint32_t s;
+  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, tri_off;
 
-  __device__ __forceinline__ void bind(const unsigned char* base, const SceneDesc& s) {
-    inner = reinterpret_cast<const float4*>(base + s.inner_off);
-    spheres = reinterpret_cast<const float4*>(base + s.sphere_off);
-    leaf_count = reinterpret_cast<const uint32_t*>(base + s.leaf_count_off);
-    mat_index = reinterpret_cast<const uint32_t*>(base + s.mat_index_off);
+  __device__ __forceinline__ void bind(const unsigned char* base, const SceneDesc& d) {
+    g = base;
+    s = SMEM ? smem_u32(base) : 0u;
+    inner_off = d.inner_off; sphere_off = d.sphere_off; leaf_count_off = d.leaf_count_off; mat_index_off = d.mat_index_off;
+    tri_off = d.tri_off;
   }
-  __device__ __forceinline__ float4 ld4(const float4* p) const {
-    if (SMEM) return *p;
-    return __ldg(p);
+  __device__ __forceinline__ float4 triangle(uint32_t index, int k) const { return ld4(tri_off + index * 80u + (uint32_t)k * 16u); }
+  __device__ __forceinline__ float4 ld4(uint32_t off) const {
+    if (SMEM) {
+      float4 v;
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(s + off));
+      return v;
+    }
+    return __ldg(reinterpret_cast<const float4*>(g + off));
   }
-  __device__ __forceinline__ uint32_t ld1(const uint32_t* p) const {
-    if (SMEM) return *p;
-    return __ldg(p);
+  __device__ __forceinline__ uint32_t ld1(uint32_t off) const {
+    if (SMEM) {
+      uint32_t v;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s + off));
+      return v;
+    }
+    return __ldg(reinterpret_cast<const uint32_t*>(g + off));
   }
+  __device__ __forceinline__ float4 node(int index, int k) const { return ld4(inner_off + (uint32_t)index * 64u + (uint32_t)k * 16u); }
+  __device__ __forceinline__ float4 sphere(int i) const { return ld4(sphere_off + (uint32_t)i * 16u); }
+  __device__ __forceinline__ uint32_t leaf_count(int i) const { return ld1(leaf_count_off + (uint32_t)i * 4u); }
+  __device__ __forceinline__ uint32_t material_of(int i) const { return ld1(mat_index_off + (uint32_t)i * 4u); }
 };
 
 struct WorkCounters {           // per-thread tallies of the instrumented build
@@ -207,6 +226,11 @@ __device__ __forceinline__ bool aabb_hit(f3 mn, f3 mx, f3 o, f3 inv, float* t_en
   *t_enter = tmin;
   return tmin < tmax;
 }
+
+// Kernel flavours (template int FLAVOR): what the walk has to handle beyond single-sphere leaves of spheres.
+constexpr int kFlavorSpheres = 0;        // spheres only, no collapsed leaves (the fast build)
+constexpr int kFlavorChains = 1;         // + collapsed leaves: accepted hits go through chain_guard
+constexpr int kFlavorGeneral = 2;        // + EntityType.Triangle entities
 
 // The host boxes between a collapsed device leaf and sphere `idx`, applied exactly as the reference
 // would (FindHitCandidates reaches a sphere only through a chain of hit boxes, SampleBatchJob.cs:420-447).
@@ -279,6 +303,50 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
   }
 }
 
+// HitTests.Hit(this Triangle) (HitTests.cs:113-150): Moeller-Trumbore in the reference's operation order, both
+// faces.  Returns u, v and the distance when the reference would report a hit for tMin = 0, tMax = +inf
+// (FindHits, SampleBatchJob.cs:457): distance < 0 is the only rejected range.
+template <bool SMEM>
+__device__ __forceinline__ bool triangle_uvt(const SceneView<SMEM>& sv, uint32_t tri, f3 o, f3 d, float* u, float* v, float* t) {
+  const float4 a = sv.triangle(tri, 0), b = sv.triangle(tri, 1), c = sv.triangle(tri, 2);
+  const f3 data0 = um::mk(a.x, a.y, a.z), data1 = um::mk(a.w, b.x, b.y), data2 = um::mk(b.z, b.w, c.x);
+  const f3 pvec = um::cross(d, data0);
+  const float det = um::dot(data1, pvec);
+  if (det == 0) return false;
+  const float inv_det = um::div(1.0f, det);
+  const f3 tvec = o - data2;
+  *u = um::dot(tvec, pvec) * inv_det;
+  if (*u < 0 || *u > 1) return false;
+  const f3 qvec = um::cross(tvec, data1);
+  *v = um::dot(d, qvec) * inv_det;
+  if (*v < 0 || *u + *v > 1) return false;
+  *t = um::dot(data0, qvec) * inv_det;
+  return !(*t < 0.0f);
+}
+template <bool SMEM>
+__device__ __forceinline__ void triangle_hit(const SceneView<SMEM>& sv, uint32_t tri, int idx, f3 o, f3 d, float& best_t, int& best_idx) {
+  float u, v, t;
+  if (triangle_uvt(sv, tri, o, d, &u, &v, &t) && t < best_t) {
+    best_t = t;
+    best_idx = idx;
+  }
+}
+// HitRecord.Normal of the entity in slot `prim` hit at distance t (Entity.cs:57-72): sphere (HitTests.cs:41-45) or
+// triangle (interpolated vertex normals, HitTests.cs:144-147; the hit is re-derived, bit for bit, from the same ray).
+template <bool SMEM, bool TRIS>
+__device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim, f3 o, f3 d, float t) {
+  if (TRIS && prim.w != prim.w) {
+    const uint32_t tri = __float_as_uint(prim.x);
+    float u = 0, v = 0, tt = 0;
+    triangle_uvt(sv, tri, o, d, &u, &v, &tt);
+    const float4 c = sv.triangle(tri, 2), e = sv.triangle(tri, 3), f = sv.triangle(tri, 4);
+    const f3 bary = um::mk(1 - u - v, u, v);
+    return um::normalize(um::mul_cols(um::mk(c.y, c.z, c.w), um::mk(e.x, e.y, e.z), um::mk(e.w, f.x, f.y), bary));
+  }
+  const f3 oc = o + um::mk(-prim.x, -prim.y, -prim.z);
+  return um::normalize(um::mad(d, t, oc) / prim.w);
+}
+
 // Closest hit over the whole world.  Replaces FindHitCandidates + FindHits
 // (SampleBatchJob.cs:403-475): the reference collects every entity of every leaf whose box
 // chain is hit, intersects all, sorts and takes index 0.  This walk applies the SAME box
@@ -293,8 +361,7 @@ constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an 
 #define RTB_TRAVERSAL 0   // 0: one node (inner or leaf) per loop trip (measured fastest on B200); 1: while-while (inner run, then leaf run)
 #endif
 
-// CHAINS = false: the build for scenes uploaded without collapsed leaves (the accepted-hit path carries no guard).
-template <bool SMEM, bool COUNTERS, bool CHAINS>
+template <bool SMEM, bool COUNTERS, int FLAVOR>
 __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
                                             float& best_t, int& best_idx, WorkCounters& wc) {
   best_t = um::INF;
@@ -317,9 +384,11 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     const uint32_t code = (uint32_t)~ref;
     const int first = (int)(code >> 4);
     int count = (int)(code & 15u) + 1;
-    if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
+    if (count == 16) count = (int)sv.leaf_count(first);
     for (int i = 0; i < count; i++) {
-      sphere_hit<CHAINS>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, a, best_t, best_idx);
+      const float4 prim = sv.sphere(first + i);
+      if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), first + i, o, d, best_t, best_idx);
+      else sphere_hit<(FLAVOR >= kFlavorChains)>(sd, prim, first + i, o, d, inv, a, best_t, best_idx);
     }
     if (COUNTERS) wc.sphere_tests += count;
   };
@@ -337,8 +406,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     const bool keep_walking = __any_sync(mask, cur >= 0 && leaf == 0);
     if (keep_walking) {
       if (cur >= 0) {
-        const float4* n = sv.inner + 4 * cur;
-        const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+        const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
         float tl, tr;
         bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
         bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
@@ -370,8 +438,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     // inner nodes until this lane holds a leaf (or is done); the warp reconverges after the loop,
     // so the sphere tests below run with every lane that found a leaf
     while (cur >= 0) {
-      const float4* n = sv.inner + 4 * cur;
-      const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+      const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
       float tl, tr;
       bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
       bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
@@ -398,8 +465,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
 #else
   for (;;) {
     if (cur >= 0) {
-      const float4* n = sv.inner + 4 * cur;
-      const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+      const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
       float tl, tr;
       bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
       bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);

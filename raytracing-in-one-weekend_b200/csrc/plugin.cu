@@ -64,7 +64,7 @@ struct rtb_ctx {
   int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1;
   bool last_in_place = false;
   float last_ms = 0.0f;
-  bool smem_attr_set[2][4] = {};
+  bool smem_attr_set[2][6] = {};
   bool pool_attr_set[2][2] = {{false, false}, {false, false}};
 
   DeviceBuffers buf;
@@ -118,9 +118,12 @@ struct HostBlob {
 
 struct Flattener {
   const rtb_bvh_node* nodes;
-  size_t node_count, sphere_count;
+  size_t node_count, sphere_count;      // sphere_count: length of the list the leaves index (entities, or spheres)
   const rtb_sphere* spheres;
+  const rtb_entity* entities = nullptr; // nullptr: entity i is sphere i
   uint32_t collapse_k;
+  bool is_triangle(size_t e) const { return entities && entities[e].type == RTB_ENTITY_TRIANGLE; }
+  const rtb_sphere& sphere_of(size_t e) const { return spheres[entities ? entities[e].index : e]; }
   std::vector<uint8_t> visited;
   std::vector<uint32_t> subtree_spheres;   // per reference node
   std::vector<float> inner;                // 16 floats per device inner node
@@ -159,7 +162,9 @@ struct Flattener {
   // The guard in the kernel certifies the skipped boxes from the sphere's geometry; that needs every
   // skipped box to contain the sphere shrunk by kChainShrink (true for any BVH built from the spheres'
   // bounds, Sphere.cs:16-23; a host could pass anything).  Otherwise the subtree is not collapsed.
-  bool box_contains(const rtb_bvh_node& nd, const rtb_sphere& s) const {
+  bool box_contains(const rtb_bvh_node& nd, size_t e) const {
+    if (is_triangle(e)) return false;     // the guard is sphere geometry: subtrees with triangles are not collapsed
+    const rtb_sphere& s = sphere_of(e);
     const float r = std::fabs(s.radius) * (1.0f - kChainShrink);
     for (int k = 0; k < 3; k++)
       if (!(nd.bounds_min[k] <= s.center[k] - r && nd.bounds_max[k] >= s.center[k] + r)) return false;
@@ -171,7 +176,9 @@ struct Flattener {
     if (nd.first_entity >= 0) {
       if (!is_root)
         for (int i = 0; i < nd.entity_count; i++)
-          if (!box_contains(nd, spheres[nd.first_entity + i])) return false;
+          if (!box_contains(nd, (size_t)nd.first_entity + i)) return false;
+      for (int i = 0; i < nd.entity_count; i++)
+        if (is_triangle((size_t)nd.first_entity + i)) return false;
       return true;
     }
     if (!collapsible(nd.left, false) || !collapsible(nd.right, false)) return false;
@@ -183,7 +190,7 @@ struct Flattener {
         st.pop_back();
         if (x.first_entity >= 0) {
           for (int i = 0; i < x.entity_count; i++)
-            if (!box_contains(nd, spheres[x.first_entity + i])) return false;
+            if (!box_contains(nd, (size_t)x.first_entity + i)) return false;
         } else {
           st.push_back(x.left);
           st.push_back(x.right);
@@ -273,10 +280,21 @@ struct Flattener {
 
 bool almost_equals_1(float v) { return std::fabs(1.0f - v) < 1e-6f; }  // MathExtensions.cs:23-27
 
-const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials,
+const char* build_blob(const rtb_entity* entities, size_t entity_count, const rtb_sphere* spheres, size_t sphere_count,
+                       const rtb_triangle* triangles, size_t triangle_count, const rtb_material* materials,
                        size_t material_count, const rtb_bvh_node* nodes, size_t node_count, uint32_t collapse_k,
                        HostBlob* out, int* status) {
   *status = RTB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < entity_count; i++) {
+    if (entities[i].type != RTB_ENTITY_SPHERE && entities[i].type != RTB_ENTITY_TRIANGLE) {
+      *status = RTB_ERR_UNSUPPORTED;
+      return "entity type outside the supported hot path (Sphere, Triangle)";
+    }
+    if (entities[i].index >= (entities[i].type == RTB_ENTITY_SPHERE ? sphere_count : triangle_count)) return "entity index out of range";
+  }
+  for (size_t i = 0; i < triangle_count; i++)
+    if (triangles[i].material >= material_count) return "triangle material index out of range";
+  const size_t leaf_list_count = entities ? entity_count : sphere_count;
   for (size_t i = 0; i < material_count; i++) {
     if (materials[i].type > RTB_MATERIAL_DIELECTRIC) {
       *status = RTB_ERR_UNSUPPORTED;
@@ -287,7 +305,7 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
     if (spheres[i].material >= material_count) return "sphere material index out of range";
 
   Flattener f{};
-  f.nodes = nodes; f.node_count = node_count; f.sphere_count = sphere_count; f.spheres = spheres;
+  f.nodes = nodes; f.node_count = node_count; f.sphere_count = leaf_list_count; f.spheres = spheres; f.entities = entities;
   f.collapse_k = std::max<uint32_t>(1, std::min<uint32_t>(collapse_k, 15));
   f.visited.assign(node_count, 0);
   f.subtree_spheres.assign(node_count, 0);
@@ -313,6 +331,7 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
   d.n_spheres = (uint32_t)n_dev;
   d.n_materials = (uint32_t)material_count;
   d.has_chains = f.collapsed_any ? 1 : 0;
+  d.n_triangles = (uint32_t)triangle_count;
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t off = 0;
@@ -320,6 +339,7 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
   d.sphere_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 16);
   d.leaf_count_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
   d.mat_index_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
+  d.tri_off = (uint32_t)off; off = align16(off + triangle_count * 80);
   if (off == 0) off = 16;
   d.blob_bytes = (uint32_t)off;
   out->bytes.assign(off, 0);
@@ -329,13 +349,28 @@ const char* build_blob(const rtb_sphere* spheres, size_t sphere_count, const rtb
     const uint32_t h = f.order[i];
     float s[4] = {0, 0, 0, 0};
     uint32_t mat = 0;
-    if (h != 0xFFFFFFFFu) {
-      s[0] = spheres[h].center[0]; s[1] = spheres[h].center[1]; s[2] = spheres[h].center[2]; s[3] = spheres[h].radius;
-      mat = spheres[h].material;
+    if (h != 0xFFFFFFFFu && f.is_triangle(h)) {
+      const uint32_t ti = entities[h].index;        // slot = (triangle index as bits, 0, 0, NaN)
+      const uint32_t nan_bits = 0x7fc00000u;
+      memcpy(&s[0], &ti, 4);
+      memcpy(&s[3], &nan_bits, 4);
+      mat = triangles[ti].material;
+    } else if (h != 0xFFFFFFFFu) {
+      const rtb_sphere& sp = f.sphere_of(h);
+      if (sp.radius != sp.radius) return "sphere with a NaN radius";
+      s[0] = sp.center[0]; s[1] = sp.center[1]; s[2] = sp.center[2]; s[3] = sp.radius;
+      mat = sp.material;
     }
     memcpy(b + d.sphere_off + i * 16, s, 16);
     memcpy(b + d.leaf_count_off + i * 4, &f.leaf_count[i], 4);
     memcpy(b + d.mat_index_off + i * 4, &mat, 4);
+  }
+  for (size_t i = 0; i < triangle_count; i++) {
+    const rtb_triangle& t = triangles[i];
+    const float q[20] = {t.edge2[0], t.edge2[1], t.edge2[2], t.edge1[0], t.edge1[1], t.edge1[2], t.v0[0], t.v0[1], t.v0[2],
+                         t.normals[0][0], t.normals[0][1], t.normals[0][2], t.normals[1][0], t.normals[1][1], t.normals[1][2],
+                         t.normals[2][0], t.normals[2][1], t.normals[2][2], 0.0f, 0.0f};
+    memcpy(b + d.tri_off + i * 80, q, 80);
   }
   out->chain_ref = std::move(f.chain_ref);
   out->chain_boxes = std::move(f.chain_boxes);
@@ -394,13 +429,13 @@ int validate_params(rtb_ctx* ctx, const rtb_batch_params* p, int* width, int* he
 
 void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp);
 
-template <bool SMEM, bool COUNTERS, bool CHAINS>
+template <bool SMEM, bool COUNTERS, int FLAVOR>
 int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_spp) {
   const size_t smem = mega_smem_bytes(a.scene.blob_bytes, SMEM);
-  auto kernel = sample_megakernel<SMEM, COUNTERS, CHAINS>;
-  if (!ctx->smem_attr_set[SMEM][COUNTERS + 2 * CHAINS]) {
+  auto kernel = sample_megakernel<SMEM, COUNTERS, FLAVOR>;
+  if (!ctx->smem_attr_set[SMEM][COUNTERS + 2 * FLAVOR]) {
     RTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    ctx->smem_attr_set[SMEM][COUNTERS + 2 * CHAINS] = true;
+    ctx->smem_attr_set[SMEM][COUNTERS + 2 * FLAVOR] = true;
   }
   int blocks_per_sm = 0;
   RTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kMegaBlock, smem));
@@ -523,11 +558,16 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
-    const bool chains = ctx->scene.has_chains != 0;
-    if (fits) rc = counters ? launch_mega_t<true, true, true>(ctx, a, stream, max_spp)
-                   : chains ? launch_mega_t<true, false, true>(ctx, a, stream, max_spp) : launch_mega_t<true, false, false>(ctx, a, stream, max_spp);
-    else rc = counters ? launch_mega_t<false, true, true>(ctx, a, stream, max_spp)
-              : chains ? launch_mega_t<false, false, true>(ctx, a, stream, max_spp) : launch_mega_t<false, false, false>(ctx, a, stream, max_spp);
+    // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
+    const int flavor = (counters || ctx->scene.n_triangles) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
+    if (fits) rc = counters ? launch_mega_t<true, true, kFlavorGeneral>(ctx, a, stream, max_spp)
+                   : flavor == kFlavorGeneral ? launch_mega_t<true, false, kFlavorGeneral>(ctx, a, stream, max_spp)
+                   : flavor == kFlavorChains ? launch_mega_t<true, false, kFlavorChains>(ctx, a, stream, max_spp)
+                                             : launch_mega_t<true, false, kFlavorSpheres>(ctx, a, stream, max_spp);
+    else rc = counters ? launch_mega_t<false, true, kFlavorGeneral>(ctx, a, stream, max_spp)
+              : flavor == kFlavorGeneral ? launch_mega_t<false, false, kFlavorGeneral>(ctx, a, stream, max_spp)
+              : flavor == kFlavorChains ? launch_mega_t<false, false, kFlavorChains>(ctx, a, stream, max_spp)
+                                        : launch_mega_t<false, false, kFlavorSpheres>(ctx, a, stream, max_spp);
     if (rc != RTB_OK) return rc;
   }
   if (counters) {
@@ -650,15 +690,24 @@ int rtb_set_log_callback(rtb_ctx* ctx, rtb_log_fn fn, void* user) {
 
 int rtb_upload_scene(rtb_ctx* ctx, const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials,
                      size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
+  return rtb_upload_world(ctx, nullptr, 0, spheres, sphere_count, nullptr, 0, materials, material_count, nodes, node_count);
+}
+
+int rtb_upload_world(rtb_ctx* ctx, const rtb_entity* entities, size_t entity_count, const rtb_sphere* spheres, size_t sphere_count,
+                     const rtb_triangle* triangles, size_t triangle_count, const rtb_material* materials,
+                     size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
   if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if ((sphere_count && !spheres) || (material_count && !materials) || (node_count && !nodes))
+  if ((sphere_count && !spheres) || (material_count && !materials) || (node_count && !nodes) || (entity_count && !entities) ||
+      (triangle_count && !triangles))
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "NULL array with a non-zero count");
-  if (sphere_count > (1u << 28) || node_count > (1u << 29)) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "scene too large");
+  if (triangle_count && !entity_count) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "triangles need an entity list");
+  if (sphere_count > (1u << 27) || triangle_count > (1u << 25) || entity_count > (1u << 27) || node_count > (1u << 29))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "scene too large");
   std::lock_guard<std::mutex> lock(ctx->mu);
   HostBlob hb;
   int status;
-  const char* err = build_blob(spheres, sphere_count, materials, material_count, nodes, node_count,
-                               (uint32_t)ctx->opt_collapse, &hb, &status);
+  const char* err = build_blob(entity_count ? entities : nullptr, entity_count, spheres, sphere_count, triangles, triangle_count,
+                               materials, material_count, nodes, node_count, (uint32_t)ctx->opt_collapse, &hb, &status);
   if (err) return fail(ctx, status, "rtb_upload_scene: %s", err);
   DeviceGuard g(ctx->device);
   RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -704,7 +753,8 @@ int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count, const rtb
   if (leaf_spheres < 1 || leaf_spheres > 15) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "leaf_spheres must be 1..15");
   HostBlob hb;
   int status;
-  const char* err = build_blob(spheres, sphere_count, materials, material_count, nodes, node_count, (uint32_t)leaf_spheres, &hb, &status);
+  const char* err = build_blob(nullptr, 0, spheres, sphere_count, nullptr, 0, materials, material_count, nodes, node_count,
+                               (uint32_t)leaf_spheres, &hb, &status);
   if (err) return fail(nullptr, status, "rtb_describe_scene: %s", err);
   *out = rtb_scene_layout{};
   out->inner_nodes = hb.desc.n_inner;

@@ -250,13 +250,12 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
         uint32_t meta = w.meta[s];
         const uint32_t depth = meta >> 16, pixel = w.pixel[s], sample = w.sample[s];
         const int pix = (int)(meta & 0xffu);
-        const float4 sp = sv.ld4(sv.spheres + hit_idx);
-        const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
+        const float4 sp = sv.sphere(hit_idx);
+        const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(sd.materials + mi);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
-        const f3 oc = o + um::mk(-sp.x, -sp.y, -sp.z);
-        const f3 N = um::normalize(um::mad(d, t_hit, oc) / sp.w);
+        const f3 N = hit_normal<SMEM, true>(sv, sp, o, d, t_hit);
         const f3 P = um::mad(d, t_hit, o);
         const ScatterResult sc = scatter(m0, m1, m2, m3, d, N, pixel, sample, depth, p.seed);
         dielectric = __float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC;
@@ -445,8 +444,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
         if (my >= 0) {
           bool pop = true;
           if (cur >= 0) {
-            const float4* n = sv.inner + 4 * cur;
-            const float4 q0 = sv.ld4(n), q1 = sv.ld4(n + 1), q2 = sv.ld4(n + 2), q3 = sv.ld4(n + 3);
+            const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
             float tl, tr;
             bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
             bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
@@ -468,9 +466,11 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
             const uint32_t code = (uint32_t)~cur;
             const int first = (int)(code >> 4);
             int count = (int)(code & 15u) + 1;
-            if (count == 16) count = (int)sv.ld1(sv.leaf_count + first);
+            if (count == 16) count = (int)sv.leaf_count(first);
             for (int i = 0; i < count; i++) {
-              sphere_hit<true>(sd, sv.ld4(sv.spheres + first + i), first + i, o, d, inv, aa, best_t, best_idx);
+              const float4 prim = sv.sphere(first + i);
+              if (prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), first + i, o, d, best_t, best_idx);
+              else sphere_hit<true>(sd, prim, first + i, o, d, inv, aa, best_t, best_idx);
             }
             if (COUNTERS) wc.sphere_tests += count;
           }

@@ -95,7 +95,7 @@ __device__ __forceinline__ void active_pixel(const BatchArgs& a, uint32_t k, int
   *index = (uint32_t)*cy * (uint32_t)a.width + (uint32_t)*cx;
 }
 
-template <bool SMEM, bool COUNTERS, bool CHAINS>
+template <bool SMEM, bool COUNTERS, int FLAVOR>
 __global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -265,17 +265,16 @@ __global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megake
     if (alive) {
       float t_hit;
       int hit_idx;
-      closest_hit<SMEM, COUNTERS, CHAINS>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
       path_rays++;
       bool finished = false, success = false;
       if (hit_idx >= 0) {
-        const float4 s = sv.ld4(sv.spheres + hit_idx);
-        const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
+        const float4 s = sv.sphere(hit_idx);
+        const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
-        const f3 oc = ray.o + um::mk(-s.x, -s.y, -s.z);
-        const f3 N = um::normalize(um::mad(ray.d, t_hit, oc) / s.w);
+        const f3 N = hit_normal<SMEM, (FLAVOR >= kFlavorGeneral)>(sv, s, ray.o, ray.d, t_hit);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
         const ScatterResult sc = scatter(m0, m1, m2, m3, ray.d, N, pixel, sample, (uint32_t)depth, p.seed);
         if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
@@ -436,15 +435,14 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
     for (; depth < p.trace_depth; depth++) {
       float t_hit;
       int hit_idx;
-      closest_hit<false, COUNTERS, true>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      closest_hit<false, COUNTERS, kFlavorGeneral>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
       rays++;
       if (hit_idx >= 0) {
-        const float4 sp = sv.ld4(sv.spheres + hit_idx);
-        const uint32_t mi = sv.ld1(sv.mat_index + hit_idx);
+        const float4 sp = sv.sphere(hit_idx);
+        const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
-        const f3 oc = ray.o + um::mk(-sp.x, -sp.y, -sp.z);
-        const f3 N = um::normalize(um::mad(ray.d, t_hit, oc) / sp.w);
+        const f3 N = hit_normal<false, true>(sv, sp, ray.o, ray.d, t_hit);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
         const ScatterResult sc = scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed);
         if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }

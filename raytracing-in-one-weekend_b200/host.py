@@ -37,6 +37,16 @@ def lib():
             C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
         ]
         L.rtbh_build_bvh.restype = C.c_int
+        L.rtbh_build_bvh_from_bounds.argtypes = [
+            C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
+        ]
+        L.rtbh_build_bvh_from_bounds.restype = C.c_int
+        L.rtbh_sphere_bounds.argtypes = [C.c_void_p, C.c_void_p]
+        L.rtbh_sphere_bounds.restype = None
+        L.rtbh_triangle_bounds.argtypes = [C.c_void_p, C.c_void_p]
+        L.rtbh_triangle_bounds.restype = None
+        L.rtbh_make_triangle.argtypes = [abi.f32x3, abi.f32x3, abi.f32x3, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.rtbh_make_triangle.restype = None
         L.rtbh_make_view.argtypes = [
             abi.f32x3, abi.f32x3, abi.f32x3, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(abi.View)
         ]
@@ -86,6 +96,10 @@ class Scene:
     info: abi.SceneInfo
     max_bvh_depth: int
     name: str = ""
+    # mixed worlds (rtb_upload_world): the BVH-ordered entity list the leaves index, and the triangle array
+    entities: np.ndarray = None  # abi.ENTITY_DTYPE or None (entity i == sphere i)
+    triangles: np.ndarray = None  # abi.TRIANGLE_DTYPE or None
+    focus_distance: float = None  # fixed focus for worlds the sphere-only auto-focus helper cannot walk
 
 
 def generate_scene(scene_id, seed=700, target_count=0):
@@ -147,6 +161,10 @@ def view_for(scene, width, height, aperture=None, fallback_focus=1.0):
     cam = abi.Camera.from_buffer_copy(scene.camera)
     if aperture is not None:
         cam.aperture = aperture
+    if scene.focus_distance is not None:
+        v = make_view(list(cam.position), list(cam.target), (0, 1, 0), cam.vertical_fov, float(width) / float(height),
+                      cam.aperture, scene.focus_distance)
+        return v, scene.focus_distance
     v = abi.View()
     focus = C.c_float(0)
     lib().rtbh_view_from_camera(
@@ -177,6 +195,131 @@ def make_scene(name, max_bvh_depth=None, seed=700, target_count=0):
         spheres=bvh_spheres, materials=materials, nodes=nodes, camera=info.camera, environment=info.environment,
         info=info, max_bvh_depth=max_bvh_depth, name=name,
     )
+
+
+def make_triangle(v1, v2, v3, material, normals=None):
+    """new Triangle(...) (Triangle.cs:14-29): face normal, or the three vertex normals."""
+    out = np.zeros(1, dtype=abi.TRIANGLE_DTYPE)
+    ns = [None, None, None]
+    keep = []
+    if normals is not None:
+        keep = [np.ascontiguousarray(n, dtype=np.float32) for n in normals]
+        ns = [k.ctypes.data for k in keep]
+    lib().rtbh_make_triangle(_v3(v1), _v3(v2), _v3(v3), ns[0], ns[1], ns[2], int(material), out.ctypes.data)
+    return out[0]
+
+
+def build_world(spheres, triangles, materials, max_bvh_depth, camera, environment, focus_distance, name="world"):
+    """RebuildWorld for a mixed world: per-entity bounds (CreateBvhBuildingEntitiesJob), the reference's BVH
+    build + flatten order, and the BVH-ordered entity list the leaves index (bvhEntities).  Entities are
+    listed spheres first, then triangles, like RebuildEntityBuffers appends them."""
+    spheres = np.ascontiguousarray(spheres, dtype=abi.SPHERE_DTYPE)
+    triangles = np.ascontiguousarray(triangles, dtype=abi.TRIANGLE_DTYPE)
+    n = len(spheres) + len(triangles)
+    bounds = np.zeros((n, 6), np.float32)
+    for i in range(len(spheres)):
+        lib().rtbh_sphere_bounds(spheres[i:i + 1].ctypes.data, bounds[i].ctypes.data)
+    for i in range(len(triangles)):
+        lib().rtbh_triangle_bounds(triangles[i:i + 1].ctypes.data, bounds[len(spheres) + i].ctypes.data)
+    order = np.zeros(max(n, 1), np.uint32)
+    cap = max(1, 2 * n + 1)
+    nodes = np.zeros(cap, dtype=abi.BVH_NODE_DTYPE)
+    count = C.c_size_t(0)
+    rc = lib().rtbh_build_bvh_from_bounds(bounds.ctypes.data if n else None, n, int(max_bvh_depth), order.ctypes.data, n,
+                                          nodes.ctypes.data, cap, C.byref(count))
+    if rc != 0:
+        raise ValueError(f"rtbh_build_bvh_from_bounds failed: {rc}")
+    entities = np.zeros(n, dtype=abi.ENTITY_DTYPE)
+    for k in range(n):
+        e = int(order[k])
+        if e < len(spheres):
+            entities[k] = (abi.ENTITY_SPHERE, e)
+        else:
+            entities[k] = (abi.ENTITY_TRIANGLE, e - len(spheres))
+    info = abi.SceneInfo()
+    info.camera = camera
+    info.environment = environment
+    info.sphere_count = len(spheres)
+    info.material_count = len(materials)
+    return Scene(spheres=spheres, materials=np.ascontiguousarray(materials, dtype=abi.MATERIAL_DTYPE), nodes=nodes[: count.value].copy(),
+                 camera=camera, environment=environment, info=info, max_bvh_depth=max_bvh_depth, name=name,
+                 entities=entities, triangles=triangles, focus_distance=focus_distance)
+
+
+def _icosphere(center, radius, subdivisions):
+    """Unit icosahedron subdivided `subdivisions` times: (vertices, faces); vertex normals = normalised offsets."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[k] = len(v) - 1
+            return cache[k]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    normals = np.array(v, np.float32)
+    verts = (np.array(center, np.float64) + radius * np.array(v)).astype(np.float32)
+    return verts, normals, f
+
+
+def make_mesh_scene(max_bvh_depth=16, subdivisions=1):
+    """A small mixed world in the shape of what the reference's host produces at HEAD (mesh triangles,
+    Raytracer.cs:1185-1304) plus sphere entities: a two-triangle ground quad (face normals), a smooth-shaded
+    icosphere (vertex normals, glossy metal), a flat-shaded tetrahedron (Lambertian), a hollow glass sphere
+    (negative-radius inner sphere) and a diffuse sphere; gradient sky."""
+    def mat(mtype, albedo, gloss=0.0, metallic=0.0, ior=1.5, emission=(0, 0, 0)):
+        m = np.zeros(1, dtype=abi.MATERIAL_DTYPE)[0]
+        m["type"], m["albedo"], m["emission"] = mtype, albedo, emission
+        m["glossiness"], m["metallic"], m["index_of_refraction"] = gloss, metallic, ior
+        return m
+
+    materials = np.array([
+        mat(abi.MATERIAL_STANDARD, (0.5, 0.5, 0.5)),                               # 0 ground
+        mat(abi.MATERIAL_STANDARD, (0.8, 0.6, 0.2), gloss=0.8, metallic=1.0),      # 1 icosphere
+        mat(abi.MATERIAL_STANDARD, (0.7, 0.15, 0.1)),                              # 2 tetrahedron
+        mat(abi.MATERIAL_DIELECTRIC, (1, 1, 1), gloss=1.0, ior=1.5),               # 3 glass
+        mat(abi.MATERIAL_STANDARD, (0.1, 0.2, 0.5)),                               # 4 small sphere
+        mat(abi.MATERIAL_STANDARD, (0.9, 0.9, 0.9), gloss=0.4, metallic=0.3),      # 5 glossy part-metal wedge
+    ], dtype=abi.MATERIAL_DTYPE)
+    tris = []
+    g = 12.0
+    q = [(-g, 0, -g), (g, 0, -g), (g, 0, g), (-g, 0, g)]
+    tris += [make_triangle(q[0], q[2], q[1], 0), make_triangle(q[0], q[3], q[2], 0)]
+    verts, normals, faces = _icosphere((0.0, 1.0, 0.0), 1.0, subdivisions)
+    for a, b, c in faces:
+        tris.append(make_triangle(verts[a], verts[c], verts[b], 1, normals=(normals[a], normals[c], normals[b])))
+    p = np.array([(2.2, 0.0, -0.8), (3.6, 0.0, -0.6), (2.9, 0.0, 0.6), (2.9, 1.3, -0.2)], np.float32)
+    for a, b, c in ((0, 1, 3), (1, 2, 3), (2, 0, 3), (0, 2, 1)):
+        tris.append(make_triangle(p[a], p[c], p[b], 2))
+    w = np.array([(0.3, 0.0, -3.2), (1.5, 0.0, -2.7), (0.8, 1.1, -3.0)], np.float32)
+    tris.append(make_triangle(w[0], w[1], w[2], 5))          # a lone two-sided wedge (hit from both faces)
+    spheres = np.zeros(3, dtype=abi.SPHERE_DTYPE)
+    spheres[0] = ((-1.9, 0.7, -1.2), 0.7, 3, (0, 0, 0))
+    spheres[1] = ((-1.9, 0.7, -1.2), -0.62, 3, (0, 0, 0))
+    spheres[2] = ((1.2, 0.35, -1.9), 0.35, 4, (0, 0, 0))
+    cam = abi.Camera()
+    cam.position[:] = (5.0, 2.6, -6.5)
+    cam.target[:] = (0.0, 0.8, 0.0)
+    cam.aperture = 0.0
+    cam.vertical_fov = 32.0
+    env = abi.Environment()
+    env.sky_type = abi.SKY_GRADIENT
+    env.sky_bottom_color[:] = (1.0, 1.0, 1.0)
+    env.sky_top_color[:] = (0.5, 0.7, 1.0)
+    focus = float(np.linalg.norm(np.array(cam.position[:]) - np.array(cam.target[:])))
+    return build_world(spheres, np.array(tris, dtype=abi.TRIANGLE_DTYPE), materials, max_bvh_depth, cam, env, focus, name="mesh")
 
 
 def make_params(scene, width, height, spp, trace_depth, seed=1, aperture=None, jitter=True,

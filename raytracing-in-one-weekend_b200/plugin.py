@@ -15,7 +15,7 @@ from . import build as _build
 
 EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
-    "rtb_upload_scene", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_upload_scene", "rtb_upload_world", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
@@ -49,6 +49,7 @@ def lib():
         L.rtb_last_error.restype = C.c_char_p
         L.rtb_set_log_callback.argtypes = [vp, vp, vp]
         L.rtb_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+        L.rtb_upload_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
         L.rtb_describe_scene.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.POINTER(abi.SceneLayout)]
         L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
         L.rtb_sample_batch_device.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
@@ -192,8 +193,24 @@ class Context:
             materials.ctypes.data if len(materials) else None, len(materials),
             nodes.ctypes.data if len(nodes) else None, len(nodes)))
 
+    def upload_world(self, entities, spheres, triangles, materials, nodes):
+        """rtb_upload_world: leaves of `nodes` index `entities`, each naming a sphere or a triangle."""
+        entities = np.ascontiguousarray(entities, dtype=abi.ENTITY_DTYPE)
+        spheres = np.ascontiguousarray(spheres, dtype=abi.SPHERE_DTYPE)
+        triangles = np.ascontiguousarray(triangles, dtype=abi.TRIANGLE_DTYPE)
+        materials = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DTYPE)
+        nodes = np.ascontiguousarray(nodes, dtype=abi.BVH_NODE_DTYPE)
+
+        def ptr(a):
+            return a.ctypes.data if len(a) else None
+        self._check(self._L.rtb_upload_world(self._h, ptr(entities), len(entities), ptr(spheres), len(spheres), ptr(triangles),
+                                             len(triangles), ptr(materials), len(materials), ptr(nodes), len(nodes)))
+
     def upload(self, scene):
-        self.upload_scene(scene.spheres, scene.materials, scene.nodes)
+        if getattr(scene, "entities", None) is not None:
+            self.upload_world(scene.entities, scene.spheres, scene.triangles, scene.materials, scene.nodes)
+        else:
+            self.upload_scene(scene.spheres, scene.materials, scene.nodes)
 
     # ---- the hot path ------------------------------------------------------------------
     def sample_batch(self, params, buffers, cancel=None):

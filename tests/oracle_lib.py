@@ -36,6 +36,13 @@ def lib(fast=False):
             C.POINTER(abi.BatchBuffers), C.c_int, C.c_int, C.c_int64, C.c_int64,
         ]
         L.oracle_sample_batch.restype = C.c_int
+        L.oracle_sample_batch_world.argtypes = [
+            C.POINTER(abi.BatchParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+            C.c_void_p, C.c_size_t, C.POINTER(abi.BatchBuffers), C.c_int, C.c_int, C.c_int64, C.c_int64,
+        ]
+        L.oracle_sample_batch_world.restype = C.c_int
+        L.oracle_triangle_hit.argtypes = [C.c_void_p, abi.f32x3, abi.f32x3, C.POINTER(C.c_float), abi.f32x3, abi.f32x3]
+        L.oracle_triangle_hit.restype = C.c_int
         L.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.oracle_unity_random.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_sphere_hit.argtypes = [abi.f32x3, C.c_float, abi.f32x3, abi.f32x3, C.POINTER(C.c_float), abi.f32x3, abi.f32x3]
@@ -108,6 +115,16 @@ class Buffers:
 def sample_batch(scene, params, buffers, noise=NOISE_PHILOX, threads=None, fast=False, index_range=(0, 0)):
     threads = threads or os.cpu_count() or 1
     b = buffers.as_struct()
+    if getattr(scene, "entities", None) is not None:
+        tris = scene.triangles
+        rc = lib(fast).oracle_sample_batch_world(
+            C.byref(params), scene.entities.ctypes.data, len(scene.entities), scene.spheres.ctypes.data, len(scene.spheres),
+            tris.ctypes.data if len(tris) else None, len(tris), scene.materials.ctypes.data, len(scene.materials),
+            scene.nodes.ctypes.data, len(scene.nodes), C.byref(b), noise, threads, index_range[0], index_range[1],
+        )
+        if rc != 0:
+            raise RuntimeError(f"oracle_sample_batch_world failed: {rc}")
+        return buffers
     rc = lib(fast).oracle_sample_batch(
         C.byref(params), scene.spheres.ctypes.data, len(scene.spheres), scene.materials.ctypes.data, len(scene.materials),
         scene.nodes.ctypes.data, len(scene.nodes), C.byref(b), noise, threads, index_range[0], index_range[1],

@@ -152,6 +152,35 @@ def test_stress_scene_walks_the_world_in_hbm(rtb, oracle, ctx, kernel):
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
+@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("depth,aperture", [(16, 0.0), (2, 0.15), (0, 0.0)])
+def test_mesh_world_matches_the_oracle(rtb, oracle, ctx, kernel, depth, aperture):
+    """rtb_upload_world: EntityType.Triangle entities (what the reference's host ingests at HEAD,
+    Raytracer.cs:1185-1304) mixed with spheres — flat and smooth shading, two-sided hits, multi-entity leaves."""
+    W, H, spp = 112, 63, 12
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=depth)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=aperture)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    got = render_gpu(rtb, ctx, scene, p, W, H, k)
+    assert_parity(ref, got, exact=(kernel == "simple"))
+
+
+def test_world_upload_rejects_what_it_cannot_render(rtb, ctx):
+    scene = rtb.host.make_mesh_scene()
+    ents = scene.entities.copy()
+    ents["type"][0] = rtb.abi.ENTITY_BOX
+    with pytest.raises(rtb.plugin.RtbError) as e:
+        ctx.upload_world(ents, scene.spheres, scene.triangles, scene.materials, scene.nodes)
+    assert e.value.code == rtb.abi.RTB_ERR_UNSUPPORTED
+    ents = scene.entities.copy()
+    ents["index"][0] = 10 ** 6
+    with pytest.raises(rtb.plugin.RtbError) as e:
+        ctx.upload_world(ents, scene.spheres, scene.triangles, scene.materials, scene.nodes)
+    assert e.value.code == rtb.abi.RTB_ERR_INVALID_ARGUMENT
+
+
 def test_pinned_host_arrays_are_used_in_place(rtb, ctx):
     """rtb_sample_batch on registered (pinned) host arrays runs the kernel on them in place; pageable arrays are
     staged through device copies.  Same bytes either way, also with interlaced rows and a previous accumulation."""
