@@ -42,6 +42,16 @@ namespace B200PathTracer
 		public Diagnostics* OutDiagnostics; // FULL_DIAGNOSTICS layout: 4 floats (Raytracer.cs:54-64)
 	}
 
+	// rtb_triangle: EntityTypes/Triangle.cs:10-11 (Data columns, Normals columns), world space
+	[StructLayout(LayoutKind.Sequential)] public struct RtbTriangle
+	{
+		public float3 Edge2, Edge1, V0;     // Triangle.Data[0], Data[1], Data[2]
+		public float3 N0, N1, N2;           // Triangle.Normals columns
+		public uint Material, Reserved;
+	}
+	// rtb_entity: one element of bvhEntities (BvhNodeData.cs:157-160): Entity.Type + index of Entity.Content
+	[StructLayout(LayoutKind.Sequential)] public struct RtbEntity { public uint Type; /* EntityType: 1 Sphere, 4 Triangle */ public uint Index; }
+
 	public static unsafe class Api
 	{
 		const string Lib = "rtb";           // librtb.so / rtb.dll next to the other native plugins
@@ -50,6 +60,9 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern RtbStatus rtb_destroy(IntPtr ctx);
 		[DllImport(Lib)] public static extern IntPtr rtb_last_error(IntPtr ctx);
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_scene(IntPtr ctx, RtbSphere* spheres, UIntPtr sphereCount,
+			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
+		[DllImport(Lib)] public static extern RtbStatus rtb_upload_world(IntPtr ctx, RtbEntity* entities, UIntPtr entityCount,
+			RtbSphere* spheres, UIntPtr sphereCount, RtbTriangle* triangles, UIntPtr triangleCount,
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
 		[DllImport(Lib)] public static extern RtbStatus rtb_sample_batch(IntPtr ctx, RtbBatchParams* p, RtbBatchBuffers* hostBuffers, bool* cancel);
 		[DllImport(Lib)] public static extern RtbStatus rtb_register_host_buffer(IntPtr ctx, void* ptr, UIntPtr bytes);

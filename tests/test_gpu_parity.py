@@ -75,7 +75,7 @@ def test_sample_batch_matches_the_oracle(rtb, oracle, ctx, case, kernel):
 
 
 @pytest.mark.parametrize("case", ["three_spheres_32x18x4_d8_philox", "final_linear_32x18x4_d50_philox",
-                                  "final_bvh16_defocus_48x27x8_d50_philox"])
+                                  "final_bvh16_defocus_48x27x8_d50_philox", "mesh_bvh16_48x27x8_d50_philox"])
 def test_gpu_matches_golden_fixtures(rtb, ctx, case):
     import importlib.util
 
@@ -83,7 +83,7 @@ def test_gpu_matches_golden_fixtures(rtb, ctx, case):
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
     name, depth, W, H, spp, td, ap, _ = mg.CASES[case]
-    scene = rtb.host.make_scene(name, max_bvh_depth=depth)
+    scene = mg.make_scene(name, depth)
     p = rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
     simple = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE)

@@ -20,12 +20,20 @@ CASES = {
     "final_linear_32x18x4_d50_philox": ("final", 0, 32, 18, 4, 50, None, O.NOISE_PHILOX),
     "final_bvh16_defocus_48x27x8_d50_philox": ("final", 16, 48, 27, 8, 50, 0.1, O.NOISE_PHILOX),
     "three_spheres_32x18x4_d8_xorshift": ("three_spheres", 0, 32, 18, 4, 8, None, O.NOISE_XORSHIFT),
+    "mesh_bvh16_48x27x8_d50_philox": ("mesh", 16, 48, 27, 8, 50, None, O.NOISE_PHILOX),
 }
+
+
+def make_scene(name, depth):
+    if name == "mesh":
+        return O.rtb.host.make_mesh_scene(max_bvh_depth=depth)
+    return O.rtb.host.make_scene(name, max_bvh_depth=depth)
+
 
 
 def render(case):
     name, depth, W, H, spp, td, ap, noise = CASES[case]
-    scene = O.rtb.host.make_scene(name, max_bvh_depth=depth)
+    scene = make_scene(name, depth)
     p = O.rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
     b = O.Buffers(W, H)
     O.sample_batch(scene, p, b, noise=noise, threads=1)
@@ -35,7 +43,10 @@ def render(case):
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for case in CASES:
+        if only and case not in only:
+            continue
         b = render(case)
         np.savez_compressed(
             os.path.join(out_dir, case + ".npz"), color=b.out_color, normal=b.out_normal, albedo=b.out_albedo,
