@@ -274,11 +274,12 @@ def _icosphere(center, radius, subdivisions):
     return verts, normals, f
 
 
-def make_mesh_scene(max_bvh_depth=16, subdivisions=1):
+def make_mesh_scene(max_bvh_depth=16, subdivisions=1, emissive=False):
     """A small mixed world in the shape of what the reference's host produces at HEAD (mesh triangles,
     Raytracer.cs:1185-1304) plus sphere entities: a two-triangle ground quad (face normals), a smooth-shaded
     icosphere (vertex normals, glossy metal), a flat-shaded tetrahedron (Lambertian), a hollow glass sphere
-    (negative-radius inner sphere) and a diffuse sphere; gradient sky."""
+    (negative-radius inner sphere) and a diffuse sphere; gradient sky.  emissive=True: no sky (SkyType.None,
+    Environment.cs:5-10) and an emissive panel overhead (Material.Emit, Material.cs:175-179) as the only light."""
     def mat(mtype, albedo, gloss=0.0, metallic=0.0, ior=1.5, emission=(0, 0, 0)):
         m = np.zeros(1, dtype=abi.MATERIAL_DTYPE)[0]
         m["type"], m["albedo"], m["emission"] = mtype, albedo, emission
@@ -292,6 +293,7 @@ def make_mesh_scene(max_bvh_depth=16, subdivisions=1):
         mat(abi.MATERIAL_DIELECTRIC, (1, 1, 1), gloss=1.0, ior=1.5),               # 3 glass
         mat(abi.MATERIAL_STANDARD, (0.1, 0.2, 0.5)),                               # 4 small sphere
         mat(abi.MATERIAL_STANDARD, (0.9, 0.9, 0.9), gloss=0.4, metallic=0.3),      # 5 glossy part-metal wedge
+        mat(abi.MATERIAL_STANDARD, (0.3, 0.3, 0.3), emission=(9.0, 8.0, 6.0)),     # 6 light panel
     ], dtype=abi.MATERIAL_DTYPE)
     tris = []
     g = 12.0
@@ -305,6 +307,9 @@ def make_mesh_scene(max_bvh_depth=16, subdivisions=1):
         tris.append(make_triangle(p[a], p[c], p[b], 2))
     w = np.array([(0.3, 0.0, -3.2), (1.5, 0.0, -2.7), (0.8, 1.1, -3.0)], np.float32)
     tris.append(make_triangle(w[0], w[1], w[2], 5))          # a lone two-sided wedge (hit from both faces)
+    if emissive:
+        l = [(-2.5, 4.0, -2.5), (2.5, 4.0, -2.5), (2.5, 4.0, 2.5), (-2.5, 4.0, 2.5)]
+        tris += [make_triangle(l[0], l[1], l[2], 6), make_triangle(l[0], l[2], l[3], 6)]
     spheres = np.zeros(3, dtype=abi.SPHERE_DTYPE)
     spheres[0] = ((-1.9, 0.7, -1.2), 0.7, 3, (0, 0, 0))
     spheres[1] = ((-1.9, 0.7, -1.2), -0.62, 3, (0, 0, 0))
@@ -315,7 +320,7 @@ def make_mesh_scene(max_bvh_depth=16, subdivisions=1):
     cam.aperture = 0.0
     cam.vertical_fov = 32.0
     env = abi.Environment()
-    env.sky_type = abi.SKY_GRADIENT
+    env.sky_type = abi.SKY_NONE if emissive else abi.SKY_GRADIENT
     env.sky_bottom_color[:] = (1.0, 1.0, 1.0)
     env.sky_top_color[:] = (0.5, 0.7, 1.0)
     focus = float(np.linalg.norm(np.array(cam.position[:]) - np.array(cam.target[:])))

@@ -167,6 +167,21 @@ def test_mesh_world_matches_the_oracle(rtb, oracle, ctx, kernel, depth, aperture
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
+@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+def test_emissive_panel_without_sky(rtb, oracle, ctx, kernel):
+    """Material.Emit (Material.cs:175-179) + SkyType.None: the overhead panel is the only light, so every pixel's
+    radiance is emission carried down the path by the attenuation product (SampleBatchJob.cs:383-396)."""
+    W, H, spp = 96, 54, 16
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=16, emissive=True)
+    p = rtb.host.make_params(scene, W, H, spp, 12)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    assert ref.rgb().max() > 0.5 and (ref.rgb().reshape(-1, 3).max(axis=1) == 0).mean() > 0.05   # lit floor, black sky
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    got = render_gpu(rtb, ctx, scene, p, W, H, k)
+    assert_parity(ref, got, exact=(kernel == "simple"))
+
+
 def test_world_upload_rejects_what_it_cannot_render(rtb, ctx):
     scene = rtb.host.make_mesh_scene()
     ents = scene.entities.copy()
