@@ -273,6 +273,13 @@ RTB_API int rtb_combine_device(rtb_ctx* ctx, int width, int height, int debug_mo
                                float* out_color3, float* out_normal3, float* out_albedo3,
                                void* cuda_stream);
 
+/* FinalizeTexturesJob (FinalizeTexturesJob.cs:23-55): saturate(LinearToGamma(x)) * 255 -> RGBA32 for the colour,
+ * normal * 0.5 + 0.5 and albedo images (float3 in, 4 bytes per pixel out).  Device pointers; any in/out pair may be NULL. */
+RTB_API int rtb_finalize_device(rtb_ctx* ctx, int width, int height,
+                                const float* color3, const float* normal3, const float* albedo3,
+                                uint32_t* out_color_rgba, uint32_t* out_normal_rgba, uint32_t* out_albedo_rgba,
+                                void* cuda_stream);
+
 /* ReduceMetricsJob (ReduceMetricsJob.cs:22-45) on device buffers. */
 typedef struct rtb_metrics {
   int64_t total_ray_count;

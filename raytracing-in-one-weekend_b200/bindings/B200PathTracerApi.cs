@@ -67,6 +67,10 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern RtbStatus rtb_sample_batch(IntPtr ctx, RtbBatchParams* p, RtbBatchBuffers* hostBuffers, bool* cancel);
 		[DllImport(Lib)] public static extern RtbStatus rtb_register_host_buffer(IntPtr ctx, void* ptr, UIntPtr bytes);
 		[DllImport(Lib)] public static extern RtbStatus rtb_unregister_host_buffer(IntPtr ctx, void* ptr);
+		[DllImport(Lib)] public static extern RtbStatus rtb_combine_device(IntPtr ctx, int width, int height, int debugMode, int ldrAlbedo,
+			float* color4, float* normal3, float* albedo3, float* outColor3, float* outNormal3, float* outAlbedo3, IntPtr cudaStream);
+		[DllImport(Lib)] public static extern RtbStatus rtb_finalize_device(IntPtr ctx, int width, int height,
+			float* color3, float* normal3, float* albedo3, uint* outColorRgba, uint* outNormalRgba, uint* outAlbedoRgba, IntPtr cudaStream);
 		// rtb_option (include/rtb.h): Counters = 1, Kernel = 2, CancelChunkRows = 3, LeafSpheres = 4, AlwaysWalkChains = 5, HostAccess = 6
 		[DllImport(Lib)] public static extern RtbStatus rtb_set_option(IntPtr ctx, int option, long value);
 		[DllImport(Lib)] public static extern RtbStatus rtb_last_kernel_ms(IntPtr ctx, out float ms);

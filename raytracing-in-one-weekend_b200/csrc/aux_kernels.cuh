@@ -2,6 +2,7 @@
 // reference's per-batch pipeline (Raytracer.cs:745-754, :844), as HBM-bound device kernels:
 //   combine_kernel         CombineJob.Execute        (Runtime/Jobs/CombineJob.cs:29-71)
 //   reduce_metrics_kernel  ReduceMetricsJob.Execute  (Runtime/Jobs/ReduceMetricsJob.cs:22-45)
+//   finalize_kernel        FinalizeTexturesJob.Execute (Runtime/Jobs/FinalizeTexturesJob.cs:23-55)
 #pragma once
 
 #include "kernel_common.cuh"
@@ -45,6 +46,30 @@ __global__ void combine_kernel(int width, int height, int debug_mode, int ldr_al
       nn = len2 > 1.175494351e-38f ? nn * um::rsqrt(len2) : um::mk(0.0f);
       out_normal[3 * (size_t)index] = nn.x; out_normal[3 * (size_t)index + 1] = nn.y; out_normal[3 * (size_t)index + 2] = nn.z;
     }
+  }
+}
+
+// MathExtensions.LinearToGamma (Util/MathExtensions.cs:17-21): max(1.055 * pow(max(v, 0), 0.416666667) - 0.055, 0),
+// then FinalizeTexturesJob's saturate(...) * 255 truncated to a byte.  pow through the shared exp2/log of umath.h.
+__device__ __forceinline__ uint32_t gamma_byte(float v) {
+  v = um::max(v, 0.0f);
+  const float p = v > 0.0f ? um::pow_pos(v, 0.416666667f) : 0.0f;
+  const float g = um::max(1.055f * p - 0.055f, 0.0f);
+  return (uint32_t)(um::saturate(g) * 255.0f);
+}
+__device__ __forceinline__ uint32_t rgba32(f3 c) {      // PixelFormats.RGBA32: r, g, b, a = 255 in memory order
+  return gamma_byte(c.x) | (gamma_byte(c.y) << 8) | (gamma_byte(c.z) << 16) | 0xff000000u;
+}
+
+// FinalizeTexturesJob: three float3 images -> three RGBA32 images (colour, normal * 0.5 + 0.5, albedo).
+// HBM-bound: 36 B read + 12 B written per pixel.  Any in/out pair may be NULL.
+__global__ void finalize_kernel(int n, const float* __restrict__ color, const float* __restrict__ normal,
+                                const float* __restrict__ albedo, uint32_t* __restrict__ out_color,
+                                uint32_t* __restrict__ out_normal, uint32_t* __restrict__ out_albedo) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (out_color) out_color[i] = rgba32(v3(color + 3 * (size_t)i));
+    if (out_normal) out_normal[i] = rgba32(v3(normal + 3 * (size_t)i) * 0.5f + um::mk(0.5f));
+    if (out_albedo) out_albedo[i] = rgba32(v3(albedo + 3 * (size_t)i));
   }
 }
 

@@ -917,6 +917,20 @@ int rtb_combine_device(rtb_ctx* ctx, int width, int height, int debug_mode, int 
   return RTB_OK;
 }
 
+int rtb_finalize_device(rtb_ctx* ctx, int width, int height, const float* color3, const float* normal3, const float* albedo3,
+                        uint32_t* out_color_rgba, uint32_t* out_normal_rgba, uint32_t* out_albedo_rgba, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (width < 1 || height < 1) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_finalize_device: bad size");
+  if ((out_color_rgba && !color3) || (out_normal_rgba && !normal3) || (out_albedo_rgba && !albedo3))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_finalize_device: missing input");
+  DeviceGuard g(ctx->device);
+  const int n = width * height;
+  const int grid = std::max(1, std::min((n + 255) / 256, ctx->sm_count * 16));
+  finalize_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(n, color3, normal3, albedo3, out_color_rgba, out_normal_rgba, out_albedo_rgba);
+  RTB_CUDA(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
 int rtb_reduce_metrics_device(rtb_ctx* ctx, int width, int height, const rtb_diagnostics* diagnostics, const float* color4,
                               const float* sample_count_weight, rtb_metrics* out_host, void* cuda_stream) {
   if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");

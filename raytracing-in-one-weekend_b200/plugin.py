@@ -17,7 +17,7 @@ EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
     "rtb_upload_scene", "rtb_upload_world", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
-    "rtb_combine_device", "rtb_reduce_metrics_device",
+    "rtb_combine_device", "rtb_finalize_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
 ]
 
@@ -56,6 +56,7 @@ def lib():
         L.rtb_register_host_buffer.argtypes = [vp, vp, sz]
         L.rtb_unregister_host_buffer.argtypes = [vp, vp]
         L.rtb_combine_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.rtb_finalize_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.rtb_reduce_metrics_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(abi.Metrics), vp]
         L.rtb_get_counters.argtypes = [vp, C.POINTER(abi.Counters)]
         L.rtb_set_option.argtypes = [vp, C.c_int, C.c_int64]
@@ -240,6 +241,13 @@ class Context:
         self._check(self._L.rtb_combine_device(self._h, width, height, int(debug_mode), int(ldr_albedo), ptr(color4),
                                                ptr(normal3), ptr(albedo3), ptr(out_color3), ptr(out_normal3),
                                                ptr(out_albedo3), stream))
+
+    def finalize_device(self, width, height, color3, normal3, albedo3, out_color, out_normal, out_albedo, stream=None):
+        """FinalizeTexturesJob on device buffers: float3 images -> RGBA32 (one uint32 per pixel)."""
+        def ptr(x):
+            return None if x is None else (x.data_ptr() if hasattr(x, "data_ptr") else int(x))
+        self._check(self._L.rtb_finalize_device(self._h, width, height, ptr(color3), ptr(normal3), ptr(albedo3), ptr(out_color),
+                                                ptr(out_normal), ptr(out_albedo), stream))
 
     def reduce_metrics_device(self, width, height, diagnostics, color4, weight, stream=None):
         def ptr(x):
