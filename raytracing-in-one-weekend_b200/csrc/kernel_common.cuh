@@ -183,6 +183,11 @@ struct SceneView {
   __device__ __forceinline__ void bind(const unsigned char* base, const SceneDesc& d) {
     g = base;
     s = SMEM ? smem_u32(base) : 0u;
+#ifndef RTB_NO_OPAQUE_SMEM_BASE
+    // opaque to the optimiser: otherwise it rebuilds the window address (S2UR CgaCtaId, UMOV, ULEA) around every group
+    // of loads instead of keeping it in a register (3 of the walk's 65 instructions per node; measured 148.4 -> 144.5 ms)
+    asm volatile("mov.u32 %0, %0;" : "+r"(s));
+#endif
     inner_off = d.inner_off; sphere_off = d.sphere_off; leaf_count_off = d.leaf_count_off; mat_index_off = d.mat_index_off;
     tri_off = d.tri_off;
   }
@@ -282,13 +287,8 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
 #if !defined(RTB_NO_ROOT_SHORTCUTS)
   if (disc > 0.0f && !(c > 0.0f && b >= 0.0f)) {
     const float sq = um::sqrt(disc);
-    float t;
-    if (c > 0.0f) {
-      t = um::div(-b - sq, a);
-      if (!(t > 0.0f)) t = um::div(-b + sq, a);      // t1 rounded to 0: the reference moves on to t2
-    } else {
-      t = um::div(-b + sq, a);
-    }
+    float t = um::div(c > 0.0f ? -b - sq : -b + sq, a);
+    if (c > 0.0f && !(t > 0.0f)) t = um::div(-b + sq, a);      // t1 rounded to 0: the reference moves on to t2
 #else
   if (disc > 0.0f) {
     float sq = um::sqrt(disc);
@@ -357,6 +357,10 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 constexpr float kPruneMargin = 1.0005f;
 constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
 
+#ifndef RTB_LEAF_UNROLL
+#define RTB_LEAF_UNROLL 1
+#endif
+constexpr int kLeafUnroll = RTB_LEAF_UNROLL;   // unrolling of the multi-entity leaf loop (single-entity leaves have their own path)
 #ifndef RTB_TRAVERSAL
 #define RTB_TRAVERSAL 0   // 0: one node (inner or leaf) per loop trip (measured fastest on B200); 1: while-while (inner run, then leaf run)
 #endif
@@ -380,16 +384,31 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   stack[0] = kTraversalDone;
   int sp = 1;
   int cur = sd.root_ref;
+  auto test_prim = [&](int slot) {
+    const float4 prim = sv.sphere(slot);
+    if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx);
+    else sphere_hit<(FLAVOR >= kFlavorChains)>(sd, prim, slot, o, d, inv, a, best_t, best_idx);
+  };
   auto test_leaf = [&](int ref) {
     const uint32_t code = (uint32_t)~ref;
     const int first = (int)(code >> 4);
-    int count = (int)(code & 15u) + 1;
-    if (count == 16) count = (int)sv.leaf_count(first);
-    for (int i = 0; i < count; i++) {
-      const float4 prim = sv.sphere(first + i);
-      if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), first + i, o, d, best_t, best_idx);
-      else sphere_hit<(FLAVOR >= kFlavorChains)>(sd, prim, first + i, o, d, inv, a, best_t, best_idx);
+    if ((code & 15u) == 0u) {            // the common leaf: one entity (BvhNodeData.cs:155 splits down to n <= 1)
+      test_prim(first);
+      if (COUNTERS) wc.sphere_tests++;
+      return;
     }
+    int count = (int)(code & 15u) + 1;
+    if (count == 16) {                   // a big leaf (a "linear hit list" is one leaf holding the world): unrolled in the lean builds
+      count = (int)sv.leaf_count(first);
+      if (FLAVOR < kFlavorGeneral) {
+#pragma unroll 4
+        for (int i = 0; i < count; i++) test_prim(first + i);
+        if (COUNTERS) wc.sphere_tests += count;
+        return;
+      }
+    }
+#pragma unroll kLeafUnroll
+    for (int i = 0; i < count; i++) test_prim(first + i);
     if (COUNTERS) wc.sphere_tests += count;
   };
 #if RTB_TRAVERSAL == 2

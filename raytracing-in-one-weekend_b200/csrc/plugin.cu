@@ -431,7 +431,8 @@ void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp);
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
 int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_spp) {
-  const size_t smem = mega_smem_bytes(a.scene.blob_bytes, SMEM);
+  constexpr int kMegaBlock = mega_block(FLAVOR), kMegaWarps = kMegaBlock / 32;
+  const size_t smem = mega_smem_bytes(a.scene.blob_bytes, SMEM, FLAVOR);
   auto kernel = sample_megakernel<SMEM, COUNTERS, FLAVOR>;
   if (!ctx->smem_attr_set[SMEM][COUNTERS + 2 * FLAVOR]) {
     RTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
@@ -555,11 +556,11 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     else rc = counters ? launch_pool_t<false, true>(ctx, a, stream, max_spp) : launch_pool_t<false, false>(ctx, a, stream, max_spp);
     if (rc != RTB_OK) return rc;
   } else {
-    const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
-                      ctx->scene.blob_bytes < (1u << 20);
-    int rc;
     // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
     const int flavor = (counters || ctx->scene.n_triangles) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
+    const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true, flavor) <= (size_t)ctx->max_smem_optin &&
+                      ctx->scene.blob_bytes < (1u << 20);
+    int rc;
     if (fits) rc = counters ? launch_mega_t<true, true, kFlavorGeneral>(ctx, a, stream, max_spp)
                    : flavor == kFlavorGeneral ? launch_mega_t<true, false, kFlavorGeneral>(ctx, a, stream, max_spp)
                    : flavor == kFlavorChains ? launch_mega_t<true, false, kFlavorChains>(ctx, a, stream, max_spp)

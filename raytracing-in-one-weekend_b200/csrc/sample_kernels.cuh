@@ -21,8 +21,12 @@ namespace rtbk {
 #ifndef RTB_MEGA_MIN_BLOCKS
 #define RTB_MEGA_MIN_BLOCKS 1
 #endif
-constexpr int kMegaBlock = RTB_MEGA_BLOCK;
-constexpr int kMegaWarps = kMegaBlock / 32;
+#ifndef RTB_MEGA_BLOCK_GENERAL
+#define RTB_MEGA_BLOCK_GENERAL 896    // the general flavour (triangles) needs 72 registers to stay out of local memory
+#endif
+// Threads per CTA by kernel flavour (measured on B200, profiles/README.md): 1024 x 64 registers for the lean sphere
+// builds, 896 x 72 registers for the general build.
+constexpr int mega_block(int flavor) { return flavor >= kFlavorGeneral ? RTB_MEGA_BLOCK_GENERAL : RTB_MEGA_BLOCK; }
 constexpr float kFixedScale = 4294967296.0f;            // 2^32
 constexpr float kFixedInvScale = 2.3283064365386963e-10f;  // 2^-32
 constexpr int kAccValues = 10;           // color.xyz, normal.xyz, albedo.xyz, sampleCountWeight
@@ -80,11 +84,11 @@ __device__ __forceinline__ float fixed_read(const WarpTile& t, int slot, int v) 
   return __ll2float_rn(q) * kFixedInvScale;
 }
 
-__host__ __device__ inline size_t mega_smem_bytes(uint32_t blob_bytes, bool scene_in_smem) {
+__host__ __device__ inline size_t mega_smem_bytes(uint32_t blob_bytes, bool scene_in_smem, int flavor) {
   size_t s = 16;  // mbarrier
   if (scene_in_smem) s += blob_bytes;
   s = (s + 15) & ~(size_t)15;
-  return s + sizeof(WarpTile) * kMegaWarps;
+  return s + sizeof(WarpTile) * (size_t)(mega_block(flavor) / 32);
 }
 
 // Active pixel k (0 <= k < n_active_pixels) -> image coordinates and the reference's index.
@@ -96,7 +100,7 @@ __device__ __forceinline__ void active_pixel(const BatchArgs& a, uint32_t k, int
 }
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
-__global__ void __launch_bounds__(kMegaBlock, RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* blob_smem = smem + 16;
