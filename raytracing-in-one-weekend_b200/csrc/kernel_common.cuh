@@ -32,8 +32,10 @@ using um::f3;
 //                    q1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
 //                    q2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)
 //                    q3 = (left_ref, right_ref, -, -) as int32
-//                  ref >= 0: inner node index; ref < 0: leaf, ~ref = first sphere << 4 | (count - 1)
-//                  (count - 1 == 15: the count is leaf_count[first])
+//                  ref >= 0: inner node, byte offset of its record (index * 64);
+//                  ref < 0: leaf, ~ref = byte offset of its first slot in `spheres` | (count - 1)
+//                  (count - 1 == 15: the count is leaf_count[first slot])
+//                  Entities are named by the byte offset of their slot ("slot" below) everywhere in the kernels.
 //   spheres      : n_spheres * 16 B  float4 (center.xyz, radius), depth-first leaf order
 //   leaf_count   : n_spheres * 4 B   sphere count of the leaf that STARTS at this sphere
 //   mat_index    : n_spheres * 4 B   material index of the sphere
@@ -208,10 +210,12 @@ struct SceneView {
     }
     return __ldg(reinterpret_cast<const uint32_t*>(g + off));
   }
-  __device__ __forceinline__ float4 node(int index, int k) const { return ld4(inner_off + (uint32_t)index * 64u + (uint32_t)k * 16u); }
-  __device__ __forceinline__ float4 sphere(int i) const { return ld4(sphere_off + (uint32_t)i * 16u); }
-  __device__ __forceinline__ uint32_t leaf_count(int i) const { return ld1(leaf_count_off + (uint32_t)i * 4u); }
-  __device__ __forceinline__ uint32_t material_of(int i) const { return ld1(mat_index_off + (uint32_t)i * 4u); }
+  // `ref` = an inner child ref: the byte offset of the node record (the inner section starts the blob)
+  __device__ __forceinline__ float4 node(int ref, int k) const { return ld4((uint32_t)ref + (uint32_t)k * 16u); }
+  // `slot` = byte offset of an entity's 16-byte slot in the blob
+  __device__ __forceinline__ float4 sphere(int slot) const { return ld4((uint32_t)slot); }
+  __device__ __forceinline__ uint32_t leaf_count(int slot) const { return ld1(leaf_count_off + (((uint32_t)slot - sphere_off) >> 2)); }
+  __device__ __forceinline__ uint32_t material_of(int slot) const { return ld1(mat_index_off + (((uint32_t)slot - sphere_off) >> 2)); }
 };
 
 struct WorkCounters {           // per-thread tallies of the instrumented build
@@ -239,8 +243,8 @@ constexpr int kFlavorGeneral = 2;        // + EntityType.Triangle entities
 
 // The host boxes between a collapsed device leaf and sphere `idx`, applied exactly as the reference
 // would (FindHitCandidates reaches a sphere only through a chain of hit boxes, SampleBatchJob.cs:420-447).
-__device__ __noinline__ bool chain_boxes_hit(const SceneDesc& sd, int idx, f3 o, f3 inv) {
-  const uint32_t ref = __ldg(sd.chain_ref + idx);
+__device__ __noinline__ bool chain_boxes_hit(const SceneDesc& sd, int slot, f3 o, f3 inv) {
+  const uint32_t ref = __ldg(sd.chain_ref + (((uint32_t)slot - sd.sphere_off) >> 4));
   const float4* b = sd.chain_boxes + 2 * (size_t)(ref & 0xffffffu);
   for (uint32_t k = ref >> 24; k > 0; k--, b += 2) {
     const float4 mn = __ldg(b), mx = __ldg(b + 1);
@@ -391,7 +395,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   };
   auto test_leaf = [&](int ref) {
     const uint32_t code = (uint32_t)~ref;
-    const int first = (int)(code >> 4);
+    const int first = (int)(code & ~15u);
     if ((code & 15u) == 0u) {            // the common leaf: one entity (BvhNodeData.cs:155 splits down to n <= 1)
       test_prim(first);
       if (COUNTERS) wc.sphere_tests++;
@@ -402,13 +406,13 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       count = (int)sv.leaf_count(first);
       if (FLAVOR < kFlavorGeneral) {
 #pragma unroll 4
-        for (int i = 0; i < count; i++) test_prim(first + i);
+        for (int i = 0; i < count; i++) test_prim(first + 16 * i);
         if (COUNTERS) wc.sphere_tests += count;
         return;
       }
     }
 #pragma unroll kLeafUnroll
-    for (int i = 0; i < count; i++) test_prim(first + i);
+    for (int i = 0; i < count; i++) test_prim(first + 16 * i);
     if (COUNTERS) wc.sphere_tests += count;
   };
 #if RTB_TRAVERSAL == 2

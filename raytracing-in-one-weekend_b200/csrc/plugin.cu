@@ -250,6 +250,7 @@ struct Flattener {
       return leaf_ref(first, c);
     }
     const int32_t self = (int32_t)(inner.size() / 16);
+    if (self >= (1 << 24)) { error = "scene too large"; return 0; }
     inner.resize(inner.size() + 16, 0.0f);
     const rtb_bvh_node& l = nodes[nd.left];
     const rtb_bvh_node& r = nodes[nd.right];
@@ -262,7 +263,7 @@ struct Flattener {
     q[8] = r.bounds_min[2]; q[9] = r.bounds_max[0]; q[10] = r.bounds_max[1]; q[11] = r.bounds_max[2];
     memcpy(&q[12], &lref, 4);
     memcpy(&q[13], &rref, 4);
-    return self;
+    return self * 64;                   // inner refs are BYTE offsets of the node record in the blob (inner_off == 0)
   }
   // a chain holds at most 255 boxes
   bool path_len_ok(int32_t n) const {
@@ -344,6 +345,21 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   d.blob_bytes = (uint32_t)off;
   out->bytes.assign(off, 0);
   unsigned char* b = out->bytes.data();
+  // leaf refs leave the recursion as ~(first slot << 4 | count code); now that the layout is known they become
+  // ~(byte offset of the first slot in the blob | count code) (slots are 16 bytes, so the low 4 bits are free)
+  if (d.sphere_off + (n_dev + 1) * 16 >= (1ull << 31)) return "scene too large";
+  auto patch = [&](int32_t ref) {
+    if (ref >= 0) return ref;
+    const uint32_t code = (uint32_t)~ref;
+    return ~(int32_t)((d.sphere_off + (code >> 4) * 16u) | (code & 15u));
+  };
+  for (uint32_t i = 0; i < d.n_inner; i++) {
+    int32_t r[2];
+    memcpy(r, &f.inner[(size_t)i * 16 + 12], 8);
+    r[0] = patch(r[0]); r[1] = patch(r[1]);
+    memcpy(&f.inner[(size_t)i * 16 + 12], r, 8);
+  }
+  if (d.has_root) d.root_ref = patch(d.root_ref);
   if (d.n_inner) memcpy(b + d.inner_off, f.inner.data(), (size_t)d.n_inner * 64);
   for (size_t i = 0; i < n_dev; i++) {
     const uint32_t h = f.order[i];

@@ -464,13 +464,13 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
             }
           } else {
             const uint32_t code = (uint32_t)~cur;
-            const int first = (int)(code >> 4);
+            const int first = (int)(code & ~15u);
             int count = (int)(code & 15u) + 1;
             if (count == 16) count = (int)sv.leaf_count(first);
             for (int i = 0; i < count; i++) {
-              const float4 prim = sv.sphere(first + i);
-              if (prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), first + i, o, d, best_t, best_idx);
-              else sphere_hit<true>(sd, prim, first + i, o, d, inv, aa, best_t, best_idx);
+              const float4 prim = sv.sphere(first + 16 * i);
+              if (prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), first + 16 * i, o, d, best_t, best_idx);
+              else sphere_hit<true>(sd, prim, first + 16 * i, o, d, inv, aa, best_t, best_idx);
             }
             if (COUNTERS) wc.sphere_tests += count;
           }
