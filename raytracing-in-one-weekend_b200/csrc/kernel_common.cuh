@@ -267,6 +267,14 @@ __device__ __forceinline__ bool chain_guard(float a, float b, float oc2, float r
   return b <= 0.0f && disc >= a * (8.0e-3f * r2 + 2.0e-6f * (oc2 + r2)) && b * b <= 1.0e6f * (a * r2);
 }
 
+// The same slab arithmetic returning both ends: the box is hit iff *t_enter < *t_exit.
+__device__ __forceinline__ void aabb_range(f3 mn, f3 mx, f3 o, f3 inv, float* t_enter, float* t_exit) {
+  f3 t0 = (mn - o) * inv;
+  f3 t1 = (mx - o) * inv;
+  *t_enter = fmaxf(0.0f, fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z)));
+  *t_exit = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+}
+
 // HitTests.Hit(this Sphere) (HitTests.cs:23-60) behind Entity.HitInternal (Entity.cs:74-103)
 // for a static, unrotated entity: entity-space origin = o + (-center), direction unchanged.
 // `a` = dot(d, d) is hoisted out by the caller.  Updates (best_t, best_idx) when this sphere
@@ -490,12 +498,23 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     if (cur >= 0) {
       const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
       float tl, tr;
+#ifndef RTB_NO_FUSED_LIMIT
+      // "box hit (t_enter < t_exit) and not beyond the best hit (t_enter < limit)" as ONE comparison per child
+      // against min(t_exit, limit) (t_exit is never NaN: fminf/fmaxf drop NaN operands)
+      float xl, xr;
+      aabb_range(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl, &xl);
+      aabb_range(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr, &xr);
+      const float limit = best_t * kPruneMargin;
+      const bool hl = tl < fminf(xl, limit);
+      const bool hr = tr < fminf(xr, limit);
+#else
       bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
       bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
-      if (COUNTERS) wc.node_tests += 2;
       const float limit = best_t * kPruneMargin;
       hl = hl && tl < limit;
       hr = hr && tr < limit;
+#endif
+      if (COUNTERS) wc.node_tests += 2;
       const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
       if (hl && hr) {
         const bool left_first = tl <= tr;
