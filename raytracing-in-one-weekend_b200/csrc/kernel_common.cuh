@@ -494,6 +494,9 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     }
   }
 #else
+#ifndef RTB_INDEX_STACK
+  int* top = stack + 1;
+#endif
   for (;;) {
     if (cur >= 0) {
       const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
@@ -518,7 +521,11 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
       if (hl && hr) {
         const bool left_first = tl <= tr;
+#ifndef RTB_INDEX_STACK
+        *top++ = left_first ? right : left;
+#else
         stack[sp++] = left_first ? right : left;
+#endif
         cur = left_first ? left : right;
         continue;
       }
@@ -527,7 +534,11 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     } else {
       test_leaf(cur);
     }
+#ifndef RTB_INDEX_STACK
+    cur = *--top;
+#else
     cur = stack[--sp];
+#endif
     if (cur == kTraversalDone) break;
   }
 #endif
