@@ -373,6 +373,9 @@ constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an 
 #define RTB_LEAF_UNROLL 1
 #endif
 constexpr int kLeafUnroll = RTB_LEAF_UNROLL;   // unrolling of the multi-entity leaf loop (single-entity leaves have their own path)
+#ifndef RTB_SPLIT_TRIPS
+#define RTB_SPLIT_TRIPS 0   // 1: the lean builds also use one node (inner OR leaf) per trip
+#endif
 #ifndef RTB_TRAVERSAL
 #define RTB_TRAVERSAL 0   // 0: one node (inner or leaf) per loop trip (measured fastest on B200); 1: while-while (inner run, then leaf run)
 #endif
@@ -494,6 +497,46 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     }
   }
 #else
+  if (FLAVOR < kFlavorGeneral && !RTB_SPLIT_TRIPS) {
+  // The lean builds.  One trip = [box visit if the lane holds an inner node] -> [leaf test if it now holds a leaf] ->
+  // [pop if it needs one]: a lane that descends into a leaf tests it in the same trip, and every lane passes the pop
+  // once per trip (measured 131.4 -> 129.1 ms on config 3; the general flavour is faster with the split trips below).
+  {
+    int* top = stack + 1;
+    for (;;) {
+      bool need_pop = false;
+      if (cur >= 0) {
+        const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
+        float tl, tr, xl, xr;
+        aabb_range(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl, &xl);
+        aabb_range(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr, &xr);
+        const float limit = best_t * kPruneMargin;
+        const bool hl = tl < fminf(xl, limit);
+        const bool hr = tr < fminf(xr, limit);
+        if (COUNTERS) wc.node_tests += 2;
+        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+        if (hl && hr) {
+          const bool left_first = tl <= tr;
+          *top++ = left_first ? right : left;
+          cur = left_first ? left : right;
+        } else if (hl || hr) {
+          cur = hl ? left : right;
+        } else {
+          need_pop = true;
+        }
+      }
+      if (!need_pop && cur < 0) {
+        test_leaf(cur);
+        need_pop = true;
+      }
+      if (need_pop) {
+        cur = *--top;
+        if (cur == kTraversalDone) break;
+      }
+    }
+  }
+    return;
+  }
 #ifndef RTB_INDEX_STACK
   int* top = stack + 1;
 #endif
