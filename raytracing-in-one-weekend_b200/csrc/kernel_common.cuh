@@ -657,29 +657,36 @@ struct PathRay {
 
 // View.GetRay (View.cs:38-48) with the uv of SampleBatchJob.cs:134.  The ray-time draw
 // (View.cs:47, slot 4) is not generated: nothing on the supported path reads Ray.Time.
-__device__ __forceinline__ PathRay camera_ray(const rtb_batch_params& p, int cx, int cy, uint32_t pixel, uint32_t sample) {
+// Split in two so that a kernel can draw the Philox block and evaluate the sincos for camera rays and for bounces in
+// ONE converged step (sample_megakernel): camera_ray_finish consumes the block r = Philox(pixel, sample, CAMERA, 0) and
+// (s, c) = sincos(u2f(r.z) * 2 PI) — RandomSource.InUnitDisk's theta = u * (2 PI - 0) + 0 is the same float.
+__device__ __forceinline__ PathRay camera_ray_finish(const rtb_batch_params& p, int cx, int cy, uint4 r, float s, float c) {
   const rtb_view& v = p.view;
   const bool lens = v.lens_radius != 0;
   float jx = 0.5f, jy = 0.5f, rdx = 0, rdy = 0;
-  if (p.sub_pixel_jitter || lens) {
-    uint4 r = philox4x32_10(pixel, sample, kBounceCamera, 0, p.seed, kPhiloxKey1);
-    if (p.sub_pixel_jitter) { jx = u2f(r.x); jy = u2f(r.y); }
-    if (lens) {  // RandomSource.InUnitDisk (RandomSource.cs:40-61)
-      float theta = u2f(r.z) * (2 * um::PI - 0) + 0;
-      float radius = um::sqrt(u2f(r.w));
-      float s, c;
-      um::sincos(theta, &s, &c);   // theta == u * 2 * PI bit for bit (see unit_angle_sincos)
-      rdx = v.lens_radius * (radius * c);
-      rdy = v.lens_radius * (radius * s);
-    }
+  if (p.sub_pixel_jitter) { jx = u2f(r.x); jy = u2f(r.y); }
+  if (lens) {  // RandomSource.InUnitDisk (RandomSource.cs:40-61)
+    float radius = um::sqrt(u2f(r.w));
+    rdx = v.lens_radius * (radius * c);
+    rdy = v.lens_radius * (radius * s);
   }
   float nx = um::div((float)cx + jx, p.size[0]);
   float ny = um::div((float)cy + jy, p.size[1]);
   f3 offset = v3(v.right) * rdx + v3(v.up) * rdy;
-  PathRay r;
-  r.d = um::normalize(v3(v.lower_left_corner) - offset + nx * v3(v.horizontal) + ny * v3(v.vertical));
-  r.o = v3(v.origin) + offset;
-  return r;
+  PathRay ray;
+  ray.d = um::normalize(v3(v.lower_left_corner) - offset + nx * v3(v.horizontal) + ny * v3(v.vertical));
+  ray.o = v3(v.origin) + offset;
+  return ray;
+}
+__device__ __forceinline__ PathRay camera_ray(const rtb_batch_params& p, int cx, int cy, uint32_t pixel, uint32_t sample) {
+  const bool lens = p.view.lens_radius != 0;
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  float s = 0, c = 1;
+  if (p.sub_pixel_jitter || lens) {
+    r = philox4x32_10(pixel, sample, kBounceCamera, 0, p.seed, kPhiloxKey1);
+    if (lens) unit_angle_sincos(u2f(r.z), &s, &c);
+  }
+  return camera_ray_finish(p, cx, cy, r, s, c);
 }
 
 struct ScatterResult {
@@ -696,22 +703,42 @@ struct ScatterResult {
 // the pieces every material needs are executed ONCE, converged, with per-lane operands — one Philox
 // block (its index is the only per-material difference), one sincos, one cosine-hemisphere sample —
 // and only the short material-specific tails diverge.
-__device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N,
-                                                 uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
-  ScatterResult out;
-  out.reflectance = um::mk(m0.x, m0.y, m0.z);
-  const bool standard = __float_as_uint(m0.w) == RTB_MATERIAL_STANDARD;   // else Dielectric (upload rejects the rest)
+struct ScatterPlan {   // what a bounce needs from the shared draw step: which Philox block, and whether sincos(u2f(r.y) * 2 PI)
+  bool standard, pure_diffuse, need_angle;
+  uint32_t block;
+};
+__device__ __forceinline__ ScatterPlan scatter_plan(float4 m0, float4 m1, float4 m2) {
+  ScatterPlan pl;
+  pl.standard = __float_as_uint(m0.w) == RTB_MATERIAL_STANDARD;   // else Dielectric (upload rejects the rest)
   const float glossiness = m1.w, metallic = m2.x, roughness = m2.w;
   // With glossiness == 0 the reflection chance saturate(fresnel * 0 * G) is exactly 0 and with
   // metallic == 0 the rough normal has no other consumer: the first draw pair (slots 0,1) is skipped
   // and the diffuse draw (block 1) is the only one — same result as evaluating Material.cs:83-89.
-  const bool pure_diffuse = standard && glossiness == 0.0f && metallic == 0.0f;
-  const uint4 r = philox4x32_10(pixel, sample, bounce, pure_diffuse ? 1u : 0u, seed, kPhiloxKey1);
-  const float ux = u2f(r.x), uy = u2f(r.y);
+  pl.pure_diffuse = pl.standard && glossiness == 0.0f && metallic == 0.0f;
+  pl.block = pl.pure_diffuse ? 1u : 0u;
   // Dielectric with roughness 0: normalize(N + 0 * randomDirection) == normalize(N); the direction is not evaluated.
-  const bool need_angle = standard ? (pure_diffuse || roughness > 0) : (roughness > 0);
+  pl.need_angle = pl.standard ? (pl.pure_diffuse || roughness > 0) : (roughness > 0);
+  return pl;
+}
+__device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, ScatterPlan pl,
+                                                        uint4 r, float sn, float cs,
+                                                        uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed);
+__device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N,
+                                                 uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
+  const ScatterPlan pl = scatter_plan(m0, m1, m2);
+  const uint4 r = philox4x32_10(pixel, sample, bounce, pl.block, seed, kPhiloxKey1);
   float sn = 0, cs = 1;
-  if (need_angle) unit_angle_sincos(uy, &sn, &cs);
+  if (pl.need_angle) unit_angle_sincos(u2f(r.y), &sn, &cs);
+  return scatter_finish(m0, m1, m2, m3, D, N, pl, r, sn, cs, pixel, sample, bounce, seed);
+}
+__device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, ScatterPlan pl,
+                                                        uint4 r, float sn, float cs,
+                                                        uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
+  ScatterResult out;
+  out.reflectance = um::mk(m0.x, m0.y, m0.z);
+  const bool standard = pl.standard, pure_diffuse = pl.pure_diffuse, need_angle = pl.need_angle;
+  const float glossiness = m1.w, metallic = m2.x, roughness = m2.w;
+  const float ux = u2f(r.x);
   f3 hemi = N;
   if (standard && need_angle) hemi = cosine_hemisphere(N, ux, sn, cs);
 

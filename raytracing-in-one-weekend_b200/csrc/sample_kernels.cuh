@@ -153,39 +153,52 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
   uint32_t tile_base = 0, next_item = 0, total_items = 0;
   int tile_n = 0;
 
-  for (;;) {
-    // (1) refill dead lanes from the tile's work stream
-    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
-    if (need) {
-      const uint32_t my_item = next_item + __popc(need & lt_mask);
-      if (!alive && my_item < total_items) {
-        // item -> (pixel slot, sample) through the tile's prefix table
-        int lo = 0, hi = tile_n;   // find the last slot with prefix[slot] <= my_item
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (tile.prefix[mid] <= my_item) lo = mid; else hi = mid;
-        }
-        slot = lo;
-        sample = my_item - tile.prefix[lo];
-        int cx, cy;
-        active_pixel(a, tile_base + (uint32_t)slot, &cx, &cy, &pixel);
-        ray = camera_ray(p, cx, cy, pixel, sample);
-        alive = true;
-        depth = 0;
-        first_non_specular = false;
-        throughput = um::mk(1.0f);
-        radiance = um::mk(0.0f);
-        set_normal(um::mk(0.0f));
-        set_albedo(um::mk(0.0f));
-        events_acc = 0;
-        inv_pow2depth = 1;
-        path_rays = 0;
-      }
-      next_item = min(next_item + (uint32_t)__popc(need), total_items);
+  // A finished path (sky reached: success; TraceDepth exhausted: failed, SampleBatchJob.cs:379-381) is added to the
+  // lane's private partial sums for its pixel; the lane is then free for the tile's next pixel-sample.
+  auto finish_path = [&](bool success) {
+    alive = false;
+    if (acc_slot != slot) {
+      if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
+      acc_slot = slot;
     }
+    if (COUNTERS) {
+      atomicAdd(&tile.node_tests[slot], wc.node_tests);
+      atomicAdd(&tile.sphere_tests[slot], wc.sphere_tests);
+      if (a.counters) {
+        if (wc.shade_standard) atomicAdd(&a.counters[4], (unsigned long long)wc.shade_standard);
+        if (wc.shade_dielectric) atomicAdd(&a.counters[5], (unsigned long long)wc.shade_dielectric);
+      }
+      wc = WorkCounters();
+    }
+    uint32_t counts = tile.lane_counts[lane] + path_rays;
+    if (success) {
+      const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, tile.aov[0][lane], tile.aov[1][lane], tile.aov[2][lane],
+                                      tile.aov[3][lane], tile.aov[4][lane], tile.aov[5][lane], events_acc};
+      bool finite = true;
+#pragma unroll
+      for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
+      if (finite) {
+#pragma unroll
+        for (int k = 0; k < kAccValues; k++) lane_add(tile, lane, k, vals[k]);
+      } else {
+        tile.non_finite[slot] = 1;
+      }
+      counts += 1u << 20;
+    }
+    tile.lane_counts[lane] = counts;
+    // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps
+    if ((counts >> 20) >= 2048u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
+  };
 
-    // (2) nothing in flight and nothing left in the tile: retire it, fetch the next one
-    if (__ballot_sync(0xffffffffu, alive) == 0) {
+  // One trip of the loop, for every lane of the warp:
+  //   (1) walk    closest hit for the lane's ray; a ray that leaves the world ends its path here (sky, accumulate)
+  //   (2) refill  lanes without a path take the tile's next pixel-samples (ballot / popc compaction of the work stream)
+  //   (3) draw    ONE converged step serves both kinds of lanes: the Philox block of the bounce (hit lanes) or of the
+  //               camera ray (refilled lanes), and the sincos both need
+  //   (4) shade   hit lanes finish Material.Scatter and form the next ray; refilled lanes form their camera ray
+  for (;;) {
+    // nothing in flight and nothing left in the tile: retire it, claim the next one
+    if (__ballot_sync(0xffffffffu, alive) == 0 && next_item >= total_items) {
       if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
       acc_slot = -1;
       __syncwarp();
@@ -262,53 +275,26 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       if (lane == 0) tile.prefix[tile_n] = total_items;
       next_item = 0;
       __syncwarp();
-      continue;
     }
 
-    // (3) one bounce for every live lane (SampleBatchJob.cs:184-377)
+    // (1) one walk for every live lane (SampleBatchJob.cs:184-206, 341-374)
+    bool hit = false;
+    float t_hit = 0;
+    float4 m0 = make_float4(0, 0, 0, 0), m1 = m0, m2 = m0, m3 = m0;
+    f3 N = um::mk(0.0f), P = um::mk(0.0f);
     if (alive) {
-      float t_hit;
       int hit_idx;
       closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
       path_rays++;
-      bool finished = false, success = false;
       if (hit_idx >= 0) {
+        hit = true;
         const float4 s = sv.sphere(hit_idx);
         const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
-        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+        m0 = __ldg(mp); m1 = __ldg(mp + 1); m2 = __ldg(mp + 2); m3 = __ldg(mp + 3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
-        const f3 N = hit_normal<SMEM, (FLAVOR >= kFlavorGeneral)>(sv, s, ray.o, ray.d, t_hit);
-        const f3 P = um::mad(ray.d, t_hit, ray.o);
-        const ScatterResult sc = scatter(m0, m1, m2, m3, ray.d, N, pixel, sample, (uint32_t)depth, p.seed);
-        if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
-        const f3 emission = um::mk(m1.x, m1.y, m1.z);
-        if (depth == 0) {
-          set_normal(N);
-          if (sample == 0) { tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z; }
-        }
-        if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
-          const f3 s_albedo = emission + sc.reflectance;
-          set_albedo(s_albedo);
-          set_normal(N);
-          first_non_specular = true;
-          if (sample == 0) {
-            tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z;
-            tile.fallback[slot][3] = s_albedo.x; tile.fallback[slot][4] = s_albedo.y; tile.fallback[slot][5] = s_albedo.z;
-          }
-        }
-        // forward form of the emission/attenuation unstack (SampleBatchJob.cs:383-396)
-        radiance = um::mad(throughput, emission, radiance);
-        throughput = throughput * sc.reflectance;
-        // RandomEvents / pow(2, depth) (SampleBatchJob.cs:332): dividing by a power of two == multiplying by its inverse, exactly
-        events_acc += sc.random_events * inv_pow2depth;
-        // next ray (SampleBatchJob.cs:335-336, Ray.cs:18)
-        const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
-        ray.o = um::mad(off_n, 0.001f, P);
-        ray.d = sc.dir;
-        depth++;
-        inv_pow2depth *= 0.5f;
-        if (depth == p.trace_depth) finished = true;   // failed sample (:379-381)
+        N = hit_normal<SMEM, (FLAVOR >= kFlavorGeneral)>(sv, s, ray.o, ray.d, t_hit);
+        P = um::mad(ray.d, t_hit, ray.o);
       } else {
         const f3 sky = sky_color(p.environment, ray.d);
         radiance = um::mad(throughput, sky, radiance);
@@ -321,43 +307,95 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
             tile.fallback[slot][3] = sky.x; tile.fallback[slot][4] = sky.y; tile.fallback[slot][5] = sky.z;
           }
         }
-        finished = true;
-        success = true;
+        finish_path(true);
       }
-      if (finished) {
-        alive = false;
-        if (acc_slot != slot) {
-          if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
-          acc_slot = slot;
+    }
+
+    // (2) refill dead lanes from the tile's work stream
+    bool fresh = false;
+    int cx = 0, cy = 0;
+    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+    if (need) {
+      const uint32_t my_item = next_item + __popc(need & lt_mask);
+      if (!alive && my_item < total_items) {
+        // item -> (pixel slot, sample) through the tile's prefix table
+        int lo = 0, hi = tile_n;   // find the last slot with prefix[slot] <= my_item
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (tile.prefix[mid] <= my_item) lo = mid; else hi = mid;
         }
-        if (COUNTERS) {
-          atomicAdd(&tile.node_tests[slot], wc.node_tests);
-          atomicAdd(&tile.sphere_tests[slot], wc.sphere_tests);
-          if (a.counters) {
-            if (wc.shade_standard) atomicAdd(&a.counters[4], (unsigned long long)wc.shade_standard);
-            if (wc.shade_dielectric) atomicAdd(&a.counters[5], (unsigned long long)wc.shade_dielectric);
-          }
-          wc = WorkCounters();
-        }
-        uint32_t counts = tile.lane_counts[lane] + path_rays;
-        if (success) {
-          const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, tile.aov[0][lane], tile.aov[1][lane], tile.aov[2][lane],
-                                          tile.aov[3][lane], tile.aov[4][lane], tile.aov[5][lane], events_acc};
-          bool finite = true;
-#pragma unroll
-          for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
-          if (finite) {
-#pragma unroll
-            for (int k = 0; k < kAccValues; k++) lane_add(tile, lane, k, vals[k]);
-          } else {
-            tile.non_finite[slot] = 1;
-          }
-          counts += 1u << 20;
-        }
-        tile.lane_counts[lane] = counts;
-        // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps
-        if ((counts >> 20) >= 2048u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
+        slot = lo;
+        sample = my_item - tile.prefix[lo];
+        active_pixel(a, tile_base + (uint32_t)slot, &cx, &cy, &pixel);
+        fresh = true;
+        depth = 0;
+        first_non_specular = false;
+        throughput = um::mk(1.0f);
+        radiance = um::mk(0.0f);
+        set_normal(um::mk(0.0f));
+        set_albedo(um::mk(0.0f));
+        events_acc = 0;
+        inv_pow2depth = 1;
+        path_rays = 0;
       }
+      next_item = min(next_item + (uint32_t)__popc(need), total_items);
+    }
+
+    // (3) the shared draw: Philox(pixel, sample, bounce | CAMERA, block) and sincos(u * 2 PI)
+    ScatterPlan pl{};
+    bool want_rng = false, want_angle = false;
+    uint32_t c2 = kBounceCamera, c3 = 0;
+    if (hit) {
+      pl = scatter_plan(m0, m1, m2);
+      c2 = (uint32_t)depth;
+      c3 = pl.block;
+      want_rng = true;
+      want_angle = pl.need_angle;
+    } else if (fresh) {
+      want_angle = p.view.lens_radius != 0;
+      want_rng = p.sub_pixel_jitter || want_angle;
+    }
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    float sn = 0, cs = 1;
+    if (want_rng) {
+      r = philox4x32_10(pixel, sample, c2, c3, p.seed, kPhiloxKey1);
+      if (want_angle) unit_angle_sincos(u2f(hit ? r.y : r.z), &sn, &cs);
+    }
+
+    // (4) shade / camera ray
+    if (hit) {
+      const ScatterResult sc = scatter_finish(m0, m1, m2, m3, ray.d, N, pl, r, sn, cs, pixel, sample, (uint32_t)depth, p.seed);
+      if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+      const f3 emission = um::mk(m1.x, m1.y, m1.z);
+      if (depth == 0) {
+        set_normal(N);
+        if (sample == 0) { tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z; }
+      }
+      if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
+        const f3 s_albedo = emission + sc.reflectance;
+        set_albedo(s_albedo);
+        set_normal(N);
+        first_non_specular = true;
+        if (sample == 0) {
+          tile.fallback[slot][0] = N.x; tile.fallback[slot][1] = N.y; tile.fallback[slot][2] = N.z;
+          tile.fallback[slot][3] = s_albedo.x; tile.fallback[slot][4] = s_albedo.y; tile.fallback[slot][5] = s_albedo.z;
+        }
+      }
+      // forward form of the emission/attenuation unstack (SampleBatchJob.cs:383-396)
+      radiance = um::mad(throughput, emission, radiance);
+      throughput = throughput * sc.reflectance;
+      // RandomEvents / pow(2, depth) (SampleBatchJob.cs:332): dividing by a power of two == multiplying by its inverse, exactly
+      events_acc += sc.random_events * inv_pow2depth;
+      // next ray (SampleBatchJob.cs:335-336, Ray.cs:18)
+      const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
+      ray.o = um::mad(off_n, 0.001f, P);
+      ray.d = sc.dir;
+      depth++;
+      inv_pow2depth *= 0.5f;
+      if (depth == p.trace_depth) finish_path(false);   // failed sample (:379-381)
+    } else if (fresh) {
+      ray = camera_ray_finish(p, cx, cy, r, sn, cs);
+      alive = true;
     }
     __syncwarp();
   }
