@@ -142,8 +142,8 @@ def cpu_reference(cfg, threads, target_seconds=12.0, steps=1, warmup=0):
     # Raytracer.cs:56-60; SampleBatchJob.cs:203,428,439), to set beside the pruned walk's executed counts
     d = buf.diagnostics
     rays = float(d["ray_count"].astype("float64").sum())
-    cpu_reference.work = {"rays": rays, "box_tests_per_ray": float(d["bounds_hit_count"].astype("float64").sum()) / max(rays, 1.0),
-                          "sphere_tests_per_ray": float(d["candidate_count"].astype("float64").sum()) / max(rays, 1.0)}
+    cpu_reference.work = {"rays": rays, "boxes_hit_per_ray": float(d["bounds_hit_count"].astype("float64").sum()) / max(rays, 1.0),
+                          "candidates_per_ray": float(d["candidate_count"].astype("float64").sum()) / max(rays, 1.0)}
     return vals, desc
 
 
