@@ -51,6 +51,7 @@ struct WarpTile {
   uint32_t non_finite[kTilePixelsMax];
   float fallback[kTilePixelsMax][6];     // first sample's normal/albedo (SampleBatchJob.cs:152-156)
   uint32_t prefix[kTilePixelsMax + 1];   // exclusive prefix of per-pixel sample counts
+  uint32_t pix_xy[kTilePixelsMax];       // image coordinates of the tile's pixels: x | y << 16
 };
 
 // lane-private += x (exact: x * 2^32 is an integer for |x| >= 2^-9, rounded to 2^-32 below that)
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         int cx, cy;
         uint32_t index;
         active_pixel(a, tile_base + (uint32_t)lane, &cx, &cy, &index);
+        tile.pix_xy[lane] = (uint32_t)cx | ((uint32_t)cy << 16);
         const float in_w = a.b.in_color[4 * (size_t)index + 3];
         const float in_weight = a.b.in_sample_count_weight[index];
         float scw;
@@ -326,7 +328,10 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         }
         slot = lo;
         sample = my_item - tile.prefix[lo];
-        active_pixel(a, tile_base + (uint32_t)slot, &cx, &cy, &pixel);
+        const uint32_t xy = tile.pix_xy[lo];
+        cx = (int)(xy & 0xffffu);
+        cy = (int)(xy >> 16);
+        pixel = (uint32_t)cy * (uint32_t)a.width + (uint32_t)cx;
         fresh = true;
         depth = 0;
         first_non_specular = false;
