@@ -826,6 +826,13 @@ __global__ void derive_materials_kernel(DevMaterial* m, uint32_t n) {
   m[i] = x;
 }
 
+// 2^-depth exactly as repeated halving produces it (normal, denormal, then 0)
+__device__ __forceinline__ float pow2_neg(uint32_t depth) {
+  if (depth <= 126u) return __uint_as_float((127u - depth) << 23);
+  if (depth <= 149u) return __uint_as_float(1u << (149u - depth));
+  return 0.0f;
+}
+
 // Sky (SampleBatchJob.cs:348-374; Environment.cs)
 __device__ __forceinline__ f3 sky_color(const rtb_environment& e, f3 d) {
   if (e.sky_type == RTB_SKY_GRADIENT)

@@ -71,13 +71,6 @@ __host__ __device__ inline size_t pool_smem_bytes(uint32_t blob_bytes, bool scen
   return s + sizeof(WarpPool) * kPoolWarps;
 }
 
-// 2^-depth exactly as repeated halving produces it (normal, denormal, then 0)
-__device__ __forceinline__ float pow2_neg(uint32_t depth) {
-  if (depth <= 126u) return __uint_as_float((127u - depth) << 23);
-  if (depth <= 149u) return __uint_as_float(1u << (149u - depth));
-  return 0.0f;
-}
-
 // Sum of a 64-bit two's-complement value over the warp (all 32 lanes call; every lane gets the sum).
 __device__ __forceinline__ unsigned long long warp_sum64(unsigned long long q) {
   const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);

@@ -140,10 +140,9 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
   bool first_non_specular = false;
   PathRay ray{um::mk(0.0f), um::mk(0.0f)};
   f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
-  float events_acc = 0, inv_pow2depth = 1;
+  float events_acc = 0;
   auto set_normal = [&](f3 n) { tile.aov[0][lane] = n.x; tile.aov[1][lane] = n.y; tile.aov[2][lane] = n.z; };
   auto set_albedo = [&](f3 c) { tile.aov[3][lane] = c.x; tile.aov[4][lane] = c.y; tile.aov[5][lane] = c.z; };
-  uint32_t path_rays = 0;
   int acc_slot = -1;          // pixel slot this lane's private partial sums belong to
   WorkCounters wc;
 #pragma unroll
@@ -171,7 +170,8 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       }
       wc = WorkCounters();
     }
-    uint32_t counts = tile.lane_counts[lane] + path_rays;
+    // bounce-loop iterations of this path (SampleBatchJob.cs:203): every hit so far, plus the miss that ended it
+    uint32_t counts = tile.lane_counts[lane] + (uint32_t)depth + (success ? 1u : 0u);
     if (success) {
       const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, tile.aov[0][lane], tile.aov[1][lane], tile.aov[2][lane],
                                       tile.aov[3][lane], tile.aov[4][lane], tile.aov[5][lane], events_acc};
@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     if (alive) {
       int hit_idx;
       closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
-      path_rays++;
       if (hit_idx >= 0) {
         hit = true;
         const float4 s = sv.sphere(hit_idx);
@@ -340,8 +339,6 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         set_normal(um::mk(0.0f));
         set_albedo(um::mk(0.0f));
         events_acc = 0;
-        inv_pow2depth = 1;
-        path_rays = 0;
       }
       next_item = min(next_item + (uint32_t)__popc(need), total_items);
     }
@@ -390,13 +387,12 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       radiance = um::mad(throughput, emission, radiance);
       throughput = throughput * sc.reflectance;
       // RandomEvents / pow(2, depth) (SampleBatchJob.cs:332): dividing by a power of two == multiplying by its inverse, exactly
-      events_acc += sc.random_events * inv_pow2depth;
+      events_acc += sc.random_events * pow2_neg((uint32_t)depth);
       // next ray (SampleBatchJob.cs:335-336, Ray.cs:18)
       const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
       ray.o = um::mad(off_n, 0.001f, P);
       ray.d = sc.dir;
       depth++;
-      inv_pow2depth *= 0.5f;
       if (depth == p.trace_depth) finish_path(false);   // failed sample (:379-381)
     } else if (fresh) {
       ray = camera_ray_finish(p, cx, cy, r, sn, cs);
