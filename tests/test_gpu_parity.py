@@ -182,6 +182,25 @@ def test_emissive_panel_without_sky(rtb, oracle, ctx, kernel):
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
+@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+def test_emissive_sphere_in_a_sphere_world(rtb, oracle, ctx, kernel):
+    """Material.Emit on sphere entities (the lean sphere build carries radiance along the path too)."""
+    W, H, spp = 80, 45, 16
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    scene.materials["emission"][scene.spheres["material"][5]] = (4.0, 3.0, 2.0)
+    scene.materials["emission"][scene.spheres["material"][40]] = (0.0, 2.5, 6.0)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    dark = rtb.host.make_scene("final", max_bvh_depth=16)
+    base = oracle.Buffers(W, H)
+    oracle.sample_batch(dark, p, base)
+    assert np.abs(ref.rgb() - base.rgb()).max() > 0.5            # the emitters are visible
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    got = render_gpu(rtb, ctx, scene, p, W, H, k)
+    assert_parity(ref, got, exact=(kernel == "simple"))
+
+
 def test_world_upload_rejects_what_it_cannot_render(rtb, ctx):
     scene = rtb.host.make_mesh_scene()
     ents = scene.entities.copy()
