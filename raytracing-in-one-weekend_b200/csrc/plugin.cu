@@ -540,7 +540,6 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   a.counters = counters ? ctx->d_counters : nullptr;
   const uint32_t max_spp = std::max(p.sample_count_range[0], p.sample_count_range[1]);
 
-  rtb_diagnostics* user_diag = dev.out_diagnostics;
   if (counters) {
     if (!a.b.out_diagnostics) {  // the counter pass reads the per-pixel diagnostics
       const size_t need = (size_t)width * height;
@@ -555,7 +554,6 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     }
     RTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
   }
-  (void)user_diag;
 
   int kernel_kind = (int)ctx->opt_kernel;
   if (kernel_kind == 0) kernel_kind = ctx->default_kernel;
