@@ -575,3 +575,27 @@ def test_finalize_device_matches_the_restated_job_and_runs_at_hbm_rate(rtb, orac
     gbs = 20 * n * 48 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
     print(f"finalize_kernel: {gbs:.0f} GB/s algorithmic")
     assert gbs > 2000
+
+
+def test_full_size_properties_config4(rtb, oracle, ctx):
+    """BASELINE config 4 at full size on one GPU (3840x2160, 1024 spp, depth 50: 8.5 G camera paths): every sample
+    accounted for, finite, radiance bounded by the sky, and one row checked against the oracle exactly."""
+    W, H, spp = 3840, 2160, 1024
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    a = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    cnt = a.out_color[:, 3]
+    assert cnt.max() == spp and cnt.min() >= spp // 2 and (W * H * spp - cnt.astype(np.int64).sum()) < 1e-3 * W * H * spp
+    assert np.isfinite(a.out_color).all()
+    rgb = a.rgb()
+    assert 0.0 <= rgb.min() and rgb.max() <= 1.0 + 1e-5
+    rays = a.diagnostics["ray_count"].astype(np.int64)
+    assert rays.min() >= spp and rays.sum() > 2 * W * H * spp
+    row = 700
+    pr = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1, row_begin=row, row_end=row + 1)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, pr, ref)
+    rs = slice(row * W, (row + 1) * W)
+    assert np.array_equal(ref.out_color[rs, 3], a.out_color[rs, 3])
+    assert np.array_equal(ref.diagnostics["ray_count"][rs], a.diagnostics["ray_count"][rs])
+    assert np.abs(ref.rgb()[row] - rgb[row]).max() <= RGB_TOL
