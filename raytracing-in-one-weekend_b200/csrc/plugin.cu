@@ -433,6 +433,8 @@ int validate_params(rtb_ctx* ctx, const rtb_batch_params* p, int* width, int* he
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "Size out of range");
   *width = (int)p->size[0];
   *height = (int)p->size[1];
+  if ((uint64_t)*width * (uint64_t)*height >= (1ull << 31))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "Size: more than 2^31 pixels");
   if (p->slice_divider < 1 || p->slice_offset < 0 || p->slice_offset >= p->slice_divider)
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "SliceOffset/SliceDivider invalid");
   if (p->trace_depth < 0 || p->trace_depth > 65535) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "TraceDepth out of range");
