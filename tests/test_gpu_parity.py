@@ -599,3 +599,17 @@ def test_full_size_properties_config4(rtb, oracle, ctx):
     assert np.array_equal(ref.out_color[rs, 3], a.out_color[rs, 3])
     assert np.array_equal(ref.diagnostics["ray_count"][rs], a.diagnostics["ray_count"][rs])
     assert np.abs(ref.rgb()[row] - rgb[row]).max() <= RGB_TOL
+
+
+@pytest.mark.parametrize("name,count,spp", [("final", 0, 8), ("stress", 10000, 4)])
+def test_full_frame_decisions_match_the_oracle(rtb, oracle, ctx, name, count, spp):
+    """Every pixel of a full 1920x1080 frame (config 3's camera, BVH + defocus, depth 50) at a few spp: per-pixel
+    successful-sample counts and ray counts equal the oracle's exactly, RGB within tolerance — 2 M pixels of evidence
+    that no path takes a different decision anywhere in the frame."""
+    W, H = 1920, 1080
+    scene = rtb.host.make_scene(name, max_bvh_depth=16, target_count=count)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    assert_parity(ref, got, exact=False)
