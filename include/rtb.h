@@ -139,7 +139,7 @@ typedef struct rtb_view {       /* View.cs:8-14, 88 bytes */
 typedef enum rtb_sky_type {     /* Environment.cs:5-10 */
   RTB_SKY_NONE = 0,
   RTB_SKY_GRADIENT = 1,
-  RTB_SKY_CUBEMAP = 2           /* not on the hot path: RTB_ERR_UNSUPPORTED */
+  RTB_SKY_CUBEMAP = 2           /* needs rtb_upload_sky_cubemap */
 } rtb_sky_type;
 
 typedef struct rtb_environment {/* Environment.cs:12-18 */
@@ -221,6 +221,13 @@ RTB_API int rtb_upload_world(rtb_ctx* ctx,
                              const rtb_triangle* triangles, size_t triangle_count,
                              const rtb_material* materials, size_t material_count,
                              const rtb_bvh_node* nodes, size_t node_count);
+
+/* Environment.SkyCubemap (Runtime/Texture.cs:141-211; the host builds it from the scene's HDRI sky,
+ * Raytracer.cs:663-665): six faces of R16G16B16A16_SFloat texels — the only format the reference accepts
+ * (Texture.cs:155-163) — in CubemapFace order +X, -X, +Y, -Y, +Z, -Z, each face_height rows of face_width
+ * texels of 4 halves.  Copied to the device; sampled (nearest texel, Cubemap.Sample) by batches whose
+ * environment.sky_type is RTB_SKY_CUBEMAP.  NULL removes it. */
+RTB_API int rtb_upload_sky_cubemap(rtb_ctx* ctx, const uint16_t* half_rgba, int face_width, int face_height);
 
 /* How rtb_upload_scene would lay this world out on the device (no device needed; for tests and
  * tuning).  `leaf_spheres` as RTB_OPT_LEAF_SPHERES. */

@@ -236,6 +236,21 @@ UM_HD float pow_pos(float x, float y) {           /* x > 0 */
   return exp2_poly(um::log(x) * LOG2E * y);
 }
 
+/* half -> float (IEEE binary16, exact), as (float)half does in Unity.Mathematics */
+UM_HD float half_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  if (e == 0) {
+    if (m == 0) return asfloat(sign);
+    int shift = 0;                                   /* subnormal: normalise */
+    while (!(m & 0x400u)) { m <<= 1; shift++; }
+    m &= 0x3ffu;
+    return asfloat(sign | ((uint32_t)(113 - shift) << 23) | (m << 13));
+  }
+  if (e == 31) return asfloat(sign | 0x7f800000u | (m << 13));
+  return asfloat(sign | ((e + 112u) << 23) | (m << 13));
+}
+
 } /* namespace um */
 
 #endif /* RTB_UMATH_H */

@@ -485,6 +485,35 @@ void FindHits(const Scene& sc, const Ray& ray, Work& w) {
                      [](const HitRecord& a, const HitRecord& b) { return a.Distance < b.Distance; });
 }
 
+// Cubemap (Texture.cs:141-211) over R16G16B16A16_SFloat faces; set by oracle_set_sky_cubemap (test infrastructure: one
+// global sky for the process, like Environment.SkyCubemap is one per job)
+const uint16_t* g_sky_faces = nullptr;
+int g_sky_w = 0, g_sky_h = 0;
+f3 CubemapSample(f3 vector) {
+  if (!g_sky_faces) return um::mk(0.0f);
+  const float absVector[4] = {um::abs(vector.x), um::abs(vector.y), um::abs(vector.z), 0.0f};
+  float maxDistance = um::max(um::max(um::max(absVector[0], absVector[1]), absVector[2]), absVector[3]);
+  int firstLane = 0;
+  while (firstLane < 3 && !(maxDistance == absVector[firstLane])) firstLane++;     // tzcnt(bitmask(maxDistance == absVector))
+  const float comp = firstLane == 0 ? vector.x : (firstLane == 1 ? vector.y : vector.z);
+  const bool positive = comp >= 0;
+  float u, v;
+  switch (firstLane) {
+    case 0: u = positive ? -vector.z : vector.z; v = -vector.y; break;
+    case 1: u = vector.x; v = positive ? vector.z : -vector.z; break;
+    default: u = positive ? vector.x : -vector.x; v = -vector.y; break;
+  }
+  u = um::div(u, absVector[firstLane > 2 ? 2 : firstLane]);
+  v = um::div(v, absVector[firstLane > 2 ? 2 : firstLane]);
+  const int halfW = g_sky_w / 2, halfH = g_sky_h / 2;
+  int cx = (int)((u + 1) * (float)halfW), cy = (int)((v + 1) * (float)halfH);
+  if (cx > g_sky_w - 1) cx = g_sky_w - 1;
+  if (cy > g_sky_h - 1) cy = g_sky_h - 1;
+  const int face = (firstLane > 2 ? 2 : firstLane) * 2 + (positive ? 0 : 1);
+  const uint16_t* px = g_sky_faces + ((size_t)face * g_sky_w * g_sky_h + (size_t)cy * g_sky_w + cx) * 4;
+  return um::mk(um::half_to_float(px[0]), um::half_to_float(px[1]), um::half_to_float(px[2]));
+}
+
 // SampleBatchJob.Sample (:166-401).  The ProbabilisticVolume branches (:194-201, :212-303)
 // are unreachable without a volume material (upload rejects them), so they are omitted.
 bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleColor, f3* sampleNormal,
@@ -529,7 +558,9 @@ bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleCo
       ray = ray.OffsetTowards(um::dot(scatteredRay.Direction, rec.Normal) >= 0 ? rec.Normal : -rec.Normal);
     } else {
       f3 hitSkyColor = um::mk(0.0f);
-      if (p.environment.sky_type == RTB_SKY_GRADIENT)
+      if (p.environment.sky_type == RTB_SKY_CUBEMAP)
+        hitSkyColor = CubemapSample(ray.Direction);
+      else if (p.environment.sky_type == RTB_SKY_GRADIENT)
         hitSkyColor = um::lerp(v3(p.environment.sky_bottom_color), v3(p.environment.sky_top_color),
                                0.5f * (ray.Direction.y + 1));
       w.emission.push_back(hitSkyColor);
@@ -672,7 +703,7 @@ ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
   }
   for (size_t i = 0; i < material_count; i++)
     if (materials[i].type > RTB_MATERIAL_DIELECTRIC) return RTB_ERR_UNSUPPORTED;
-  if (params->environment.sky_type == RTB_SKY_CUBEMAP) return RTB_ERR_UNSUPPORTED;
+  if (params->environment.sky_type == RTB_SKY_CUBEMAP && !g_sky_faces) return RTB_ERR_NO_SCENE;
   Scene sc{spheres, sphere_count, materials, material_count, nodes, node_count, {}, {}};
   sc.entities = entity_count ? entities : nullptr;
   sc.entity_count = entity_count;
@@ -704,6 +735,16 @@ ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
   worker();
   for (auto& t : pool) t.join();
   return RTB_OK;
+}
+
+ORACLE_API void oracle_set_sky_cubemap(const uint16_t* half_rgba, int face_width, int face_height) {
+  g_sky_faces = half_rgba;     // borrowed: the caller keeps the array alive while it renders
+  g_sky_w = face_width;
+  g_sky_h = face_height;
+}
+ORACLE_API void oracle_cubemap_sample(const float dir[3], float out[3]) {
+  const f3 c = CubemapSample(um::mk(dir[0], dir[1], dir[2]));
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
 }
 
 // ---- known-answer-test hooks (tests/test_oracle_kat.py) ---------------------------------

@@ -64,6 +64,8 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_world(IntPtr ctx, RtbEntity* entities, UIntPtr entityCount,
 			RtbSphere* spheres, UIntPtr sphereCount, RtbTriangle* triangles, UIntPtr triangleCount,
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
+		// Environment.SkyCubemap: cubemap.GetPixelData<byte>(0, CubemapFace.PositiveX) of an R16G16B16A16_SFloat cubemap (Texture.cs:155-167)
+		[DllImport(Lib)] public static extern RtbStatus rtb_upload_sky_cubemap(IntPtr ctx, ushort* halfRgba, int faceWidth, int faceHeight);
 		[DllImport(Lib)] public static extern RtbStatus rtb_sample_batch(IntPtr ctx, RtbBatchParams* p, RtbBatchBuffers* hostBuffers, bool* cancel);
 		[DllImport(Lib)] public static extern RtbStatus rtb_register_host_buffer(IntPtr ctx, void* ptr, UIntPtr bytes);
 		[DllImport(Lib)] public static extern RtbStatus rtb_unregister_host_buffer(IntPtr ctx, void* ptr);

@@ -76,6 +76,8 @@ struct SceneDesc {
   uint32_t has_root;            // 0: empty world (node_count == 0)
   float root_min[3], root_max[3];
   uint32_t max_depth;           // deepest root-to-leaf path (stack bound)
+  const uint16_t* sky_faces;    // Environment.SkyCubemap texels (6 faces of RGBA halves) or nullptr
+  int sky_w, sky_h;
   uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
   const uint32_t* chain_ref;    // per sphere: first chain box | box count << 24
   const float4* chain_boxes;    // 2 x float4 per box (min.xyz, max.xyz), tightest first
@@ -833,10 +835,32 @@ __device__ __forceinline__ float pow2_neg(uint32_t depth) {
   return 0.0f;
 }
 
+// Cubemap.Sample (Texture.cs:171-210): major axis (lowest index on ties), face uv, nearest texel, halves -> floats
+__device__ __forceinline__ f3 cubemap_sample(const uint16_t* faces, int fw, int fh, f3 v) {
+  if (!faces) return um::mk(0.0f);
+  const float ax = um::abs(v.x), ay = um::abs(v.y), az = um::abs(v.z);
+  const float max_distance = um::max(um::max(um::max(ax, ay), az), 0.0f);
+  const int lane = max_distance == ax ? 0 : (max_distance == ay ? 1 : (max_distance == az ? 2 : 3));
+  float major = ax, comp = v.x, u, w;
+  if (lane == 0) { const bool positive = v.x >= 0; u = positive ? -v.z : v.z; w = -v.y; }
+  else if (lane == 1) { const bool positive = v.y >= 0; major = ay; comp = v.y; u = v.x; w = positive ? v.z : -v.z; }
+  else { const bool positive = v.z >= 0; major = az; comp = v.z; u = positive ? v.x : -v.x; w = -v.y; }
+  const bool positive = comp >= 0;
+  u = um::div(u, major);
+  w = um::div(w, major);
+  const int cx = min((int)((u + 1) * (float)(fw / 2)), fw - 1);
+  const int cy = min((int)((w + 1) * (float)(fh / 2)), fh - 1);
+  const uint16_t* px = faces + ((size_t)((lane > 2 ? 2 : lane) * 2 + (positive ? 0 : 1)) * (size_t)fw * (size_t)fh + (size_t)cy * (size_t)fw + (size_t)cx) * 4;
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(px));
+  return um::mk(um::half_to_float((uint16_t)(raw.x & 0xffffu)), um::half_to_float((uint16_t)(raw.x >> 16)),
+                um::half_to_float((uint16_t)(raw.y & 0xffffu)));
+}
+
 // Sky (SampleBatchJob.cs:348-374; Environment.cs)
-__device__ __forceinline__ f3 sky_color(const rtb_environment& e, f3 d) {
+__device__ __forceinline__ f3 sky_color(const rtb_environment& e, const SceneDesc& sd, f3 d) {
   if (e.sky_type == RTB_SKY_GRADIENT)
     return um::lerp(v3(e.sky_bottom_color), v3(e.sky_top_color), 0.5f * (d.y + 1));
+  if (e.sky_type == RTB_SKY_CUBEMAP) return cubemap_sample(sd.sky_faces, sd.sky_w, sd.sky_h, d);
   return um::mk(0.0f);
 }
 

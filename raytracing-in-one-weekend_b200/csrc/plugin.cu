@@ -51,6 +51,8 @@ struct rtb_ctx {
   // scene
   unsigned char* d_blob = nullptr;
   DevMaterial* d_materials = nullptr;
+  uint16_t* d_sky = nullptr;
+  int sky_w = 0, sky_h = 0;
   uint32_t* d_chain_ref = nullptr;
   float4* d_chain_boxes = nullptr;
   SceneDesc scene{};
@@ -438,8 +440,9 @@ int validate_params(rtb_ctx* ctx, const rtb_batch_params* p, int* width, int* he
   if (p->slice_divider < 1 || p->slice_offset < 0 || p->slice_offset >= p->slice_divider)
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "SliceOffset/SliceDivider invalid");
   if (p->trace_depth < 0 || p->trace_depth > 65535) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "TraceDepth out of range");
-  if (p->environment.sky_type > RTB_SKY_GRADIENT)
-    return fail(ctx, RTB_ERR_UNSUPPORTED, "sky type outside the supported hot path (None, GradientSky)");
+  if (p->environment.sky_type > RTB_SKY_CUBEMAP) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "unknown sky type");
+  if (p->environment.sky_type == RTB_SKY_CUBEMAP && !ctx->d_sky)
+    return fail(ctx, RTB_ERR_NO_SCENE, "SkyType.CubeMap without rtb_upload_sky_cubemap");
   if (p->row_begin < 0 || p->row_end < 0 || p->row_end > *height)
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "row_begin/row_end out of range");
   return RTB_OK;
@@ -531,6 +534,9 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   a.p = p;
   a.b = dev;
   a.scene = ctx->scene;
+  a.scene.sky_faces = ctx->d_sky;
+  a.scene.sky_w = ctx->sky_w;
+  a.scene.sky_h = ctx->sky_h;
   a.width = width;
   a.height = height;
   a.first_row = rows.first_row;
@@ -686,7 +692,7 @@ int rtb_destroy(rtb_ctx* ctx) {
     for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
     DeviceBuffers& b = ctx->buf;
     void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
-                    b.diagnostics, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+                    b.diagnostics, ctx->d_sky, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -759,6 +765,25 @@ int rtb_upload_world(rtb_ctx* ctx, const rtb_entity* entities, size_t entity_cou
   ctx->scene.chain_boxes = ctx->d_chain_boxes;
   if (ctx->scene.has_chains && ctx->opt_walk_chains) ctx->scene.has_chains = 2u;
   ctx->has_scene = true;
+  return RTB_OK;
+}
+
+int rtb_upload_sky_cubemap(rtb_ctx* ctx, const uint16_t* half_rgba, int face_width, int face_height) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (half_rgba && (face_width < 1 || face_height < 1 || face_width > 16384 || face_height > 16384))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_upload_sky_cubemap: bad face size");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_sky) cudaFree(ctx->d_sky);
+  ctx->d_sky = nullptr;
+  ctx->sky_w = ctx->sky_h = 0;
+  if (!half_rgba) return RTB_OK;
+  const size_t bytes = (size_t)6 * face_width * face_height * 4 * sizeof(uint16_t);
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_sky, bytes));
+  RTB_CUDA(ctx, cudaMemcpy(ctx->d_sky, half_rgba, bytes, cudaMemcpyHostToDevice));
+  ctx->sky_w = face_width;
+  ctx->sky_h = face_height;
   return RTB_OK;
 }
 

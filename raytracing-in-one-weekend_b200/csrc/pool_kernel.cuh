@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
             success = true;
             path_rays = depth + 1;
             const f3 d = um::mk(w.dx[s], w.dy[s], w.dz[s]);
-            const f3 sky = sky_color(p.environment, d);
+            const f3 sky = sky_color(p.environment, sd, d);
             const f3 rad = um::mad(um::mk(w.thx[s], w.thy[s], w.thz[s]), sky, um::mk(w.rx[s], w.ry[s], w.rz[s]));
             f3 s_normal = um::mk(w.nx[s], w.ny[s], w.nz[s]), s_albedo = um::mk(w.ax[s], w.ay[s], w.az[s]);
             if (!(meta & kMetaNonSpecular)) {         // SampleBatchJob.cs:366-370

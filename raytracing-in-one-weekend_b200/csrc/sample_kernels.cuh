@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         N = hit_normal<SMEM, (FLAVOR >= kFlavorGeneral)>(sv, s, ray.o, ray.d, t_hit);
         P = um::mad(ray.d, t_hit, ray.o);
       } else {
-        const f3 sky = sky_color(p.environment, ray.d);
+        const f3 sky = sky_color(p.environment, a.scene, ray.d);
         radiance = um::mad(throughput, sky, radiance);
         if (!first_non_specular) {
           const f3 s_normal = -ray.d;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
         ray.d = sc.dir;
         pow2depth *= 2.0f;
       } else {
-        const f3 sky = sky_color(p.environment, ray.d);
+        const f3 sky = sky_color(p.environment, a.scene, ray.d);
         if (exact) { emi[entries] = sky; att[entries] = um::mk(1.0f); entries++; }
         radiance = um::mad(throughput, sky, radiance);
         if (!first_non_specular) { s_albedo = sky; s_normal = -ray.d; }

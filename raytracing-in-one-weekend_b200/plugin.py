@@ -15,7 +15,7 @@ from . import build as _build
 
 EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
-    "rtb_upload_scene", "rtb_upload_world", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_finalize_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
@@ -50,6 +50,7 @@ def lib():
         L.rtb_set_log_callback.argtypes = [vp, vp, vp]
         L.rtb_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
+        L.rtb_upload_sky_cubemap.argtypes = [vp, vp, C.c_int, C.c_int]
         L.rtb_describe_scene.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.POINTER(abi.SceneLayout)]
         L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
         L.rtb_sample_batch_device.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
@@ -206,6 +207,19 @@ class Context:
             return a.ctypes.data if len(a) else None
         self._check(self._L.rtb_upload_world(self._h, ptr(entities), len(entities), ptr(spheres), len(spheres), ptr(triangles),
                                              len(triangles), ptr(materials), len(materials), ptr(nodes), len(nodes)))
+
+    def upload_sky_cubemap(self, faces):
+        """Environment.SkyCubemap: `faces` is a [6, H, W, 4] array of float16 (or their uint16 bits), +X -X +Y -Y +Z -Z;
+        None removes it."""
+        if faces is None:
+            self._check(self._L.rtb_upload_sky_cubemap(self._h, None, 0, 0))
+            return
+        f = np.ascontiguousarray(faces)
+        if f.dtype == np.float16:
+            f = f.view(np.uint16)
+        if f.dtype != np.uint16 or f.ndim != 4 or f.shape[0] != 6 or f.shape[3] != 4:
+            raise ValueError("cubemap faces must be [6, H, W, 4] float16")
+        self._check(self._L.rtb_upload_sky_cubemap(self._h, f.ctypes.data, f.shape[2], f.shape[1]))
 
     def upload(self, scene):
         if getattr(scene, "entities", None) is not None:

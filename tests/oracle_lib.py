@@ -41,6 +41,10 @@ def lib(fast=False):
             C.c_void_p, C.c_size_t, C.POINTER(abi.BatchBuffers), C.c_int, C.c_int, C.c_int64, C.c_int64,
         ]
         L.oracle_sample_batch_world.restype = C.c_int
+        L.oracle_set_sky_cubemap.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_set_sky_cubemap.restype = None
+        L.oracle_cubemap_sample.argtypes = [abi.f32x3, abi.f32x3]
+        L.oracle_cubemap_sample.restype = None
         L.oracle_triangle_hit.argtypes = [C.c_void_p, abi.f32x3, abi.f32x3, C.POINTER(C.c_float), abi.f32x3, abi.f32x3]
         L.oracle_triangle_hit.restype = C.c_int
         L.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -110,6 +114,23 @@ class Buffers:
             rgb = self.out_color[:, :3] / np.maximum(n, 1)[:, None].astype(np.float32)
         rgb[n == 0] = 0
         return rgb.reshape(self.height, self.width, 3)
+
+
+_sky_keepalive = {}
+
+
+def set_sky_cubemap(faces, fast=False):
+    """Environment.SkyCubemap for subsequent oracle batches: [6, H, W, 4] float16, or None."""
+    L = lib(fast)
+    if faces is None:
+        _sky_keepalive.pop(fast, None)
+        L.oracle_set_sky_cubemap(None, 0, 0)
+        return
+    f = np.ascontiguousarray(faces)
+    if f.dtype == np.float16:
+        f = f.view(np.uint16)
+    _sky_keepalive[fast] = f
+    L.oracle_set_sky_cubemap(f.ctypes.data, f.shape[2], f.shape[1])
 
 
 def sample_batch(scene, params, buffers, noise=NOISE_PHILOX, threads=None, fast=False, index_range=(0, 0)):

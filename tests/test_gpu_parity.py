@@ -201,6 +201,46 @@ def test_emissive_sphere_in_a_sphere_world(rtb, oracle, ctx, kernel):
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
+def _test_cubemap(size=16):
+    """A deterministic HDR sky: a different tint per face, a gradient across it and one bright 'sun' texel."""
+    rng = np.random.default_rng(11)
+    faces = np.zeros((6, size, size, 4), np.float32)
+    tint = np.array([(1, .8, .6), (.5, .7, 1), (.9, .95, 1), (.3, .25, .2), (.7, 1, .7), (1, .6, .9)], np.float32)
+    g = np.linspace(0.4, 1.2, size, dtype=np.float32)
+    for f in range(6):
+        faces[f, :, :, :3] = tint[f] * g[None, :, None] * g[::-1][:, None, None] + 0.05 * rng.random((size, size, 3), dtype=np.float32)
+    faces[2, size // 3, size // 2, :3] = (40.0, 36.0, 30.0)
+    faces[..., 3] = 1
+    return faces.astype(np.float16)
+
+
+@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("world", ["mesh", "final"])
+def test_cubemap_sky(rtb, oracle, ctx, kernel, world):
+    """SkyType.CubeMap (Environment.cs, Texture.cs:141-211) — the sky the reference's host builds from the scene's HDRI
+    sky at HEAD (Raytracer.cs:663-665): nearest-texel lookups of R16G16B16A16_SFloat faces."""
+    W, H, spp = 96, 54, 12
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=16) if world == "mesh" else rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.05)
+    p.environment.sky_type = rtb.abi.SKY_CUBEMAP
+    faces = _test_cubemap()
+    oracle.set_sky_cubemap(faces)
+    ctx.upload_sky_cubemap(faces)
+    try:
+        ref = oracle.Buffers(W, H)
+        oracle.sample_batch(scene, p, ref)
+        assert ref.rgb().max() > 2.0                            # the sun texel is seen (directly or in a reflection)
+        k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+        got = render_gpu(rtb, ctx, scene, p, W, H, k)
+        assert_parity(ref, got, exact=(kernel == "simple"))
+    finally:
+        oracle.set_sky_cubemap(None)
+        ctx.upload_sky_cubemap(None)
+    with pytest.raises(rtb.plugin.RtbError) as e:               # cube-map sky requested, none uploaded
+        ctx.sample_batch(p, rtb.plugin.HostBuffers(W, H))
+    assert e.value.code == rtb.abi.RTB_ERR_NO_SCENE
+
+
 def test_world_upload_rejects_what_it_cannot_render(rtb, ctx):
     scene = rtb.host.make_mesh_scene()
     ents = scene.entities.copy()
@@ -421,10 +461,14 @@ def test_error_behaviour(rtb):
             c.sample_batch(p, b)
         assert e.value.code == abi.RTB_ERR_INVALID_ARGUMENT
         p.slice_divider = 1
-        p.environment.sky_type = abi.SKY_CUBEMAP
+        p.environment.sky_type = abi.SKY_CUBEMAP          # cube-map sky without rtb_upload_sky_cubemap
         with pytest.raises(rtb.plugin.RtbError) as e:
             c.sample_batch(p, b)
-        assert e.value.code == abi.RTB_ERR_UNSUPPORTED
+        assert e.value.code == abi.RTB_ERR_NO_SCENE
+        p.environment.sky_type = 7
+        with pytest.raises(rtb.plugin.RtbError) as e:
+            c.sample_batch(p, b)
+        assert e.value.code == abi.RTB_ERR_INVALID_ARGUMENT
         p.environment.sky_type = abi.SKY_GRADIENT
         cancel = np.ones(1, np.uint8)
         with pytest.raises(rtb.plugin.RtbError) as e:
