@@ -155,8 +155,8 @@ typedef struct rtb_batch_params {
   uint32_t seed;                        /* Seed (frameSeed, Raytracer.cs:660) — the Philox key */
   rtb_view view;                        /* View */
   rtb_environment environment;          /* Environment */
-  uint32_t sample_count_range[2];       /* SampleCountRange */
-  int32_t trace_depth;                  /* TraceDepth (1..500, Raytracer.cs:90) */
+  uint32_t sample_count_range[2];       /* SampleCountRange (each <= 2^20) */
+  int32_t trace_depth;                  /* TraceDepth (1..500, Raytracer.cs:90; accepted: 1..65535) */
   uint32_t sub_pixel_jitter;            /* SubPixelJitter (bool) */
   float sample_count_weight_extrema[2]; /* SampleCountWeightExtrema */
   /* Extension (not a SampleBatchJob field): restrict the batch to rows [row_begin, row_end).

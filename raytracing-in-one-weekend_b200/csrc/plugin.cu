@@ -439,7 +439,10 @@ int validate_params(rtb_ctx* ctx, const rtb_batch_params* p, int* width, int* he
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "Size: more than 2^31 pixels");
   if (p->slice_divider < 1 || p->slice_offset < 0 || p->slice_offset >= p->slice_divider)
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "SliceOffset/SliceDivider invalid");
-  if (p->trace_depth < 0 || p->trace_depth > 65535) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "TraceDepth out of range");
+  // TraceDepth is 1..500 in the reference (Raytracer.cs:90); 0 would mean "no bounce iteration at all"
+  if (p->trace_depth < 1 || p->trace_depth > 65535) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "TraceDepth out of range (1..65535)");
+  if (p->sample_count_range[0] > (1u << 20) || p->sample_count_range[1] > (1u << 20))
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "SampleCountRange above 2^20 samples per pixel per batch");
   if (p->environment.sky_type > RTB_SKY_CUBEMAP) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "unknown sky type");
   if (p->environment.sky_type == RTB_SKY_CUBEMAP && !ctx->d_sky)
     return fail(ctx, RTB_ERR_NO_SCENE, "SkyType.CubeMap without rtb_upload_sky_cubemap");

@@ -657,3 +657,42 @@ def test_full_frame_decisions_match_the_oracle(rtb, oracle, ctx, name, count, sp
     oracle.sample_batch(scene, p, ref)
     got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
     assert_parity(ref, got, exact=False)
+
+
+def test_random_small_batches_agree_across_kernels_and_with_the_oracle(rtb, oracle, ctx):
+    """Fuzz: 40 random small batches (ragged sizes, 0..20 spp, depth 1..12, interlacing, row ranges, jitter on / off,
+    adaptive sample ranges, previous accumulation) — the three kernels and the oracle take the same decisions."""
+    rng = np.random.default_rng(2026)
+    scenes = [rtb.host.make_scene("three_spheres", max_bvh_depth=int(d)) for d in (0, 2)] + \
+             [rtb.host.make_scene("final", max_bvh_depth=int(d)) for d in (3, 16)] + [rtb.host.make_mesh_scene(max_bvh_depth=4)]
+    for case in range(40):
+        scene = scenes[int(rng.integers(len(scenes)))]
+        W, H = int(rng.integers(1, 41)), int(rng.integers(1, 25))
+        spp = int(rng.integers(0, 21))
+        spp_max = spp + int(rng.integers(0, 6)) if rng.random() < 0.4 else None
+        divider = int(rng.integers(1, 4))
+        offset = int(rng.integers(0, divider))
+        rb = int(rng.integers(0, H)) if rng.random() < 0.4 else 0
+        re = int(rng.integers(rb + 1, H + 1)) if rb or rng.random() < 0.2 else 0
+        p = rtb.host.make_params(scene, W, H, spp, int(rng.integers(1, 13)), seed=int(rng.integers(1, 1000)),
+                                 aperture=float(rng.choice([0.0, 0.1, 0.4])), jitter=bool(rng.random() < 0.8),
+                                 slice_offset=offset, slice_divider=divider, row_begin=rb, row_end=re, spp_max=spp_max)
+        p.sample_count_weight_extrema[0], p.sample_count_weight_extrema[1] = 0.5, 2.5
+        prev_n = rng.integers(0, 4, W * H).astype(np.float32)
+        inputs = ((rng.random((W * H, 4)) * prev_n[:, None]).astype(np.float32), (rng.random(W * H) * 3 * prev_n).astype(np.float32),
+                  (rng.random((W * H, 3)) * prev_n[:, None]).astype(np.float32), (rng.random((W * H, 3)) * prev_n[:, None]).astype(np.float32))
+        inputs[0][:, 3] = prev_n
+        ref = oracle.Buffers(W, H)
+        ref.in_color[:], ref.in_weight[:], ref.in_normal[:], ref.in_albedo[:] = inputs
+        oracle.sample_batch(scene, p, ref)
+        for kernel, exact in ((rtb.abi.KERNEL_SIMPLE, True), (rtb.abi.KERNEL_MEGA, False), (rtb.abi.KERNEL_POOL, False)):
+            got = render_gpu(rtb, ctx, scene, p, W, H, kernel, inputs=inputs)
+            try:
+                assert np.array_equal(ref.out_color[:, 3], got.out_color[:, 3])
+                assert np.array_equal(ref.diagnostics["ray_count"], got.diagnostics["ray_count"])
+                if exact:
+                    assert np.array_equal(ref.out_color, got.out_color) and np.array_equal(ref.out_weight, got.out_weight)
+                else:
+                    assert np.abs(ref.out_color[:, :3] - got.out_color[:, :3]).max() <= 1e-4 * max(1.0, float(ref.out_color[:, 3].max()))
+            except AssertionError:
+                raise AssertionError(f"case {case}: {scene.name} {W}x{H} spp {spp}..{spp_max} div {divider}/{offset} rows {rb}:{re} kernel {kernel}")
