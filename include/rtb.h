@@ -323,6 +323,10 @@ typedef enum rtb_option {
                                  * at the next rtb_upload_scene) */
   RTB_OPT_HOST_ACCESS = 6,      /* 1 (default): rtb_sample_batch lets the kernel read/write PINNED host arrays in place over PCIe
                                  * (rtb_register_host_buffer or cudaHostAlloc memory); 0: always stage through device copies */
+  RTB_OPT_NOISE = 7,            /* 0 (default): Philox4x32-10 keyed (pixel, sample, bounce); 1: the reference's own white noise
+                                 * (NoiseColor.White: one sequential Unity.Mathematics.Random xorshift32 stream per pixel per batch,
+                                 * SampleBatchJob.cs:91) — validation only, needs RTB_OPT_KERNEL = 1 (a sequential stream cannot be
+                                 * split over lanes) */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
                                  * instead of only when the hit geometry does not already prove them (same results, slower) */
 } rtb_option;

@@ -61,7 +61,8 @@ RTB_ERR_UNSUPPORTED = 4
 RTB_ERR_OUT_OF_MEMORY = 5
 RTB_ERR_CUDA = 100
 
-OPT_COUNTERS, OPT_KERNEL, OPT_CANCEL_CHUNK_ROWS, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS, OPT_HOST_ACCESS = 1, 2, 3, 4, 5, 6
+OPT_COUNTERS, OPT_KERNEL, OPT_CANCEL_CHUNK_ROWS, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS, OPT_HOST_ACCESS, OPT_NOISE = 1, 2, 3, 4, 5, 6, 7
+NOISE_PHILOX, NOISE_WHITE = 0, 1
 KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA, KERNEL_POOL = 0, 1, 2, 3
 
 f32 = C.c_float

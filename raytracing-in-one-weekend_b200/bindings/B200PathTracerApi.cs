@@ -73,7 +73,7 @@ namespace B200PathTracer
 			float* color4, float* normal3, float* albedo3, float* outColor3, float* outNormal3, float* outAlbedo3, IntPtr cudaStream);
 		[DllImport(Lib)] public static extern RtbStatus rtb_finalize_device(IntPtr ctx, int width, int height,
 			float* color3, float* normal3, float* albedo3, uint* outColorRgba, uint* outNormalRgba, uint* outAlbedoRgba, IntPtr cudaStream);
-		// rtb_option (include/rtb.h): Counters = 1, Kernel = 2, CancelChunkRows = 3, LeafSpheres = 4, AlwaysWalkChains = 5, HostAccess = 6
+		// rtb_option (include/rtb.h): Counters = 1, Kernel = 2, CancelChunkRows = 3, LeafSpheres = 4, AlwaysWalkChains = 5, HostAccess = 6, Noise = 7
 		[DllImport(Lib)] public static extern RtbStatus rtb_set_option(IntPtr ctx, int option, long value);
 		[DllImport(Lib)] public static extern RtbStatus rtb_last_kernel_ms(IntPtr ctx, out float ms);
 		[DllImport(Lib)] public static extern RtbStatus rtb_last_batch_in_place(IntPtr ctx, out int inPlace);

@@ -810,6 +810,109 @@ __device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, fl
   return out;
 }
 
+// ---------------------------------------------------------------------------------------
+// The reference's OWN random stream (NoiseColor.White): Unity.Mathematics.Random, one xorshift32 state per pixel per
+// batch seeded (Seed * 0x8C4CA03F) ^ (index * 0x7383ED49) (SampleBatchJob.cs:91), consumed in call order — a draw
+// that the reference skips is not made (RandomSource.cs; draw order: SURVEY.md appendix A.2).  Only the
+// thread-per-pixel kernel can follow a sequential stream (RTB_OPT_NOISE = 1): it reproduces the CPU restatement of
+// the reference run with its own generator, bit for bit.
+// ---------------------------------------------------------------------------------------
+struct WhiteNoise {
+  uint32_t state;
+  __device__ __forceinline__ void init(uint32_t seed) { state = seed; next_state(); }       // Random(uint seed)
+  __device__ __forceinline__ uint32_t next_state() {
+    const uint32_t t = state;
+    state ^= state << 13;
+    state ^= state >> 17;
+    state ^= state << 5;
+    return t;
+  }
+  __device__ __forceinline__ float next_float() { return u2f(next_state()); }
+};
+
+// View.GetRay (View.cs:38-48) after the jitter draw of SampleBatchJob.cs:134: lens disk (2 draws, only with a lens), time (1 draw, always)
+__device__ __forceinline__ PathRay camera_ray_white(const rtb_batch_params& p, int cx, int cy, WhiteNoise& rng) {
+  const rtb_view& v = p.view;
+  float jx = 0.5f, jy = 0.5f, rdx = 0, rdy = 0;
+  if (p.sub_pixel_jitter) { jx = rng.next_float(); jy = rng.next_float(); }
+  const float nx = um::div((float)cx + jx, p.size[0]);
+  const float ny = um::div((float)cy + jy, p.size[1]);
+  if (v.lens_radius != 0) {   // RandomSource.InUnitDisk (RandomSource.cs:40-61)
+    const float theta = rng.next_float() * (2 * um::PI - 0) + 0;
+    const float radius = um::sqrt(rng.next_float());
+    float s, c;
+    um::sincos(theta, &s, &c);
+    rdx = v.lens_radius * (radius * c);
+    rdy = v.lens_radius * (radius * s);
+  }
+  const f3 offset = v3(v.right) * rdx + v3(v.up) * rdy;
+  PathRay ray;
+  ray.d = um::normalize(v3(v.lower_left_corner) - offset + nx * v3(v.horizontal) + ny * v3(v.vertical));
+  ray.o = v3(v.origin) + offset;
+  (void)rng.next_float();     // Ray.Time (View.cs:47): drawn even though nothing on this path moves
+  return ray;
+}
+
+// Material.Scatter (Material.cs:67-173) with the reference's draws in the reference's order
+__device__ __forceinline__ ScatterResult scatter_white(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, WhiteNoise& rng) {
+  ScatterResult out;
+  out.reflectance = um::mk(m0.x, m0.y, m0.z);
+  const float glossiness = m1.w, metallic = m2.x, roughness = m2.w;
+  auto cosine_sample = [&](f3 normal) {          // RandomSource.OnCosineWeightedHemisphere: NextFloat2, x then y
+    const float ux = rng.next_float(), uy = rng.next_float();
+    float s, c;
+    unit_angle_sincos(uy, &s, &c);
+    return cosine_hemisphere(normal, ux, s, c);
+  };
+  if (__float_as_uint(m0.w) == RTB_MATERIAL_STANDARD) {
+    const f3 rough_normal = roughness > 0 ? um::normalize(um::lerp(N, cosine_sample(N), roughness)) : N;   // :83
+    const float incident_cosine = -um::dot(D, rough_normal);
+    const float fresnel = schlick(incident_cosine, m3.y, m3.z);
+    const float g = smith_masking_shadowing(D, N, m3.x);
+    const float chance = um::saturate(fresnel * glossiness * g);
+    if (chance > 0 && rng.next_float() < chance) {                                                          // :91
+      out.dir = um::reflect(D, rough_normal);
+      out.reflectance = um::mk(1.0f);
+    } else if (metallic > 0 && rng.next_float() < metallic) {                                               // :99
+      out.dir = um::reflect(D, rough_normal);
+    } else {
+      out.dir = cosine_sample(N);                                                                           // :107
+    }
+    float ev = 0;
+    if (chance > 0 && chance < 1) ev++;
+    if (metallic > 0 && metallic < 1) ev++;
+    ev += roughness * (chance + (1 - chance) * metallic);
+    ev += (1 - chance) * (1 - metallic);
+    out.random_events = ev;
+  } else {
+    const float ior = m2.y;
+    const float rx = rng.next_float(), ry = rng.next_float();          // NextFloat3Direction: always drawn (:124)
+    float s, c;
+    unit_angle_sincos(ry, &s, &c);
+    const f3 rough_normal = um::normalize(N + roughness * random_direction(rx, s, c));
+    float ni_over_nt, cosine;
+    f3 outward;
+    const float ddn = um::dot(D, rough_normal);
+    if (ddn > 0) { outward = -rough_normal; ni_over_nt = ior; cosine = ior * ddn; }
+    else { outward = rough_normal; ni_over_nt = um::div(1.0f, ior); cosine = -ddn; }
+    const float dt = um::dot(D, outward);
+    const float disc = 1 - ni_over_nt * ni_over_nt * (1 - dt * dt);
+    bool refracted = false;
+    if (disc > 0) {                                                     // Refract succeeded: the Schlick draw is made (:142-143)
+      if (rng.next_float() > schlick(cosine, m3.y, m3.z)) {
+        out.dir = ni_over_nt * (D - outward * dt) - outward * um::sqrt(disc);
+        refracted = true;
+      }
+    }
+    if (!refracted) {
+      out.dir = um::reflect(D, rough_normal);
+      out.reflectance = um::mk(1.0f);
+    }
+    out.random_events = 1.0f + roughness;
+  }
+  return out;
+}
+
 // Fills DevMaterial's derived constants on the device (one thread per material, at upload).
 __global__ void derive_materials_kernel(DevMaterial* m, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,7 +63,7 @@ struct rtb_ctx {
   unsigned long long* d_counters = nullptr;
   rtb_counters counters{};
   int default_kernel = 2;
-  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1;
+  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0;
   bool last_in_place = false;
   float last_ms = 0.0f;
   bool smem_attr_set[2][6] = {};
@@ -568,10 +568,17 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
 
   int kernel_kind = (int)ctx->opt_kernel;
   if (kernel_kind == 0) kernel_kind = ctx->default_kernel;
+  if (ctx->opt_noise && kernel_kind != 1)
+    return fail(ctx, RTB_ERR_UNSUPPORTED, "RTB_OPT_NOISE = 1 (the reference's sequential white-noise stream) needs RTB_OPT_KERNEL = 1");
   if (kernel_kind == 1) {
     const uint32_t grid = (a.n_active_pixels + 127) / 128;
-    if (counters) sample_simple<true><<<grid, 128, 0, stream>>>(a);
-    else sample_simple<false><<<grid, 128, 0, stream>>>(a);
+    if (ctx->opt_noise) {
+      if (counters) sample_simple<true, true><<<grid, 128, 0, stream>>>(a);
+      else sample_simple<false, true><<<grid, 128, 0, stream>>>(a);
+    } else {
+      if (counters) sample_simple<true, false><<<grid, 128, 0, stream>>>(a);
+      else sample_simple<false, false><<<grid, 128, 0, stream>>>(a);
+    }
     RTB_CUDA(ctx, cudaGetLastError());
   } else if (kernel_kind == 3) {
     const bool fits = pool_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
@@ -1032,6 +1039,10 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
     case RTB_OPT_LEAF_SPHERES:
       if (value < 1 || value > 15) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_LEAF_SPHERES must be 1..15");
       ctx->opt_collapse = value;
+      return RTB_OK;
+    case RTB_OPT_NOISE:
+      if (value < 0 || value > 1) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_NOISE must be 0 or 1");
+      ctx->opt_noise = value;
       return RTB_OK;
     case RTB_OPT_HOST_ACCESS:
       ctx->opt_host_access = value ? 1 : 0;

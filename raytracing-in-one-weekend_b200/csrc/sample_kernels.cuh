@@ -443,7 +443,7 @@ __global__ void counters_from_diagnostics(const rtb_diagnostics* __restrict__ di
 // ---------------------------------------------------------------------------------------
 constexpr int kSimpleStack = 64;
 
-template <bool COUNTERS>
+template <bool COUNTERS, bool WHITE>
 __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ BatchArgs a) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.n_active_pixels) return;
@@ -467,9 +467,11 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
   WorkCounters wc;
   const bool exact = p.trace_depth <= kSimpleStack;
   f3 att[kSimpleStack], emi[kSimpleStack];
+  WhiteNoise white{};
+  if (WHITE) white.init((p.seed * 0x8C4CA03Fu) ^ (index * 0x7383ED49u));      // SampleBatchJob.cs:91
 
   for (uint32_t s = 0; s < n; s++) {
-    PathRay ray = camera_ray(p, cx, cy, index, s);
+    PathRay ray = WHITE ? camera_ray_white(p, cx, cy, white) : camera_ray(p, cx, cy, index, s);
     f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
     f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
     bool first_non_specular = false;
@@ -487,7 +489,8 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
         const f3 N = hit_normal<false, true>(sv, sp, ray.o, ray.d, t_hit);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
-        const ScatterResult sc = scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed);
+        const ScatterResult sc = WHITE ? scatter_white(m0, m1, m2, m3, ray.d, N, white)
+                                       : scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed);
         if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
         const f3 emission = um::mk(m1.x, m1.y, m1.z);
         if (depth == 0) s_normal = N;

@@ -241,6 +241,42 @@ def test_cubemap_sky(rtb, oracle, ctx, kernel, world):
     assert e.value.code == rtb.abi.RTB_ERR_NO_SCENE
 
 
+@pytest.mark.parametrize("world,depth,td,ap", [("three_spheres", 0, 8, None), ("final", 16, 50, 0.1), ("final", 3, 12, 0.0), ("mesh", 16, 50, 0.0)])
+def test_reference_white_noise_stream_is_reproduced_bit_for_bit(rtb, oracle, ctx, world, depth, td, ap):
+    """RTB_OPT_NOISE = 1: the thread-per-pixel kernel consumes the reference's OWN random stream (NoiseColor.White:
+    Unity.Mathematics.Random seeded (Seed * 0x8C4CA03F) ^ (index * 0x7383ED49), SampleBatchJob.cs:91, draws made and
+    skipped exactly as Material.Scatter / View.GetRay make them) and equals the CPU restatement run with that
+    generator in every output bit — the algorithm AND the generator of the reference, not only the Philox substitute."""
+    W, H, spp = 72, 40, 6
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=depth) if world == "mesh" else rtb.host.make_scene(world, max_bvh_depth=depth)
+    p = rtb.host.make_params(scene, W, H, spp, td, aperture=ap, seed=3)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref, noise=oracle.NOISE_XORSHIFT)
+    philox = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, philox, noise=oracle.NOISE_PHILOX)
+    assert not np.array_equal(ref.out_color, philox.out_color)          # a different stream, a different image
+    ctx.set_option(rtb.abi.OPT_NOISE, rtb.abi.NOISE_WHITE)
+    try:
+        got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE)
+        assert_parity(ref, got, exact=True)
+        with pytest.raises(rtb.plugin.RtbError) as e:                   # a sequential stream cannot be split over lanes
+            render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+        assert e.value.code == rtb.abi.RTB_ERR_UNSUPPORTED
+    finally:
+        ctx.set_option(rtb.abi.OPT_NOISE, rtb.abi.NOISE_PHILOX)
+        ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_AUTO)
+    if world == "three_spheres":                                         # and the committed xorshift fixture
+        g = np.load(os.path.join(GOLDEN, "three_spheres_32x18x4_d8_xorshift.npz"))
+        p2 = rtb.host.make_params(scene, 32, 18, 4, 8)
+        ctx.set_option(rtb.abi.OPT_NOISE, rtb.abi.NOISE_WHITE)
+        try:
+            fx = render_gpu(rtb, ctx, scene, p2, 32, 18, rtb.abi.KERNEL_SIMPLE)
+        finally:
+            ctx.set_option(rtb.abi.OPT_NOISE, rtb.abi.NOISE_PHILOX)
+        assert np.array_equal(fx.out_color, g["color"]) and np.array_equal(fx.out_normal, g["normal"])
+        assert np.array_equal(fx.out_albedo, g["albedo"]) and np.array_equal(fx.out_weight, g["weight"])
+
+
 def test_world_upload_rejects_what_it_cannot_render(rtb, ctx):
     scene = rtb.host.make_mesh_scene()
     ents = scene.entities.copy()
