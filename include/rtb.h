@@ -248,8 +248,9 @@ RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* Replaces `sampleBatchJob.Schedule(W*H, 1, dep).Complete()` (Raytracer.cs:730-736) with HOST
- * buffers: uploads the four input accumulators, runs the megakernel, downloads the four
- * outputs (+diagnostics), returns when the out_* arrays are fully written.
+ * buffers: returns when the out_* arrays are fully written.  Pinned arrays (rtb_register_host_buffer /
+ * cudaHostAlloc) are read and written in place by the megakernel over PCIe; pageable ones are staged
+ * through device copies of the four inputs and the four outputs (+diagnostics).
  * `cancel` (may be NULL) is the CancellationToken (SampleBatchJob.cs:23,61): polled between
  * kernel chunks; when set the call returns RTB_ERR_CANCELLED promptly. */
 RTB_API int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params,
