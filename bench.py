@@ -304,8 +304,33 @@ def run_ours(args):
             fr.ctx.sample_batch(params, hb)
             return n * 44, n * (48 + 16)
     else:
-        def e2e_step():
-            return fr.render_host(params, host)
+        # One host, N GPUs: the frame lives in ONE set of pinned host arrays (one /dev/shm mapping across the N rank
+        # processes, registered with each rank's context) and every rank's rtb_sample_batch renders its row tile
+        # straight into them — inputs and outputs cross each GPU's own PCIe link inside its kernel; no gather is
+        # needed on this path.  Falls back to H2D / kernel / NCCL gather / D2H when shared memory is not available.
+        shared = _shared_host_frame(W, H, rank, abi, rtb) if not args.no_shared_host else None
+        if shared is not None:
+            try:
+                fr.ctx.register_host_buffers(shared)      # cudaHostRegister of the shared pages in this rank's context
+            except Exception as e:      # noqa: BLE001 — any failure here means "use the staged path"
+                sys.stderr.write(f"rank {rank}: cannot pin the shared frame: {e}\n")
+                shared = None
+        ok = torch.tensor([1.0 if shared is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0:
+            hb = shared
+
+            def e2e_step():
+                return fr.render_host_in_place(params, hb)
+            e2e_api = ("FrameRenderer.render_host_in_place: rtb_sample_batch per rank on ONE pinned host frame shared by the ranks (/dev/shm mapping): each GPU's "
+                       "kernel reads and writes its row tile in place over its own PCIe link")
+            host["out_color"] = torch.from_numpy(hb.out_color)
+        else:
+            shared = None
+
+            def e2e_step():
+                return fr.render_host(params, host)
+            e2e_api = "FrameRenderer.render_host (H2D own rows, rtb_sample_batch_device, NCCL gather, D2H on rank 0)"
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -351,7 +376,7 @@ def run_ours(args):
                 "outputs": "color + normal + albedo + sampleCountWeight + diagnostics (full job contract)",
             },
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": ("rtb_sample_batch (C ABI, pinned host buffers" + (", read and written in place by the kernel over PCIe)" if in_place else ", staged H2D/D2H copies)")) if world == 1 else "FrameRenderer.render_host (H2D own rows, rtb_sample_batch_device, NCCL gather, D2H on rank 0)",
+                    "api": ("rtb_sample_batch (C ABI, pinned host buffers" + (", read and written in place by the kernel over PCIe)" if in_place else ", staged H2D/D2H copies)")) if world == 1 else e2e_api,
                     "out_color_checksum": checksum},
             "gpu_launches": args.steps * world,
             "kernel_ms_rank0": kernel_ms, "kernel_ms_max_rank": kernel_ms_max, "kernel_ms_per_rank": kernel_ms_per_rank,
@@ -378,6 +403,45 @@ def run_ours(args):
     fr.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _shared_host_frame(W, H, rank, abi, rtb):
+    """HostBuffers over files in /dev/shm mapped by every rank: rank 0 creates them, the others map the same pages."""
+    import numpy as np
+    import torch.distributed as dist
+    n = W * H
+    spec = [("in_color", (n, 4), np.float32), ("in_weight", (n,), np.float32), ("in_normal", (n, 3), np.float32),
+            ("in_albedo", (n, 3), np.float32), ("out_color", (n, 4), np.float32), ("out_weight", (n,), np.float32),
+            ("out_normal", (n, 3), np.float32), ("out_albedo", (n, 3), np.float32), ("diagnostics", (n,), abi.DIAGNOSTICS_DTYPE)]
+    stem = f"/dev/shm/rtb_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_"
+    hb, err = None, None
+    try:
+        if rank == 0:
+            for name, shape, dt in spec:
+                m = np.memmap(stem + name, dtype=dt, mode="w+", shape=shape)
+                m[...] = 0
+                m.flush()
+    except OSError as e:
+        err = e
+    dist.barrier()
+    try:
+        if err is None:
+            hb = rtb.plugin.HostBuffers(1, 1)
+            hb.width, hb.height = W, H
+            for name, shape, dt in spec:
+                setattr(hb, name, np.memmap(stem + name, dtype=dt, mode="r+", shape=shape))
+    except OSError as e:
+        hb, err = None, e
+    dist.barrier()
+    if rank == 0:       # every rank holds its mapping now: the names can go
+        for name, _, _ in spec:
+            try:
+                os.unlink(stem + name)
+            except OSError:
+                pass
+    if err is not None:
+        sys.stderr.write(f"shared host frame unavailable on rank {rank}: {err}\n")
+    return hb
 
 
 def _hbm_peak():
@@ -408,6 +472,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--equal-tiles", action="store_true", help="contiguous equal row tiles instead of ray-count balanced ones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shared-host", action="store_true", help="N > 1: end-to-end through H2D / gather / D2H instead of one shared pinned host frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -110,5 +110,16 @@ class FrameRenderer:
         torch.cuda.current_stream().synchronize()
         return h2d, d2h
 
+    def render_host_in_place(self, params, shared):
+        """End-to-end batch on ONE set of pinned host arrays every rank maps (`shared`: plugin.HostBuffers over
+        the same pages in all rank processes, registered with `ctx.register_host_buffers`): each rank's
+        rtb_sample_batch reads and writes its own row tile of the host frame in place over its GPU's PCIe
+        link, so the frame needs no gather.  Returns the (read, written) host bytes of this rank."""
+        b, e = self.my_rows
+        if e > b:
+            self.ctx.sample_batch(self._tile_params(params), shared)
+        px = (e - b) * self.width
+        return px * 44, px * (48 + 16)
+
     def close(self):
         self.ctx.close()
