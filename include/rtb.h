@@ -79,17 +79,38 @@ typedef struct rtb_triangle {
 
 typedef enum rtb_entity_type {  /* Entity.cs:13-20 */
   RTB_ENTITY_SPHERE = 1,
-  RTB_ENTITY_RECT = 2,          /* not on the hot path: RTB_ERR_UNSUPPORTED */
-  RTB_ENTITY_BOX = 3,           /* not on the hot path: RTB_ERR_UNSUPPORTED */
-  RTB_ENTITY_TRIANGLE = 4
+  RTB_ENTITY_RECT = 2,          /* always a placed entity (rtb_upload_placed_world) */
+  RTB_ENTITY_BOX = 3,           /* always a placed entity */
+  RTB_ENTITY_TRIANGLE = 4,
+  /* Flag ORed into rtb_entity.type: `index` points into the placed-entity array (the reference's full Entity
+   * record: rotation, motion, content) instead of the sphere array.  Implied for RECT and BOX. */
+  RTB_ENTITY_PLACED = 0x100
 } rtb_entity_type;
 
 /* One element of the BVH-ordered entity list the leaves point into (bvhEntities, BvhNodeData.cs:157-160):
- * the entity's type and its index in the sphere / triangle array (Entity.Content). */
+ * the entity's type and its index in the sphere / triangle / placed-entity array (Entity.Content). */
 typedef struct rtb_entity {
-  uint32_t type;                /* rtb_entity_type */
+  uint32_t type;                /* rtb_entity_type (| RTB_ENTITY_PLACED) */
   uint32_t index;
 } rtb_entity;
+
+/* The reference's Entity (Entity.cs:24-55) with its Content inlined, for everything a plain rtb_sphere cannot
+ * say: a rotated entity, a moving one (Entity.TransformAtTime, Entity.cs:124-127, evaluated at the ray's time),
+ * EntityType.Rect (EntityTypes/Rect.cs: the XY rectangle of `size` centred on the entity's origin, hit from
+ * +Z only, HitTests.cs:62-78) and EntityType.Box (EntityTypes/Box.cs, HitTests.cs:80-111).  The ray is taken
+ * into entity space with the inverse of the transform (Entity.cs:74-103). */
+typedef struct rtb_placed_entity {
+  uint32_t type;                /* RTB_ENTITY_SPHERE, RTB_ENTITY_RECT or RTB_ENTITY_BOX */
+  uint32_t material;
+  uint32_t moving;              /* Entity.Moving */
+  uint32_t reserved;
+  float rotation[4];            /* OriginTransform.rot as (x, y, z, w) */
+  float position[3];            /* OriginTransform.pos */
+  float destination_offset[3];  /* DestinationOffset */
+  float time_range[2];          /* TimeRange (moving: x != y, Entity.cs:53-54) */
+  float size[3];                /* Sphere: (radius, -, -); Rect: the ctor's size.xy; Box: the ctor's size.xyz */
+  float reserved2;
+} rtb_placed_entity;            /* 80 bytes */
 
 typedef enum rtb_material_type {     /* Material.cs:9-14 */
   RTB_MATERIAL_STANDARD = 0,
@@ -221,6 +242,17 @@ RTB_API int rtb_upload_world(rtb_ctx* ctx,
                              const rtb_triangle* triangles, size_t triangle_count,
                              const rtb_material* materials, size_t material_count,
                              const rtb_bvh_node* nodes, size_t node_count);
+
+/* rtb_upload_world plus placed entities: entities[i] of type RECT, BOX, or any type | RTB_ENTITY_PLACED index
+ * `placed`.  Worlds with placed entities run the kernel flavour that carries entity transforms and the ray's
+ * time; worlds without are exactly rtb_upload_world. */
+RTB_API int rtb_upload_placed_world(rtb_ctx* ctx,
+                                    const rtb_entity* entities, size_t entity_count,
+                                    const rtb_sphere* spheres, size_t sphere_count,
+                                    const rtb_triangle* triangles, size_t triangle_count,
+                                    const rtb_placed_entity* placed, size_t placed_count,
+                                    const rtb_material* materials, size_t material_count,
+                                    const rtb_bvh_node* nodes, size_t node_count);
 
 /* Environment.SkyCubemap (Runtime/Texture.cs:141-211; the host builds it from the scene's HDRI sky,
  * Raytracer.cs:663-665): six faces of R16G16B16A16_SFloat texels — the only format the reference accepts

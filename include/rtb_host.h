@@ -80,6 +80,9 @@ RTB_API int rtbh_build_bvh_from_bounds(const float* bounds, size_t entity_count,
  * transform (Sphere.cs:16-23, BvhNodeData.cs:41-78); Triangle.Bounds (Triangle.cs:38-49). */
 RTB_API void rtbh_sphere_bounds(const rtb_sphere* sphere, float out_bounds[6]);
 RTB_API void rtbh_triangle_bounds(const rtb_triangle* triangle, float out_bounds[6]);
+/* A placed entity's world bounds (BvhBuildingEntity ctor, BvhNodeData.cs:28-80): the content's local box
+ * (Sphere.cs:16-23, Rect.cs:17-19, Box.cs:17) through OriginTransform, swept over the motion when moving. */
+RTB_API void rtbh_placed_bounds(const rtb_placed_entity* entity, float out_bounds[6]);
 /* Triangle constructors (Triangle.cs:14-29): n1..n3 NULL = the face-normal form. */
 RTB_API void rtbh_make_triangle(const float v1[3], const float v2[3], const float v3[3],
                                 const float* n1, const float* n2, const float* n3,

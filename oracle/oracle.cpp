@@ -193,9 +193,16 @@ struct Scene {
   // bvhEntities: what the leaves index (nullptr: entity i is sphere i); Entity.Type / Entity.Content
   const rtb_entity* entities = nullptr; size_t entity_count = 0;
   const rtb_triangle* triangles = nullptr; size_t triangle_count = 0;
+  // entities with the reference's full Entity record (rotation, motion, Rect / Box content)
+  const rtb_placed_entity* placed = nullptr; size_t placed_count = 0;
+  std::vector<um::rigid> placed_inverse;  // Entity.InverseTransform of the static ones (Entity ctor, Entity.cs:51-52)
+  static bool is_placed(const rtb_entity& e) {
+    return (e.type & RTB_ENTITY_PLACED) || e.type == RTB_ENTITY_RECT || e.type == RTB_ENTITY_BOX;
+  }
   uint32_t material_of(int entity) const {
     if (!entities) return spheres[entity].material;
     const rtb_entity& e = entities[entity];
+    if (is_placed(e)) return placed[e.index].material;
     return e.type == RTB_ENTITY_TRIANGLE ? triangles[e.index].material : spheres[e.index].material;
   }
 };
@@ -262,11 +269,103 @@ bool TriangleHit(const rtb_triangle& tri, const Ray& r, float tMin, float tMax, 
   return true;
 }
 
+// math.sign: (x > 0 ? 1 : 0) - (x < 0 ? 1 : 0)
+float Sign(float x) { return (x > 0 ? 1.0f : 0.0f) - (x < 0 ? 1.0f : 0.0f); }
+
+// HitTests.Hit(this Rect) (HitTests.cs:62-78); Rect ctor (Rect.cs:11-15): From = -size / 2, To = size / 2
+bool RectHit(const float size[3], const Ray& r, float tMin, float tMax, float* distance, f3* normal) {
+  *distance = 0;
+  *normal = um::mk(0.0f);
+  const float fromX = um::div(-size[0], 2.0f), fromY = um::div(-size[1], 2.0f);
+  const float toX = um::div(size[0], 2.0f), toY = um::div(size[1], 2.0f);
+  if (r.Direction.z >= 0) return false;
+  float t = um::div(-r.Origin.z, r.Direction.z);
+  if (t < tMin || t > tMax) return false;
+  float x = r.Origin.x + t * r.Direction.x, y = r.Origin.y + t * r.Direction.y;
+  if (x < fromX || y < fromY || x > toX || y > toY) return false;
+  *distance = t;
+  *normal = um::mk(0.0f, 0.0f, 1.0f);
+  return true;
+}
+
+// HitTests.Hit(this Box) (HitTests.cs:80-111, Majercik et al.); Box ctor (Box.cs:11-15): Extents = size / 2,
+// InverseExtents = 1 / Extents
+bool BoxHit(const float size[3], const Ray& ray, float tMin, float tMax, float* distance, f3* normal) {
+  *distance = 0;
+  *normal = um::mk(0.0f);
+  const f3 extents = um::mk(um::div(size[0], 2.0f), um::div(size[1], 2.0f), um::div(size[2], 2.0f));
+  const f3 inverseExtents = um::rcp(extents);
+  const f3 origin = ray.Origin + ray.Direction * tMin;   // "offset origin by tMin"
+  const f3 rayDirection = ray.Direction;
+  const f3 ao = um::mk(um::abs(origin.x), um::abs(origin.y), um::abs(origin.z)) * inverseExtents;
+  const float winding = um::cmax(ao) < 1 ? -1.0f : 1.0f;
+  f3 sgn = um::mk(-Sign(rayDirection.x), -Sign(rayDirection.y), -Sign(rayDirection.z));
+  const f3 num = extents * winding * sgn - origin;
+  const f3 distanceToPlane = um::mk(um::div(num.x, rayDirection.x), um::div(num.y, rayDirection.y), um::div(num.z, rayDirection.z));
+  auto inside = [](float o1, float d1, float o2, float d2, float t, float e1, float e2) {
+    return um::abs(o1 + d1 * t) < e1 && um::abs(o2 + d2 * t) < e2;
+  };
+  const bool testX = distanceToPlane.x >= 0 &&
+                     inside(origin.y, rayDirection.y, origin.z, rayDirection.z, distanceToPlane.x, extents.y, extents.z);
+  const bool testY = distanceToPlane.y >= 0 &&
+                     inside(origin.z, rayDirection.z, origin.x, rayDirection.x, distanceToPlane.y, extents.z, extents.x);
+  const bool testZ = distanceToPlane.z >= 0 &&
+                     inside(origin.x, rayDirection.x, origin.y, rayDirection.y, distanceToPlane.z, extents.x, extents.y);
+  sgn = testX ? um::mk(sgn.x, 0, 0) : testY ? um::mk(0, sgn.y, 0) : um::mk(0, 0, testZ ? sgn.z : 0.0f);
+  const bool nzX = sgn.x != 0, nzY = sgn.y != 0, nzZ = sgn.z != 0;
+  if (!(nzX || nzY || nzZ)) return false;
+  float d = nzX ? distanceToPlane.x : nzY ? distanceToPlane.y : distanceToPlane.z;
+  d += tMin;
+  if (d > tMax) return false;
+  *distance = d;
+  *normal = sgn;
+  return true;
+}
+
+// Entity.TransformAtTime (Entity.cs:124-127)
+um::rigid TransformAtTime(const rtb_placed_entity& e, float t) {
+  const float s = um::clamp(um::unlerp(e.time_range[0], e.time_range[1], t), 0.0f, 1.0f);
+  um::rigid r;
+  r.rot = um::quat{e.rotation[0], e.rotation[1], e.rotation[2], e.rotation[3]};
+  r.pos = v3(e.position) + v3(e.destination_offset) * s;
+  return r;
+}
+
+// Entity.Hit -> HitInternal -> HitContent (Entity.cs:57-122) for an entity with the full record
+bool PlacedHit(const Scene& sc, uint32_t index, int entity, const Ray& ray, float tMin, float tMax, HitRecord* rec) {
+  const rtb_placed_entity& e = sc.placed[index];
+  um::rigid transformAtTime, inverseTransform;
+  if (!e.moving) {
+    transformAtTime = um::rigid{um::quat{e.rotation[0], e.rotation[1], e.rotation[2], e.rotation[3]}, v3(e.position)};
+    inverseTransform = sc.placed_inverse[index];
+  } else {
+    transformAtTime = TransformAtTime(e, ray.Time);
+    inverseTransform = um::inverse(transformAtTime);
+  }
+  Ray entitySpaceRay{um::transform(inverseTransform, ray.Origin), um::rotate(inverseTransform.rot, ray.Direction), ray.Time};
+  float distance;
+  f3 entityLocalNormal;
+  bool hit;
+  switch (e.type) {
+    case RTB_ENTITY_SPHERE: hit = SphereHit(e.size[0], entitySpaceRay, tMin, tMax, &distance, &entityLocalNormal); break;
+    case RTB_ENTITY_RECT: hit = RectHit(e.size, entitySpaceRay, tMin, tMax, &distance, &entityLocalNormal); break;
+    case RTB_ENTITY_BOX: hit = BoxHit(e.size, entitySpaceRay, tMin, tMax, &distance, &entityLocalNormal); break;
+    default: hit = false;
+  }
+  if (!hit) return false;
+  rec->Distance = distance;
+  rec->Point = ray.GetPoint(distance);
+  rec->Normal = um::normalize(um::rotate(transformAtTime.rot, entityLocalNormal));
+  rec->Entity = entity;
+  return true;
+}
+
 // Entity.Hit -> HitInternal -> HitContent (Entity.cs:57-122): static sphere entity, or world-space triangle
 bool EntityHit(const Scene& sc, int entity, const Ray& ray, float tMin, float tMax, HitRecord* rec) {
   int sphere = entity;
   if (sc.entities) {
     const rtb_entity& e = sc.entities[entity];
+    if (Scene::is_placed(e)) return PlacedHit(sc, e.index, entity, ray, tMin, tMax, rec);
     if (e.type == RTB_ENTITY_TRIANGLE) {
       // "Triangles are always world-space" (Entity.cs:92-93); OriginTransform is the identity the mesh job gives
       // every triangle entity (AddMeshRuntimeEntitiesJob.cs), so rotate(transformAtTime, n) == n
@@ -678,6 +777,16 @@ ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
                                          const rtb_batch_buffers* buffers, int noise, int threads,
                                          int64_t index_begin, int64_t index_end);
 
+ORACLE_API int oracle_sample_batch_placed(const rtb_batch_params* params,
+                                          const rtb_entity* entities, size_t entity_count,
+                                          const rtb_sphere* spheres, size_t sphere_count,
+                                          const rtb_triangle* triangles, size_t triangle_count,
+                                          const rtb_placed_entity* placed, size_t placed_count,
+                                          const rtb_material* materials, size_t material_count,
+                                          const rtb_bvh_node* nodes, size_t node_count,
+                                          const rtb_batch_buffers* buffers, int noise, int threads,
+                                          int64_t index_begin, int64_t index_end);
+
 ORACLE_API int oracle_sample_batch(const rtb_batch_params* params,
                                    const rtb_sphere* spheres, size_t sphere_count,
                                    const rtb_material* materials, size_t material_count,
@@ -696,10 +805,29 @@ ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
                                          const rtb_bvh_node* nodes, size_t node_count,
                                          const rtb_batch_buffers* buffers, int noise, int threads,
                                          int64_t index_begin, int64_t index_end) {
+  return oracle_sample_batch_placed(params, entities, entity_count, spheres, sphere_count, triangles, triangle_count, nullptr, 0,
+                                    materials, material_count, nodes, node_count, buffers, noise, threads, index_begin, index_end);
+}
+
+ORACLE_API int oracle_sample_batch_placed(const rtb_batch_params* params,
+                                          const rtb_entity* entities, size_t entity_count,
+                                          const rtb_sphere* spheres, size_t sphere_count,
+                                          const rtb_triangle* triangles, size_t triangle_count,
+                                          const rtb_placed_entity* placed, size_t placed_count,
+                                          const rtb_material* materials, size_t material_count,
+                                          const rtb_bvh_node* nodes, size_t node_count,
+                                          const rtb_batch_buffers* buffers, int noise, int threads,
+                                          int64_t index_begin, int64_t index_end) {
   if (!params || !buffers || params->slice_divider < 1 || params->trace_depth < 0) return RTB_ERR_INVALID_ARGUMENT;
   for (size_t i = 0; i < entity_count; i++) {
-    if (entities[i].type != RTB_ENTITY_SPHERE && entities[i].type != RTB_ENTITY_TRIANGLE) return RTB_ERR_UNSUPPORTED;
-    if (entities[i].index >= (entities[i].type == RTB_ENTITY_SPHERE ? sphere_count : triangle_count)) return RTB_ERR_INVALID_ARGUMENT;
+    const uint32_t base = entities[i].type & ~(uint32_t)RTB_ENTITY_PLACED;
+    if (base < RTB_ENTITY_SPHERE || base > RTB_ENTITY_TRIANGLE) return RTB_ERR_UNSUPPORTED;
+    if (Scene::is_placed(entities[i])) {
+      if (base == RTB_ENTITY_TRIANGLE || entities[i].index >= placed_count || placed[entities[i].index].type != base)
+        return RTB_ERR_INVALID_ARGUMENT;
+    } else if (entities[i].index >= (base == RTB_ENTITY_SPHERE ? sphere_count : triangle_count)) {
+      return RTB_ERR_INVALID_ARGUMENT;
+    }
   }
   for (size_t i = 0; i < material_count; i++)
     if (materials[i].type > RTB_MATERIAL_DIELECTRIC) return RTB_ERR_UNSUPPORTED;
@@ -709,6 +837,13 @@ ORACLE_API int oracle_sample_batch_world(const rtb_batch_params* params,
   sc.entity_count = entity_count;
   sc.triangles = triangles;
   sc.triangle_count = triangle_count;
+  sc.placed = placed;
+  sc.placed_count = placed_count;
+  sc.placed_inverse.resize(placed_count);
+  for (size_t i = 0; i < placed_count; i++) {
+    const rtb_placed_entity& e = placed[i];
+    sc.placed_inverse[i] = um::inverse(um::rigid{um::quat{e.rotation[0], e.rotation[1], e.rotation[2], e.rotation[3]}, v3(e.position)});
+  }
   sc.origin_transform.resize(sphere_count);
   sc.inverse_transform.resize(sphere_count);
   for (size_t i = 0; i < sphere_count; i++) {
@@ -782,6 +917,20 @@ ORACLE_API int oracle_triangle_hit(const rtb_triangle* tri, const float origin[3
   sc.entities = &e; sc.entity_count = 1; sc.triangles = tri; sc.triangle_count = 1;
   HitRecord rec;
   Ray ray{v3(origin), v3(dir), 0};
+  if (!EntityHit(sc, 0, ray, 0, um::INF, &rec)) return 0;
+  *distance = rec.Distance;
+  point[0] = rec.Point.x; point[1] = rec.Point.y; point[2] = rec.Point.z;
+  normal[0] = rec.Normal.x; normal[1] = rec.Normal.y; normal[2] = rec.Normal.z;
+  return 1;
+}
+ORACLE_API int oracle_placed_hit(const rtb_placed_entity* e, const float origin[3], const float dir[3], float time,
+                                 float* distance, float point[3], float normal[3]) {
+  rtb_entity ent{e->type | RTB_ENTITY_PLACED, 0};
+  Scene sc{nullptr, 0, nullptr, 0, nullptr, 0, {}, {}};
+  sc.entities = &ent; sc.entity_count = 1; sc.placed = e; sc.placed_count = 1;
+  sc.placed_inverse.push_back(um::inverse(um::rigid{um::quat{e->rotation[0], e->rotation[1], e->rotation[2], e->rotation[3]}, v3(e->position)}));
+  HitRecord rec;
+  Ray ray{v3(origin), v3(dir), time};
   if (!EntityHit(sc, 0, ray, 0, um::INF, &rec)) return 0;
   *distance = rec.Distance;
   point[0] = rec.Point.x; point[1] = rec.Point.y; point[2] = rec.Point.z;

@@ -44,6 +44,13 @@ TRIANGLE_DTYPE = np.dtype(
 )  # rtb_triangle, 80 B
 ENTITY_DTYPE = np.dtype([("type", "<u4"), ("index", "<u4")])  # rtb_entity, 8 B
 ENTITY_SPHERE, ENTITY_RECT, ENTITY_BOX, ENTITY_TRIANGLE = 1, 2, 3, 4
+ENTITY_PLACED = 0x100  # flag: rtb_entity.index points into the placed-entity array
+PLACED_DTYPE = np.dtype(
+    [("type", "<u4"), ("material", "<u4"), ("moving", "<u4"), ("reserved", "<u4"), ("rotation", "<f4", 4), ("position", "<f4", 3),
+     ("destination_offset", "<f4", 3), ("time_range", "<f4", 2), ("size", "<f4", 3), ("reserved2", "<f4")],
+    align=False,
+)  # rtb_placed_entity, 80 B
+assert PLACED_DTYPE.itemsize == 80
 
 assert SPHERE_DTYPE.itemsize == 32 and MATERIAL_DTYPE.itemsize == 48 and BVH_NODE_DTYPE.itemsize == 40
 assert TRIANGLE_DTYPE.itemsize == 80 and ENTITY_DTYPE.itemsize == 8
@@ -174,6 +181,7 @@ STRUCT_SIZES = {  # name in the headers -> python mirror; checked against sizeof
     "rtb_bvh_node": BVH_NODE_DTYPE.itemsize,
     "rtb_triangle": TRIANGLE_DTYPE.itemsize,
     "rtb_entity": ENTITY_DTYPE.itemsize,
+    "rtb_placed_entity": PLACED_DTYPE.itemsize,
     "rtb_diagnostics": DIAGNOSTICS_DTYPE.itemsize,
     "rtb_view": C.sizeof(View),
     "rtb_environment": C.sizeof(Environment),

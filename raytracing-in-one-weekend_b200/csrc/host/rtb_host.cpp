@@ -482,6 +482,44 @@ void rtbh_triangle_bounds(const rtb_triangle* t, float out_bounds[6]) {
   out_bounds[3] = mx.x; out_bounds[4] = mx.y; out_bounds[5] = mx.z;
 }
 
+void rtbh_placed_bounds(const rtb_placed_entity* e, float out_bounds[6]) {
+  // BvhBuildingEntity ctor (BvhNodeData.cs:28-80): the content's local bounds (Sphere.cs:16-23, Rect.cs:17-19,
+  // Box.cs:17), their 8 corners through OriginTransform; a moving entity takes the minimum through the transform
+  // at min(origin, destination) and the maximum through the one at max(origin, destination) (:58-70)
+  f3 lo, hi;
+  if (e->type == RTB_ENTITY_SPHERE) {
+    const float ar = std::fabs(e->size[0]);
+    lo = um::mk(-ar); hi = um::mk(ar);
+  } else if (e->type == RTB_ENTITY_RECT) {
+    lo = um::mk(um::div(-e->size[0], 2.0f), um::div(-e->size[1], 2.0f), -0.001f);
+    hi = um::mk(um::div(e->size[0], 2.0f), um::div(e->size[1], 2.0f), 0.001f);
+  } else {
+    hi = um::mk(um::div(e->size[0], 2.0f), um::div(e->size[1], 2.0f), um::div(e->size[2], 2.0f));
+    lo = -hi;
+  }
+  um::rigid a, b;
+  a.rot.x = e->rotation[0]; a.rot.y = e->rotation[1]; a.rot.z = e->rotation[2]; a.rot.w = e->rotation[3];
+  a.pos = um::mk(e->position[0], e->position[1], e->position[2]);
+  b = a;
+  if (e->moving) {
+    const f3 dest = a.pos + um::mk(e->destination_offset[0], e->destination_offset[1], e->destination_offset[2]);
+    const f3 origin = a.pos;
+    a.pos = um::min(origin, dest);
+    b.pos = um::max(origin, dest);
+  }
+  f3 mn = um::mk(std::numeric_limits<float>::infinity());
+  f3 mx = um::mk(-std::numeric_limits<float>::infinity());
+  // corner order of BvhNodeData.cs:43-53 (min / max are order-independent; kept for readability)
+  const int order[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {1, 0, 0}, {0, 1, 1}, {1, 1, 0}, {1, 0, 1}, {1, 1, 1}};
+  for (int i = 0; i < 8; i++) {
+    const f3 c = um::mk(order[i][0] ? hi.x : lo.x, order[i][1] ? hi.y : lo.y, order[i][2] ? hi.z : lo.z);
+    mn = um::min(mn, um::transform(a, c));
+    mx = um::max(mx, um::transform(b, c));
+  }
+  out_bounds[0] = mn.x; out_bounds[1] = mn.y; out_bounds[2] = mn.z;
+  out_bounds[3] = mx.x; out_bounds[4] = mx.y; out_bounds[5] = mx.z;
+}
+
 void rtbh_make_triangle(const float v1[3], const float v2[3], const float v3[3], const float* n1, const float* n2,
                         const float* n3, uint32_t material, rtb_triangle* out) {
   // Data = float3x3(v3 - v1, v2 - v1, v1) (Triangle.cs:16,25)

@@ -43,6 +43,13 @@ using um::f3;
 //                    T0 = (Data[0].xyz, Data[1].x)  T1 = (Data[1].yz, Data[2].xy)  T2 = (Data[2].z, n0.xyz)
 //                    T3 = (n1.xyz, n2.x)            T4 = (n2.yz, -, -)          (Triangle.cs:10-11)
 //                  a triangle entity's slot in `spheres` is (triangle index as bits, 0, 0, NaN): NaN radius = triangle
+//   placed       : n_placed * 112 B  7 x float4 per entity with the reference's full Entity record (rtb_placed_entity:
+//                  rotated or moving spheres, EntityType.Rect, EntityType.Box):
+//                    P0 = OriginTransform.rot (x, y, z, w)      P1 = (OriginTransform.pos, type | moving << 8 as bits)
+//                    P2 = InverseTransform.rot                   P3 = (InverseTransform.pos, -)      (static entities)
+//                    P4 = (DestinationOffset, TimeRange.x)       P5 = (TimeRange.y, c0, c1, c2)      P6 = (c3, c4, c5, -)
+//                  content c: Sphere (radius); Rect (From.xy, To.xy); Box (Extents.xyz, InverseExtents.xyz)
+//                  a placed entity's slot in `spheres` is (placed index as bits, 1 as bits, 0, NaN)
 // A device leaf is a subtree of the host's BVH with at most RTB_OPT_LEAF_SPHERES spheres
 // (plugin.cu: Flattener); the host boxes it no longer walks are in chain_ref / chain_boxes (HBM).
 // Materials (n_materials * 64 B DevMaterial) stay in HBM behind the read-only path: they are
@@ -69,9 +76,9 @@ static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
 struct SceneDesc {
   const unsigned char* blob;    // device pointer
   uint32_t blob_bytes;          // multiple of 16
-  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, tri_off;
+  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, tri_off, placed_off;
   const DevMaterial* materials; // device pointer
-  uint32_t n_inner, n_spheres, n_materials, n_triangles;
+  uint32_t n_inner, n_spheres, n_materials, n_triangles, n_placed;
   int32_t root_ref;             // as child refs; meaningful when has_root
   uint32_t has_root;            // 0: empty world (node_count == 0)
   float root_min[3], root_max[3];
@@ -182,7 +189,7 @@ struct SceneView {
   // else `g` is the blob in HBM.
   const unsigned char* g;
   uint32_t s;
-  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, tri_off;
+  uint32_t inner_off, sphere_off, leaf_count_off, mat_index_off, tri_off, placed_off;
 
   __device__ __forceinline__ void bind(const unsigned char* base, const SceneDesc& d) {
     g = base;
@@ -194,8 +201,10 @@ struct SceneView {
 #endif
     inner_off = d.inner_off; sphere_off = d.sphere_off; leaf_count_off = d.leaf_count_off; mat_index_off = d.mat_index_off;
     tri_off = d.tri_off;
+    placed_off = d.placed_off;
   }
   __device__ __forceinline__ float4 triangle(uint32_t index, int k) const { return ld4(tri_off + index * 80u + (uint32_t)k * 16u); }
+  __device__ __forceinline__ float4 placed(uint32_t index, int k) const { return ld4(placed_off + index * 112u + (uint32_t)k * 16u); }
   __device__ __forceinline__ float4 ld4(uint32_t off) const {
     if (SMEM) {
       float4 v;
@@ -242,6 +251,21 @@ __device__ __forceinline__ bool aabb_hit(f3 mn, f3 mx, f3 o, f3 inv, float* t_en
 constexpr int kFlavorSpheres = 0;        // spheres only, no collapsed leaves (the fast build)
 constexpr int kFlavorChains = 1;         // + collapsed leaves: accepted hits go through chain_guard
 constexpr int kFlavorGeneral = 2;        // + EntityType.Triangle entities
+constexpr int kFlavorPlaced = 3;         // + placed entities: rotation, motion (Ray.Time), EntityType.Rect, EntityType.Box
+
+// Ray.Time (View.cs:47; kept by every scattered ray, Material.cs:95-159): one draw per camera path, slot 4 of the
+// camera ray's draws = word 0 of Philox block 1.  Only moving entities read it, so the megakernel re-derives it from
+// the path's counters when one is tested instead of carrying it; the per-pixel kernel (whose white-noise mode has to
+// draw it in stream order anyway) passes the value.
+struct RayClock {
+  uint32_t pixel, sample, seed;
+  float value;
+  bool known;
+  __device__ __forceinline__ float time() const {
+    if (known) return value;
+    return u2f(philox4x32_10(pixel, sample, kBounceCamera, 1u, seed, kPhiloxKey1).x);
+  }
+};
 
 // The host boxes between a collapsed device leaf and sphere `idx`, applied exactly as the reference
 // would (FindHitCandidates reaches a sphere only through a chain of hit boxes, SampleBatchJob.cs:420-447).
@@ -345,10 +369,106 @@ __device__ __forceinline__ void triangle_hit(const SceneView<SMEM>& sv, uint32_t
     best_idx = idx;
   }
 }
-// HitRecord.Normal of the entity in slot `prim` hit at distance t (Entity.cs:57-72): sphere (HitTests.cs:41-45) or
-// triangle (interpolated vertex normals, HitTests.cs:144-147; the hit is re-derived, bit for bit, from the same ray).
-template <bool SMEM, bool TRIS>
-__device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim, f3 o, f3 d, float t) {
+// math.sign
+__device__ __forceinline__ float sign_of(float x) { return (x > 0 ? 1.0f : 0.0f) - (x < 0 ? 1.0f : 0.0f); }
+
+// Entity.HitInternal + HitContent (Entity.cs:74-122) for a placed entity with tMin = 0, tMax = +inf (FindHits,
+// SampleBatchJob.cs:457): the transform at the ray's time, the ray in entity space, then the Sphere / Rect / Box test
+// (HitTests.cs:23-111) in the reference's operation order.  Returns the distance and the entity-space normal rotated
+// back by the transform (not yet normalised).
+template <bool SMEM>
+__device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pidx, f3 o, f3 d, const RayClock& clk,
+                                         float* t_out, f3* n_out) {
+  const float4 p0 = sv.placed(pidx, 0), p1 = sv.placed(pidx, 1);
+  const uint32_t flags = __float_as_uint(p1.w);
+  um::quat rot;
+  rot.x = p0.x; rot.y = p0.y; rot.z = p0.z; rot.w = p0.w;
+  um::rigid inv;
+  if ((flags >> 8) == 0u) {                     // static: InverseTransform from the Entity ctor (Entity.cs:51-52)
+    const float4 p2 = sv.placed(pidx, 2), p3 = sv.placed(pidx, 3);
+    inv.rot.x = p2.x; inv.rot.y = p2.y; inv.rot.z = p2.z; inv.rot.w = p2.w;
+    inv.pos = um::mk(p3.x, p3.y, p3.z);
+  } else {                                      // Entity.TransformAtTime (Entity.cs:124-127), inverted per ray (:87-88)
+    const float4 p4 = sv.placed(pidx, 4);
+    const float tr_y = sv.placed(pidx, 5).x;
+    const float k = um::clamp(um::unlerp(p4.w, tr_y, clk.time()), 0.0f, 1.0f);
+    um::rigid at;
+    at.rot = rot;
+    at.pos = um::mk(p1.x, p1.y, p1.z) + um::mk(p4.x, p4.y, p4.z) * k;
+    inv = um::inverse(at);
+  }
+  const f3 eo = um::transform(inv, o);
+  const f3 ed = um::rotate(inv.rot, d);
+  const float4 p5 = sv.placed(pidx, 5);
+  const uint32_t type = flags & 0xffu;
+  float t;
+  f3 n;
+  if (type == RTB_ENTITY_SPHERE) {              // HitTests.cs:23-60
+    const float radius = p5.y;
+    const float a = um::dot(ed, ed), b = um::dot(eo, ed), c = um::dot(eo, eo) - radius * radius;
+    const float disc = um::fma(b, b, -(a * c));
+    if (!(disc > 0)) return false;
+    const float sq = um::sqrt(disc);
+    t = um::div(-b - sq, a);
+    if (!(t < um::INF && t > 0.0f)) {
+      t = um::div(-b + sq, a);
+      if (!(t < um::INF && t > 0.0f)) return false;
+    }
+    n = um::mad(ed, t, eo) / radius;
+  } else if (type == RTB_ENTITY_RECT) {         // HitTests.cs:62-78
+    if (ed.z >= 0) return false;
+    t = um::div(-eo.z, ed.z);
+    if (t < 0.0f || t > um::INF) return false;
+    const float x = eo.x + t * ed.x, y = eo.y + t * ed.y;
+    const float to_y = sv.placed(pidx, 6).x;
+    if (x < p5.y || y < p5.z || x > p5.w || y > to_y) return false;
+    n = um::mk(0.0f, 0.0f, 1.0f);
+  } else {                                      // Box, HitTests.cs:80-111
+    const float4 p6 = sv.placed(pidx, 6);
+    const f3 ext = um::mk(p5.y, p5.z, p5.w), inv_ext = um::mk(p6.x, p6.y, p6.z);
+    const f3 bo = eo + ed * 0.0f;               // "offset origin by tMin"
+    const f3 ao = um::mk(um::abs(bo.x), um::abs(bo.y), um::abs(bo.z)) * inv_ext;
+    const float winding = um::cmax(ao) < 1 ? -1.0f : 1.0f;
+    const f3 sgn = um::mk(-sign_of(ed.x), -sign_of(ed.y), -sign_of(ed.z));
+    const f3 num = ext * winding * sgn - bo;
+    const f3 dp = um::mk(um::div(num.x, ed.x), um::div(num.y, ed.y), um::div(num.z, ed.z));
+    const bool tx = dp.x >= 0 && um::abs(bo.y + ed.y * dp.x) < ext.y && um::abs(bo.z + ed.z * dp.x) < ext.z;
+    const bool ty = dp.y >= 0 && um::abs(bo.z + ed.z * dp.y) < ext.z && um::abs(bo.x + ed.x * dp.y) < ext.x;
+    const bool tz = dp.z >= 0 && um::abs(bo.x + ed.x * dp.z) < ext.x && um::abs(bo.y + ed.y * dp.z) < ext.y;
+    n = tx ? um::mk(sgn.x, 0.0f, 0.0f) : ty ? um::mk(0.0f, sgn.y, 0.0f) : um::mk(0.0f, 0.0f, tz ? sgn.z : 0.0f);
+    const bool nzx = n.x != 0, nzy = n.y != 0, nzz = n.z != 0;
+    if (!(nzx || nzy || nzz)) return false;
+    t = nzx ? dp.x : nzy ? dp.y : dp.z;
+    t += 0.0f;
+    if (t > um::INF) return false;
+  }
+  *t_out = t;
+  *n_out = um::rotate(rot, n);
+  return true;
+}
+template <bool SMEM>
+__device__ __forceinline__ void placed_hit(const SceneView<SMEM>& sv, uint32_t pidx, int idx, f3 o, f3 d, const RayClock& clk,
+                                           float& best_t, int& best_idx) {
+  float t;
+  f3 n;
+  if (placed_test(sv, pidx, o, d, clk, &t, &n) && t < best_t) {
+    best_t = t;
+    best_idx = idx;
+  }
+}
+
+// HitRecord.Normal of the entity in slot `prim` hit at distance t (Entity.cs:57-72): sphere (HitTests.cs:41-45),
+// triangle (interpolated vertex normals, HitTests.cs:144-147) or placed entity (the hit is re-derived, bit for bit,
+// from the same ray).
+template <bool SMEM, int FLAVOR>
+__device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim, f3 o, f3 d, float t, const RayClock& clk) {
+  constexpr bool TRIS = FLAVOR >= kFlavorGeneral;
+  if (FLAVOR >= kFlavorPlaced && prim.w != prim.w && __float_as_uint(prim.y) != 0u) {
+    float tt = 0;
+    f3 n = um::mk(0.0f);
+    placed_test(sv, __float_as_uint(prim.x), o, d, clk, &tt, &n);
+    return um::normalize(n);
+  }
   if (TRIS && prim.w != prim.w) {
     const uint32_t tri = __float_as_uint(prim.x);
     float u = 0, v = 0, tt = 0;
@@ -384,7 +504,7 @@ constexpr int kLeafUnroll = RTB_LEAF_UNROLL;   // unrolling of the multi-entity 
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
 __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
-                                            float& best_t, int& best_idx, WorkCounters& wc) {
+                                            float& best_t, int& best_idx, WorkCounters& wc, const RayClock& clk) {
   best_t = um::INF;
   best_idx = -1;
   if (!sd.has_root) return;
@@ -403,7 +523,8 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   int cur = sd.root_ref;
   auto test_prim = [&](int slot) {
     const float4 prim = sv.sphere(slot);
-    if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx);
+    if (FLAVOR >= kFlavorPlaced && prim.w != prim.w && __float_as_uint(prim.y) != 0u) placed_hit(sv, __float_as_uint(prim.x), slot, o, d, clk, best_t, best_idx);
+    else if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx);
     else sphere_hit<(FLAVOR >= kFlavorChains)>(sd, prim, slot, o, d, inv, a, best_t, best_idx);
   };
   auto test_leaf = [&](int ref) {
@@ -658,7 +779,7 @@ struct PathRay {
 };
 
 // View.GetRay (View.cs:38-48) with the uv of SampleBatchJob.cs:134.  The ray-time draw
-// (View.cs:47, slot 4) is not generated: nothing on the supported path reads Ray.Time.
+// (View.cs:47, slot 4) is not generated here: only moving entities read Ray.Time (RayClock).
 // Split in two so that a kernel can draw the Philox block and evaluate the sincos for camera rays and for bounces in
 // ONE converged step (sample_megakernel): camera_ray_finish consumes the block r = Philox(pixel, sample, CAMERA, 0) and
 // (s, c) = sincos(u2f(r.z) * 2 PI) — RandomSource.InUnitDisk's theta = u * (2 PI - 0) + 0 is the same float.
@@ -831,7 +952,7 @@ struct WhiteNoise {
 };
 
 // View.GetRay (View.cs:38-48) after the jitter draw of SampleBatchJob.cs:134: lens disk (2 draws, only with a lens), time (1 draw, always)
-__device__ __forceinline__ PathRay camera_ray_white(const rtb_batch_params& p, int cx, int cy, WhiteNoise& rng) {
+__device__ __forceinline__ PathRay camera_ray_white(const rtb_batch_params& p, int cx, int cy, WhiteNoise& rng, float* time) {
   const rtb_view& v = p.view;
   float jx = 0.5f, jy = 0.5f, rdx = 0, rdy = 0;
   if (p.sub_pixel_jitter) { jx = rng.next_float(); jy = rng.next_float(); }
@@ -849,7 +970,7 @@ __device__ __forceinline__ PathRay camera_ray_white(const rtb_batch_params& p, i
   PathRay ray;
   ray.d = um::normalize(v3(v.lower_left_corner) - offset + nx * v3(v.horizontal) + ny * v3(v.vertical));
   ray.o = v3(v.origin) + offset;
-  (void)rng.next_float();     // Ray.Time (View.cs:47): drawn even though nothing on this path moves
+  *time = rng.next_float();   // Ray.Time (View.cs:47): always drawn; read by moving entities only
   return ray;
 }
 

@@ -66,7 +66,7 @@ struct rtb_ctx {
   int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0;
   bool last_in_place = false;
   float last_ms = 0.0f;
-  bool smem_attr_set[2][6] = {};
+  bool smem_attr_set[2][8] = {};
   bool pool_attr_set[2][2] = {{false, false}, {false, false}};
 
   DeviceBuffers buf;
@@ -124,7 +124,10 @@ struct Flattener {
   const rtb_sphere* spheres;
   const rtb_entity* entities = nullptr; // nullptr: entity i is sphere i
   uint32_t collapse_k;
+  static bool is_placed_type(uint32_t t) { return (t & RTB_ENTITY_PLACED) || t == RTB_ENTITY_RECT || t == RTB_ENTITY_BOX; }
+  bool is_placed(size_t e) const { return entities && is_placed_type(entities[e].type); }
   bool is_triangle(size_t e) const { return entities && entities[e].type == RTB_ENTITY_TRIANGLE; }
+  bool not_plain_sphere(size_t e) const { return is_triangle(e) || is_placed(e); }
   const rtb_sphere& sphere_of(size_t e) const { return spheres[entities ? entities[e].index : e]; }
   std::vector<uint8_t> visited;
   std::vector<uint32_t> subtree_spheres;   // per reference node
@@ -165,7 +168,7 @@ struct Flattener {
   // skipped box to contain the sphere shrunk by kChainShrink (true for any BVH built from the spheres'
   // bounds, Sphere.cs:16-23; a host could pass anything).  Otherwise the subtree is not collapsed.
   bool box_contains(const rtb_bvh_node& nd, size_t e) const {
-    if (is_triangle(e)) return false;     // the guard is sphere geometry: subtrees with triangles are not collapsed
+    if (not_plain_sphere(e)) return false;     // the guard is sphere geometry: subtrees with anything else are not collapsed
     const rtb_sphere& s = sphere_of(e);
     const float r = std::fabs(s.radius) * (1.0f - kChainShrink);
     for (int k = 0; k < 3; k++)
@@ -180,7 +183,7 @@ struct Flattener {
         for (int i = 0; i < nd.entity_count; i++)
           if (!box_contains(nd, (size_t)nd.first_entity + i)) return false;
       for (int i = 0; i < nd.entity_count; i++)
-        if (is_triangle((size_t)nd.first_entity + i)) return false;
+        if (not_plain_sphere((size_t)nd.first_entity + i)) return false;
       return true;
     }
     if (!collapsible(nd.left, false) || !collapsible(nd.right, false)) return false;
@@ -284,16 +287,29 @@ struct Flattener {
 bool almost_equals_1(float v) { return std::fabs(1.0f - v) < 1e-6f; }  // MathExtensions.cs:23-27
 
 const char* build_blob(const rtb_entity* entities, size_t entity_count, const rtb_sphere* spheres, size_t sphere_count,
-                       const rtb_triangle* triangles, size_t triangle_count, const rtb_material* materials,
-                       size_t material_count, const rtb_bvh_node* nodes, size_t node_count, uint32_t collapse_k,
-                       HostBlob* out, int* status) {
+                       const rtb_triangle* triangles, size_t triangle_count, const rtb_placed_entity* placed, size_t placed_count,
+                       const rtb_material* materials, size_t material_count, const rtb_bvh_node* nodes, size_t node_count,
+                       uint32_t collapse_k, HostBlob* out, int* status) {
   *status = RTB_ERR_INVALID_ARGUMENT;
   for (size_t i = 0; i < entity_count; i++) {
-    if (entities[i].type != RTB_ENTITY_SPHERE && entities[i].type != RTB_ENTITY_TRIANGLE) {
+    const uint32_t base = entities[i].type & ~(uint32_t)RTB_ENTITY_PLACED;
+    if (base < RTB_ENTITY_SPHERE || base > RTB_ENTITY_TRIANGLE) {
       *status = RTB_ERR_UNSUPPORTED;
-      return "entity type outside the supported hot path (Sphere, Triangle)";
+      return "unknown entity type";
     }
-    if (entities[i].index >= (entities[i].type == RTB_ENTITY_SPHERE ? sphere_count : triangle_count)) return "entity index out of range";
+    if (Flattener::is_placed_type(entities[i].type)) {
+      if (base == RTB_ENTITY_TRIANGLE) return "triangles are always world-space (Entity.cs:92-93): not a placed entity";
+      if (entities[i].index >= placed_count) return "entity index out of range";
+      if (placed[entities[i].index].type != base) return "entity type differs from its placed record";
+    } else if (entities[i].index >= (base == RTB_ENTITY_SPHERE ? sphere_count : triangle_count)) {
+      return "entity index out of range";
+    }
+  }
+  for (size_t i = 0; i < placed_count; i++) {
+    const rtb_placed_entity& e = placed[i];
+    if (e.type != RTB_ENTITY_SPHERE && e.type != RTB_ENTITY_RECT && e.type != RTB_ENTITY_BOX) return "placed entity of an unknown type";
+    if (e.material >= material_count) return "placed entity material index out of range";
+    if (e.moving && e.time_range[0] == e.time_range[1]) return "time range cannot be empty for moving entities (Entity.cs:54)";
   }
   for (size_t i = 0; i < triangle_count; i++)
     if (triangles[i].material >= material_count) return "triangle material index out of range";
@@ -335,6 +351,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   d.n_materials = (uint32_t)material_count;
   d.has_chains = f.collapsed_any ? 1 : 0;
   d.n_triangles = (uint32_t)triangle_count;
+  d.n_placed = (uint32_t)placed_count;
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t off = 0;
@@ -343,6 +360,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   d.leaf_count_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
   d.mat_index_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
   d.tri_off = (uint32_t)off; off = align16(off + triangle_count * 80);
+  d.placed_off = (uint32_t)off; off = align16(off + placed_count * 112);
   if (off == 0) off = 16;
   d.blob_bytes = (uint32_t)off;
   out->bytes.assign(off, 0);
@@ -367,7 +385,14 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
     const uint32_t h = f.order[i];
     float s[4] = {0, 0, 0, 0};
     uint32_t mat = 0;
-    if (h != 0xFFFFFFFFu && f.is_triangle(h)) {
+    if (h != 0xFFFFFFFFu && f.is_placed(h)) {
+      const uint32_t pi = entities[h].index;        // slot = (placed index as bits, 1 as bits, 0, NaN)
+      const uint32_t nan_bits = 0x7fc00000u, one = 1u;
+      memcpy(&s[0], &pi, 4);
+      memcpy(&s[1], &one, 4);
+      memcpy(&s[3], &nan_bits, 4);
+      mat = placed[pi].material;
+    } else if (h != 0xFFFFFFFFu && f.is_triangle(h)) {
       const uint32_t ti = entities[h].index;        // slot = (triangle index as bits, 0, 0, NaN)
       const uint32_t nan_bits = 0x7fc00000u;
       memcpy(&s[0], &ti, 4);
@@ -389,6 +414,33 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
                          t.normals[0][0], t.normals[0][1], t.normals[0][2], t.normals[1][0], t.normals[1][1], t.normals[1][2],
                          t.normals[2][0], t.normals[2][1], t.normals[2][2], 0.0f, 0.0f};
     memcpy(b + d.tri_off + i * 80, q, 80);
+  }
+  for (size_t i = 0; i < placed_count; i++) {
+    const rtb_placed_entity& e = placed[i];
+    um::rigid origin;
+    origin.rot.x = e.rotation[0]; origin.rot.y = e.rotation[1]; origin.rot.z = e.rotation[2]; origin.rot.w = e.rotation[3];
+    origin.pos = um::mk(e.position[0], e.position[1], e.position[2]);
+    const um::rigid inv = um::inverse(origin);     // Entity ctor (Entity.cs:51-52); used by static entities only
+    float c[6] = {0, 0, 0, 0, 0, 0};
+    if (e.type == RTB_ENTITY_SPHERE) {
+      c[0] = e.size[0];
+    } else if (e.type == RTB_ENTITY_RECT) {        // Rect ctor (Rect.cs:11-15)
+      c[0] = um::div(-e.size[0], 2.0f); c[1] = um::div(-e.size[1], 2.0f);
+      c[2] = um::div(e.size[0], 2.0f); c[3] = um::div(e.size[1], 2.0f);
+    } else {                                       // Box ctor (Box.cs:11-15)
+      for (int k = 0; k < 3; k++) { c[k] = um::div(e.size[k], 2.0f); c[3 + k] = um::rcp(c[k]); }
+    }
+    const uint32_t flags = e.type | (e.moving ? 1u << 8 : 0u);
+    float flags_f;
+    memcpy(&flags_f, &flags, 4);
+    const float q[28] = {origin.rot.x, origin.rot.y, origin.rot.z, origin.rot.w,
+                         origin.pos.x, origin.pos.y, origin.pos.z, flags_f,
+                         inv.rot.x, inv.rot.y, inv.rot.z, inv.rot.w,
+                         inv.pos.x, inv.pos.y, inv.pos.z, 0.0f,
+                         e.destination_offset[0], e.destination_offset[1], e.destination_offset[2], e.time_range[0],
+                         e.time_range[1], c[0], c[1], c[2],
+                         c[3], c[4], c[5], 0.0f};
+    memcpy(b + d.placed_off + i * 112, q, 112);
   }
   out->chain_ref = std::move(f.chain_ref);
   out->chain_boxes = std::move(f.chain_boxes);
@@ -581,6 +633,7 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     }
     RTB_CUDA(ctx, cudaGetLastError());
   } else if (kernel_kind == 3) {
+    if (ctx->scene.n_placed) return fail(ctx, RTB_ERR_UNSUPPORTED, "the experimental pool kernel does not handle placed entities");
     const bool fits = pool_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
@@ -589,10 +642,15 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     if (rc != RTB_OK) return rc;
   } else {
     // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
-    const int flavor = (counters || ctx->scene.n_triangles) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
+    const int flavor = ctx->scene.n_placed ? kFlavorPlaced
+                       : (counters || ctx->scene.n_triangles) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
     const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true, flavor) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
+    if (flavor == kFlavorPlaced) {
+      if (fits) rc = counters ? launch_mega_t<true, true, kFlavorPlaced>(ctx, a, stream, max_spp) : launch_mega_t<true, false, kFlavorPlaced>(ctx, a, stream, max_spp);
+      else rc = counters ? launch_mega_t<false, true, kFlavorPlaced>(ctx, a, stream, max_spp) : launch_mega_t<false, false, kFlavorPlaced>(ctx, a, stream, max_spp);
+    } else
     if (fits) rc = counters ? launch_mega_t<true, true, kFlavorGeneral>(ctx, a, stream, max_spp)
                    : flavor == kFlavorGeneral ? launch_mega_t<true, false, kFlavorGeneral>(ctx, a, stream, max_spp)
                    : flavor == kFlavorChains ? launch_mega_t<true, false, kFlavorChains>(ctx, a, stream, max_spp)
@@ -729,18 +787,28 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_sphere* spheres, size_t sphere_coun
 int rtb_upload_world(rtb_ctx* ctx, const rtb_entity* entities, size_t entity_count, const rtb_sphere* spheres, size_t sphere_count,
                      const rtb_triangle* triangles, size_t triangle_count, const rtb_material* materials,
                      size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
+  return rtb_upload_placed_world(ctx, entities, entity_count, spheres, sphere_count, triangles, triangle_count, nullptr, 0, materials,
+                                 material_count, nodes, node_count);
+}
+
+int rtb_upload_placed_world(rtb_ctx* ctx, const rtb_entity* entities, size_t entity_count, const rtb_sphere* spheres,
+                            size_t sphere_count, const rtb_triangle* triangles, size_t triangle_count,
+                            const rtb_placed_entity* placed, size_t placed_count, const rtb_material* materials,
+                            size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
   if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if ((sphere_count && !spheres) || (material_count && !materials) || (node_count && !nodes) || (entity_count && !entities) ||
-      (triangle_count && !triangles))
+      (triangle_count && !triangles) || (placed_count && !placed))
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "NULL array with a non-zero count");
-  if (triangle_count && !entity_count) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "triangles need an entity list");
-  if (sphere_count > (1u << 27) || triangle_count > (1u << 25) || entity_count > (1u << 27) || node_count > (1u << 29))
+  if ((triangle_count || placed_count) && !entity_count) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "triangles and placed entities need an entity list");
+  if (sphere_count > (1u << 27) || triangle_count > (1u << 25) || placed_count > (1u << 24) || entity_count > (1u << 27) ||
+      node_count > (1u << 29))
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "scene too large");
   std::lock_guard<std::mutex> lock(ctx->mu);
   HostBlob hb;
   int status;
   const char* err = build_blob(entity_count ? entities : nullptr, entity_count, spheres, sphere_count, triangles, triangle_count,
-                               materials, material_count, nodes, node_count, (uint32_t)ctx->opt_collapse, &hb, &status);
+                               placed, placed_count, materials, material_count, nodes, node_count, (uint32_t)ctx->opt_collapse, &hb,
+                               &status);
   if (err) return fail(ctx, status, "rtb_upload_scene: %s", err);
   DeviceGuard g(ctx->device);
   RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -805,7 +873,7 @@ int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count, const rtb
   if (leaf_spheres < 1 || leaf_spheres > 15) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "leaf_spheres must be 1..15");
   HostBlob hb;
   int status;
-  const char* err = build_blob(nullptr, 0, spheres, sphere_count, nullptr, 0, materials, material_count, nodes, node_count,
+  const char* err = build_blob(nullptr, 0, spheres, sphere_count, nullptr, 0, nullptr, 0, materials, material_count, nodes, node_count,
                                (uint32_t)leaf_spheres, &hb, &status);
   if (err) return fail(nullptr, status, "rtb_describe_scene: %s", err);
   *out = rtb_scene_layout{};

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) sample_poolkernel(const __grid_
         const float4* mp = reinterpret_cast<const float4*>(sd.materials + mi);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
-        const f3 N = hit_normal<SMEM, true>(sv, sp, o, d, t_hit);
+        const f3 N = hit_normal<SMEM, kFlavorGeneral>(sv, sp, o, d, t_hit, RayClock{});
         const f3 P = um::mad(d, t_hit, o);
         const ScatterResult sc = scatter(m0, m1, m2, m3, d, N, pixel, sample, depth, p.seed);
         dielectric = __float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC;

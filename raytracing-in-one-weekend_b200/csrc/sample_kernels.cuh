@@ -24,9 +24,14 @@ namespace rtbk {
 #ifndef RTB_MEGA_BLOCK_GENERAL
 #define RTB_MEGA_BLOCK_GENERAL 896    // the general flavour (triangles) needs 72 registers to stay out of local memory
 #endif
+#ifndef RTB_MEGA_BLOCK_PLACED
+#define RTB_MEGA_BLOCK_PLACED 640     // the placed-entity flavour (transforms, Rect, Box): 96 registers (measured: 512 / 640 / 768 / 896 threads = 131 / 120 / 141 / 148 ms on the Cornell world)
+#endif
 // Threads per CTA by kernel flavour (measured on B200, profiles/README.md): 1024 x 64 registers for the lean sphere
 // builds, 896 x 72 registers for the general build.
-constexpr int mega_block(int flavor) { return flavor >= kFlavorGeneral ? RTB_MEGA_BLOCK_GENERAL : RTB_MEGA_BLOCK; }
+__host__ __device__ constexpr int mega_block(int flavor) {
+  return flavor >= kFlavorPlaced ? RTB_MEGA_BLOCK_PLACED : flavor >= kFlavorGeneral ? RTB_MEGA_BLOCK_GENERAL : RTB_MEGA_BLOCK;
+}
 constexpr float kFixedScale = 4294967296.0f;            // 2^32
 constexpr float kFixedInvScale = 2.3283064365386963e-10f;  // 2^-32
 constexpr int kAccValues = 10;           // color.xyz, normal.xyz, albedo.xyz, sampleCountWeight
@@ -286,7 +291,8 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     f3 N = um::mk(0.0f), P = um::mk(0.0f);
     if (alive) {
       int hit_idx;
-      closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      const RayClock clk{pixel, sample, p.seed, 0.0f, false};
+      closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
       if (hit_idx >= 0) {
         hit = true;
         const float4 s = sv.sphere(hit_idx);
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
         m0 = __ldg(mp); m1 = __ldg(mp + 1); m2 = __ldg(mp + 2); m3 = __ldg(mp + 3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
-        N = hit_normal<SMEM, (FLAVOR >= kFlavorGeneral)>(sv, s, ray.o, ray.d, t_hit);
+        N = hit_normal<SMEM, FLAVOR>(sv, s, ray.o, ray.d, t_hit, clk);
         P = um::mad(ray.d, t_hit, ray.o);
       } else {
         const f3 sky = sky_color(p.environment, a.scene, ray.d);
@@ -471,7 +477,9 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
   if (WHITE) white.init((p.seed * 0x8C4CA03Fu) ^ (index * 0x7383ED49u));      // SampleBatchJob.cs:91
 
   for (uint32_t s = 0; s < n; s++) {
-    PathRay ray = WHITE ? camera_ray_white(p, cx, cy, white) : camera_ray(p, cx, cy, index, s);
+    RayClock clk{index, s, p.seed, 0.0f, true};
+    PathRay ray = WHITE ? camera_ray_white(p, cx, cy, white, &clk.value) : camera_ray(p, cx, cy, index, s);
+    if (!WHITE && a.scene.n_placed) { clk.known = false; clk.value = clk.time(); clk.known = true; }
     f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
     f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
     bool first_non_specular = false;
@@ -480,14 +488,14 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
     for (; depth < p.trace_depth; depth++) {
       float t_hit;
       int hit_idx;
-      closest_hit<false, COUNTERS, kFlavorGeneral>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc);
+      closest_hit<false, COUNTERS, kFlavorPlaced>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
       rays++;
       if (hit_idx >= 0) {
         const float4 sp = sv.sphere(hit_idx);
         const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
-        const f3 N = hit_normal<false, true>(sv, sp, ray.o, ray.d, t_hit);
+        const f3 N = hit_normal<false, kFlavorPlaced>(sv, sp, ray.o, ray.d, t_hit, clk);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
         const ScatterResult sc = WHITE ? scatter_white(m0, m1, m2, m3, ray.d, N, white)
                                        : scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed);

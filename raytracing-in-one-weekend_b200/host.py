@@ -45,6 +45,8 @@ def lib():
         L.rtbh_sphere_bounds.restype = None
         L.rtbh_triangle_bounds.argtypes = [C.c_void_p, C.c_void_p]
         L.rtbh_triangle_bounds.restype = None
+        L.rtbh_placed_bounds.argtypes = [C.c_void_p, C.c_void_p]
+        L.rtbh_placed_bounds.restype = None
         L.rtbh_make_triangle.argtypes = [abi.f32x3, abi.f32x3, abi.f32x3, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.rtbh_make_triangle.restype = None
         L.rtbh_make_view.argtypes = [
@@ -100,6 +102,7 @@ class Scene:
     entities: np.ndarray = None  # abi.ENTITY_DTYPE or None (entity i == sphere i)
     triangles: np.ndarray = None  # abi.TRIANGLE_DTYPE or None
     focus_distance: float = None  # fixed focus for worlds the sphere-only auto-focus helper cannot walk
+    placed: np.ndarray = None  # abi.PLACED_DTYPE or None: entities with the full Entity record (rtb_upload_placed_world)
 
 
 def generate_scene(scene_id, seed=700, target_count=0):
@@ -209,18 +212,55 @@ def make_triangle(v1, v2, v3, material, normals=None):
     return out[0]
 
 
-def build_world(spheres, triangles, materials, max_bvh_depth, camera, environment, focus_distance, name="world"):
+def quat_from_to(a, b):
+    """Unit quaternion (x, y, z, w) turning direction a into direction b (float64 arithmetic, rounded once)."""
+    a = np.asarray(a, np.float64) / np.linalg.norm(a)
+    b = np.asarray(b, np.float64) / np.linalg.norm(b)
+    d = float(np.dot(a, b))
+    if d < -1 + 1e-12:      # opposite: half a turn about any axis perpendicular to a
+        axis = np.cross(a, (1.0, 0.0, 0.0)) if abs(a[0]) < 0.9 else np.cross(a, (0.0, 1.0, 0.0))
+        axis /= np.linalg.norm(axis)
+        return np.array([axis[0], axis[1], axis[2], 0.0], np.float32)
+    q = np.array([*np.cross(a, b), 1.0 + d])
+    return (q / np.linalg.norm(q)).astype(np.float32)
+
+
+def quat_axis_angle(axis, degrees):
+    axis = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+    h = np.radians(degrees) / 2
+    return np.array([*(axis * np.sin(h)), np.cos(h)], np.float32)
+
+
+def make_placed(entity_type, material, size, position, rotation=(0, 0, 0, 1), destination_offset=None, time_range=(0.0, 1.0)):
+    """new Entity(type, content, new RigidTransform(rotation, position), material, moving, destinationOffset, timeRange)
+    (Entity.cs:39-55) with its content: Sphere(radius) / Rect(size.xy) / Box(size.xyz)."""
+    e = np.zeros(1, dtype=abi.PLACED_DTYPE)[0]
+    e["type"], e["material"] = entity_type, material
+    e["rotation"], e["position"] = rotation, position
+    sz = np.zeros(3, np.float32)
+    sz[: len(np.atleast_1d(size))] = np.atleast_1d(size)
+    e["size"] = sz
+    if destination_offset is not None:
+        e["moving"], e["destination_offset"], e["time_range"] = 1, destination_offset, time_range
+    return e
+
+
+def build_world(spheres, triangles, materials, max_bvh_depth, camera, environment, focus_distance, name="world", placed=None):
     """RebuildWorld for a mixed world: per-entity bounds (CreateBvhBuildingEntitiesJob), the reference's BVH
     build + flatten order, and the BVH-ordered entity list the leaves index (bvhEntities).  Entities are
-    listed spheres first, then triangles, like RebuildEntityBuffers appends them."""
+    listed spheres first, then triangles, then placed entities."""
     spheres = np.ascontiguousarray(spheres, dtype=abi.SPHERE_DTYPE)
     triangles = np.ascontiguousarray(triangles, dtype=abi.TRIANGLE_DTYPE)
-    n = len(spheres) + len(triangles)
+    placed = np.ascontiguousarray(placed if placed is not None else [], dtype=abi.PLACED_DTYPE)
+    n_st = len(spheres) + len(triangles)
+    n = n_st + len(placed)
     bounds = np.zeros((n, 6), np.float32)
     for i in range(len(spheres)):
         lib().rtbh_sphere_bounds(spheres[i:i + 1].ctypes.data, bounds[i].ctypes.data)
     for i in range(len(triangles)):
         lib().rtbh_triangle_bounds(triangles[i:i + 1].ctypes.data, bounds[len(spheres) + i].ctypes.data)
+    for i in range(len(placed)):
+        lib().rtbh_placed_bounds(placed[i:i + 1].ctypes.data, bounds[n_st + i].ctypes.data)
     order = np.zeros(max(n, 1), np.uint32)
     cap = max(1, 2 * n + 1)
     nodes = np.zeros(cap, dtype=abi.BVH_NODE_DTYPE)
@@ -234,8 +274,10 @@ def build_world(spheres, triangles, materials, max_bvh_depth, camera, environmen
         e = int(order[k])
         if e < len(spheres):
             entities[k] = (abi.ENTITY_SPHERE, e)
-        else:
+        elif e < n_st:
             entities[k] = (abi.ENTITY_TRIANGLE, e - len(spheres))
+        else:
+            entities[k] = (int(placed[e - n_st]["type"]) | abi.ENTITY_PLACED, e - n_st)
     info = abi.SceneInfo()
     info.camera = camera
     info.environment = environment
@@ -243,7 +285,8 @@ def build_world(spheres, triangles, materials, max_bvh_depth, camera, environmen
     info.material_count = len(materials)
     return Scene(spheres=spheres, materials=np.ascontiguousarray(materials, dtype=abi.MATERIAL_DTYPE), nodes=nodes[: count.value].copy(),
                  camera=camera, environment=environment, info=info, max_bvh_depth=max_bvh_depth, name=name,
-                 entities=entities, triangles=triangles, focus_distance=focus_distance)
+                 entities=entities, triangles=triangles, focus_distance=focus_distance,
+                 placed=placed if len(placed) else None)
 
 
 def _icosphere(center, radius, subdivisions):
@@ -325,6 +368,59 @@ def make_mesh_scene(max_bvh_depth=16, subdivisions=1, emissive=False):
     env.sky_top_color[:] = (0.5, 0.7, 1.0)
     focus = float(np.linalg.norm(np.array(cam.position[:]) - np.array(cam.target[:])))
     return build_world(spheres, np.array(tris, dtype=abi.TRIANGLE_DTYPE), materials, max_bvh_depth, cam, env, focus, name="mesh")
+
+
+def _material(mtype, albedo, gloss=0.0, metallic=0.0, ior=1.5, emission=(0, 0, 0)):
+    m = np.zeros(1, dtype=abi.MATERIAL_DTYPE)[0]
+    m["type"], m["albedo"], m["emission"] = mtype, albedo, emission
+    m["glossiness"], m["metallic"], m["index_of_refraction"] = gloss, metallic, ior
+    return m
+
+
+def make_cornell_scene(max_bvh_depth=16, moving=True):
+    """A Cornell box in the reference's entity vocabulary (the kind of world its Rect / Box entities exist for):
+    five Rect walls and an emissive Rect light (Rect.cs: an XY rectangle hit from +Z only, turned into place by the
+    entity's rotation), two Box entities turned about Y, a glass sphere (plain sphere entity) and — moving=True — a
+    sphere that moves during the exposure (Entity.TransformAtTime) plus a moving, rotated box.  The front is open and
+    there is no sky: the light panel is the only emitter (Material.Emit), a path ends when it leaves through the front."""
+    S = 5.55
+    materials = np.array([
+        _material(abi.MATERIAL_STANDARD, (0.73, 0.73, 0.73)),                          # 0 white
+        _material(abi.MATERIAL_STANDARD, (0.65, 0.05, 0.05)),                          # 1 red
+        _material(abi.MATERIAL_STANDARD, (0.12, 0.45, 0.15)),                          # 2 green
+        _material(abi.MATERIAL_STANDARD, (0.0, 0.0, 0.0), emission=(15.0, 15.0, 15.0)),  # 3 light
+        _material(abi.MATERIAL_DIELECTRIC, (1, 1, 1), gloss=1.0, ior=1.5),             # 4 glass
+        _material(abi.MATERIAL_STANDARD, (0.8, 0.8, 0.9), gloss=0.9, metallic=1.0),    # 5 polished metal (tall box)
+        _material(abi.MATERIAL_STANDARD, (0.2, 0.3, 0.8)),                             # 6 blue (moving sphere)
+    ], dtype=abi.MATERIAL_DTYPE)
+    z = (0.0, 0.0, 1.0)
+    h = S / 2
+    placed = [
+        make_placed(abi.ENTITY_RECT, 0, (S, S), (h, 0.0, h), quat_from_to(z, (0, 1, 0))),        # floor
+        make_placed(abi.ENTITY_RECT, 0, (S, S), (h, S, h), quat_from_to(z, (0, -1, 0))),         # ceiling
+        make_placed(abi.ENTITY_RECT, 0, (S, S), (h, h, S), quat_from_to(z, (0, 0, -1))),         # back wall
+        make_placed(abi.ENTITY_RECT, 1, (S, S), (0.0, h, h), quat_from_to(z, (1, 0, 0))),        # red wall
+        make_placed(abi.ENTITY_RECT, 2, (S, S), (S, h, h), quat_from_to(z, (-1, 0, 0))),         # green wall
+        make_placed(abi.ENTITY_RECT, 3, (1.3, 1.05), (h, S - 0.01, h), quat_from_to(z, (0, -1, 0))),   # light
+        make_placed(abi.ENTITY_BOX, 5, (1.65, 3.3, 1.65), (3.6, 1.65, 3.5), quat_axis_angle((0, 1, 0), 15.0)),
+        make_placed(abi.ENTITY_BOX, 0, (1.65, 1.65, 1.65), (1.8, 0.825, 1.7), quat_axis_angle((0, 1, 0), -18.0)),
+    ]
+    if moving:
+        placed.append(make_placed(abi.ENTITY_SPHERE, 6, 0.45, (4.4, 0.45, 1.2), quat_axis_angle((1, 2, 3), 40.0),
+                                  destination_offset=(0.0, 0.5, 0.3), time_range=(0.0, 1.0)))
+        placed.append(make_placed(abi.ENTITY_BOX, 1, (0.5, 0.5, 0.5), (0.9, 3.6, 3.9), quat_axis_angle((1, 1, 0), 30.0),
+                                  destination_offset=(0.4, -0.3, 0.0), time_range=(0.25, 0.75)))
+    spheres = np.zeros(1, dtype=abi.SPHERE_DTYPE)
+    spheres[0] = ((1.8, 1.65 + 0.6, 1.7), 0.6, 4, (0, 0, 0))
+    cam = abi.Camera()
+    cam.position[:] = (h, h, -8.0)
+    cam.target[:] = (h, h, 0.0)
+    cam.aperture = 0.0
+    cam.vertical_fov = 40.0
+    env = abi.Environment()
+    env.sky_type = abi.SKY_NONE
+    return build_world(spheres, [], materials, max_bvh_depth, cam, env, 8.0 + h, name="cornell",
+                       placed=np.array(placed, dtype=abi.PLACED_DTYPE))
 
 
 def make_params(scene, width, height, spp, trace_depth, seed=1, aperture=None, jitter=True,

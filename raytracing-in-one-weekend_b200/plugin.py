@@ -15,7 +15,7 @@ from . import build as _build
 
 EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
-    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_placed_world", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_finalize_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
@@ -50,6 +50,7 @@ def lib():
         L.rtb_set_log_callback.argtypes = [vp, vp, vp]
         L.rtb_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
+        L.rtb_upload_placed_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_sky_cubemap.argtypes = [vp, vp, C.c_int, C.c_int]
         L.rtb_describe_scene.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.POINTER(abi.SceneLayout)]
         L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
@@ -208,6 +209,22 @@ class Context:
         self._check(self._L.rtb_upload_world(self._h, ptr(entities), len(entities), ptr(spheres), len(spheres), ptr(triangles),
                                              len(triangles), ptr(materials), len(materials), ptr(nodes), len(nodes)))
 
+    def upload_placed_world(self, entities, spheres, triangles, placed, materials, nodes):
+        """rtb_upload_placed_world: upload_world plus entities with the reference's full Entity record (rotation,
+        motion, Rect / Box content)."""
+        entities = np.ascontiguousarray(entities, dtype=abi.ENTITY_DTYPE)
+        spheres = np.ascontiguousarray(spheres, dtype=abi.SPHERE_DTYPE)
+        triangles = np.ascontiguousarray(triangles, dtype=abi.TRIANGLE_DTYPE)
+        placed = np.ascontiguousarray(placed, dtype=abi.PLACED_DTYPE)
+        materials = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DTYPE)
+        nodes = np.ascontiguousarray(nodes, dtype=abi.BVH_NODE_DTYPE)
+
+        def ptr(a):
+            return a.ctypes.data if len(a) else None
+        self._check(self._L.rtb_upload_placed_world(self._h, ptr(entities), len(entities), ptr(spheres), len(spheres), ptr(triangles),
+                                                    len(triangles), ptr(placed), len(placed), ptr(materials), len(materials),
+                                                    ptr(nodes), len(nodes)))
+
     def upload_sky_cubemap(self, faces):
         """Environment.SkyCubemap: `faces` is a [6, H, W, 4] array of float16 (or their uint16 bits), +X -X +Y -Y +Z -Z;
         None removes it."""
@@ -222,7 +239,9 @@ class Context:
         self._check(self._L.rtb_upload_sky_cubemap(self._h, f.ctypes.data, f.shape[2], f.shape[1]))
 
     def upload(self, scene):
-        if getattr(scene, "entities", None) is not None:
+        if getattr(scene, "placed", None) is not None and len(scene.placed):
+            self.upload_placed_world(scene.entities, scene.spheres, scene.triangles, scene.placed, scene.materials, scene.nodes)
+        elif getattr(scene, "entities", None) is not None:
             self.upload_world(scene.entities, scene.spheres, scene.triangles, scene.materials, scene.nodes)
         else:
             self.upload_scene(scene.spheres, scene.materials, scene.nodes)

@@ -41,6 +41,13 @@ def lib(fast=False):
             C.c_void_p, C.c_size_t, C.POINTER(abi.BatchBuffers), C.c_int, C.c_int, C.c_int64, C.c_int64,
         ]
         L.oracle_sample_batch_world.restype = C.c_int
+        L.oracle_sample_batch_placed.argtypes = [
+            C.POINTER(abi.BatchParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+            C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(abi.BatchBuffers), C.c_int, C.c_int, C.c_int64, C.c_int64,
+        ]
+        L.oracle_sample_batch_placed.restype = C.c_int
+        L.oracle_placed_hit.argtypes = [C.c_void_p, abi.f32x3, abi.f32x3, C.c_float, C.POINTER(C.c_float), abi.f32x3, abi.f32x3]
+        L.oracle_placed_hit.restype = C.c_int
         L.oracle_set_sky_cubemap.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_set_sky_cubemap.restype = None
         L.oracle_cubemap_sample.argtypes = [abi.f32x3, abi.f32x3]
@@ -136,6 +143,17 @@ def set_sky_cubemap(faces, fast=False):
 def sample_batch(scene, params, buffers, noise=NOISE_PHILOX, threads=None, fast=False, index_range=(0, 0)):
     threads = threads or os.cpu_count() or 1
     b = buffers.as_struct()
+    if getattr(scene, "placed", None) is not None and len(scene.placed):
+        tris, sph = scene.triangles, scene.spheres
+        rc = lib(fast).oracle_sample_batch_placed(
+            C.byref(params), scene.entities.ctypes.data, len(scene.entities), sph.ctypes.data if len(sph) else None, len(sph),
+            tris.ctypes.data if len(tris) else None, len(tris), scene.placed.ctypes.data, len(scene.placed),
+            scene.materials.ctypes.data, len(scene.materials), scene.nodes.ctypes.data, len(scene.nodes), C.byref(b), noise, threads,
+            index_range[0], index_range[1],
+        )
+        if rc != 0:
+            raise RuntimeError(f"oracle_sample_batch_placed failed: {rc}")
+        return buffers
     if getattr(scene, "entities", None) is not None:
         tris = scene.triangles
         rc = lib(fast).oracle_sample_batch_world(
