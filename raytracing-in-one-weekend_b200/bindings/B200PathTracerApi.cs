@@ -50,7 +50,15 @@ namespace B200PathTracer
 		public uint Material, Reserved;
 	}
 	// rtb_entity: one element of bvhEntities (BvhNodeData.cs:157-160): Entity.Type + index of Entity.Content
-	[StructLayout(LayoutKind.Sequential)] public struct RtbEntity { public uint Type; /* EntityType: 1 Sphere, 4 Triangle */ public uint Index; }
+	[StructLayout(LayoutKind.Sequential)] public struct RtbEntity { public uint Type; /* EntityType: 1 Sphere, 2 Rect, 3 Box, 4 Triangle; | 0x100: Index is into the placed-entity array */ public uint Index; }
+	// rtb_placed_entity: Entity.cs:24-37 with the content inlined (rotated / moving entities, Rect, Box)
+	[StructLayout(LayoutKind.Sequential)] public struct RtbPlacedEntity
+	{
+		public uint Type, Material, Moving, Reserved;       // Entity.Type, Material - materialBuffer.ptr, Entity.Moving
+		public quaternion Rotation; public float3 Position;  // Entity.OriginTransform
+		public float3 DestinationOffset; public float2 TimeRange;
+		public float3 Size; public float Reserved2;          // Sphere: (Radius, -, -); Rect: ctor size.xy; Box: ctor size.xyz
+	}
 
 	public static unsafe class Api
 	{
@@ -63,6 +71,9 @@ namespace B200PathTracer
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_world(IntPtr ctx, RtbEntity* entities, UIntPtr entityCount,
 			RtbSphere* spheres, UIntPtr sphereCount, RtbTriangle* triangles, UIntPtr triangleCount,
+			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
+		[DllImport(Lib)] public static extern RtbStatus rtb_upload_placed_world(IntPtr ctx, RtbEntity* entities, UIntPtr entityCount,
+			RtbSphere* spheres, UIntPtr sphereCount, RtbTriangle* triangles, UIntPtr triangleCount, RtbPlacedEntity* placed, UIntPtr placedCount,
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
 		// Environment.SkyCubemap: cubemap.GetPixelData<byte>(0, CubemapFace.PositiveX) of an R16G16B16A16_SFloat cubemap (Texture.cs:155-167)
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_sky_cubemap(IntPtr ctx, ushort* halfRgba, int faceWidth, int faceHeight);
