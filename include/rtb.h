@@ -254,6 +254,39 @@ RTB_API int rtb_upload_placed_world(rtb_ctx* ctx,
                                     const rtb_material* materials, size_t material_count,
                                     const rtb_bvh_node* nodes, size_t node_count);
 
+/* Image textures (TextureType.Image, Runtime/Texture.cs:80-89,128-137) — what the reference's host builds for mesh
+ * materials whose Unity material carries a base-colour / emissive / metallic-gloss map (Raytracer.cs:1210-1267).
+ * A material's four textures (Albedo, Emission, Glossiness, Metallic; Material.cs:22) are each either the constant in
+ * rtb_material or an image whose texel scales that constant: colour = rgb / 255 * MainColor, scalar =
+ * texel[channel] / 255 * MainColor[channel] (for a scalar the rtb_material value is the MainColor the host passes,
+ * Raytracer.cs:1249,1258).  The texel is (int2)(TexCoords * ImageSize), row-major from `pixels`; the reference does
+ * not wrap or clamp (it reads past the image for a coordinate of exactly 1): this plugin clamps to the image.
+ * HitRecord.TexCoords are the triangle's interpolated vertex coordinates (HitTests.cs:147); every other entity
+ * type has TexCoords = 0 (Entity.cs:107). */
+typedef struct rtb_image {
+  const uint8_t* pixels;        /* height rows of width texels of pixel_stride bytes */
+  int32_t width, height;
+  int32_t pixel_stride;         /* 3 = RGB24, 4 = RGBA32 */
+  int32_t reserved;
+} rtb_image;
+
+typedef struct rtb_material_textures {  /* per material; image index or -1 = constant */
+  int32_t albedo_image;
+  int32_t emission_image;
+  int32_t glossiness_image;
+  int32_t metallic_image;
+  int32_t glossiness_channel;   /* Texture.ScalarValueChannel (3 = the alpha of an RGBA32 map, Raytracer.cs:1260-1265) */
+  int32_t metallic_channel;
+  int32_t reserved[2];
+} rtb_material_textures;        /* 32 bytes */
+
+/* Attaches images to the world of the last rtb_upload_* call: material_count must equal that world's, triangle_uvs
+ * (6 floats per triangle: the t1, t2, t3 of the Triangle ctor, Triangle.cs:14-29; NULL = all zero) its triangle
+ * count.  Everything is copied.  A later rtb_upload_scene / _world / _placed_world drops the textures. */
+RTB_API int rtb_upload_textures(rtb_ctx* ctx, const rtb_image* images, size_t image_count,
+                                const rtb_material_textures* material_textures, size_t material_count,
+                                const float* triangle_uvs, size_t triangle_count);
+
 /* Environment.SkyCubemap (Runtime/Texture.cs:141-211; the host builds it from the scene's HDRI sky,
  * Raytracer.cs:663-665): six faces of R16G16B16A16_SFloat texels — the only format the reference accepts
  * (Texture.cs:155-163) — in CubemapFace order +X, -X, +Y, -Y, +Z, -Z, each face_height rows of face_width

@@ -183,7 +183,22 @@ struct HitRecord {  // HitRecord.cs
   float Distance;
   f3 Point, Normal;
   int Entity;  // index instead of Entity*
+  float TexU = 0, TexV = 0;  // HitRecord.TexCoords: triangles only ("TODO: Texcoord support for primitives", Entity.cs:107)
 };
+
+// Image textures (TextureType.Image, Texture.cs:80-89,128-137): set by oracle_set_textures (test infrastructure: one set
+// for the process, like the sky).  Images are borrowed; texels are clamped to the image like the plugin does (the
+// reference reads past it for a coordinate of exactly 1).
+const rtb_image* g_images = nullptr; size_t g_image_count = 0;
+const rtb_material_textures* g_mat_tex = nullptr; size_t g_mat_tex_count = 0;
+const float* g_tri_uv = nullptr; size_t g_tri_uv_count = 0;
+const uint8_t* TexelOf(int image, float tu, float tv) {
+  const rtb_image& im = g_images[image];
+  int cx = (int)(tu * (float)im.width), cy = (int)(tv * (float)im.height);   // (int2)(textureCoordinates * ImageSize)
+  cx = cx < 0 ? 0 : (cx > im.width - 1 ? im.width - 1 : cx);
+  cy = cy < 0 ? 0 : (cy > im.height - 1 ? im.height - 1 : cy);
+  return im.pixels + ((size_t)cy * im.width + cx) * im.pixel_stride;
+}
 
 struct Scene {
   const rtb_sphere* spheres; size_t sphere_count;
@@ -247,7 +262,8 @@ bool SphereHit(float radius, const Ray& r, float tMin, float tMax, float* distan
 }
 
 // HitTests.Hit(this Triangle) (HitTests.cs:113-150): Moeller-Trumbore, both faces, vertex normals interpolated
-bool TriangleHit(const rtb_triangle& tri, const Ray& r, float tMin, float tMax, float* distance, f3* normal) {
+bool TriangleHit(const rtb_triangle& tri, const Ray& r, float tMin, float tMax, float* distance, f3* normal,
+                 const float* uv6 = nullptr, float* texU = nullptr, float* texV = nullptr) {
   *distance = 0;
   *normal = um::mk(0.0f);
   const f3 data0 = v3(tri.edge2), data1 = v3(tri.edge1), data2 = v3(tri.v0);
@@ -266,6 +282,10 @@ bool TriangleHit(const rtb_triangle& tri, const Ray& r, float tMin, float tMax, 
   *distance = d;
   f3 barycentricCoords = um::mk(1 - u - v, u, v);
   *normal = um::mul_cols(v3(tri.normals[0]), v3(tri.normals[1]), v3(tri.normals[2]), barycentricCoords);
+  if (uv6 && texU && texV) {  // texCoord = mul(tri.TextureCoordinates, barycentricCoords) (HitTests.cs:147)
+    *texU = um::fma(uv6[4], barycentricCoords.z, um::fma(uv6[2], barycentricCoords.y, uv6[0] * barycentricCoords.x));
+    *texV = um::fma(uv6[5], barycentricCoords.z, um::fma(uv6[3], barycentricCoords.y, uv6[1] * barycentricCoords.x));
+  }
   return true;
 }
 
@@ -371,7 +391,9 @@ bool EntityHit(const Scene& sc, int entity, const Ray& ray, float tMin, float tM
       // every triangle entity (AddMeshRuntimeEntitiesJob.cs), so rotate(transformAtTime, n) == n
       float distance;
       f3 entityLocalNormal;
-      if (!TriangleHit(sc.triangles[e.index], ray, tMin, tMax, &distance, &entityLocalNormal)) return false;
+      const float* uv6 = (g_tri_uv && e.index < g_tri_uv_count) ? g_tri_uv + 6 * (size_t)e.index : nullptr;
+      rec->TexU = rec->TexV = 0;
+      if (!TriangleHit(sc.triangles[e.index], ray, tMin, tMax, &distance, &entityLocalNormal, uv6, &rec->TexU, &rec->TexV)) return false;
       rec->Distance = distance;
       rec->Point = ray.GetPoint(distance);
       rec->Normal = um::normalize(um::rotate(um::quat_identity(), entityLocalNormal));
@@ -434,12 +456,39 @@ float SmithMaskingShadowing(f3 w, f3 normal, float roughness) {  // Microfacet.c
 }
 
 bool AlmostEquals1(float v) { return um::abs(1.0f - v) < 1e-6f; }  // MathExtensions.cs:23-27
-bool IsPerfectSpecular(const rtb_material& m) {                    // Material.cs:181-196
+bool IsPerfectSpecular(const rtb_material& m, uint32_t materialIndex) {  // Material.cs:181-196
   switch (m.type) {
     case RTB_MATERIAL_DIELECTRIC: return true;
-    case RTB_MATERIAL_STANDARD: return AlmostEquals1(m.metallic) && AlmostEquals1(m.glossiness);
+    case RTB_MATERIAL_STANDARD: {
+      // Metallic.Type == Constant && ... && Glossiness.Type == Constant && ...
+      if (g_mat_tex && materialIndex < g_mat_tex_count &&
+          (g_mat_tex[materialIndex].metallic_image >= 0 || g_mat_tex[materialIndex].glossiness_image >= 0))
+        return false;
+      return AlmostEquals1(m.metallic) && AlmostEquals1(m.glossiness);
+    }
   }
   return false;
+}
+
+// What Albedo / Emission .SampleColor and Glossiness / Metallic .SampleScalar return at the hit's TexCoords
+// (Texture.cs:50-138): the material with its image textures evaluated, so that Scatter / Emit below read plain values.
+rtb_material SampleTextures(const rtb_material& m, uint32_t materialIndex, const HitRecord& rec) {
+  rtb_material r = m;
+  if (!g_mat_tex || materialIndex >= g_mat_tex_count) return r;
+  const rtb_material_textures& t = g_mat_tex[materialIndex];
+  if (t.albedo_image >= 0) {   // float3(p[0], p[1], p[2]) / 255 * MainColor
+    const uint8_t* p = TexelOf(t.albedo_image, rec.TexU, rec.TexV);
+    for (int k = 0; k < 3; k++) r.albedo[k] = um::div((float)p[k], 255.0f) * m.albedo[k];
+  }
+  if (t.emission_image >= 0) {
+    const uint8_t* p = TexelOf(t.emission_image, rec.TexU, rec.TexV);
+    for (int k = 0; k < 3; k++) r.emission[k] = um::div((float)p[k], 255.0f) * m.emission[k];
+  }
+  if (t.glossiness_image >= 0)  // p[ScalarValueChannel] / 255.0f * MainColor[ScalarValueChannel]
+    r.glossiness = um::div((float)TexelOf(t.glossiness_image, rec.TexU, rec.TexV)[t.glossiness_channel], 255.0f) * m.glossiness;
+  if (t.metallic_image >= 0)
+    r.metallic = um::div((float)TexelOf(t.metallic_image, rec.TexU, rec.TexV)[t.metallic_channel], 255.0f) * m.metallic;
+  return r;
 }
 
 // Material.Scatter (Material.cs:67-173), Standard and Dielectric; constant textures
@@ -636,7 +685,8 @@ bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleCo
 
     if (!w.hits.empty()) {
       const HitRecord rec = w.hits[0];
-      const rtb_material& material = sc.materials[sc.material_of(rec.Entity)];
+      const uint32_t materialIndex = sc.material_of(rec.Entity);
+      const rtb_material material = SampleTextures(sc.materials[materialIndex], materialIndex, rec);
       f3 albedo;
       Ray scatteredRay;
       Scatter(material, ray, rec, rng, &albedo, &scatteredRay);
@@ -644,7 +694,7 @@ bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleCo
       w.emission.push_back(emission);
       if (depth == 0) *sampleNormal = rec.Normal;
       if (!firstNonSpecularHit) {
-        if (!IsPerfectSpecular(material)) {
+        if (!IsPerfectSpecular(material, materialIndex)) {
           *sampleAlbedo = emission + albedo;
           *sampleNormal = rec.Normal;
           firstNonSpecularHit = true;
@@ -872,6 +922,12 @@ ORACLE_API int oracle_sample_batch_placed(const rtb_batch_params* params,
   return RTB_OK;
 }
 
+ORACLE_API void oracle_set_textures(const rtb_image* images, size_t image_count, const rtb_material_textures* material_textures,
+                                    size_t material_count, const float* triangle_uvs, size_t triangle_count) {
+  g_images = images; g_image_count = image_count;            // borrowed: the caller keeps the arrays alive while it renders
+  g_mat_tex = material_textures; g_mat_tex_count = material_count;
+  g_tri_uv = triangle_uvs; g_tri_uv_count = triangle_count;
+}
 ORACLE_API void oracle_set_sky_cubemap(const uint16_t* half_rgba, int face_width, int face_height) {
   g_sky_faces = half_rgba;     // borrowed: the caller keeps the array alive while it renders
   g_sky_w = face_width;

@@ -52,6 +52,17 @@ PLACED_DTYPE = np.dtype(
 )  # rtb_placed_entity, 80 B
 assert PLACED_DTYPE.itemsize == 80
 
+
+class Image(C.Structure):  # rtb_image
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pixel_stride", C.c_int32), ("reserved", C.c_int32)]
+
+
+MATERIAL_TEXTURES_DTYPE = np.dtype(
+    [("albedo_image", "<i4"), ("emission_image", "<i4"), ("glossiness_image", "<i4"), ("metallic_image", "<i4"),
+     ("glossiness_channel", "<i4"), ("metallic_channel", "<i4"), ("reserved", "<i4", 2)]
+)  # rtb_material_textures, 32 B
+assert MATERIAL_TEXTURES_DTYPE.itemsize == 32
+
 assert SPHERE_DTYPE.itemsize == 32 and MATERIAL_DTYPE.itemsize == 48 and BVH_NODE_DTYPE.itemsize == 40
 assert TRIANGLE_DTYPE.itemsize == 80 and ENTITY_DTYPE.itemsize == 8
 
@@ -182,6 +193,8 @@ STRUCT_SIZES = {  # name in the headers -> python mirror; checked against sizeof
     "rtb_triangle": TRIANGLE_DTYPE.itemsize,
     "rtb_entity": ENTITY_DTYPE.itemsize,
     "rtb_placed_entity": PLACED_DTYPE.itemsize,
+    "rtb_image": C.sizeof(Image),
+    "rtb_material_textures": MATERIAL_TEXTURES_DTYPE.itemsize,
     "rtb_diagnostics": DIAGNOSTICS_DTYPE.itemsize,
     "rtb_view": C.sizeof(View),
     "rtb_environment": C.sizeof(Environment),

@@ -69,7 +69,7 @@ struct DevMaterial {            // 64 bytes = 4 x float4; lives in HBM (read-onl
   float alpha;                  // Microfacet.RoughnessToAlpha(roughness) (Standard)
   float r0;                     // Schlick: ((1 - ior) / (1 + ior))^2
   float one_minus_r0;
-  uint32_t pad;
+  uint32_t textured;            // some texture of this material is an image (rtb_upload_textures): resolve_textures per hit
 };
 static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
 
@@ -83,6 +83,11 @@ struct SceneDesc {
   uint32_t has_root;            // 0: empty world (node_count == 0)
   float root_min[3], root_max[3];
   uint32_t max_depth;           // deepest root-to-leaf path (stack bound)
+  // image textures (rtb_upload_textures); all in HBM, read only on hits of textured materials
+  const unsigned char* tex_pixels;   // every image, back to back
+  const int4* tex_images;            // per image: (byte offset, width, height, pixel stride)
+  const int4* mat_textures;          // per material, 2 x int4: (albedo, emission, glossiness, metallic image or -1), (gloss channel, metallic channel, -, -)
+  const float2* tri_uv;              // 3 per triangle (Triangle.TextureCoordinates columns) or nullptr
   const uint16_t* sky_faces;    // Environment.SkyCubemap texels (6 faces of RGBA halves) or nullptr
   int sky_w, sky_h;
   uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
@@ -1034,11 +1039,67 @@ __device__ __forceinline__ ScatterResult scatter_white(float4 m0, float4 m1, flo
   return out;
 }
 
+// Texture.SampleColor / SampleScalar for TextureType.Image (Texture.cs:80-89,128-137), texel clamped to the image.
+__device__ __forceinline__ const unsigned char* texel_of(const SceneDesc& sd, int image, float tu, float tv) {
+  const int4 im = __ldg(sd.tex_images + image);
+  int cx = (int)(tu * (float)im.y), cy = (int)(tv * (float)im.z);
+  cx = min(max(cx, 0), im.y - 1);
+  cy = min(max(cy, 0), im.z - 1);
+  return sd.tex_pixels + (size_t)(uint32_t)im.x + ((size_t)cy * (size_t)im.y + (size_t)cx) * (size_t)im.w;
+}
+
+__device__ __forceinline__ void derive_material(DevMaterial& x);
+
+// A hit on a material with image textures: Material.Scatter / Emit sample Albedo, Metallic, Glossiness and Emission at
+// HitRecord.TexCoords first (Material.cs:70-77,175-179).  The sampled values replace the constants in the material
+// registers and the derived Scatter constants are re-evaluated by the function the upload kernel uses.
+template <bool SMEM>
+__device__ __noinline__ void resolve_textures(const SceneView<SMEM>& sv, const SceneDesc& sd, uint32_t material, float4 prim, f3 o, f3 d,
+                                              float4& m0, float4& m1, float4& m2, float4& m3) {
+  float tu = 0, tv = 0;                          // "TODO: Texcoord support for primitives" (Entity.cs:107)
+  if (prim.w != prim.w && __float_as_uint(prim.y) == 0u && sd.tri_uv) {
+    const uint32_t tri = __float_as_uint(prim.x);
+    float u = 0, v = 0, t = 0;
+    triangle_uvt(sv, tri, o, d, &u, &v, &t);
+    const float bx = 1 - u - v;
+    const float2 t0 = __ldg(sd.tri_uv + 3 * (size_t)tri), t1 = __ldg(sd.tri_uv + 3 * (size_t)tri + 1), t2 = __ldg(sd.tri_uv + 3 * (size_t)tri + 2);
+    tu = um::fma(t2.x, v, um::fma(t1.x, u, t0.x * bx));     // mul(float2x3, barycentricCoords) (HitTests.cs:147)
+    tv = um::fma(t2.y, v, um::fma(t1.y, u, t0.y * bx));
+  }
+  const int4 ti = __ldg(sd.mat_textures + 2 * (size_t)material), tc = __ldg(sd.mat_textures + 2 * (size_t)material + 1);
+  DevMaterial x;
+  x.albedo[0] = m0.x; x.albedo[1] = m0.y; x.albedo[2] = m0.z; x.type = __float_as_uint(m0.w);
+  x.emission[0] = m1.x; x.emission[1] = m1.y; x.emission[2] = m1.z; x.glossiness = m1.w;
+  x.metallic = m2.x; x.ior = m2.y; x.perfect_specular = __float_as_uint(m2.z); x.roughness = m2.w;
+  x.alpha = m3.x; x.r0 = m3.y; x.one_minus_r0 = m3.z; x.textured = __float_as_uint(m3.w);
+  if (ti.x >= 0) {
+    const unsigned char* px = texel_of(sd, ti.x, tu, tv);
+    for (int k = 0; k < 3; k++) x.albedo[k] = um::div((float)px[k], 255.0f) * x.albedo[k];
+  }
+  if (ti.y >= 0) {
+    const unsigned char* px = texel_of(sd, ti.y, tu, tv);
+    for (int k = 0; k < 3; k++) x.emission[k] = um::div((float)px[k], 255.0f) * x.emission[k];
+  }
+  if (ti.z >= 0) x.glossiness = um::div((float)texel_of(sd, ti.z, tu, tv)[tc.x], 255.0f) * x.glossiness;
+  if (ti.w >= 0) x.metallic = um::div((float)texel_of(sd, ti.w, tu, tv)[tc.y], 255.0f) * x.metallic;
+  if (x.type == RTB_MATERIAL_DIELECTRIC) x.ior = m2.y;      // IndexOfRefraction is not a texture
+  derive_material(x);
+  m0 = make_float4(x.albedo[0], x.albedo[1], x.albedo[2], m0.w);
+  m1 = make_float4(x.emission[0], x.emission[1], x.emission[2], x.glossiness);
+  m2 = make_float4(x.metallic, x.ior, m2.z, x.roughness);
+  m3 = make_float4(x.alpha, x.r0, x.one_minus_r0, m3.w);
+}
+
+// DevMaterial's derived constants from (type, glossiness, metallic, ior): the per-material part of Material.Scatter.
 // Fills DevMaterial's derived constants on the device (one thread per material, at upload).
 __global__ void derive_materials_kernel(DevMaterial* m, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   DevMaterial x = m[i];
+  derive_material(x);
+  m[i] = x;
+}
+__device__ __forceinline__ void derive_material(DevMaterial& x) {
   if (x.type == RTB_MATERIAL_STANDARD) {
     x.roughness = um::pow2(1 - x.glossiness);
     x.ior = um::lerp(1.5f, 1.1f, x.metallic);        // PlasticIor, MetalIor (Material.cs:18-19)
@@ -1049,7 +1110,6 @@ __global__ void derive_materials_kernel(DevMaterial* m, uint32_t n) {
   }
   x.r0 = schlick_r0(x.ior);
   x.one_minus_r0 = 1 - x.r0;
-  m[i] = x;
 }
 
 // 2^-depth exactly as repeated halving produces it (normal, denormal, then 0)

@@ -53,6 +53,11 @@ struct rtb_ctx {
   DevMaterial* d_materials = nullptr;
   uint16_t* d_sky = nullptr;
   int sky_w = 0, sky_h = 0;
+  std::vector<DevMaterial> host_materials;   // as uploaded (before derive_materials_kernel), for rtb_upload_textures
+  unsigned char* d_tex_pixels = nullptr;
+  int4* d_tex_images = nullptr;
+  int4* d_mat_textures = nullptr;
+  float2* d_tri_uv = nullptr;
   uint32_t* d_chain_ref = nullptr;
   float4* d_chain_boxes = nullptr;
   SceneDesc scene{};
@@ -590,6 +595,10 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   a.b = dev;
   a.scene = ctx->scene;
   a.scene.sky_faces = ctx->d_sky;
+  a.scene.tex_pixels = ctx->d_tex_pixels;
+  a.scene.tex_images = ctx->d_tex_images;
+  a.scene.mat_textures = ctx->d_mat_textures;
+  a.scene.tri_uv = ctx->d_tri_uv;
   a.scene.sky_w = ctx->sky_w;
   a.scene.sky_h = ctx->sky_h;
   a.width = width;
@@ -633,7 +642,8 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     }
     RTB_CUDA(ctx, cudaGetLastError());
   } else if (kernel_kind == 3) {
-    if (ctx->scene.n_placed) return fail(ctx, RTB_ERR_UNSUPPORTED, "the experimental pool kernel does not handle placed entities");
+    if (ctx->scene.n_placed || ctx->d_mat_textures)
+      return fail(ctx, RTB_ERR_UNSUPPORTED, "the experimental pool kernel does not handle placed entities or image textures");
     const bool fits = pool_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
@@ -643,7 +653,7 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   } else {
     // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
     const int flavor = ctx->scene.n_placed ? kFlavorPlaced
-                       : (counters || ctx->scene.n_triangles) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
+                       : (counters || ctx->scene.n_triangles || ctx->d_mat_textures) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
     const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true, flavor) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
@@ -692,6 +702,15 @@ cudaError_t copy_rows(void* dst, const void* src, size_t elem_bytes, int width, 
   if (rows.row_step == 1)
     return cudaMemcpyAsync((char*)dst + offset, (const char*)src + offset, row_bytes * (size_t)rows.n_rows, kind, stream);
   return cudaMemcpy2DAsync((char*)dst + offset, pitch, (const char*)src + offset, pitch, row_bytes, (size_t)rows.n_rows, kind, stream);
+}
+
+void drop_textures(rtb_ctx* ctx) {
+  void* ptrs[] = {ctx->d_tex_pixels, ctx->d_tex_images, ctx->d_mat_textures, ctx->d_tri_uv};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  ctx->d_tex_pixels = nullptr;
+  ctx->d_tex_images = nullptr;
+  ctx->d_mat_textures = nullptr;
+  ctx->d_tri_uv = nullptr;
 }
 
 struct DeviceGuard {
@@ -760,7 +779,7 @@ int rtb_destroy(rtb_ctx* ctx) {
     for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
     DeviceBuffers& b = ctx->buf;
     void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
-                    b.diagnostics, ctx->d_sky, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+                    b.diagnostics, ctx->d_sky, ctx->d_tex_pixels, ctx->d_tex_images, ctx->d_mat_textures, ctx->d_tri_uv, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -821,6 +840,8 @@ int rtb_upload_placed_world(rtb_ctx* ctx, const rtb_entity* entities, size_t ent
   ctx->d_chain_ref = nullptr;
   ctx->d_chain_boxes = nullptr;
   ctx->has_scene = false;
+  drop_textures(ctx);
+  ctx->host_materials = hb.materials;
   RTB_CUDA(ctx, cudaMalloc(&ctx->d_blob, hb.bytes.size()));
   RTB_CUDA(ctx, cudaMemcpy(ctx->d_blob, hb.bytes.data(), hb.bytes.size(), cudaMemcpyHostToDevice));
   RTB_CUDA(ctx, cudaMalloc(&ctx->d_materials, hb.materials.size() * sizeof(DevMaterial)));
@@ -843,6 +864,69 @@ int rtb_upload_placed_world(rtb_ctx* ctx, const rtb_entity* entities, size_t ent
   ctx->scene.chain_boxes = ctx->d_chain_boxes;
   if (ctx->scene.has_chains && ctx->opt_walk_chains) ctx->scene.has_chains = 2u;
   ctx->has_scene = true;
+  return RTB_OK;
+}
+
+int rtb_upload_textures(rtb_ctx* ctx, const rtb_image* images, size_t image_count, const rtb_material_textures* mt,
+                        size_t material_count, const float* triangle_uvs, size_t triangle_count) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (!ctx->has_scene) return fail(ctx, RTB_ERR_NO_SCENE, "rtb_upload_textures before a world was uploaded");
+  if ((image_count && !images) || (material_count && !mt)) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "NULL array with a non-zero count");
+  if (material_count != ctx->scene.n_materials) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_upload_textures: material count differs from the world's");
+  if (triangle_uvs && triangle_count != ctx->scene.n_triangles)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_upload_textures: triangle count differs from the world's");
+  if (image_count > (1u << 20)) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "too many images");
+  std::vector<int4> desc(std::max<size_t>(image_count, 1));
+  size_t total = 0;
+  for (size_t i = 0; i < image_count; i++) {
+    const rtb_image& im = images[i];
+    if (!im.pixels || im.width < 1 || im.height < 1 || im.width > 32768 || im.height > 32768 || (im.pixel_stride != 3 && im.pixel_stride != 4))
+      return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_upload_textures: image %zu: need pixels, a size in 1..32768 and a stride of 3 or 4", i);
+    if (total > 0x7fffffffu) return fail(ctx, RTB_ERR_UNSUPPORTED, "more than 2 GB of image data");
+    desc[i] = make_int4((int)total, im.width, im.height, im.pixel_stride);
+    total += (size_t)im.width * im.height * im.pixel_stride;
+  }
+  std::vector<int4> mat(std::max<size_t>(material_count, 1) * 2);
+  std::vector<DevMaterial> dm = ctx->host_materials;
+  for (size_t i = 0; i < material_count; i++) {
+    const int32_t idx[4] = {mt[i].albedo_image, mt[i].emission_image, mt[i].glossiness_image, mt[i].metallic_image};
+    const int32_t ch[4] = {0, 0, mt[i].glossiness_channel, mt[i].metallic_channel};
+    bool any = false;
+    for (int k = 0; k < 4; k++) {
+      if (idx[k] < 0) continue;
+      if ((size_t)idx[k] >= image_count) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_upload_textures: material %zu names image %d", i, idx[k]);
+      const int need = k < 2 ? 3 : ch[k] + 1;      // a colour reads bytes 0..2 (Texture.cs:88), a scalar its channel (:136)
+      if (ch[k] < 0 || need > images[idx[k]].pixel_stride) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_upload_textures: material %zu reads a channel its image does not have", i);
+      any = true;
+    }
+    mat[2 * i] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+    mat[2 * i + 1] = make_int4(ch[2], ch[3], 0, 0);
+    dm[i].textured = any ? 1u : 0u;
+    // Material.IsPerfectSpecular needs CONSTANT Metallic and Glossiness textures (Material.cs:190-192)
+    if (dm[i].type == RTB_MATERIAL_STANDARD && (idx[2] >= 0 || idx[3] >= 0)) dm[i].perfect_specular = 0;
+  }
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  drop_textures(ctx);
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_tex_pixels, std::max<size_t>(total, 16)));
+  for (size_t i = 0; i < image_count; i++)
+    RTB_CUDA(ctx, cudaMemcpy(ctx->d_tex_pixels + desc[i].x, images[i].pixels, (size_t)images[i].width * images[i].height * images[i].pixel_stride,
+                             cudaMemcpyHostToDevice));
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_tex_images, desc.size() * sizeof(int4)));
+  RTB_CUDA(ctx, cudaMemcpy(ctx->d_tex_images, desc.data(), desc.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  RTB_CUDA(ctx, cudaMalloc(&ctx->d_mat_textures, mat.size() * sizeof(int4)));
+  RTB_CUDA(ctx, cudaMemcpy(ctx->d_mat_textures, mat.data(), mat.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (triangle_uvs && triangle_count) {
+    RTB_CUDA(ctx, cudaMalloc(&ctx->d_tri_uv, triangle_count * 6 * sizeof(float)));
+    RTB_CUDA(ctx, cudaMemcpy(ctx->d_tri_uv, triangle_uvs, triangle_count * 6 * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (material_count) {
+    RTB_CUDA(ctx, cudaMemcpy(ctx->d_materials, dm.data(), material_count * sizeof(DevMaterial), cudaMemcpyHostToDevice));
+    derive_materials_kernel<<<(unsigned)((material_count + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_materials, (uint32_t)material_count);
+    RTB_CUDA(ctx, cudaGetLastError());
+    RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return RTB_OK;
 }
 

@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
         m0 = __ldg(mp); m1 = __ldg(mp + 1); m2 = __ldg(mp + 2); m3 = __ldg(mp + 3);
+        if (FLAVOR >= kFlavorGeneral && __float_as_uint(m3.w) != 0u) resolve_textures(sv, a.scene, mi, s, ray.o, ray.d, m0, m1, m2, m3);
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
         N = hit_normal<SMEM, FLAVOR>(sv, s, ray.o, ray.d, t_hit, clk);
         P = um::mad(ray.d, t_hit, ray.o);
@@ -494,7 +495,8 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
         const float4 sp = sv.sphere(hit_idx);
         const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
-        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+        float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+        if (__float_as_uint(m3.w) != 0u) resolve_textures(sv, a.scene, mi, sp, ray.o, ray.d, m0, m1, m2, m3);
         const f3 N = hit_normal<false, kFlavorPlaced>(sv, sp, ray.o, ray.d, t_hit, clk);
         const f3 P = um::mad(ray.d, t_hit, ray.o);
         const ScatterResult sc = WHITE ? scatter_white(m0, m1, m2, m3, ray.d, N, white)

@@ -103,6 +103,10 @@ class Scene:
     triangles: np.ndarray = None  # abi.TRIANGLE_DTYPE or None
     focus_distance: float = None  # fixed focus for worlds the sphere-only auto-focus helper cannot walk
     placed: np.ndarray = None  # abi.PLACED_DTYPE or None: entities with the full Entity record (rtb_upload_placed_world)
+    # image textures (rtb_upload_textures): uint8 [H, W, 3|4] arrays, one record per material, [n_triangles, 3, 2] vertex uvs
+    images: list = None
+    material_textures: np.ndarray = None  # abi.MATERIAL_TEXTURES_DTYPE or None
+    triangle_uvs: np.ndarray = None
 
 
 def generate_scene(scene_id, seed=700, target_count=0):
@@ -317,7 +321,29 @@ def _icosphere(center, radius, subdivisions):
     return verts, normals, f
 
 
-def make_mesh_scene(max_bvh_depth=16, subdivisions=1, emissive=False):
+def _test_images():
+    """Small deterministic images in the two formats the reference's host accepts (RGB24, RGBA32; Raytracer.cs:1214-1265)."""
+    yy, xx = np.mgrid[0:32, 0:32]
+    checker = np.zeros((32, 32, 3), np.uint8)
+    on = ((xx // 4 + yy // 4) % 2) == 0
+    checker[on] = (230, 220, 200)
+    checker[~on] = (40, 60, 90)
+    checker[:, :, 0] = np.where(xx > 24, 255, checker[:, :, 0])
+    rgba = np.zeros((16, 24, 4), np.uint8)                     # base colour map whose alpha is the smoothness
+    y2, x2 = np.mgrid[0:16, 0:24]
+    rgba[..., 0] = 120 + 5 * x2
+    rgba[..., 1] = 250 - 9 * y2
+    rgba[..., 2] = 90 + ((x2 * 7 + y2 * 13) % 160)
+    rgba[..., 3] = np.where((x2 + y2) % 3 == 0, 255, 60 + 8 * y2)
+    metal = np.zeros((8, 8, 3), np.uint8)
+    metal[..., 0] = np.where(np.mgrid[0:8, 0:8][1] % 2 == 0, 255, 0)
+    glow = np.zeros((4, 4, 3), np.uint8)
+    glow[..., 0], glow[..., 1], glow[..., 2] = 255, 180, 60
+    glow[1:3, 1:3] = (20, 60, 255)
+    return [checker, rgba, metal, glow]
+
+
+def make_mesh_scene(max_bvh_depth=16, subdivisions=1, emissive=False, textured=False):
     """A small mixed world in the shape of what the reference's host produces at HEAD (mesh triangles,
     Raytracer.cs:1185-1304) plus sphere entities: a two-triangle ground quad (face normals), a smooth-shaded
     icosphere (vertex normals, glossy metal), a flat-shaded tetrahedron (Lambertian), a hollow glass sphere
@@ -367,7 +393,32 @@ def make_mesh_scene(max_bvh_depth=16, subdivisions=1, emissive=False):
     env.sky_bottom_color[:] = (1.0, 1.0, 1.0)
     env.sky_top_color[:] = (0.5, 0.7, 1.0)
     focus = float(np.linalg.norm(np.array(cam.position[:]) - np.array(cam.target[:])))
-    return build_world(spheres, np.array(tris, dtype=abi.TRIANGLE_DTYPE), materials, max_bvh_depth, cam, env, focus, name="mesh")
+    scene = build_world(spheres, np.array(tris, dtype=abi.TRIANGLE_DTYPE), materials, max_bvh_depth, cam, env, focus, name="mesh")
+    if textured:
+        # what the host builds for Unity materials with maps (Raytracer.cs:1210-1267): a base-colour map on the ground
+        # (RGB24, uv reaching exactly 1 at the far edges), an RGBA32 base-colour map on the icosphere whose alpha is its
+        # smoothness plus a metallic map, an emissive map on the light panel; sphere entities have TexCoords = 0
+        t = scene.triangles
+        v = np.stack([t["v0"], t["v0"] + t["edge1"], t["v0"] + t["edge2"]], axis=1).astype(np.float64)   # ctor order v1, v2, v3
+        uv = np.zeros((len(t), 3, 2), np.float32)
+        m = t["material"]
+        uv[m == 0] = ((v[m == 0][:, :, [0, 2]] + g) / (2 * g)).astype(np.float32)
+        c = v[m == 1] - np.array([0.0, 1.0, 0.0])
+        uv[m == 1, :, 0] = (np.arctan2(c[..., 2], c[..., 0]) / (2 * np.pi) + 0.5).astype(np.float32)
+        uv[m == 1, :, 1] = (np.arccos(np.clip(c[..., 1], -1, 1)) / np.pi).astype(np.float32)
+        uv[m == 2] = (v[m == 2][:, :, [0, 1]] % 1.0).astype(np.float32)
+        uv[m == 6] = ((v[m == 6][:, :, [0, 2]] + 2.5) / 5.0).astype(np.float32)
+        mt = np.zeros(len(materials), dtype=abi.MATERIAL_TEXTURES_DTYPE)
+        for k in ("albedo_image", "emission_image", "glossiness_image", "metallic_image"):
+            mt[k] = -1
+        mt[0]["albedo_image"] = 0
+        mt[1]["albedo_image"], mt[1]["glossiness_image"], mt[1]["glossiness_channel"], mt[1]["metallic_image"] = 1, 1, 3, 2
+        mt[2]["albedo_image"] = 1
+        mt[3]["glossiness_image"], mt[3]["glossiness_channel"] = 1, 3
+        mt[4]["albedo_image"] = 0
+        mt[6]["emission_image"] = 3
+        scene.images, scene.material_textures, scene.triangle_uvs = _test_images(), mt, uv
+    return scene
 
 
 def _material(mtype, albedo, gloss=0.0, metallic=0.0, ior=1.5, emission=(0, 0, 0)):

@@ -15,7 +15,7 @@ from . import build as _build
 
 EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
-    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_placed_world", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_placed_world", "rtb_upload_textures", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_finalize_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
@@ -51,6 +51,7 @@ def lib():
         L.rtb_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_placed_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
+        L.rtb_upload_textures.argtypes = [vp, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_sky_cubemap.argtypes = [vp, vp, C.c_int, C.c_int]
         L.rtb_describe_scene.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.POINTER(abi.SceneLayout)]
         L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
@@ -139,6 +140,20 @@ def device_buffers_struct(in_color, in_weight, in_normal, in_albedo, out_color, 
     return b
 
 
+def image_structs(images):
+    """(ctypes array of rtb_image, the contiguous pixel arrays it points into)."""
+    keep = []
+    for im in images:
+        a = np.ascontiguousarray(im, dtype=np.uint8)
+        if a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise ValueError("an image is a uint8 array [H, W, 3 or 4]")
+        keep.append(a)
+    arr = (abi.Image * max(len(keep), 1))()
+    for i, a in enumerate(keep):
+        arr[i].pixels, arr[i].width, arr[i].height, arr[i].pixel_stride = a.ctypes.data, a.shape[1], a.shape[0], a.shape[2]
+    return arr, keep
+
+
 def describe_scene(scene, leaf_spheres=1):
     """rtb_describe_scene: how the device would lay `scene` out (host-side only, no GPU needed)."""
     spheres = np.ascontiguousarray(scene.spheres, dtype=abi.SPHERE_DTYPE)
@@ -225,6 +240,16 @@ class Context:
                                                     len(triangles), ptr(placed), len(placed), ptr(materials), len(materials),
                                                     ptr(nodes), len(nodes)))
 
+    def upload_textures(self, images, material_textures, triangle_uvs=None):
+        """rtb_upload_textures: `images` = list of uint8 arrays [H, W, 3 or 4]; `material_textures` = MATERIAL_TEXTURES_DTYPE per
+        material of the uploaded world; `triangle_uvs` = float32 [n_triangles, 3, 2] or None."""
+        imgs, keep = image_structs(images)
+        mt = np.ascontiguousarray(material_textures, dtype=abi.MATERIAL_TEXTURES_DTYPE)
+        uv = None if triangle_uvs is None else np.ascontiguousarray(triangle_uvs, dtype=np.float32)
+        self._check(self._L.rtb_upload_textures(self._h, C.addressof(imgs) if len(keep) else None, len(keep), mt.ctypes.data if len(mt) else None,
+                                                len(mt), uv.ctypes.data if uv is not None and uv.size else None,
+                                                0 if uv is None else uv.size // 6))
+
     def upload_sky_cubemap(self, faces):
         """Environment.SkyCubemap: `faces` is a [6, H, W, 4] array of float16 (or their uint16 bits), +X -X +Y -Y +Z -Z;
         None removes it."""
@@ -245,6 +270,8 @@ class Context:
             self.upload_world(scene.entities, scene.spheres, scene.triangles, scene.materials, scene.nodes)
         else:
             self.upload_scene(scene.spheres, scene.materials, scene.nodes)
+        if getattr(scene, "material_textures", None) is not None:
+            self.upload_textures(scene.images, scene.material_textures, scene.triangle_uvs)
 
     # ---- the hot path ------------------------------------------------------------------
     def sample_batch(self, params, buffers, cancel=None):

@@ -48,6 +48,8 @@ def lib(fast=False):
         L.oracle_sample_batch_placed.restype = C.c_int
         L.oracle_placed_hit.argtypes = [C.c_void_p, abi.f32x3, abi.f32x3, C.c_float, C.POINTER(C.c_float), abi.f32x3, abi.f32x3]
         L.oracle_placed_hit.restype = C.c_int
+        L.oracle_set_textures.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.oracle_set_textures.restype = None
         L.oracle_set_sky_cubemap.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_set_sky_cubemap.restype = None
         L.oracle_cubemap_sample.argtypes = [abi.f32x3, abi.f32x3]
@@ -140,9 +142,28 @@ def set_sky_cubemap(faces, fast=False):
     L.oracle_set_sky_cubemap(f.ctypes.data, f.shape[2], f.shape[1])
 
 
+_tex_keepalive = {}
+
+
+def set_textures(scene, fast=False):
+    """Image textures of `scene` (images, material_textures, triangle_uvs) for subsequent oracle batches, or none."""
+    L = lib(fast)
+    if scene is None or getattr(scene, "material_textures", None) is None:
+        _tex_keepalive.pop(fast, None)
+        L.oracle_set_textures(None, 0, None, 0, None, 0)
+        return
+    imgs, keep = rtb.plugin.image_structs(scene.images)
+    mt = np.ascontiguousarray(scene.material_textures, dtype=abi.MATERIAL_TEXTURES_DTYPE)
+    uv = None if scene.triangle_uvs is None else np.ascontiguousarray(scene.triangle_uvs, dtype=np.float32)
+    _tex_keepalive[fast] = (imgs, keep, mt, uv)
+    L.oracle_set_textures(C.addressof(imgs), len(keep), mt.ctypes.data, len(mt), None if uv is None else uv.ctypes.data,
+                          0 if uv is None else uv.size // 6)
+
+
 def sample_batch(scene, params, buffers, noise=NOISE_PHILOX, threads=None, fast=False, index_range=(0, 0)):
     threads = threads or os.cpu_count() or 1
     b = buffers.as_struct()
+    set_textures(scene, fast)       # a scene's image textures travel with it (none: cleared)
     if getattr(scene, "placed", None) is not None and len(scene.placed):
         tris, sph = scene.triangles, scene.spheres
         rc = lib(fast).oracle_sample_batch_placed(

@@ -223,6 +223,60 @@ def test_moving_entities_blur_and_static_ones_do_not(rtb, ctx):
     assert np.abs(nb - nc).max() <= 1e-3          # frozen at the destination == a static entity placed there
 
 
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
+@pytest.mark.parametrize("depth,emissive", [(16, False), (16, True), (2, False)])
+def test_textured_mesh_world_matches_the_oracle(rtb, oracle, ctx, kernel, depth, emissive):
+    """rtb_upload_textures: TextureType.Image albedo / emission / glossiness (alpha of an RGBA32 map) / metallic maps on mesh
+    materials, sampled at the triangles' interpolated vertex uvs (Texture.cs:80-89,128-137; HitTests.cs:147); sphere entities
+    sample texel (0, 0) (Entity.cs:107) — including a Dielectric whose roughness comes from a map."""
+    W, H, spp = 112, 63, 12
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=depth, emissive=emissive, textured=True)
+    p = rtb.host.make_params(scene, W, H, spp, 12 if emissive else 50)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    plain = oracle.Buffers(W, H)
+    oracle.sample_batch(rtb.host.make_mesh_scene(max_bvh_depth=depth, emissive=emissive), p, plain)
+    assert np.abs(ref.rgb() - plain.rgb()).max() > 0.2                       # the maps are visible
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
+    got = render_gpu(rtb, ctx, scene, p, W, H, k)
+    assert_parity(ref, got, exact=(kernel == "simple"))
+    # a later world upload drops the textures
+    got2 = render_gpu(rtb, ctx, rtb.host.make_mesh_scene(max_bvh_depth=depth, emissive=emissive), p, W, H, k)
+    assert_parity(plain, got2, exact=(kernel == "simple"))
+
+
+def test_textures_on_a_sphere_world_and_argument_checks(rtb, oracle, ctx):
+    """Sphere entities have TexCoords = 0: a textured material on a sphere world takes texel (0, 0) everywhere — and moves the
+    world to the general kernel flavour.  Wrong counts / channels are rejected."""
+    W, H, spp = 64, 36, 8
+    scene = rtb.host.make_scene("three_spheres", max_bvh_depth=2)
+    img = np.zeros((4, 4, 3), np.uint8)
+    img[0, 0] = (255, 128, 0)
+    img[1:, 1:] = (0, 0, 255)
+    mt = np.zeros(len(scene.materials), dtype=rtb.abi.MATERIAL_TEXTURES_DTYPE)
+    for k in ("albedo_image", "emission_image", "glossiness_image", "metallic_image"):
+        mt[k] = -1
+    mt[0]["albedo_image"] = 0
+    scene.images, scene.material_textures, scene.triangle_uvs = [img], mt, None
+    p = rtb.host.make_params(scene, W, H, spp, 50)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    for k in (rtb.abi.KERNEL_SIMPLE, rtb.abi.KERNEL_MEGA):
+        got = render_gpu(rtb, ctx, scene, p, W, H, k)
+        assert_parity(ref, got, exact=(k == rtb.abi.KERNEL_SIMPLE))
+    with pytest.raises(rtb.plugin.RtbError):
+        ctx.upload_textures([img], mt[:-1])                                    # material count differs from the world's
+    bad = mt.copy()
+    bad[1]["glossiness_image"], bad[1]["glossiness_channel"] = 0, 3            # alpha of an RGB24 image
+    with pytest.raises(rtb.plugin.RtbError):
+        ctx.upload_textures([img], bad)
+    ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_POOL)
+    ctx.upload(scene)
+    with pytest.raises(rtb.plugin.RtbError):
+        ctx.sample_batch(p, rtb.plugin.HostBuffers(W, H))                      # the experimental kernel refuses textures
+    ctx.set_option(rtb.abi.OPT_KERNEL, 0)
+
+
 @pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
 def test_emissive_panel_without_sky(rtb, oracle, ctx, kernel):
     """Material.Emit (Material.cs:175-179) + SkyType.None: the overhead panel is the only light, so every pixel's
