@@ -88,6 +88,16 @@ RTB_API void rtbh_make_triangle(const float v1[3], const float v2[3], const floa
                                 const float* n1, const float* n2, const float* n3,
                                 uint32_t material, rtb_triangle* out);
 
+/* Mesh ingestion (Runtime/Jobs/AddMeshRuntimeEntitiesJob.cs:30-96): one world-space triangle per index triple of a
+ * Unity mesh (16-bit indices), the renderer's rigid transform and uniform scale (csum(lossyScale) / 3,
+ * Raytracer.cs:1296) baked into the vertices, vertex normals rotated; normals == NULL selects the face-normal
+ * ctor (MeshData.FaceNormals).  uvs (2 per vertex, TexCoord0) may be NULL; out_uvs (6 per triangle, for
+ * rtb_upload_textures) may be NULL. */
+RTB_API int rtbh_add_mesh(const float* vertices, const float* normals, const float* uvs, size_t vertex_count,
+                          const uint16_t* indices, size_t index_count,
+                          const float rotation[4], const float position[3], float scale, uint32_t material,
+                          rtb_triangle* out_triangles, float* out_uvs, size_t triangle_capacity, size_t* out_triangle_count);
+
 /* ---- camera ----------------------------------------------------------------------------- */
 RTB_API void rtbh_make_view(const float origin[3], const float look_at[3], const float up[3],
                             float vertical_fov_degrees, float aspect, float aperture,

@@ -60,6 +60,14 @@ namespace B200PathTracer
 		public float3 Size; public float Reserved2;          // Sphere: (Radius, -, -); Rect: ctor size.xy; Box: ctor size.xyz
 	}
 
+	// rtb_image / rtb_material_textures: TextureType.Image textures (Texture.cs:22-48) of the mesh materials (Raytracer.cs:1210-1267)
+	[StructLayout(LayoutKind.Sequential)] public unsafe struct RtbImage { public byte* Pixels; public int Width, Height, PixelStride, Reserved; }
+	[StructLayout(LayoutKind.Sequential)] public struct RtbMaterialTextures
+	{
+		public int AlbedoImage, EmissionImage, GlossinessImage, MetallicImage;   // index into the image array or -1 (TextureType.Constant)
+		public int GlossinessChannel, MetallicChannel, Reserved0, Reserved1;     // Texture.ScalarValueChannel
+	}
+
 	public static unsafe class Api
 	{
 		const string Lib = "rtb";           // librtb.so / rtb.dll next to the other native plugins
@@ -75,6 +83,8 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_placed_world(IntPtr ctx, RtbEntity* entities, UIntPtr entityCount,
 			RtbSphere* spheres, UIntPtr sphereCount, RtbTriangle* triangles, UIntPtr triangleCount, RtbPlacedEntity* placed, UIntPtr placedCount,
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
+		[DllImport(Lib)] public static extern RtbStatus rtb_upload_textures(IntPtr ctx, RtbImage* images, UIntPtr imageCount,
+			RtbMaterialTextures* materialTextures, UIntPtr materialCount, float* triangleUvs, UIntPtr triangleCount);
 		// Environment.SkyCubemap: cubemap.GetPixelData<byte>(0, CubemapFace.PositiveX) of an R16G16B16A16_SFloat cubemap (Texture.cs:155-167)
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_sky_cubemap(IntPtr ctx, ushort* halfRgba, int faceWidth, int faceHeight);
 		[DllImport(Lib)] public static extern RtbStatus rtb_sample_batch(IntPtr ctx, RtbBatchParams* p, RtbBatchBuffers* hostBuffers, bool* cancel);

@@ -541,6 +541,42 @@ void rtbh_make_triangle(const float v1[3], const float v2[3], const float v3[3],
   out->material = material;
 }
 
+int rtbh_add_mesh(const float* vertices, const float* normals, const float* uvs, size_t vertex_count, const uint16_t* indices,
+                  size_t index_count, const float rotation[4], const float position[3], float scale, uint32_t material,
+                  rtb_triangle* out_triangles, float* out_uvs, size_t triangle_capacity, size_t* out_triangle_count) {
+  // AddMeshRuntimeEntitiesJob.Execute (AddMeshRuntimeEntitiesJob.cs:30-96): per index triple, bake the transform into the
+  // vertices (transform(RigidTransform, vertex * Scale)) and rotate the vertex normals (mul(RigidTransform.rot, normal)),
+  // then the face-normal or vertex-normal Triangle ctor; uvs pass through (default = 0 without TexCoord0)
+  if (!vertices || !indices || !rotation || !position || !out_triangles || !out_triangle_count) return RTB_ERR_INVALID_ARGUMENT;
+  if (index_count % 3 != 0 || triangle_capacity < index_count / 3) return RTB_ERR_INVALID_ARGUMENT;
+  um::rigid xf;
+  xf.rot.x = rotation[0]; xf.rot.y = rotation[1]; xf.rot.z = rotation[2]; xf.rot.w = rotation[3];
+  xf.pos = um::mk(position[0], position[1], position[2]);
+  size_t n = 0;
+  for (size_t i = 0; i < index_count; i += 3) {
+    float wv[3][3], wn[3][3];
+    for (int j = 0; j < 3; j++) {
+      const size_t k = indices[i + j];
+      if (k >= vertex_count) return RTB_ERR_INVALID_ARGUMENT;
+      const f3 v = um::transform(xf, um::mk(vertices[3 * k], vertices[3 * k + 1], vertices[3 * k + 2]) * scale);
+      wv[j][0] = v.x; wv[j][1] = v.y; wv[j][2] = v.z;
+      if (normals) {
+        const f3 nn = um::rotate(xf.rot, um::mk(normals[3 * k], normals[3 * k + 1], normals[3 * k + 2]));
+        wn[j][0] = nn.x; wn[j][1] = nn.y; wn[j][2] = nn.z;
+      }
+      if (out_uvs) {
+        out_uvs[6 * n + 2 * j] = uvs ? uvs[2 * k] : 0.0f;
+        out_uvs[6 * n + 2 * j + 1] = uvs ? uvs[2 * k + 1] : 0.0f;
+      }
+    }
+    rtbh_make_triangle(wv[0], wv[1], wv[2], normals ? wn[0] : nullptr, normals ? wn[1] : nullptr, normals ? wn[2] : nullptr, material,
+                       &out_triangles[n]);
+    n++;
+  }
+  *out_triangle_count = n;
+  return RTB_OK;
+}
+
 void rtbh_make_view(const float origin[3], const float look_at[3], const float up_in[3],
                     float vertical_fov_degrees, float aspect, float aperture,
                     float focus_distance, rtb_view* out) {

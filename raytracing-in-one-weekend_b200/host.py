@@ -49,6 +49,9 @@ def lib():
         L.rtbh_placed_bounds.restype = None
         L.rtbh_make_triangle.argtypes = [abi.f32x3, abi.f32x3, abi.f32x3, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.rtbh_make_triangle.restype = None
+        L.rtbh_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rtbh_add_mesh.restype = C.c_int
         L.rtbh_make_view.argtypes = [
             abi.f32x3, abi.f32x3, abi.f32x3, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(abi.View)
         ]
@@ -247,6 +250,27 @@ def make_placed(entity_type, material, size, position, rotation=(0, 0, 0, 1), de
     if destination_offset is not None:
         e["moving"], e["destination_offset"], e["time_range"] = 1, destination_offset, time_range
     return e
+
+
+def add_mesh(vertices, indices, material, normals=None, uvs=None, rotation=(0, 0, 0, 1), position=(0, 0, 0), scale=1.0):
+    """AddMeshRuntimeEntitiesJob: (triangles, per-triangle uvs [n, 3, 2]) of one mesh renderer — transform baked in,
+    vertex normals rotated (normals=None: face normals)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, dtype=np.uint16).reshape(-1)
+    nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    tex = None if uvs is None else np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+    rot = np.ascontiguousarray(rotation, dtype=np.float32)
+    pos = np.ascontiguousarray(position, dtype=np.float32)
+    n = len(idx) // 3
+    tris = np.zeros(n, dtype=abi.TRIANGLE_DTYPE)
+    out_uv = np.zeros((n, 3, 2), np.float32)
+    count = C.c_size_t(0)
+    rc = lib().rtbh_add_mesh(v.ctypes.data, None if nrm is None else nrm.ctypes.data, None if tex is None else tex.ctypes.data, len(v),
+                             idx.ctypes.data, len(idx), rot.ctypes.data, pos.ctypes.data, float(scale), int(material),
+                             tris.ctypes.data if n else None, out_uv.ctypes.data, n, C.byref(count))
+    if rc != 0:
+        raise ValueError(f"rtbh_add_mesh failed: {rc}")
+    return tris[: count.value], out_uv[: count.value]
 
 
 def build_world(spheres, triangles, materials, max_bvh_depth, camera, environment, focus_distance, name="world", placed=None):

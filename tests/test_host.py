@@ -89,3 +89,29 @@ def test_device_layout_collapses_small_subtrees(rtb, name, depth):
             assert lay["chain_boxes"] > 0 and lay["max_leaf_spheres"] <= max(k, one["max_leaf_spheres"])
     if name == "final" and depth == 16:
         assert rtb.plugin.describe_scene(scene, 8)["inner_nodes"] < n_ref_inner // 3
+
+
+def test_add_mesh_bakes_the_transform_and_rotates_normals(rtb):
+    """AddMeshRuntimeEntitiesJob.cs:60-80: vertices -> transform(rigid, v * scale), normals -> rotate(rot, n), uvs pass through;
+    the triangles equal the ones the Triangle ctors give for the transformed vertices."""
+    host = rtb.host
+    v = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], np.float32)
+    nrm = np.array([(0, 0, -1), (1, 0, 0), (0, 1, 0), (0, 0, 1)], np.float32)
+    uv = np.array([(0, 0), (1, 0), (0, 1), (0.5, 0.5)], np.float32)
+    idx = [0, 1, 2, 0, 2, 3]
+    q = host.quat_axis_angle((0, 1, 0), 90.0)
+    tris, tuv = host.add_mesh(v, idx, 3, normals=nrm, uvs=uv, rotation=q, position=(10, 0, 0), scale=2.0)
+    assert len(tris) == 2 and (tris["material"] == 3).all()
+    # a quarter turn about +Y takes x to -z and z to x (rotate(q, v), right-handed algebra), then scale 2 and the offset
+    np.testing.assert_allclose(tris[0]["v0"], (10, 0, 0), atol=1e-6)
+    np.testing.assert_allclose(tris[0]["edge1"], (0, 0, -2), atol=1e-6)      # v2 - v1
+    np.testing.assert_allclose(tris[0]["edge2"], (0, 2, 0), atol=1e-6)       # v3 - v1
+    np.testing.assert_allclose(tris[0]["normals"][1], (0, 0, -1), atol=1e-6)  # (1, 0, 0) rotated
+    np.testing.assert_allclose(tris[1]["edge2"], (2, 0, 0), atol=1e-6)       # (0, 0, 1) * 2 rotated
+    assert np.array_equal(tuv[0], uv[[0, 1, 2]]) and np.array_equal(tuv[1], uv[[0, 2, 3]])
+    # face-normal form: the ctor's normalize(cross(Data[1], Data[0]))
+    flat, _ = host.add_mesh(v, idx, 0, rotation=q, position=(10, 0, 0), scale=2.0)
+    want = host.make_triangle(tris[0]["v0"], tris[0]["v0"] + tris[0]["edge1"], tris[0]["v0"] + tris[0]["edge2"], 0)
+    assert flat[0].tobytes() == want.tobytes()
+    with pytest.raises(ValueError):
+        host.add_mesh(v, [0, 1, 9], 0)                                        # index past the vertex array
