@@ -257,6 +257,9 @@ constexpr int kFlavorSpheres = 0;        // spheres only, no collapsed leaves (t
 constexpr int kFlavorChains = 1;         // + collapsed leaves: accepted hits go through chain_guard
 constexpr int kFlavorGeneral = 2;        // + EntityType.Triangle entities
 constexpr int kFlavorPlaced = 3;         // + placed entities: rotation, motion (Ray.Time), EntityType.Rect, EntityType.Box
+constexpr int kFlavorPlacedTextured = 4; // the same with image textures (the general flavour always has them; here the
+                                         // texture code costs the untextured walk 14 %, so it is its own instantiation)
+__host__ __device__ constexpr bool flavor_has_textures(int flavor) { return flavor == kFlavorGeneral || flavor >= kFlavorPlacedTextured; }
 
 // Ray.Time (View.cs:47; kept by every scattered ray, Material.cs:95-159): one draw per camera path, slot 4 of the
 // camera ray's draws = word 0 of Philox block 1.  Only moving entities read it, so the megakernel re-derives it from

@@ -71,7 +71,7 @@ struct rtb_ctx {
   int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0;
   bool last_in_place = false;
   float last_ms = 0.0f;
-  bool smem_attr_set[2][8] = {};
+  bool smem_attr_set[2][10] = {};
   bool pool_attr_set[2][2] = {{false, false}, {false, false}};
 
   DeviceBuffers buf;
@@ -652,7 +652,7 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     if (rc != RTB_OK) return rc;
   } else {
     // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
-    const int flavor = ctx->scene.n_placed ? kFlavorPlaced
+    const int flavor = ctx->scene.n_placed ? (ctx->d_mat_textures ? kFlavorPlacedTextured : kFlavorPlaced)
                        : (counters || ctx->scene.n_triangles || ctx->d_mat_textures) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
     const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true, flavor) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
@@ -660,6 +660,9 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
     if (flavor == kFlavorPlaced) {
       if (fits) rc = counters ? launch_mega_t<true, true, kFlavorPlaced>(ctx, a, stream, max_spp) : launch_mega_t<true, false, kFlavorPlaced>(ctx, a, stream, max_spp);
       else rc = counters ? launch_mega_t<false, true, kFlavorPlaced>(ctx, a, stream, max_spp) : launch_mega_t<false, false, kFlavorPlaced>(ctx, a, stream, max_spp);
+    } else if (flavor == kFlavorPlacedTextured) {
+      if (fits) rc = counters ? launch_mega_t<true, true, kFlavorPlacedTextured>(ctx, a, stream, max_spp) : launch_mega_t<true, false, kFlavorPlacedTextured>(ctx, a, stream, max_spp);
+      else rc = counters ? launch_mega_t<false, true, kFlavorPlacedTextured>(ctx, a, stream, max_spp) : launch_mega_t<false, false, kFlavorPlacedTextured>(ctx, a, stream, max_spp);
     } else
     if (fits) rc = counters ? launch_mega_t<true, true, kFlavorGeneral>(ctx, a, stream, max_spp)
                    : flavor == kFlavorGeneral ? launch_mega_t<true, false, kFlavorGeneral>(ctx, a, stream, max_spp)

@@ -299,7 +299,12 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
         m0 = __ldg(mp); m1 = __ldg(mp + 1); m2 = __ldg(mp + 2); m3 = __ldg(mp + 3);
-        if (FLAVOR >= kFlavorGeneral && __float_as_uint(m3.w) != 0u) resolve_textures(sv, a.scene, mi, s, ray.o, ray.d, m0, m1, m2, m3);
+        if (flavor_has_textures(FLAVOR) && __float_as_uint(m3.w) != 0u) {
+          // through copies: the out-of-line call takes addresses, and the material registers must not move to local memory for it
+          float4 t0 = m0, t1 = m1, t2 = m2, t3 = m3;
+          resolve_textures(sv, a.scene, mi, s, ray.o, ray.d, t0, t1, t2, t3);
+          m0 = t0; m1 = t1; m2 = t2; m3 = t3;
+        }
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
         N = hit_normal<SMEM, FLAVOR>(sv, s, ray.o, ray.d, t_hit, clk);
         P = um::mad(ray.d, t_hit, ray.o);

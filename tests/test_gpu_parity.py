@@ -245,6 +245,32 @@ def test_textured_mesh_world_matches_the_oracle(rtb, oracle, ctx, kernel, depth,
     assert_parity(plain, got2, exact=(kernel == "simple"))
 
 
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
+def test_textured_cornell_world_matches_the_oracle(rtb, oracle, ctx, kernel):
+    """Placed entities with image-textured materials (the kernel flavour that carries both): Rect / Box / sphere entities
+    have TexCoords = 0, so each takes texel (0, 0) of its maps — albedo, a glossiness map on the metal box (no longer a
+    perfect mirror: Material.cs:190-192) and an emission map on the light."""
+    W, H, spp = 96, 54, 16
+    scene = rtb.host.make_cornell_scene(max_bvh_depth=16, moving=True)
+    mt = np.zeros(len(scene.materials), dtype=rtb.abi.MATERIAL_TEXTURES_DTYPE)
+    for k in ("albedo_image", "emission_image", "glossiness_image", "metallic_image"):
+        mt[k] = -1
+    mt[0]["albedo_image"] = 1
+    mt[3]["emission_image"] = 3
+    mt[5]["glossiness_image"], mt[5]["glossiness_channel"] = 1, 3
+    mt[6]["albedo_image"], mt[6]["metallic_image"] = 0, 2
+    scene.images, scene.material_textures, scene.triangle_uvs = rtb.host._test_images(), mt, None
+    p = rtb.host.make_params(scene, W, H, spp, 50)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    plain = oracle.Buffers(W, H)
+    oracle.sample_batch(rtb.host.make_cornell_scene(max_bvh_depth=16, moving=True), p, plain)
+    assert np.abs(ref.rgb() - plain.rgb()).max() > 0.2
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
+    got = render_gpu(rtb, ctx, scene, p, W, H, k)
+    assert_parity(ref, got, exact=(kernel == "simple"))
+
+
 def test_textures_on_a_sphere_world_and_argument_checks(rtb, oracle, ctx):
     """Sphere entities have TexCoords = 0: a textured material on a sphere world takes texel (0, 0) everywhere — and moves the
     world to the general kernel flavour.  Wrong counts / channels are rejected."""
@@ -390,10 +416,15 @@ def test_reference_white_noise_stream_is_reproduced_bit_for_bit(rtb, oracle, ctx
 def test_world_upload_rejects_what_it_cannot_render(rtb, ctx):
     scene = rtb.host.make_mesh_scene()
     ents = scene.entities.copy()
-    ents["type"][0] = rtb.abi.ENTITY_BOX
+    ents["type"][0] = 9                                      # not an EntityType
     with pytest.raises(rtb.plugin.RtbError) as e:
         ctx.upload_world(ents, scene.spheres, scene.triangles, scene.materials, scene.nodes)
     assert e.value.code == rtb.abi.RTB_ERR_UNSUPPORTED
+    ents = scene.entities.copy()
+    ents["type"][0] = rtb.abi.ENTITY_BOX                     # a Box is a placed entity: there is no placed array in this call
+    with pytest.raises(rtb.plugin.RtbError) as e:
+        ctx.upload_world(ents, scene.spheres, scene.triangles, scene.materials, scene.nodes)
+    assert e.value.code == rtb.abi.RTB_ERR_INVALID_ARGUMENT
     ents = scene.entities.copy()
     ents["index"][0] = 10 ** 6
     with pytest.raises(rtb.plugin.RtbError) as e:
