@@ -498,6 +498,61 @@ def make_cornell_scene(max_bvh_depth=16, moving=True):
                        placed=np.array(placed, dtype=abi.PLACED_DTYPE))
 
 
+def make_random_placed_scene(seed, count=24, max_bvh_depth=8):
+    """A random world of every entity kind (plain spheres, rotated / moving spheres, Rects, Boxes, a few triangles) with
+    random Standard / Dielectric / emissive materials, inside a gradient sky: the fuzz input of the parity tests."""
+    rng = np.random.default_rng(seed)
+    mats = []
+    for _ in range(8):
+        u = rng.random()
+        if u < 0.5:
+            mats.append(_material(abi.MATERIAL_STANDARD, rng.random(3), gloss=float(rng.choice([0.0, 0.0, 0.6, 1.0])),
+                                  metallic=float(rng.choice([0.0, 0.0, 0.5, 1.0]))))
+        elif u < 0.75:
+            mats.append(_material(abi.MATERIAL_DIELECTRIC, (1, 1, 1), gloss=float(rng.choice([1.0, 0.8])), ior=1.5))
+        else:
+            mats.append(_material(abi.MATERIAL_STANDARD, rng.random(3) * 0.5, emission=rng.random(3) * 4))
+    materials = np.array(mats, dtype=abi.MATERIAL_DTYPE)
+
+    def rand_quat():
+        q = rng.normal(size=4)
+        return (q / np.linalg.norm(q)).astype(np.float32)
+
+    spheres, placed, tris = [], [], []
+    placed.append(make_placed(abi.ENTITY_RECT, 0, (14.0, 14.0), (0.0, -0.05, 0.0), quat_from_to((0, 0, 1), (0, 1, 0))))   # a floor
+    for _ in range(count):
+        pos = (rng.random(3) * (6, 2.5, 6) - (3, 0, 3)).astype(np.float32)
+        m = int(rng.integers(len(mats)))
+        kind = rng.integers(6)
+        motion = dict(destination_offset=(rng.random(3) - 0.5).astype(np.float32) * 2,
+                      time_range=(float(rng.random() * 0.5), float(0.5 + rng.random() * 0.5))) if rng.random() < 0.3 else {}
+        if kind == 0:
+            spheres.append((tuple(pos), float(0.3 + rng.random() * 0.9) * (1 if rng.random() < 0.9 else -1), m, (0, 0, 0)))
+        elif kind == 1:
+            placed.append(make_placed(abi.ENTITY_SPHERE, m, float(0.3 + rng.random() * 0.9), pos, rand_quat(), **motion))
+        elif kind in (2, 3):
+            rot = rand_quat() if rng.random() < 0.7 else quat_from_to((0, 0, 1), [(0, 1, 0), (1, 0, 0), (0, 0, -1)][int(rng.integers(3))])
+            placed.append(make_placed(abi.ENTITY_RECT, m, rng.random(2) * 3 + 0.3, pos, rot, **motion))
+        elif kind == 4:
+            rot = rand_quat() if rng.random() < 0.7 else (0, 0, 0, 1)
+            placed.append(make_placed(abi.ENTITY_BOX, m, rng.random(3) * 2.0 + 0.3, pos, rot, **motion))
+        else:
+            a = pos + (rng.random(3) - 0.5) * 3
+            tris.append(make_triangle(pos, a, pos + (rng.random(3) - 0.5) * 4, m))
+    cam = abi.Camera()
+    cam.position[:] = (0.3, 1.6, -9.0)
+    cam.target[:] = (0.0, 1.2, 0.0)
+    cam.aperture = 0.0
+    cam.vertical_fov = 45.0
+    env = abi.Environment()
+    env.sky_type = abi.SKY_GRADIENT
+    env.sky_bottom_color[:] = (1.0, 1.0, 1.0)
+    env.sky_top_color[:] = (0.5, 0.7, 1.0)
+    return build_world(np.array(spheres, dtype=abi.SPHERE_DTYPE) if spheres else np.zeros(0, abi.SPHERE_DTYPE),
+                       np.array(tris, dtype=abi.TRIANGLE_DTYPE) if tris else np.zeros(0, abi.TRIANGLE_DTYPE), materials, max_bvh_depth,
+                       cam, env, 9.0, name=f"random{seed}", placed=np.array(placed, dtype=abi.PLACED_DTYPE) if placed else None)
+
+
 def make_params(scene, width, height, spp, trace_depth, seed=1, aperture=None, jitter=True,
                 slice_offset=0, slice_divider=1, row_begin=0, row_end=0, spp_max=None):
     """Fills the uniform fields of the job the way ScheduleSample does (Raytracer.cs:671-712)."""
