@@ -210,6 +210,9 @@ UM_HD float log(float x) {
   return um::fma(fe, 0.693359375f, m + y);
 }
 
+/* log of a uniform draw in [0, 1): log(0) = -inf like math.log (Material.ProbabilisticHit, Material.cs:56) */
+UM_HD float log_unit(float x) { return x == 0.0f ? -INF : um::log(x); }
+
 /* pow(x, 2) and pow(x, 5) as the reference calls them (Material.cs:82,216).  A
  * correctly-rounded powf(x,2) IS x*x; x^5 is evaluated as (x^2)^2 * x (<= 1.5 ULP,
  * sign-correct for negative x, which happens for cosine > 1 in Dielectric). */

@@ -83,7 +83,8 @@ enum Slot {
   SLOT_ROUGH = 0,        // 2 floats: block 0 [0,1]   (Material.cs:83 / :124)
   SLOT_REFLECT = 2,      // 1 float : block 0 [2]     (Material.cs:91 / :143)
   SLOT_METAL = 3,        // 1 float : block 0 [3]     (Material.cs:99)
-  SLOT_DIFFUSE = 4       // 2 floats: block 1 [0,1]   (Material.cs:107)
+  SLOT_DIFFUSE = 4,      // 2 floats: block 1 [0,1]   (Material.cs:107)
+  SLOT_VOLUME = 8        // 1 float per Material.ProbabilisticHit call of the bounce: block 2 + k / 4 [k % 4] (Material.cs:56)
 };
 constexpr uint32_t BOUNCE_CAMERA = 0xFFFFFFFFu;
 constexpr uint32_t PHILOX_KEY1 = 0x52544232u;  // "RTB2"
@@ -210,9 +211,15 @@ struct Scene {
   const rtb_triangle* triangles = nullptr; size_t triangle_count = 0;
   // entities with the reference's full Entity record (rotation, motion, Rect / Box content)
   const rtb_placed_entity* placed = nullptr; size_t placed_count = 0;
+  bool has_volumes = false;  // some material is a ProbabilisticVolume (DetermineVolumeContainment is a no-op otherwise)
   std::vector<um::rigid> placed_inverse;  // Entity.InverseTransform of the static ones (Entity ctor, Entity.cs:51-52)
   static bool is_placed(const rtb_entity& e) {
     return (e.type & RTB_ENTITY_PLACED) || e.type == RTB_ENTITY_RECT || e.type == RTB_ENTITY_BOX;
+  }
+  bool is_convex_hull(int entity) const {  // EntityType.IsConvexHull (Entity.cs:22-25): Box or Sphere
+    if (!entities) return true;
+    const uint32_t base = entities[entity].type & ~(uint32_t)RTB_ENTITY_PLACED;
+    return base == RTB_ENTITY_SPHERE || base == RTB_ENTITY_BOX;
   }
   uint32_t material_of(int entity) const {
     if (!entities) return spheres[entity].material;
@@ -491,10 +498,29 @@ rtb_material SampleTextures(const rtb_material& m, uint32_t materialIndex, const
   return r;
 }
 
+// Material.ProbabilisticHit (Material.cs:48-65); Density = Material.parameter = rtb_material.index_of_refraction
+bool ProbabilisticHit(const rtb_material& m, float* hitDistance, RandomSource& rng, int* volumeDraws) {
+  if (m.type != RTB_MATERIAL_PROBABILISTIC_VOLUME) return false;
+  rng.random_events++;
+  const float EPSILON = 1.1920928955078125e-7f;  // math.EPSILON
+  float volumeHitDistance = -um::div(1.0f, um::max(m.index_of_refraction, EPSILON)) * um::log_unit(rng.NextFloat(SLOT_VOLUME + (*volumeDraws)++));
+  if (volumeHitDistance < *hitDistance) {
+    *hitDistance = volumeHitDistance;
+    return true;
+  }
+  return false;
+}
+
 // Material.Scatter (Material.cs:67-173), Standard and Dielectric; constant textures
 // (Texture.cs:50-59,101-108).
 void Scatter(const rtb_material& m, const Ray& ray, const HitRecord& rec, RandomSource& rng,
              f3* reflectance, Ray* scattered) {
+  if (m.type == RTB_MATERIAL_PROBABILISTIC_VOLUME) {  // Material.cs:163-168: isotropic; the ray's time is NOT carried over
+    *reflectance = um::mk(m.albedo[0], m.albedo[1], m.albedo[2]);
+    *scattered = Ray{rec.Point, rng.NextFloat3Direction(SLOT_ROUGH), 0.0f};
+    rng.random_events += 2;
+    return;
+  }
   *reflectance = um::mk(m.albedo[0], m.albedo[1], m.albedo[2]);
   switch (m.type) {
     case RTB_MATERIAL_STANDARD: {
@@ -626,7 +652,14 @@ void FindHits(const Scene& sc, const Ray& ray, Work& w) {
     int e = w.candidates.back();
     w.candidates.pop_back();
     HitRecord rec;
-    if (EntityHit(sc, e, ray, 0, um::INF, &rec)) w.hits.push_back(rec);
+    if (EntityHit(sc, e, ray, 0, um::INF, &rec)) {
+      w.hits.push_back(rec);
+      // Inject exit hits for probabilistic convex hulls (:462-469)
+      HitRecord exitRec;
+      if (sc.materials[sc.material_of(e)].type == RTB_MATERIAL_PROBABILISTIC_VOLUME && sc.is_convex_hull(e) &&
+          EntityHit(sc, e, ray, rec.Distance + 0.001f, um::INF, &exitRec))
+        w.hits.push_back(exitRec);
+    }
   }
   if (!w.hits.empty())
     std::stable_sort(w.hits.begin(), w.hits.end(),
@@ -662,8 +695,37 @@ f3 CubemapSample(f3 vector) {
   return um::mk(um::half_to_float(px[0]), um::half_to_float(px[1]), um::half_to_float(px[2]));
 }
 
-// SampleBatchJob.Sample (:166-401).  The ProbabilisticVolume branches (:194-201, :212-303)
-// are unreachable without a volume material (upload rejects them), so they are omitted.
+// SampleBatchJob.AnyBackwardsVolumeEntryHit (:508-524): scans the candidates of the backwards traversal (not popped)
+bool AnyBackwardsVolumeEntryHit(const Scene& sc, const Ray& backwardsRay, Work& w) {
+  for (size_t i = 0; i < w.candidates.size(); i++) {
+    const int hitCandidate = w.candidates[i];
+    HitRecord hitRecord;
+    if (sc.materials[sc.material_of(hitCandidate)].type == RTB_MATERIAL_PROBABILISTIC_VOLUME &&
+        EntityHit(sc, hitCandidate, backwardsRay, 0, um::INF, &hitRecord) &&
+        um::dot(hitRecord.Normal, backwardsRay.Direction) > 0)
+      return true;
+  }
+  return false;
+}
+
+// SampleBatchJob.DetermineVolumeContainment (:477-506): -1 = not inside a volume, else its material index
+int DetermineVolumeContainment(const Scene& sc, const Ray& ray, Work& w, rtb_diagnostics& diag) {
+  for (size_t i = 0; i < w.hits.size(); i++) {
+    const HitRecord hit = w.hits[i];
+    const uint32_t hitMaterial = sc.material_of(hit.Entity);
+    if (sc.materials[hitMaterial].type == RTB_MATERIAL_PROBABILISTIC_VOLUME) {
+      // Entry hit, early out
+      if (um::dot(hit.Normal, ray.Direction) < 0) break;
+      // Exit hit before an entry hit, we are likely inside this volume; throw a ray backwards to make sure
+      Ray backwardsRay{ray.Origin, -ray.Direction, ray.Time};
+      FindHitCandidates(sc, backwardsRay, w, diag);
+      if (AnyBackwardsVolumeEntryHit(sc, backwardsRay, w)) return (int)hitMaterial;
+    }
+  }
+  return -1;
+}
+
+// SampleBatchJob.Sample (:166-401)
 bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleColor, f3* sampleNormal,
             f3* sampleAlbedo, rtb_diagnostics& diag, float* randomEventsAcc) {
   const Scene& sc = *job.scene;
@@ -674,18 +736,81 @@ bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleCo
   int depth = 0;
   bool firstNonSpecularHit = false;
   *sampleColor = *sampleNormal = *sampleAlbedo = um::mk(0.0f);
+  int currentProbabilisticVolumeMaterial = -1;  // Material* -> material index, null -> -1
   Ray ray = eyeRay;
   float pow2depth = 1.0f;  // pow(2, depth), exact (inf from depth 128 on, like powf)
 
   for (; depth < p.trace_depth; depth++) {
     rng.bounce = (uint32_t)depth;
+    int volumeDraws = 0;  // Philox slot of the k-th ProbabilisticHit draw of this bounce
     FindHitCandidates(sc, ray, w, diag);
     FindHits(sc, ray, w);
+    if (sc.has_volumes && currentProbabilisticVolumeMaterial < 0)
+      currentProbabilisticVolumeMaterial = DetermineVolumeContainment(sc, ray, w, diag);
     diag.ray_count++;
 
-    if (!w.hits.empty()) {
-      const HitRecord rec = w.hits[0];
-      const uint32_t materialIndex = sc.material_of(rec.Entity);
+    size_t hitIndex = 0;
+    while (hitIndex < w.hits.size()) {
+      HitRecord rec = w.hits[hitIndex];
+      uint32_t materialIndex = sc.material_of(rec.Entity);
+
+      if (currentProbabilisticVolumeMaterial >= 0 ||                                        // Inside a volume
+          sc.materials[materialIndex].type == RTB_MATERIAL_PROBABILISTIC_VOLUME) {          // Entering a volume
+        const bool isEntryHit = currentProbabilisticVolumeMaterial < 0;
+        if (currentProbabilisticVolumeMaterial < 0) currentProbabilisticVolumeMaterial = (int)materialIndex;
+
+        // Look for an obstacle or an exit hit
+        size_t exitHitIndex = hitIndex;
+        long lastExitIndex = -1;
+        int sameMaterialEntries = 0;
+        while (exitHitIndex < w.hits.size()) {
+          const HitRecord& hit = w.hits[exitHitIndex];
+          if ((int)sc.material_of(hit.Entity) == currentProbabilisticVolumeMaterial) {
+            if (um::dot(hit.Normal, ray.Direction) < 0) {
+              sameMaterialEntries++;
+            } else {
+              sameMaterialEntries--;
+              lastExitIndex = (long)exitHitIndex;
+            }
+            if (sameMaterialEntries <= 0) break;
+          } else {
+            break;
+          }
+          exitHitIndex++;
+        }
+        if (sameMaterialEntries > 0 && lastExitIndex != -1) exitHitIndex = (size_t)lastExitIndex;
+
+        if (exitHitIndex < w.hits.size()) {
+          const HitRecord exitHitRecord = w.hits[exitHitIndex];
+          float distanceInProbabilisticVolume = exitHitRecord.Distance;
+          float probabilisticVolumeEntryDistance = 0;
+          if (isEntryHit) {  // Factor in entry distance
+            probabilisticVolumeEntryDistance = rec.Distance;
+            distanceInProbabilisticVolume -= rec.Distance;
+          }
+          if (ProbabilisticHit(sc.materials[currentProbabilisticVolumeMaterial], &distanceInProbabilisticVolume, rng, &volumeDraws)) {
+            // We hit inside the volume; hijack the current hit record's distance and material
+            const float totalDistance = probabilisticVolumeEntryDistance + distanceInProbabilisticVolume;
+            rec = HitRecord{totalDistance, ray.GetPoint(totalDistance), -ray.Direction, -1};
+            materialIndex = (uint32_t)currentProbabilisticVolumeMaterial;
+          } else {
+            // No hit inside the volume, exit it
+            currentProbabilisticVolumeMaterial = -1;
+            if (sc.materials[sc.material_of(exitHitRecord.Entity)].type == RTB_MATERIAL_PROBABILISTIC_VOLUME &&
+                um::dot(exitHitRecord.Normal, ray.Direction) > 0) {
+              hitIndex = exitHitIndex + 1;  // Volume exit, move to next hit
+              continue;
+            }
+            rec = exitHitRecord;  // Obstacle, scatter on the exit hit
+            materialIndex = sc.material_of(rec.Entity);
+          }
+        } else {
+          // No more surfaces to hit (probabilistic volume has holes)
+          w.hits.clear();
+          break;
+        }
+      }
+
       const rtb_material material = SampleTextures(sc.materials[materialIndex], materialIndex, rec);
       f3 albedo;
       Ray scatteredRay;
@@ -705,7 +830,11 @@ bool Sample(const Job& job, Ray eyeRay, RandomSource& rng, Work& w, f3* sampleCo
       rng.random_events = 0;
       ray = scatteredRay;
       ray = ray.OffsetTowards(um::dot(scatteredRay.Direction, rec.Normal) >= 0 ? rec.Normal : -rec.Normal);
-    } else {
+      break;
+    }
+
+    // No hit?
+    if (hitIndex >= w.hits.size()) {
       f3 hitSkyColor = um::mk(0.0f);
       if (p.environment.sky_type == RTB_SKY_CUBEMAP)
         hitSkyColor = CubemapSample(ray.Direction);
@@ -879,8 +1008,11 @@ ORACLE_API int oracle_sample_batch_placed(const rtb_batch_params* params,
       return RTB_ERR_INVALID_ARGUMENT;
     }
   }
-  for (size_t i = 0; i < material_count; i++)
-    if (materials[i].type > RTB_MATERIAL_DIELECTRIC) return RTB_ERR_UNSUPPORTED;
+  bool has_volumes = false;
+  for (size_t i = 0; i < material_count; i++) {
+    if (materials[i].type > RTB_MATERIAL_PROBABILISTIC_VOLUME) return RTB_ERR_UNSUPPORTED;
+    has_volumes = has_volumes || materials[i].type == RTB_MATERIAL_PROBABILISTIC_VOLUME;
+  }
   if (params->environment.sky_type == RTB_SKY_CUBEMAP && !g_sky_faces) return RTB_ERR_NO_SCENE;
   Scene sc{spheres, sphere_count, materials, material_count, nodes, node_count, {}, {}};
   sc.entities = entity_count ? entities : nullptr;
@@ -889,6 +1021,7 @@ ORACLE_API int oracle_sample_batch_placed(const rtb_batch_params* params,
   sc.triangle_count = triangle_count;
   sc.placed = placed;
   sc.placed_count = placed_count;
+  sc.has_volumes = has_volumes;
   sc.placed_inverse.resize(placed_count);
   for (size_t i = 0; i < placed_count; i++) {
     const rtb_placed_entity& e = placed[i];

@@ -452,7 +452,7 @@ def _material(mtype, albedo, gloss=0.0, metallic=0.0, ior=1.5, emission=(0, 0, 0
     return m
 
 
-def make_cornell_scene(max_bvh_depth=16, moving=True):
+def make_cornell_scene(max_bvh_depth=16, moving=True, fog=False):
     """A Cornell box in the reference's entity vocabulary (the kind of world its Rect / Box entities exist for):
     five Rect walls and an emissive Rect light (Rect.cs: an XY rectangle hit from +Z only, turned into place by the
     entity's rotation), two Box entities turned about Y, a glass sphere (plain sphere entity) and — moving=True — a
@@ -467,6 +467,9 @@ def make_cornell_scene(max_bvh_depth=16, moving=True):
         _material(abi.MATERIAL_DIELECTRIC, (1, 1, 1), gloss=1.0, ior=1.5),             # 4 glass
         _material(abi.MATERIAL_STANDARD, (0.8, 0.8, 0.9), gloss=0.9, metallic=1.0),    # 5 polished metal (tall box)
         _material(abi.MATERIAL_STANDARD, (0.2, 0.3, 0.8)),                             # 6 blue (moving sphere)
+        _material(abi.MATERIAL_PROBABILISTIC_VOLUME, (0.05, 0.05, 0.05), ior=0.9),     # 7 dark smoke (density in the parameter field)
+        _material(abi.MATERIAL_PROBABILISTIC_VOLUME, (0.95, 0.95, 0.95), ior=0.6),     # 8 white fog
+        _material(abi.MATERIAL_PROBABILISTIC_VOLUME, (0.3, 0.5, 0.9), ior=2.5),        # 9 dense blue medium inside the glass ball
     ], dtype=abi.MATERIAL_DTYPE)
     z = (0.0, 0.0, 1.0)
     h = S / 2
@@ -487,6 +490,18 @@ def make_cornell_scene(max_bvh_depth=16, moving=True):
                                   destination_offset=(0.4, -0.3, 0.0), time_range=(0.25, 0.75)))
     spheres = np.zeros(1, dtype=abi.SPHERE_DTYPE)
     spheres[0] = ((1.8, 1.65 + 0.6, 1.7), 0.6, 4, (0, 0, 0))
+    if fog:
+        # participating media (Material.ProbabilisticHit): balls of fog and smoke, a denser medium inside the glass ball
+        # (a volume sphere just inside it), and the moving sphere becomes a drifting ball of fog
+        # (a Box medium is inert in the reference — Box.Hit's normal always faces the ray, HitTests.cs:108 — so the short box
+        # only exercises that path; the visible media are spheres)
+        placed[7]["material"] = 8
+        spheres = np.concatenate([spheres, np.zeros(3, dtype=abi.SPHERE_DTYPE)])
+        spheres[1] = ((1.8, 1.65 + 0.6, 1.7), 0.55, 9, (0, 0, 0))
+        spheres[2] = ((3.9, 1.3, 1.6), 1.2, 8, (0, 0, 0))        # a ball of white fog in front of the tall box
+        spheres[3] = ((1.2, 3.6, 3.2), 1.0, 7, (0, 0, 0))        # dark smoke under the ceiling, overlapping the moving box
+        if moving:
+            placed[8]["material"] = 8
     cam = abi.Camera()
     cam.position[:] = (h, h, -8.0)
     cam.target[:] = (h, h, 0.0)
