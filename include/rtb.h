@@ -115,7 +115,8 @@ typedef struct rtb_placed_entity {
 typedef enum rtb_material_type {     /* Material.cs:9-14 */
   RTB_MATERIAL_STANDARD = 0,
   RTB_MATERIAL_DIELECTRIC = 1,
-  RTB_MATERIAL_PROBABILISTIC_VOLUME = 2   /* not on the hot path: rtb_upload_scene returns RTB_ERR_UNSUPPORTED */
+  RTB_MATERIAL_PROBABILISTIC_VOLUME = 2   /* participating medium (Material.cs:48-65,163-168): albedo = Albedo.MainColor, density in
+                                           * index_of_refraction (Material.parameter); worlds with one run the collect-all kernel */
 } rtb_material_type;
 
 /* Material with constant textures only (Material.cs:16-26, Texture.cs:50-59,101-108:
@@ -127,7 +128,7 @@ typedef struct rtb_material {
   float emission[3];            /* Emission.MainColor */
   float glossiness;             /* Glossiness scalar */
   float metallic;               /* Metallic scalar */
-  float index_of_refraction;    /* Material.parameter (Dielectric) */
+  float index_of_refraction;    /* Material.parameter: IndexOfRefraction (Dielectric) or Density (ProbabilisticVolume) */
   uint32_t reserved[2];
 } rtb_material;                 /* 48 bytes */
 

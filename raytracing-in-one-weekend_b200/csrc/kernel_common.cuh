@@ -90,6 +90,7 @@ struct SceneDesc {
   const float2* tri_uv;              // 3 per triangle (Triangle.TextureCoordinates columns) or nullptr
   const uint16_t* sky_faces;    // Environment.SkyCubemap texels (6 faces of RGBA halves) or nullptr
   int sky_w, sky_h;
+  uint32_t has_volumes;         // some material is a ProbabilisticVolume: batches run sample_volumes (volume_kernel.cuh)
   uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
   const uint32_t* chain_ref;    // per sphere: first chain box | box count << 24
   const float4* chain_boxes;    // 2 x float4 per box (min.xyz, max.xyz), tightest first
@@ -386,7 +387,7 @@ __device__ __forceinline__ float sign_of(float x) { return (x > 0 ? 1.0f : 0.0f)
 // back by the transform (not yet normalised).
 template <bool SMEM>
 __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pidx, f3 o, f3 d, const RayClock& clk,
-                                         float* t_out, f3* n_out) {
+                                         float* t_out, f3* n_out, float tmin = 0.0f) {
   const float4 p0 = sv.placed(pidx, 0), p1 = sv.placed(pidx, 1);
   const uint32_t flags = __float_as_uint(p1.w);
   um::quat rot;
@@ -418,15 +419,15 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
     if (!(disc > 0)) return false;
     const float sq = um::sqrt(disc);
     t = um::div(-b - sq, a);
-    if (!(t < um::INF && t > 0.0f)) {
+    if (!(t < um::INF && t > tmin)) {
       t = um::div(-b + sq, a);
-      if (!(t < um::INF && t > 0.0f)) return false;
+      if (!(t < um::INF && t > tmin)) return false;
     }
     n = um::mad(ed, t, eo) / radius;
   } else if (type == RTB_ENTITY_RECT) {         // HitTests.cs:62-78
     if (ed.z >= 0) return false;
     t = um::div(-eo.z, ed.z);
-    if (t < 0.0f || t > um::INF) return false;
+    if (t < tmin || t > um::INF) return false;
     const float x = eo.x + t * ed.x, y = eo.y + t * ed.y;
     const float to_y = sv.placed(pidx, 6).x;
     if (x < p5.y || y < p5.z || x > p5.w || y > to_y) return false;
@@ -434,7 +435,7 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
   } else {                                      // Box, HitTests.cs:80-111
     const float4 p6 = sv.placed(pidx, 6);
     const f3 ext = um::mk(p5.y, p5.z, p5.w), inv_ext = um::mk(p6.x, p6.y, p6.z);
-    const f3 bo = eo + ed * 0.0f;               // "offset origin by tMin"
+    const f3 bo = eo + ed * tmin;               // "offset origin by tMin"
     const f3 ao = um::mk(um::abs(bo.x), um::abs(bo.y), um::abs(bo.z)) * inv_ext;
     const float winding = um::cmax(ao) < 1 ? -1.0f : 1.0f;
     const f3 sgn = um::mk(-sign_of(ed.x), -sign_of(ed.y), -sign_of(ed.z));
@@ -447,7 +448,7 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
     const bool nzx = n.x != 0, nzy = n.y != 0, nzz = n.z != 0;
     if (!(nzx || nzy || nzz)) return false;
     t = nzx ? dp.x : nzy ? dp.y : dp.z;
-    t += 0.0f;
+    t += tmin;
     if (t > um::INF) return false;
   }
   *t_out = t;
@@ -853,18 +854,20 @@ __device__ __forceinline__ ScatterPlan scatter_plan(float4 m0, float4 m1, float4
 }
 __device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, ScatterPlan pl,
                                                         uint4 r, float sn, float cs,
-                                                        uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed);
+                                                        uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed, float ev0 = 0.0f);
+// ev0: RandomSource.RandomEvents when Scatter starts (non-zero only after Material.ProbabilisticHit calls of the same bounce
+// iteration; the reference keeps adding to the same float, so the sum has to start from it to round identically)
 __device__ __forceinline__ ScatterResult scatter(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N,
-                                                 uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
+                                                 uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed, float ev0 = 0.0f) {
   const ScatterPlan pl = scatter_plan(m0, m1, m2);
   const uint4 r = philox4x32_10(pixel, sample, bounce, pl.block, seed, kPhiloxKey1);
   float sn = 0, cs = 1;
   if (pl.need_angle) unit_angle_sincos(u2f(r.y), &sn, &cs);
-  return scatter_finish(m0, m1, m2, m3, D, N, pl, r, sn, cs, pixel, sample, bounce, seed);
+  return scatter_finish(m0, m1, m2, m3, D, N, pl, r, sn, cs, pixel, sample, bounce, seed, ev0);
 }
 __device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, ScatterPlan pl,
                                                         uint4 r, float sn, float cs,
-                                                        uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed) {
+                                                        uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed, float ev0) {
   ScatterResult out;
   out.reflectance = um::mk(m0.x, m0.y, m0.z);
   const bool standard = pl.standard, pure_diffuse = pl.pure_diffuse, need_angle = pl.need_angle;
@@ -896,7 +899,7 @@ __device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, fl
       unit_angle_sincos(u2f(r1.y), &s1, &c1);
       out.dir = cosine_hemisphere(N, u2f(r1.x), s1, c1);
     }
-    float ev = 0;
+    float ev = ev0;
     if (chance > 0 && chance < 1) ev++;
     if (metallic > 0 && metallic < 1) ev++;
     ev += roughness * (chance + (1 - chance) * metallic);
@@ -931,7 +934,7 @@ __device__ __forceinline__ ScatterResult scatter_finish(float4 m0, float4 m1, fl
       out.dir = um::reflect(D, rough_normal);
       out.reflectance = um::mk(1.0f);
     }
-    float ev = 0;
+    float ev = ev0;
     ev++;
     ev += roughness;
     out.random_events = ev;
@@ -983,7 +986,7 @@ __device__ __forceinline__ PathRay camera_ray_white(const rtb_batch_params& p, i
 }
 
 // Material.Scatter (Material.cs:67-173) with the reference's draws in the reference's order
-__device__ __forceinline__ ScatterResult scatter_white(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, WhiteNoise& rng) {
+__device__ __forceinline__ ScatterResult scatter_white(float4 m0, float4 m1, float4 m2, float4 m3, f3 D, f3 N, WhiteNoise& rng, float ev0 = 0.0f) {
   ScatterResult out;
   out.reflectance = um::mk(m0.x, m0.y, m0.z);
   const float glossiness = m1.w, metallic = m2.x, roughness = m2.w;
@@ -1007,7 +1010,7 @@ __device__ __forceinline__ ScatterResult scatter_white(float4 m0, float4 m1, flo
     } else {
       out.dir = cosine_sample(N);                                                                           // :107
     }
-    float ev = 0;
+    float ev = ev0;
     if (chance > 0 && chance < 1) ev++;
     if (metallic > 0 && metallic < 1) ev++;
     ev += roughness * (chance + (1 - chance) * metallic);
@@ -1037,7 +1040,7 @@ __device__ __forceinline__ ScatterResult scatter_white(float4 m0, float4 m1, flo
       out.dir = um::reflect(D, rough_normal);
       out.reflectance = um::mk(1.0f);
     }
-    out.random_events = 1.0f + roughness;
+    out.random_events = (ev0 + 1.0f) + roughness;
   }
   return out;
 }

@@ -22,6 +22,7 @@
 #include "aux_kernels.cuh"
 #include "sample_kernels.cuh"
 #include "pool_kernel.cuh"
+#include "volume_kernel.cuh"
 
 using namespace rtbk;
 
@@ -319,12 +320,16 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   for (size_t i = 0; i < triangle_count; i++)
     if (triangles[i].material >= material_count) return "triangle material index out of range";
   const size_t leaf_list_count = entities ? entity_count : sphere_count;
+  bool has_volumes = false;
   for (size_t i = 0; i < material_count; i++) {
-    if (materials[i].type > RTB_MATERIAL_DIELECTRIC) {
+    if (materials[i].type > RTB_MATERIAL_PROBABILISTIC_VOLUME) {
       *status = RTB_ERR_UNSUPPORTED;
-      return "material type outside the supported hot path (Standard, Dielectric)";
+      return "unknown material type";
     }
+    has_volumes = has_volumes || materials[i].type == RTB_MATERIAL_PROBABILISTIC_VOLUME;
   }
+  // the volume kernel collects candidates exactly like the reference: every host leaf must stay a device leaf
+  if (has_volumes) collapse_k = 1;
   for (size_t i = 0; i < sphere_count; i++)
     if (spheres[i].material >= material_count) return "sphere material index out of range";
 
@@ -357,6 +362,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   d.has_chains = f.collapsed_any ? 1 : 0;
   d.n_triangles = (uint32_t)triangle_count;
   d.n_placed = (uint32_t)placed_count;
+  d.has_volumes = has_volumes ? 1u : 0u;
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t off = 0;
@@ -459,7 +465,8 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
     m.metallic = s.metallic;
     m.ior = s.index_of_refraction;      // Standard: replaced on the device by lerp(1.5, 1.1, metallic)
     // Material.IsPerfectSpecular (Material.cs:181-196)
-    m.perfect_specular = s.type == RTB_MATERIAL_DIELECTRIC || (almost_equals_1(s.metallic) && almost_equals_1(s.glossiness));
+    m.perfect_specular = s.type == RTB_MATERIAL_DIELECTRIC ||
+                         (s.type == RTB_MATERIAL_STANDARD && almost_equals_1(s.metallic) && almost_equals_1(s.glossiness));
     out->materials[i] = m;              // roughness / alpha / r0 are filled by derive_materials_kernel
   }
   *status = RTB_OK;
@@ -629,9 +636,22 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
 
   int kernel_kind = (int)ctx->opt_kernel;
   if (kernel_kind == 0) kernel_kind = ctx->default_kernel;
+  if (ctx->scene.has_volumes) {
+    // worlds with ProbabilisticVolume materials need every hit along a ray, sorted (volume_kernel.cuh): one kernel for them,
+    // whatever RTB_OPT_KERNEL says
+    const uint32_t grid = (a.n_active_pixels + 127) / 128;
+    if (ctx->opt_noise) {
+      if (counters) sample_volumes<true, true><<<grid, 128, 0, stream>>>(a);
+      else sample_volumes<false, true><<<grid, 128, 0, stream>>>(a);
+    } else {
+      if (counters) sample_volumes<true, false><<<grid, 128, 0, stream>>>(a);
+      else sample_volumes<false, false><<<grid, 128, 0, stream>>>(a);
+    }
+    RTB_CUDA(ctx, cudaGetLastError());
+  } else
   if (ctx->opt_noise && kernel_kind != 1)
     return fail(ctx, RTB_ERR_UNSUPPORTED, "RTB_OPT_NOISE = 1 (the reference's sequential white-noise stream) needs RTB_OPT_KERNEL = 1");
-  if (kernel_kind == 1) {
+  else if (kernel_kind == 1) {
     const uint32_t grid = (a.n_active_pixels + 127) / 128;
     if (ctx->opt_noise) {
       if (counters) sample_simple<true, true><<<grid, 128, 0, stream>>>(a);

@@ -1,0 +1,358 @@
+// sample_volumes: the sample job for worlds with MaterialType.ProbabilisticVolume materials.
+//
+// Participating media need what the closest-hit walk of the other kernels throws away: the reference decides entry /
+// exit / containment from the SORTED LIST OF ALL HITS along the ray, with an extra exit hit injected for convex media
+// and a backwards ray to find out whether the origin is inside a medium (SampleBatchJob.cs:194-303, 450-524).  This
+// kernel therefore follows the reference's shape — one thread per pixel, samples in order, collect every hit, sort,
+// run the volume bookkeeping — with the same arithmetic and the same accumulation order as sample_simple, so its
+// outputs equal the CPU oracle's bit for bit.  It is the functional path for such worlds, not a tuned one.
+#pragma once
+
+#include "sample_kernels.cuh"
+
+namespace rtbk {
+
+constexpr int kMaxRayHits = 48;     // hit records kept per ray (the reference's list starts at 32 and grows, SampleBatchJob.cs:21);
+                                    // beyond this the farthest hits are dropped
+
+struct RayHits {                    // FindHits' sorted hitBuffer
+  float t[kMaxRayHits];
+  int slot[kMaxRayHits];
+  f3 n[kMaxRayHits];
+  int count;
+};
+
+// Entity.Hit (Entity.cs:57-72) of the entity in `slot` for t in (tmin, +inf): distance and world normal.
+template <bool SMEM>
+__device__ __forceinline__ bool entity_hit(const SceneView<SMEM>& sv, int slot, f3 o, f3 d, float tmin, const RayClock& clk, float* t_out,
+                                           f3* n_out) {
+  const float4 prim = sv.sphere(slot);
+  if (prim.w != prim.w) {
+    if (__float_as_uint(prim.y) != 0u) {
+      f3 n;
+      if (!placed_test(sv, __float_as_uint(prim.x), o, d, clk, t_out, &n, tmin)) return false;
+      *n_out = um::normalize(n);
+      return true;
+    }
+    float u, v, t;
+    if (!triangle_uvt(sv, __float_as_uint(prim.x), o, d, &u, &v, &t)) return false;
+    if (t < tmin) return false;                       // HitTests.cs:141 (tMax = +inf)
+    *t_out = t;
+    *n_out = hit_normal<SMEM, kFlavorGeneral>(sv, prim, o, d, t, clk);
+    return true;
+  }
+  // HitTests.Hit(this Sphere) (HitTests.cs:23-60) behind the identity-rotation transform
+  const f3 oc = o + um::mk(-prim.x, -prim.y, -prim.z);
+  const float a = um::dot(d, d), b = um::dot(oc, d), c = um::dot(oc, oc) - prim.w * prim.w;
+  const float disc = um::fma(b, b, -(a * c));
+  if (!(disc > 0.0f)) return false;
+  const float sq = um::sqrt(disc);
+  float t = um::div(-b - sq, a);
+  if (!(t < um::INF && t > tmin)) {
+    t = um::div(-b + sq, a);
+    if (!(t < um::INF && t > tmin)) return false;
+  }
+  *t_out = t;
+  *n_out = um::normalize(um::mad(d, t, oc) / prim.w);
+  return true;
+}
+
+__device__ __forceinline__ bool is_volume(const SceneDesc& sd, uint32_t material) {
+  return __ldg(reinterpret_cast<const uint32_t*>(sd.materials + material) + 3) == RTB_MATERIAL_PROBABILISTIC_VOLUME;
+}
+// EntityType.IsConvexHull (Entity.cs:22-25): Sphere or Box
+__device__ __forceinline__ bool is_convex_hull(const SceneView<false>& sv, float4 prim) {
+  if (prim.w == prim.w) return true;
+  if (__float_as_uint(prim.y) == 0u) return false;    // triangle
+  const uint32_t type = __float_as_uint(sv.placed(__float_as_uint(prim.x), 1).w) & 0xffu;
+  return type == RTB_ENTITY_SPHERE || type == RTB_ENTITY_BOX;
+}
+
+// FindHitCandidates + FindHits (SampleBatchJob.cs:403-475) without pruning: every entity of every leaf whose box chain
+// the ray hits, in the reference's visit order (children pushed Left then Right, Right popped first).  The reference
+// pops candidates from the END of that list and then sorts by distance; with a stable order among equal distances that
+// is: a later candidate goes BEFORE an earlier one at the same distance — the insertion rule used here.
+// MODE 0: fill `hits`.  MODE 1 (AnyBackwardsVolumeEntryHit, :508-524): is there a volume entity the ray enters?
+template <int MODE, bool COUNTERS>
+__device__ __noinline__ bool collect_hits(const SceneView<false>& sv, const SceneDesc& sd, f3 o, f3 d, const RayClock& clk, RayHits* hits,
+                                          WorkCounters& wc) {
+  if (MODE == 0) hits->count = 0;
+  if (!sd.has_root) return false;
+  f3 inv = um::rcp(d);
+  inv = um::mk(um::isnan(inv.x) ? um::INF : inv.x, um::isnan(inv.y) ? um::INF : inv.y, um::isnan(inv.z) ? um::INF : inv.z);
+  float t_enter;
+  if (COUNTERS) wc.node_tests++;
+  if (!aabb_hit(v3(sd.root_min), v3(sd.root_max), o, inv, &t_enter)) return false;
+  int stack[kStackMax + 2];
+  int sp = 0;
+  stack[sp++] = sd.root_ref;
+  auto insert = [&](float t, int slot, f3 n) {
+    int pos = 0;
+    while (pos < hits->count && hits->t[pos] < t) pos++;       // before the first record that is not nearer
+    if (pos >= kMaxRayHits) return;
+    const int last = hits->count < kMaxRayHits ? hits->count : kMaxRayHits - 1;
+    for (int k = last; k > pos; k--) { hits->t[k] = hits->t[k - 1]; hits->slot[k] = hits->slot[k - 1]; hits->n[k] = hits->n[k - 1]; }
+    hits->t[pos] = t; hits->slot[pos] = slot; hits->n[pos] = n;
+    if (hits->count < kMaxRayHits) hits->count++;
+  };
+  while (sp > 0) {
+    const int cur = stack[--sp];
+    if (cur >= 0) {
+      const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
+      float tl, tr;
+      const bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
+      const bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
+      if (COUNTERS) wc.node_tests += 2;
+      if (hl) stack[sp++] = __float_as_int(q3.x);
+      if (hr) stack[sp++] = __float_as_int(q3.y);
+      continue;
+    }
+    const uint32_t code = (uint32_t)~cur;
+    const int first = (int)(code & ~15u);
+    int count = (int)(code & 15u) + 1;
+    if (count == 16) count = (int)sv.leaf_count(first);
+    if (COUNTERS) wc.sphere_tests += count;
+    for (int i = 0; i < count; i++) {
+      const int slot = first + 16 * i;
+      const uint32_t material = sv.material_of(slot);
+      if (MODE == 1 && !is_volume(sd, material)) continue;
+      float t;
+      f3 n;
+      if (!entity_hit(sv, slot, o, d, 0.0f, clk, &t, &n)) continue;
+      if (MODE == 1) {
+        if (um::dot(n, d) > 0) return true;           // (the caller passes the backwards ray)
+        continue;
+      }
+      // Inject exit hits for probabilistic convex hulls (:462-469); the pair is pushed entry first, so at equal
+      // distances the exit must end up behind the entry: insert it first
+      if (is_volume(sd, material) && is_convex_hull(sv, sv.sphere(slot))) {
+        float t2;
+        f3 n2;
+        if (entity_hit(sv, slot, o, d, t + 0.001f, clk, &t2, &n2)) insert(t2, slot, n2);
+      }
+      insert(t, slot, n);
+    }
+  }
+  return false;
+}
+
+template <bool COUNTERS, bool WHITE>
+__global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ BatchArgs a) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.n_active_pixels) return;
+  const rtb_batch_params& p = a.p;
+  const SceneDesc& sd = a.scene;
+  SceneView<false> sv;
+  sv.bind(sd.blob, sd);
+  int cx, cy;
+  uint32_t index;
+  active_pixel(a, k, &cx, &cy, &index);
+
+  const float4 in_color = reinterpret_cast<const float4*>(a.b.in_color)[index];
+  f3 color_acc = um::mk(in_color.x, in_color.y, in_color.z);
+  f3 normal_acc = v3(a.b.in_normal + 3 * (size_t)index);
+  f3 albedo_acc = v3(a.b.in_albedo + 3 * (size_t)index);
+  float weight_acc = a.b.in_sample_count_weight[index];
+  int sample_count = (int)in_color.w;
+  float scw;
+  const uint32_t n = samples_to_accumulate(p, in_color.w, weight_acc, &scw);
+  f3 fb_normal = um::mk(0.0f), fb_albedo = um::mk(0.0f);
+  uint32_t rays = 0;
+  WorkCounters wc;
+  const bool exact = p.trace_depth <= kSimpleStack;
+  f3 att[kSimpleStack], emi[kSimpleStack];
+  RayHits hits;
+  WhiteNoise white{};
+  if (WHITE) white.init((p.seed * 0x8C4CA03Fu) ^ (index * 0x7383ED49u));      // SampleBatchJob.cs:91
+
+  for (uint32_t s = 0; s < n; s++) {
+    RayClock clk{index, s, p.seed, 0.0f, true};
+    PathRay ray = WHITE ? camera_ray_white(p, cx, cy, white, &clk.value) : camera_ray(p, cx, cy, index, s);
+    if (!WHITE) { clk.known = false; clk.value = clk.time(); clk.known = true; }
+    f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
+    f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
+    bool first_non_specular = false;
+    float events_acc = 0, pow2depth = 1;
+    int depth = 0, entries = 0;
+    int current_volume = -1;                          // currentProbabilisticVolumeMaterial (material index, -1 = null)
+    for (; depth < p.trace_depth; depth++) {
+      uint32_t volume_draws = 0;
+      float events = 0;                               // rng.RandomEvents of this iteration
+      collect_hits<0, COUNTERS>(sv, sd, ray.o, ray.d, clk, &hits, wc);
+      if (current_volume < 0) {                       // DetermineVolumeContainment (:477-506)
+        for (int i = 0; i < hits.count; i++) {
+          const uint32_t hm = sv.material_of(hits.slot[i]);
+          if (!is_volume(sd, hm)) continue;
+          if (um::dot(hits.n[i], ray.d) < 0) break;   // entry hit: not inside
+          if (collect_hits<1, COUNTERS>(sv, sd, ray.o, -ray.d, clk, nullptr, wc)) { current_volume = (int)hm; break; }
+        }
+      }
+      rays++;
+
+      bool scattered = false;
+      int hit_index = 0;
+      while (hit_index < hits.count) {
+        float rec_t = hits.t[hit_index];
+        f3 rec_n = hits.n[hit_index];
+        int rec_slot = hits.slot[hit_index];
+        uint32_t mi = sv.material_of(rec_slot);
+        bool medium_hit = false;
+
+        if (current_volume >= 0 || is_volume(sd, mi)) {
+          const bool is_entry_hit = current_volume < 0;
+          if (current_volume < 0) current_volume = (int)mi;
+          int exit_index = hit_index, last_exit = -1, same_entries = 0;
+          while (exit_index < hits.count) {
+            if ((int)sv.material_of(hits.slot[exit_index]) == current_volume) {
+              if (um::dot(hits.n[exit_index], ray.d) < 0) {
+                same_entries++;
+              } else {
+                same_entries--;
+                last_exit = exit_index;
+              }
+              if (same_entries <= 0) break;
+            } else {
+              break;
+            }
+            exit_index++;
+          }
+          if (same_entries > 0 && last_exit != -1) exit_index = last_exit;
+
+          if (exit_index < hits.count) {
+            float distance_in_volume = hits.t[exit_index];
+            float entry_distance = 0;
+            if (is_entry_hit) {
+              entry_distance = rec_t;
+              distance_in_volume -= rec_t;
+            }
+            // Material.ProbabilisticHit (Material.cs:48-65); Density = the material's parameter
+            const float density = __ldg(reinterpret_cast<const float*>(sd.materials + current_volume) + 9);
+            events += 1.0f;
+            float u;
+            if (WHITE) {
+              u = white.next_float();
+            } else {
+              const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 2u + (volume_draws >> 2), p.seed, kPhiloxKey1);
+              const uint32_t w = volume_draws & 3u;
+              u = u2f(w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w);
+              volume_draws++;
+            }
+            const float volume_hit_distance = -um::div(1.0f, um::max(density, 1.1920928955078125e-7f)) * um::log_unit(u);
+            if (volume_hit_distance < distance_in_volume) {
+              // we hit inside the volume: the record becomes (distance, point, -direction), the material the medium's
+              rec_t = entry_distance + volume_hit_distance;
+              rec_n = -ray.d;
+              mi = (uint32_t)current_volume;
+              medium_hit = true;
+            } else {
+              const uint32_t exit_material = sv.material_of(hits.slot[exit_index]);
+              current_volume = -1;
+              if (is_volume(sd, exit_material) && um::dot(hits.n[exit_index], ray.d) > 0) {
+                hit_index = exit_index + 1;           // volume exit: move to the next hit
+                continue;
+              }
+              rec_t = hits.t[exit_index];             // obstacle: scatter on the exit hit
+              rec_n = hits.n[exit_index];
+              rec_slot = hits.slot[exit_index];
+              mi = exit_material;
+            }
+          } else {
+            hits.count = 0;                           // no more surfaces to hit (the volume has holes)
+            break;
+          }
+        }
+
+        const float4* mp = reinterpret_cast<const float4*>(sd.materials + mi);
+        float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+        if (__float_as_uint(m3.w) != 0u) {
+          // HitRecord.TexCoords: the hit triangle's, or 0 (other entities, and the record made inside a medium)
+          const float4 prim = medium_hit ? make_float4(0, 0, 0, 1) : sv.sphere(rec_slot);
+          resolve_textures(sv, sd, mi, prim, ray.o, ray.d, m0, m1, m2, m3);
+        }
+        const f3 N = rec_n;
+        const f3 P = um::mad(ray.d, rec_t, ray.o);
+        ScatterResult sc;
+        if (__float_as_uint(m0.w) == RTB_MATERIAL_PROBABILISTIC_VOLUME) {
+          // Material.cs:163-168: isotropic; new Ray(rec.Point, direction) has Time = 0
+          float rx, ry;
+          if (WHITE) { rx = white.next_float(); ry = white.next_float(); }
+          else { const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 0u, p.seed, kPhiloxKey1); rx = u2f(r.x); ry = u2f(r.y); }
+          float sn, cs;
+          unit_angle_sincos(ry, &sn, &cs);
+          sc.dir = random_direction(rx, sn, cs);
+          sc.reflectance = um::mk(m0.x, m0.y, m0.z);
+          sc.random_events = events + 2.0f;
+          clk.value = 0.0f;
+        } else {
+          sc = WHITE ? scatter_white(m0, m1, m2, m3, ray.d, N, white, events)
+                     : scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed, events);
+          if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+        }
+        events = sc.random_events;                   // RandomEvents after Scatter (it started from this iteration's count)
+        const f3 emission = um::mk(m1.x, m1.y, m1.z);
+        if (depth == 0) s_normal = N;
+        if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
+          s_albedo = emission + sc.reflectance;
+          s_normal = N;
+          first_non_specular = true;
+        }
+        if (exact) { emi[entries] = emission; att[entries] = sc.reflectance; entries++; }
+        radiance = um::mad(throughput, emission, radiance);
+        throughput = throughput * sc.reflectance;
+        events_acc += um::div(events, pow2depth);
+        events = 0;
+        const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
+        ray.o = um::mad(off_n, 0.001f, P);
+        ray.d = sc.dir;
+        scattered = true;
+        break;
+      }
+
+      if (!scattered) {                               // no hit (or every hit passed through / dropped): the sky ends the path
+        const f3 sky = sky_color(p.environment, sd, ray.d);
+        if (exact) { emi[entries] = sky; att[entries] = um::mk(1.0f); entries++; }
+        radiance = um::mad(throughput, sky, radiance);
+        events_acc += um::div(events, pow2depth);
+        if (!first_non_specular) { s_albedo = sky; s_normal = -ray.d; }
+        break;
+      }
+      pow2depth *= 2.0f;
+    }
+    if (depth != p.trace_depth) {
+      f3 c = radiance;
+      if (exact) {
+        c = um::mk(0.0f);
+        for (int e = entries; e-- > 0;) { c = c * att[e]; c = c + emi[e]; }
+      }
+      color_acc = color_acc + c;
+      normal_acc = normal_acc + s_normal;
+      albedo_acc = albedo_acc + s_albedo;
+      weight_acc += events_acc;
+      sample_count++;
+    }
+    if (s == 0) { fb_normal = s_normal; fb_albedo = s_albedo; }
+  }
+
+  reinterpret_cast<float4*>(a.b.out_color)[index] = make_float4(color_acc.x, color_acc.y, color_acc.z, (float)sample_count);
+  const f3 on = sample_count == 0 ? fb_normal : normal_acc;
+  const f3 oa = sample_count == 0 ? fb_albedo : albedo_acc;
+  float* pn = a.b.out_normal + 3 * (size_t)index;
+  float* pa = a.b.out_albedo + 3 * (size_t)index;
+  pn[0] = on.x; pn[1] = on.y; pn[2] = on.z;
+  pa[0] = oa.x; pa[1] = oa.y; pa[2] = oa.z;
+  a.b.out_sample_count_weight[index] = weight_acc;
+  if (COUNTERS && a.counters) {
+    if (wc.shade_standard) atomicAdd(&a.counters[4], (unsigned long long)wc.shade_standard);
+    if (wc.shade_dielectric) atomicAdd(&a.counters[5], (unsigned long long)wc.shade_dielectric);
+  }
+  if (a.b.out_diagnostics) {
+    rtb_diagnostics dg;
+    dg.ray_count = (float)rays;
+    dg.bounds_hit_count = (float)wc.node_tests;
+    dg.candidate_count = (float)wc.sphere_tests;
+    dg.sample_count_weight = scw;
+    a.b.out_diagnostics[index] = dg;
+  }
+}
+
+}  // namespace rtbk

@@ -891,3 +891,61 @@ def test_random_worlds_of_every_entity_kind(rtb, oracle, ctx):
                 assert_parity(ref, got, exact=exact)
             except AssertionError as e:
                 raise AssertionError(f"random world {seed}, kernel {kernel}: {e}")
+
+
+@pytest.mark.parametrize("depth,moving,aperture", [(16, True, 0.0), (2, False, 0.15), (0, True, 0.0)])
+def test_fog_cornell_world_matches_the_oracle(rtb, oracle, ctx, depth, moving, aperture):
+    """MaterialType.ProbabilisticVolume (SampleBatchJob.cs:194-303, 450-524; Material.cs:48-65,163-168): balls of fog and
+    smoke (one of them moving), a medium inside the glass ball, an inert Box medium — entry / exit bookkeeping over the sorted
+    list of all hits, injected exit hits, backwards containment rays.  The volume kernel is bit-identical to the oracle
+    whatever RTB_OPT_KERNEL asks for."""
+    W, H, spp = 96, 54, 16
+    scene = rtb.host.make_cornell_scene(max_bvh_depth=depth, moving=moving, fog=True)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=aperture)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    plain = oracle.Buffers(W, H)
+    oracle.sample_batch(rtb.host.make_cornell_scene(max_bvh_depth=depth, moving=moving), p, plain)
+    assert np.abs(ref.rgb() - plain.rgb()).max() > 0.5                       # the media are visible
+    for kernel in (rtb.abi.KERNEL_SIMPLE, rtb.abi.KERNEL_MEGA):
+        got = render_gpu(rtb, ctx, scene, p, W, H, kernel)
+        assert_parity(ref, got, exact=True)
+
+
+def test_fog_world_white_noise_stream_and_camera_inside_a_medium(rtb, oracle, ctx):
+    """The reference's xorshift32 stream through the media (ProbabilisticHit's draw and the isotropic direction are taken in
+    stream order), with the camera INSIDE a ball of fog so that every camera ray starts with the containment test."""
+    W, H, spp = 64, 36, 8
+    scene = rtb.host.make_cornell_scene(max_bvh_depth=16, moving=True, fog=True)
+    scene.spheres["center"][2] = (2.775, 2.775, -8.0)                        # the white fog ball now surrounds the camera
+    scene.spheres["radius"][2] = 1.5
+    scene = rtb.host.build_world(scene.spheres, [], scene.materials, 16, scene.camera, scene.environment, scene.focus_distance,
+                                 placed=scene.placed)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    for noise, opt in ((oracle.NOISE_PHILOX, rtb.abi.NOISE_PHILOX), (oracle.NOISE_XORSHIFT, rtb.abi.NOISE_WHITE)):
+        ref = oracle.Buffers(W, H)
+        oracle.sample_batch(scene, p, ref, noise=noise)
+        assert ref.diagnostics["ray_count"].min() >= spp
+        ctx.upload(scene)
+        ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_SIMPLE)
+        ctx.set_option(rtb.abi.OPT_NOISE, opt)
+        try:
+            got = rtb.plugin.HostBuffers(W, H)
+            ctx.sample_batch(p, got)
+        finally:
+            ctx.set_option(rtb.abi.OPT_NOISE, 0)
+        assert_parity(ref, got, exact=True)
+
+
+def test_black_fog_transmittance_on_the_gpu(rtb, ctx):
+    """Beer-Lambert through a non-scattering medium in front of a white sky, straight from the kernel (no oracle): the centre
+    pixel is exp(-density * chord) from outside and from inside the medium."""
+    import test_oracle_kat as kat
+    spp = 4096
+    for camera_z, length in ((-6.0, 2.0), (-0.5, 1.5)):
+        s = kat._fog_world(rtb, camera_z, density=0.8)
+        p = rtb.host.make_params(s, 3, 3, spp, 50, jitter=False)
+        b = render_gpu(rtb, ctx, s, p, 3, 3, rtb.abi.KERNEL_MEGA)
+        want = np.exp(-0.8 * length)
+        assert b.out_color[4, 3] == spp
+        assert np.allclose(b.rgb()[1, 1], want, atol=4 * np.sqrt(want * (1 - want) / spp)), (camera_z, b.rgb()[1, 1], want)
