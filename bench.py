@@ -43,6 +43,7 @@ CONFIGS = {
     "c5s": ("stress", 16, 1920, 1080, 64, 50, 0.1),     # config 5's world at a single-GPU size
     "mesh": ("mesh", 16, 1920, 1080, 64, 50, 0.1),       # triangle-mesh world (what the reference's host ingests at HEAD)
     "cornell": ("cornell", 16, 1920, 1080, 64, 50, 0.0),  # Rect / Box / moving entities behind rotated transforms
+    "fog": ("fog", 16, 1920, 1080, 64, 50, 0.0),          # the same room with participating media (ProbabilisticVolume)
 }
 STRESS_SPHERES = 10000
 
@@ -53,6 +54,8 @@ def make_scene(host, cfg):
         return host.make_mesh_scene(max_bvh_depth=depth, subdivisions=4)
     if name == "cornell":
         return host.make_cornell_scene(max_bvh_depth=depth)
+    if name == "fog":
+        return host.make_cornell_scene(max_bvh_depth=depth, fog=True)
     return host.make_scene(name, max_bvh_depth=depth, target_count=STRESS_SPHERES if name == "stress" else 0)
 
 WORKLOADS = {
@@ -62,6 +65,7 @@ WORKLOADS = {
     "c4": "book-1 final scene BVH + defocus 3840x2160x1024spp depth 50",
     "c5": "10k-sphere synthetic stress scene BVH(maxDepth 16) + defocus 4096x4096x2048spp depth 50",
     "c5s": "10k-sphere synthetic stress scene BVH(maxDepth 16) + defocus 1920x1080x64spp depth 50",
+    "fog": "Cornell box with participating media (4 ProbabilisticVolume balls, one moving; collect-all volume kernel) BVH(maxDepth 16) 1920x1080x64spp depth 50",
     "cornell": "Cornell box of placed entities (6 Rects, 3 Boxes, 2 spheres; one sphere and one box moving) BVH(maxDepth 16) 1920x1080x64spp depth 50",
     "mesh": "triangle-mesh world (5120-triangle smooth icosphere + flat-shaded solids + 3 spheres, 5135 triangles) BVH(maxDepth 16) + defocus 1920x1080x64spp depth 50",
 }

@@ -326,7 +326,18 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
       *status = RTB_ERR_UNSUPPORTED;
       return "unknown material type";
     }
-    has_volumes = has_volumes || materials[i].type == RTB_MATERIAL_PROBABILISTIC_VOLUME;
+  }
+  // a medium counts when some entity wears it (a host may keep unused materials in its buffer)
+  auto wears_volume = [&](uint32_t m) { return m < material_count && materials[m].type == RTB_MATERIAL_PROBABILISTIC_VOLUME; };
+  if (entities) {
+    for (size_t i = 0; i < entity_count && !has_volumes; i++) {
+      const uint32_t base = entities[i].type & ~(uint32_t)RTB_ENTITY_PLACED;
+      if (Flattener::is_placed_type(entities[i].type)) has_volumes = wears_volume(placed[entities[i].index].material);
+      else if (base == RTB_ENTITY_TRIANGLE) has_volumes = wears_volume(triangles[entities[i].index].material);
+      else has_volumes = wears_volume(spheres[entities[i].index].material);
+    }
+  } else {
+    for (size_t i = 0; i < sphere_count && !has_volumes; i++) has_volumes = wears_volume(spheres[i].material);
   }
   // the volume kernel collects candidates exactly like the reference: every host leaf must stay a device leaf
   if (has_volumes) collapse_k = 1;

@@ -471,6 +471,8 @@ def make_cornell_scene(max_bvh_depth=16, moving=True, fog=False):
         _material(abi.MATERIAL_PROBABILISTIC_VOLUME, (0.95, 0.95, 0.95), ior=0.6),     # 8 white fog
         _material(abi.MATERIAL_PROBABILISTIC_VOLUME, (0.3, 0.5, 0.9), ior=2.5),        # 9 dense blue medium inside the glass ball
     ], dtype=abi.MATERIAL_DTYPE)
+    if not fog:
+        materials = materials[:7]
     z = (0.0, 0.0, 1.0)
     h = S / 2
     placed = [

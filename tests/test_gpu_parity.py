@@ -949,3 +949,17 @@ def test_black_fog_transmittance_on_the_gpu(rtb, ctx):
         want = np.exp(-0.8 * length)
         assert b.out_color[4, 3] == spp
         assert np.allclose(b.rgb()[1, 1], want, atol=4 * np.sqrt(want * (1 - want) / spp)), (camera_z, b.rgb()[1, 1], want)
+
+
+def test_an_unused_volume_material_does_not_change_the_kernel(rtb, ctx):
+    """Only media that some entity wears send a world to the collect-all kernel: a ProbabilisticVolume left unused in the
+    material buffer keeps the megakernel (same bits as without it)."""
+    W, H, spp = 64, 36, 8
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    a = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    extra = rtb.host.make_scene("final", max_bvh_depth=16)
+    extra.materials = np.concatenate([extra.materials, np.array([rtb.host._material(rtb.abi.MATERIAL_PROBABILISTIC_VOLUME, (1, 1, 1), ior=2.0)],
+                                                                dtype=rtb.abi.MATERIAL_DTYPE)])
+    b = render_gpu(rtb, ctx, extra, p, W, H, rtb.abi.KERNEL_MEGA)
+    assert a.out_color.tobytes() == b.out_color.tobytes() and a.out_weight.tobytes() == b.out_weight.tobytes()
