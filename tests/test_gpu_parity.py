@@ -623,7 +623,7 @@ def test_error_behaviour(rtb):
             c.sample_batch(p, b)
         assert e.value.code == abi.RTB_ERR_NO_SCENE
         bad = scene.materials.copy()
-        bad["type"][0] = abi.MATERIAL_PROBABILISTIC_VOLUME
+        bad["type"][0] = 7                                # not a MaterialType
         with pytest.raises(rtb.plugin.RtbError) as e:
             c.upload_scene(scene.spheres, bad, scene.nodes)
         assert e.value.code == abi.RTB_ERR_UNSUPPORTED
