@@ -650,11 +650,12 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   if (ctx->scene.has_volumes) {
     // worlds with ProbabilisticVolume materials need every hit along a ray, sorted (volume_kernel.cuh): one kernel for them,
     // whatever RTB_OPT_KERNEL says
-    const uint32_t grid = (a.n_active_pixels + 127) / 128;
-    if (ctx->opt_noise) {
+    if (ctx->opt_noise) {                       // one thread per pixel (a sequential stream per pixel)
+      const uint32_t grid = (a.n_active_pixels + 127) / 128;
       if (counters) sample_volumes<true, true><<<grid, 128, 0, stream>>>(a);
       else sample_volumes<false, true><<<grid, 128, 0, stream>>>(a);
-    } else {
+    } else {                                    // one warp per pixel
+      const uint32_t grid = (a.n_active_pixels + 3) / 4;
       if (counters) sample_volumes<true, false><<<grid, 128, 0, stream>>>(a);
       else sample_volumes<false, false><<<grid, 128, 0, stream>>>(a);
     }

@@ -12,6 +12,7 @@
 
 namespace rtbk {
 
+constexpr uint32_t kLaneSamples = 8;  // samples a lane traces back to back before the warp accumulates (Philox mode)
 constexpr int kMaxRayHits = 48;     // hit records kept per ray (the reference's list starts at 32 and grows, SampleBatchJob.cs:21);
                                     // beyond this the farthest hits are dropped
 
@@ -24,8 +25,8 @@ struct RayHits {                    // FindHits' sorted hitBuffer
 
 // Entity.Hit (Entity.cs:57-72) of the entity in `slot` for t in (tmin, +inf): distance and world normal.
 template <bool SMEM>
-__device__ __forceinline__ bool entity_hit(const SceneView<SMEM>& sv, int slot, f3 o, f3 d, float tmin, const RayClock& clk, float* t_out,
-                                           f3* n_out) {
+__device__ __noinline__ bool entity_hit(const SceneView<SMEM>& sv, int slot, f3 o, f3 d, float tmin, const RayClock& clk, float* t_out,
+                                        f3* n_out) {
   const float4 prim = sv.sphere(slot);
   if (prim.w != prim.w) {
     if (__float_as_uint(prim.y) != 0u) {
@@ -73,9 +74,9 @@ __device__ __forceinline__ bool is_convex_hull(const SceneView<false>& sv, float
 // pops candidates from the END of that list and then sorts by distance; with a stable order among equal distances that
 // is: a later candidate goes BEFORE an earlier one at the same distance — the insertion rule used here.
 // MODE 0: fill `hits`.  MODE 1 (AnyBackwardsVolumeEntryHit, :508-524): is there a volume entity the ray enters?
-template <int MODE, bool COUNTERS>
-__device__ __noinline__ bool collect_hits(const SceneView<false>& sv, const SceneDesc& sd, f3 o, f3 d, const RayClock& clk, RayHits* hits,
-                                          WorkCounters& wc) {
+template <bool COUNTERS>
+__device__ __noinline__ bool collect_hits(const int MODE, const SceneView<false>& sv, const SceneDesc& sd, f3 o, f3 d, const RayClock& clk,
+                                          RayHits* hits, WorkCounters& wc) {
   if (MODE == 0) hits->count = 0;
   if (!sd.has_root) return false;
   f3 inv = um::rcp(d);
@@ -136,14 +137,197 @@ __device__ __noinline__ bool collect_hits(const SceneView<false>& sv, const Scen
   return false;
 }
 
+struct VolumeSample {            // what one camera path hands to the pixel's accumulators (SampleBatchJob.cs:136-157)
+  bool ok;                       // Sample() returned true (the path reached the sky within TraceDepth)
+  f3 color, normal, albedo;
+  float events;                  // randomEventsLocalAcc
+  uint32_t rays;                 // bounce-loop iterations (Diagnostics.RayCount)
+};
+
+// SampleBatchJob.Sample (:166-401) with the volume bookkeeping, for the path that starts with `ray`.
 template <bool COUNTERS, bool WHITE>
-__global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ BatchArgs a) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.n_active_pixels) return;
+__device__ __noinline__ VolumeSample trace_volume_sample(const BatchArgs& a, const SceneView<false>& sv, PathRay ray, RayClock clk, uint32_t index,
+                                                        uint32_t s, WhiteNoise& white, WorkCounters& wc) {
   const rtb_batch_params& p = a.p;
   const SceneDesc& sd = a.scene;
+  const bool exact = p.trace_depth <= kSimpleStack;
+  f3 att[kSimpleStack], emi[kSimpleStack];
+  RayHits hits;
+  VolumeSample out;
+  out.rays = 0;
+  f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
+  f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
+  bool first_non_specular = false;
+  float events_acc = 0, pow2depth = 1;
+  int depth = 0, entries = 0;
+  int current_volume = -1;                          // currentProbabilisticVolumeMaterial (material index, -1 = null)
+  for (; depth < p.trace_depth; depth++) {
+    uint32_t volume_draws = 0;
+    float events = 0;                               // rng.RandomEvents of this iteration
+    collect_hits<COUNTERS>(0, sv, sd, ray.o, ray.d, clk, &hits, wc);
+    if (current_volume < 0) {                       // DetermineVolumeContainment (:477-506)
+      for (int i = 0; i < hits.count; i++) {
+        const uint32_t hm = sv.material_of(hits.slot[i]);
+        if (!is_volume(sd, hm)) continue;
+        if (um::dot(hits.n[i], ray.d) < 0) break;   // entry hit: not inside
+        if (collect_hits<COUNTERS>(1, sv, sd, ray.o, -ray.d, clk, &hits, wc)) { current_volume = (int)hm; break; }
+      }
+    }
+    out.rays++;
+
+    bool scattered = false;
+    int hit_index = 0;
+    while (hit_index < hits.count) {
+      float rec_t = hits.t[hit_index];
+      f3 rec_n = hits.n[hit_index];
+      int rec_slot = hits.slot[hit_index];
+      uint32_t mi = sv.material_of(rec_slot);
+      bool medium_hit = false;
+
+      if (current_volume >= 0 || is_volume(sd, mi)) {
+        const bool is_entry_hit = current_volume < 0;
+        if (current_volume < 0) current_volume = (int)mi;
+        int exit_index = hit_index, last_exit = -1, same_entries = 0;
+        while (exit_index < hits.count) {
+          if ((int)sv.material_of(hits.slot[exit_index]) == current_volume) {
+            if (um::dot(hits.n[exit_index], ray.d) < 0) {
+              same_entries++;
+            } else {
+              same_entries--;
+              last_exit = exit_index;
+            }
+            if (same_entries <= 0) break;
+          } else {
+            break;
+          }
+          exit_index++;
+        }
+        if (same_entries > 0 && last_exit != -1) exit_index = last_exit;
+
+        if (exit_index < hits.count) {
+          float distance_in_volume = hits.t[exit_index];
+          float entry_distance = 0;
+          if (is_entry_hit) {
+            entry_distance = rec_t;
+            distance_in_volume -= rec_t;
+          }
+          // Material.ProbabilisticHit (Material.cs:48-65); Density = the material's parameter
+          const float density = __ldg(reinterpret_cast<const float*>(sd.materials + current_volume) + 9);
+          events += 1.0f;
+          float u;
+          if (WHITE) {
+            u = white.next_float();
+          } else {
+            const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 2u + (volume_draws >> 2), p.seed, kPhiloxKey1);
+            const uint32_t w = volume_draws & 3u;
+            u = u2f(w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w);
+            volume_draws++;
+          }
+          const float volume_hit_distance = -um::div(1.0f, um::max(density, 1.1920928955078125e-7f)) * um::log_unit(u);
+          if (volume_hit_distance < distance_in_volume) {
+            // we hit inside the volume: the record becomes (distance, point, -direction), the material the medium's
+            rec_t = entry_distance + volume_hit_distance;
+            rec_n = -ray.d;
+            mi = (uint32_t)current_volume;
+            medium_hit = true;
+          } else {
+            const uint32_t exit_material = sv.material_of(hits.slot[exit_index]);
+            current_volume = -1;
+            if (is_volume(sd, exit_material) && um::dot(hits.n[exit_index], ray.d) > 0) {
+              hit_index = exit_index + 1;           // volume exit: move to the next hit
+              continue;
+            }
+            rec_t = hits.t[exit_index];             // obstacle: scatter on the exit hit
+            rec_n = hits.n[exit_index];
+            rec_slot = hits.slot[exit_index];
+            mi = exit_material;
+          }
+        } else {
+          hits.count = 0;                           // no more surfaces to hit (the volume has holes)
+          break;
+        }
+      }
+
+      const float4* mp = reinterpret_cast<const float4*>(sd.materials + mi);
+      float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+      if (__float_as_uint(m3.w) != 0u) {
+        // HitRecord.TexCoords: the hit triangle's, or 0 (other entities, and the record made inside a medium)
+        const float4 prim = medium_hit ? make_float4(0, 0, 0, 1) : sv.sphere(rec_slot);
+        resolve_textures(sv, sd, mi, prim, ray.o, ray.d, m0, m1, m2, m3);
+      }
+      const f3 N = rec_n;
+      const f3 P = um::mad(ray.d, rec_t, ray.o);
+      ScatterResult sc;
+      if (__float_as_uint(m0.w) == RTB_MATERIAL_PROBABILISTIC_VOLUME) {
+        // Material.cs:163-168: isotropic; new Ray(rec.Point, direction) has Time = 0
+        float rx, ry;
+        if (WHITE) { rx = white.next_float(); ry = white.next_float(); }
+        else { const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 0u, p.seed, kPhiloxKey1); rx = u2f(r.x); ry = u2f(r.y); }
+        float sn, cs;
+        unit_angle_sincos(ry, &sn, &cs);
+        sc.dir = random_direction(rx, sn, cs);
+        sc.reflectance = um::mk(m0.x, m0.y, m0.z);
+        sc.random_events = events + 2.0f;
+        clk.value = 0.0f;
+      } else {
+        sc = WHITE ? scatter_white(m0, m1, m2, m3, ray.d, N, white, events)
+                   : scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed, events);
+        if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+      }
+      events = sc.random_events;                   // RandomEvents after Scatter (it started from this iteration's count)
+      const f3 emission = um::mk(m1.x, m1.y, m1.z);
+      if (depth == 0) s_normal = N;
+      if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
+        s_albedo = emission + sc.reflectance;
+        s_normal = N;
+        first_non_specular = true;
+      }
+      if (exact) { emi[entries] = emission; att[entries] = sc.reflectance; entries++; }
+      radiance = um::mad(throughput, emission, radiance);
+      throughput = throughput * sc.reflectance;
+      events_acc += um::div(events, pow2depth);
+      events = 0;
+      const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
+      ray.o = um::mad(off_n, 0.001f, P);
+      ray.d = sc.dir;
+      scattered = true;
+      break;
+    }
+
+    if (!scattered) {                               // no hit (or every hit passed through / dropped): the sky ends the path
+      const f3 sky = sky_color(p.environment, sd, ray.d);
+      if (exact) { emi[entries] = sky; att[entries] = um::mk(1.0f); entries++; }
+      radiance = um::mad(throughput, sky, radiance);
+      events_acc += um::div(events, pow2depth);
+      if (!first_non_specular) { s_albedo = sky; s_normal = -ray.d; }
+      break;
+    }
+    pow2depth *= 2.0f;
+  }
+  out.ok = depth != p.trace_depth;
+  f3 c = radiance;
+  if (out.ok && exact) {
+    c = um::mk(0.0f);
+    for (int e = entries; e-- > 0;) { c = c * att[e]; c = c + emi[e]; }
+  }
+  out.color = c;
+  out.normal = s_normal;
+  out.albedo = s_albedo;
+  out.events = events_acc;
+  return out;
+}
+
+// Philox mode: one WARP per pixel — the lanes trace 32 consecutive samples of the pixel (paths of one pixel cost about the
+// same, paths of neighbouring pixels do not), then the warp adds the 32 results in sample order, every lane the same sums, so
+// the accumulation order is the reference's.  White-noise mode (one sequential stream per pixel): one THREAD per pixel.
+template <bool COUNTERS, bool WHITE>
+__global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ BatchArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t k = WHITE ? blockIdx.x * blockDim.x + threadIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= a.n_active_pixels) return;
+  const rtb_batch_params& p = a.p;
   SceneView<false> sv;
-  sv.bind(sd.blob, sd);
+  sv.bind(a.scene.blob, a.scene);
   int cx, cy;
   uint32_t index;
   active_pixel(a, k, &cx, &cy, &index);
@@ -159,178 +343,72 @@ __global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ Ba
   f3 fb_normal = um::mk(0.0f), fb_albedo = um::mk(0.0f);
   uint32_t rays = 0;
   WorkCounters wc;
-  const bool exact = p.trace_depth <= kSimpleStack;
-  f3 att[kSimpleStack], emi[kSimpleStack];
-  RayHits hits;
   WhiteNoise white{};
   if (WHITE) white.init((p.seed * 0x8C4CA03Fu) ^ (index * 0x7383ED49u));      // SampleBatchJob.cs:91
 
-  for (uint32_t s = 0; s < n; s++) {
-    RayClock clk{index, s, p.seed, 0.0f, true};
-    PathRay ray = WHITE ? camera_ray_white(p, cx, cy, white, &clk.value) : camera_ray(p, cx, cy, index, s);
-    if (!WHITE) { clk.known = false; clk.value = clk.time(); clk.known = true; }
-    f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
-    f3 s_normal = um::mk(0.0f), s_albedo = um::mk(0.0f);
-    bool first_non_specular = false;
-    float events_acc = 0, pow2depth = 1;
-    int depth = 0, entries = 0;
-    int current_volume = -1;                          // currentProbabilisticVolumeMaterial (material index, -1 = null)
-    for (; depth < p.trace_depth; depth++) {
-      uint32_t volume_draws = 0;
-      float events = 0;                               // rng.RandomEvents of this iteration
-      collect_hits<0, COUNTERS>(sv, sd, ray.o, ray.d, clk, &hits, wc);
-      if (current_volume < 0) {                       // DetermineVolumeContainment (:477-506)
-        for (int i = 0; i < hits.count; i++) {
-          const uint32_t hm = sv.material_of(hits.slot[i]);
-          if (!is_volume(sd, hm)) continue;
-          if (um::dot(hits.n[i], ray.d) < 0) break;   // entry hit: not inside
-          if (collect_hits<1, COUNTERS>(sv, sd, ray.o, -ray.d, clk, nullptr, wc)) { current_volume = (int)hm; break; }
-        }
-      }
-      rays++;
-
-      bool scattered = false;
-      int hit_index = 0;
-      while (hit_index < hits.count) {
-        float rec_t = hits.t[hit_index];
-        f3 rec_n = hits.n[hit_index];
-        int rec_slot = hits.slot[hit_index];
-        uint32_t mi = sv.material_of(rec_slot);
-        bool medium_hit = false;
-
-        if (current_volume >= 0 || is_volume(sd, mi)) {
-          const bool is_entry_hit = current_volume < 0;
-          if (current_volume < 0) current_volume = (int)mi;
-          int exit_index = hit_index, last_exit = -1, same_entries = 0;
-          while (exit_index < hits.count) {
-            if ((int)sv.material_of(hits.slot[exit_index]) == current_volume) {
-              if (um::dot(hits.n[exit_index], ray.d) < 0) {
-                same_entries++;
-              } else {
-                same_entries--;
-                last_exit = exit_index;
-              }
-              if (same_entries <= 0) break;
-            } else {
-              break;
-            }
-            exit_index++;
-          }
-          if (same_entries > 0 && last_exit != -1) exit_index = last_exit;
-
-          if (exit_index < hits.count) {
-            float distance_in_volume = hits.t[exit_index];
-            float entry_distance = 0;
-            if (is_entry_hit) {
-              entry_distance = rec_t;
-              distance_in_volume -= rec_t;
-            }
-            // Material.ProbabilisticHit (Material.cs:48-65); Density = the material's parameter
-            const float density = __ldg(reinterpret_cast<const float*>(sd.materials + current_volume) + 9);
-            events += 1.0f;
-            float u;
-            if (WHITE) {
-              u = white.next_float();
-            } else {
-              const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 2u + (volume_draws >> 2), p.seed, kPhiloxKey1);
-              const uint32_t w = volume_draws & 3u;
-              u = u2f(w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w);
-              volume_draws++;
-            }
-            const float volume_hit_distance = -um::div(1.0f, um::max(density, 1.1920928955078125e-7f)) * um::log_unit(u);
-            if (volume_hit_distance < distance_in_volume) {
-              // we hit inside the volume: the record becomes (distance, point, -direction), the material the medium's
-              rec_t = entry_distance + volume_hit_distance;
-              rec_n = -ray.d;
-              mi = (uint32_t)current_volume;
-              medium_hit = true;
-            } else {
-              const uint32_t exit_material = sv.material_of(hits.slot[exit_index]);
-              current_volume = -1;
-              if (is_volume(sd, exit_material) && um::dot(hits.n[exit_index], ray.d) > 0) {
-                hit_index = exit_index + 1;           // volume exit: move to the next hit
-                continue;
-              }
-              rec_t = hits.t[exit_index];             // obstacle: scatter on the exit hit
-              rec_n = hits.n[exit_index];
-              rec_slot = hits.slot[exit_index];
-              mi = exit_material;
-            }
-          } else {
-            hits.count = 0;                           // no more surfaces to hit (the volume has holes)
-            break;
-          }
-        }
-
-        const float4* mp = reinterpret_cast<const float4*>(sd.materials + mi);
-        float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
-        if (__float_as_uint(m3.w) != 0u) {
-          // HitRecord.TexCoords: the hit triangle's, or 0 (other entities, and the record made inside a medium)
-          const float4 prim = medium_hit ? make_float4(0, 0, 0, 1) : sv.sphere(rec_slot);
-          resolve_textures(sv, sd, mi, prim, ray.o, ray.d, m0, m1, m2, m3);
-        }
-        const f3 N = rec_n;
-        const f3 P = um::mad(ray.d, rec_t, ray.o);
-        ScatterResult sc;
-        if (__float_as_uint(m0.w) == RTB_MATERIAL_PROBABILISTIC_VOLUME) {
-          // Material.cs:163-168: isotropic; new Ray(rec.Point, direction) has Time = 0
-          float rx, ry;
-          if (WHITE) { rx = white.next_float(); ry = white.next_float(); }
-          else { const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 0u, p.seed, kPhiloxKey1); rx = u2f(r.x); ry = u2f(r.y); }
-          float sn, cs;
-          unit_angle_sincos(ry, &sn, &cs);
-          sc.dir = random_direction(rx, sn, cs);
-          sc.reflectance = um::mk(m0.x, m0.y, m0.z);
-          sc.random_events = events + 2.0f;
-          clk.value = 0.0f;
-        } else {
-          sc = WHITE ? scatter_white(m0, m1, m2, m3, ray.d, N, white, events)
-                     : scatter(m0, m1, m2, m3, ray.d, N, index, s, (uint32_t)depth, p.seed, events);
-          if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
-        }
-        events = sc.random_events;                   // RandomEvents after Scatter (it started from this iteration's count)
-        const f3 emission = um::mk(m1.x, m1.y, m1.z);
-        if (depth == 0) s_normal = N;
-        if (!first_non_specular && __float_as_uint(m2.z) == 0u) {
-          s_albedo = emission + sc.reflectance;
-          s_normal = N;
-          first_non_specular = true;
-        }
-        if (exact) { emi[entries] = emission; att[entries] = sc.reflectance; entries++; }
-        radiance = um::mad(throughput, emission, radiance);
-        throughput = throughput * sc.reflectance;
-        events_acc += um::div(events, pow2depth);
-        events = 0;
-        const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
-        ray.o = um::mad(off_n, 0.001f, P);
-        ray.d = sc.dir;
-        scattered = true;
-        break;
-      }
-
-      if (!scattered) {                               // no hit (or every hit passed through / dropped): the sky ends the path
-        const f3 sky = sky_color(p.environment, sd, ray.d);
-        if (exact) { emi[entries] = sky; att[entries] = um::mk(1.0f); entries++; }
-        radiance = um::mad(throughput, sky, radiance);
-        events_acc += um::div(events, pow2depth);
-        if (!first_non_specular) { s_albedo = sky; s_normal = -ray.d; }
-        break;
-      }
-      pow2depth *= 2.0f;
-    }
-    if (depth != p.trace_depth) {
-      f3 c = radiance;
-      if (exact) {
-        c = um::mk(0.0f);
-        for (int e = entries; e-- > 0;) { c = c * att[e]; c = c + emi[e]; }
-      }
+  auto add = [&](bool ok, f3 c, f3 nrm, f3 alb, float ev, uint32_t s) {        // SampleBatchJob.cs:139-157
+    if (ok) {
       color_acc = color_acc + c;
-      normal_acc = normal_acc + s_normal;
-      albedo_acc = albedo_acc + s_albedo;
-      weight_acc += events_acc;
+      normal_acc = normal_acc + nrm;
+      albedo_acc = albedo_acc + alb;
+      weight_acc += ev;
       sample_count++;
     }
-    if (s == 0) { fb_normal = s_normal; fb_albedo = s_albedo; }
+    if (s == 0) { fb_normal = nrm; fb_albedo = alb; }
+  };
+
+  if (WHITE) {
+    for (uint32_t s = 0; s < n; s++) {
+      RayClock clk{index, s, p.seed, 0.0f, true};
+      const PathRay ray = camera_ray_white(p, cx, cy, white, &clk.value);
+      const VolumeSample r = trace_volume_sample<COUNTERS, WHITE>(a, sv, ray, clk, index, s, white, wc);
+      rays += r.rays;
+      add(r.ok, r.color, r.normal, r.albedo, r.events, s);
+    }
+  } else {
+    // chunks of 32 * kLaneSamples samples: lane l traces samples base + l, base + l + 32, ... back to back (no lane waits for
+    // another between them, so path-length differences average out), then the warp adds the chunk in sample order
+    for (uint32_t base = 0; base < n; base += 32u * kLaneSamples) {
+      VolumeSample r[kLaneSamples];
+#pragma unroll 1
+      for (uint32_t j = 0; j < kLaneSamples; j++) {
+        const uint32_t s = base + 32u * j + lane;
+        r[j].ok = false; r[j].rays = 0; r[j].events = 0;
+        r[j].color = r[j].normal = r[j].albedo = um::mk(0.0f);
+        if (s < n) {
+          RayClock clk{index, s, p.seed, 0.0f, false};
+          clk.value = clk.time();
+          clk.known = true;
+          const PathRay ray = camera_ray(p, cx, cy, index, s);
+          r[j] = trace_volume_sample<COUNTERS, WHITE>(a, sv, ray, clk, index, s, white, wc);
+          rays += r[j].rays;
+        }
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t j = 0; j < kLaneSamples; j++) {
+        if (base + 32u * j >= n) break;
+        const uint32_t m = n - (base + 32u * j) < 32u ? n - (base + 32u * j) : 32u;
+        const VolumeSample x = r[j];
+        for (uint32_t l = 0; l < m; l++) {
+          const bool ok = __shfl_sync(0xffffffffu, (int)x.ok, l) != 0;
+          const f3 c = um::mk(__shfl_sync(0xffffffffu, x.color.x, l), __shfl_sync(0xffffffffu, x.color.y, l), __shfl_sync(0xffffffffu, x.color.z, l));
+          const f3 nr = um::mk(__shfl_sync(0xffffffffu, x.normal.x, l), __shfl_sync(0xffffffffu, x.normal.y, l), __shfl_sync(0xffffffffu, x.normal.z, l));
+          const f3 al = um::mk(__shfl_sync(0xffffffffu, x.albedo.x, l), __shfl_sync(0xffffffffu, x.albedo.y, l), __shfl_sync(0xffffffffu, x.albedo.z, l));
+          const float ev = __shfl_sync(0xffffffffu, x.events, l);
+          add(ok, c, nr, al, ev, base + 32u * j + l);
+        }
+      }
+    }
+    // per-lane tallies -> the pixel's
+    for (int o = 16; o > 0; o >>= 1) {
+      rays += __shfl_xor_sync(0xffffffffu, rays, o);
+      wc.node_tests += __shfl_xor_sync(0xffffffffu, wc.node_tests, o);
+      wc.sphere_tests += __shfl_xor_sync(0xffffffffu, wc.sphere_tests, o);
+      wc.shade_standard += __shfl_xor_sync(0xffffffffu, wc.shade_standard, o);
+      wc.shade_dielectric += __shfl_xor_sync(0xffffffffu, wc.shade_dielectric, o);
+    }
+    if (lane != 0) return;
   }
 
   reinterpret_cast<float4*>(a.b.out_color)[index] = make_float4(color_acc.x, color_acc.y, color_acc.z, (float)sample_count);
