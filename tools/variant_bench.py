@@ -26,7 +26,8 @@ res["counts_equal"] = bool(np.array_equal(ref.out_color[:, 3], got.out_color[:, 
 res["aov_max"] = float(max(np.abs(ref.out_normal - got.out_normal).max(), np.abs(ref.out_albedo - got.out_albedo).max(), np.abs(ref.out_weight - got.out_weight).max()))
 for name, depth, W, H, spp, td, ap, key in [("final", 16, 1920, 1080, 256, 50, 0.1, "c3"), ("final", 0, 1280, 720, 64, 50, None, "c2"),
                                             ("stress", 16, 1920, 1080, 64, 50, 0.1, "c5s"), ("mesh", 16, 1920, 1080, 64, 50, 0.1, "mesh"),
-                                            ("cornell", 16, 1920, 1080, 64, 50, 0.0, "cornell"), ("fog", 16, 1920, 1080, 64, 50, 0.0, "fog")]:
+                                            ("cornell", 16, 1920, 1080, 64, 50, 0.0, "cornell"), ("fog", 16, 1920, 1080, 64, 50, 0.0, "fog"),
+                                            ("cornell", 0, 1920, 1080, 64, 50, 0.0, "cornell0"), ("cornell", 2, 1920, 1080, 64, 50, 0.0, "cornell2")]:
     if key not in %(cfgs)r: continue
     scene = rtb.host.make_mesh_scene(max_bvh_depth=depth, subdivisions=4) if name == "mesh" else rtb.host.make_cornell_scene(max_bvh_depth=depth, fog=(name == "fog")) if name in ("cornell", "fog") else rtb.host.make_scene(name, max_bvh_depth=depth, target_count=10000 if name == "stress" else 0)
     ctx.upload(scene)
@@ -44,7 +45,7 @@ print("RESULT " + json.dumps(res))
 def main():
     tags = [a for a in sys.argv[1:] if not a.startswith("--")]
     sweep = [a[len("--env="):] for a in sys.argv[1:] if a.startswith("--env=")]   # --env=NAME=v1,v2: default build per value
-    cfgs = ["c3"] + (["c2"] if "--c2" in sys.argv else []) + (["c5s"] if "--c5s" in sys.argv else []) + (["mesh"] if "--mesh" in sys.argv else []) + (["cornell"] if "--cornell" in sys.argv else []) + (["fog"] if "--fog" in sys.argv else [])
+    cfgs = ["c3"] + (["c2"] if "--c2" in sys.argv else []) + (["c5s"] if "--c5s" in sys.argv else []) + (["mesh"] if "--mesh" in sys.argv else []) + (["cornell"] if "--cornell" in sys.argv else []) + (["fog"] if "--fog" in sys.argv else []) + (["cornell0", "cornell2"] if "--cornell0" in sys.argv else [])
     vdir = os.path.join(ROOT, "raytracing-in-one-weekend_b200", "lib", "variants")
     libs = {"default": None}
     for f in sorted(glob.glob(os.path.join(vdir, "librtb_*.so"))):
