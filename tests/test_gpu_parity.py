@@ -74,6 +74,38 @@ def test_sample_batch_matches_the_oracle(rtb, oracle, ctx, case, kernel):
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
+@pytest.mark.parametrize("case", ["cornell_bvh16_48x27x8_d50_philox", "fog_bvh16_48x27x8_d50_philox",
+                                  "textured_mesh_bvh16_48x27x8_d50_philox", "cornell_bvh16_32x18x4_d50_xorshift",
+                                  "fog_bvh16_32x18x4_d50_xorshift"])
+def test_gpu_matches_golden_fixtures_of_the_wider_worlds(rtb, ctx, case):
+    """The committed fixtures of the worlds beyond the BASELINE configs (placed entities, media, image textures), without the
+    oracle at run time: the per-pixel / volume kernel bit for bit in both noise modes, the megakernel's decisions and RGB."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    name, depth, W, H, spp, td, ap, noise = mg.CASES[case]
+    scene = mg.make_scene(name, depth)
+    p = rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    white = case.endswith("xorshift")
+    ctx.set_option(rtb.abi.OPT_NOISE, rtb.abi.NOISE_WHITE if white else rtb.abi.NOISE_PHILOX)
+    try:
+        simple = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE)
+    finally:
+        ctx.set_option(rtb.abi.OPT_NOISE, rtb.abi.NOISE_PHILOX)
+    assert np.array_equal(simple.out_color, g["color"]) and np.array_equal(simple.out_normal, g["normal"])
+    assert np.array_equal(simple.out_albedo, g["albedo"]) and np.array_equal(simple.out_weight, g["weight"])
+    assert np.array_equal(simple.diagnostics["ray_count"], g["ray_count"])
+    if not white:
+        mega = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+        assert np.array_equal(mega.out_color[:, 3], g["color"][:, 3])
+        assert np.array_equal(mega.diagnostics["ray_count"], g["ray_count"])
+        n = np.maximum(g["color"][:, 3:4], 1)
+        assert np.abs(mega.out_color[:, :3] / n - g["color"][:, :3] / n).max() <= RGB_TOL
+
+
 @pytest.mark.parametrize("case", ["three_spheres_32x18x4_d8_philox", "final_linear_32x18x4_d50_philox",
                                   "final_bvh16_defocus_48x27x8_d50_philox", "mesh_bvh16_48x27x8_d50_philox"])
 def test_gpu_matches_golden_fixtures(rtb, ctx, case):

@@ -21,12 +21,21 @@ CASES = {
     "final_bvh16_defocus_48x27x8_d50_philox": ("final", 16, 48, 27, 8, 50, 0.1, O.NOISE_PHILOX),
     "three_spheres_32x18x4_d8_xorshift": ("three_spheres", 0, 32, 18, 4, 8, None, O.NOISE_XORSHIFT),
     "mesh_bvh16_48x27x8_d50_philox": ("mesh", 16, 48, 27, 8, 50, None, O.NOISE_PHILOX),
+    "cornell_bvh16_48x27x8_d50_philox": ("cornell", 16, 48, 27, 8, 50, None, O.NOISE_PHILOX),        # Rect / Box / moving entities
+    "cornell_bvh16_32x18x4_d50_xorshift": ("cornell", 16, 32, 18, 4, 50, None, O.NOISE_XORSHIFT),
+    "fog_bvh16_48x27x8_d50_philox": ("fog", 16, 48, 27, 8, 50, None, O.NOISE_PHILOX),               # ProbabilisticVolume media
+    "fog_bvh16_32x18x4_d50_xorshift": ("fog", 16, 32, 18, 4, 50, None, O.NOISE_XORSHIFT),
+    "textured_mesh_bvh16_48x27x8_d50_philox": ("textured_mesh", 16, 48, 27, 8, 50, None, O.NOISE_PHILOX),   # image textures
 }
 
 
 def make_scene(name, depth):
     if name == "mesh":
         return O.rtb.host.make_mesh_scene(max_bvh_depth=depth)
+    if name == "textured_mesh":
+        return O.rtb.host.make_mesh_scene(max_bvh_depth=depth, textured=True)
+    if name in ("cornell", "fog"):
+        return O.rtb.host.make_cornell_scene(max_bvh_depth=depth, fog=(name == "fog"))
     return O.rtb.host.make_scene(name, max_bvh_depth=depth)
 
 
