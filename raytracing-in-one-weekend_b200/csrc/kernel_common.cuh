@@ -121,6 +121,7 @@ struct BatchArgs {
   uint32_t phase_tile[4], phase_pixel[4];
   int phase_size[3];
   uint32_t n_tiles;
+  uint32_t refill_min;               // megakernel: free lanes a warp waits for before it refills them (plugin.cu: choose_tiles)
   uint32_t* tile_counter;            // global work counter (zeroed before launch)
   unsigned long long* counters;      // rtb_counters as 8 x u64, or nullptr
 };

@@ -555,6 +555,10 @@ int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_
 // resident warp when the image is small, never fewer than 1024 samples per tile unless the pixel count forces it.
 void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
   static const uint32_t target = [] { const char* e = getenv("RTB_TILE_SAMPLES"); return e ? (uint32_t)std::max(32, atoi(e)) : 2048u; }();
+  // free lanes a warp collects before refilling them (sample_megakernel): worth it when the walk diverges anyway (a real
+  // tree), not when the world is a linear list every lane walks in step
+  static const int refill_env = [] { const char* e = getenv("RTB_REFILL_MIN"); return e ? std::min(32, std::max(1, atoi(e))) : 0; }();
+  a.refill_min = refill_env ? (uint32_t)refill_env : (a.scene.n_inner >= 64 ? 8u : 1u);
   int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (target + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
   while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
   // guided self-scheduling: the last ~8 tiles per resident warp are a quarter of the size, the last ~8 after
