@@ -79,3 +79,44 @@ def test_row_tile_shard_and_gather_world2(tmp_path, oracle, rtb, mode):
         assert np.array_equal(got, want)
     assert np.array_equal(np.load(tmp_path / f"root_{mode}_0.npy"), want)
     assert np.array_equal(np.load(tmp_path / f"rootn_{mode}_0.npy"), full.out_normal.reshape(H, W, 3))
+
+
+def _shared_frame_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+
+    import oracle_lib as O
+
+    bench = importlib.import_module("bench")
+    sh = importlib.import_module("raytracing-in-one-weekend_b200.sharding")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        W, H, spp = 40, 22, 4
+        hb = bench._shared_host_frame(W, H, rank, O.abi, O.rtb)       # ONE frame mapped by both rank processes
+        assert hb is not None and hb.out_color.shape == (W * H, 4) and hb.diagnostics.shape == (W * H,)
+        scene = O.rtb.host.make_scene("three_spheres")
+        b, e = sh.row_tiles(H, world)[rank]
+        p = O.rtb.host.make_params(scene, W, H, spp, 8, row_begin=b, row_end=e)
+        O.sample_batch(scene, p, hb, threads=2)                        # each rank writes its own rows, in place
+        dist.barrier()
+        if rank == 0:                                                  # ... and rank 0 sees the whole frame without a gather
+            np.save(os.path.join(out_dir, "shared_color.npy"), np.array(hb.out_color))
+            np.save(os.path.join(out_dir, "shared_rays.npy"), np.array(hb.diagnostics["ray_count"]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_host_frame_shared_by_the_ranks_world2(tmp_path, oracle, rtb):
+    """bench.py's N > 1 end-to-end path: the ranks map ONE set of host arrays (/dev/shm) and each renders its row tile into
+    them in place; the frame is complete on the host without any exchange."""
+    world = 2
+    mp.spawn(_shared_frame_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    W, H, spp = 40, 22, 4
+    scene = rtb.host.make_scene("three_spheres")
+    full = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, rtb.host.make_params(scene, W, H, spp, 8), full)
+    assert np.array_equal(np.load(tmp_path / "shared_color.npy"), full.out_color)
+    assert np.array_equal(np.load(tmp_path / "shared_rays.npy"), full.diagnostics["ray_count"])
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("rtb_bench_")]      # the names are unlinked once mapped
