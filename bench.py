@@ -155,6 +155,35 @@ def cpu_reference(cfg, threads, target_seconds=12.0, steps=1, warmup=0):
     return vals, desc
 
 
+def parity_sample(cfg, frame_color4, frame_diag, threads, pixels=6144):
+    """The checker beside the measurement: the strict oracle build with the Philox slots (the arithmetic contract both sides
+    share) renders `pixels` pixels of the SAME full-size frame — three runs of consecutive pixels in the lower, middle and
+    upper third — and is compared with what the timed kernel produced there.  Returns the `parity` object of the JSON line."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as O
+
+    name, depth, W, H, spp, td, ap = CONFIGS[cfg]
+    scene = make_scene(O.rtb.host, cfg)
+    p = O.rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
+    run = pixels // 3
+    worst, counts_equal, rays_equal, over = 0.0, True, True, 0
+    ref = O.Buffers(W, H)
+    for row in (H // 6, H // 2, (5 * H) // 6):
+        lo = row * W + W // 3
+        O.sample_batch(scene, p, ref, noise=O.NOISE_PHILOX, threads=threads, index_range=(lo, lo + run))
+        r, g = ref.out_color[lo:lo + run], frame_color4[lo:lo + run]
+        counts_equal = counts_equal and bool(np.array_equal(r[:, 3], g[:, 3]))
+        rays_equal = rays_equal and bool(np.array_equal(ref.diagnostics["ray_count"][lo:lo + run], frame_diag[lo:lo + run]))
+        n = np.maximum(r[:, 3:4], 1)
+        d = np.abs(r[:, :3] / n - g[:, :3] / n)
+        worst = max(worst, float(d.max()))
+        over += int((d.max(axis=1) > 1e-4).sum())
+    return {"against": "CPU oracle, strict build, Philox slots (same arithmetic contract)", "pixels": 3 * run, "samples_per_pixel": spp,
+            "max_abs_rgb_diff": worst, "tolerance": 1e-4, "pixels_over_tolerance": over,
+            "sample_counts_equal": counts_equal, "ray_counts_equal": rays_equal}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -363,6 +392,10 @@ def run_ours(args):
         vals, desc = cpu_reference(args.config, threads, target_seconds=12.0)
         cpu = {"value": vals[0], "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": desc,
                "reference_traversal_per_ray": getattr(cpu_reference, "work", None)}
+        try:
+            parity = parity_sample(args.config, host["out_color"].numpy(), host["diag"].numpy()[:, 0], threads)
+        except Exception as e:      # noqa: BLE001 — the checker must not take the measurement down
+            parity = {"error": str(e)}
 
     if rank == 0:
         traffic = None
@@ -407,6 +440,7 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+            line["parity"] = parity
         emit(line)
     fr.close()
     if world > 1:
