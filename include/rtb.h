@@ -38,7 +38,7 @@ extern "C" {
 #define RTB_API __attribute__((visibility("default")))
 #endif
 
-#define RTB_ABI_VERSION 1
+#define RTB_ABI_VERSION 2
 
 typedef enum rtb_status {
   RTB_OK = 0,
@@ -317,8 +317,21 @@ RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
  * buffers: returns when the out_* arrays are fully written.  Pinned arrays (rtb_register_host_buffer /
  * cudaHostAlloc) are read and written in place by the megakernel over PCIe; pageable ones are staged
  * through device copies of the four inputs and the four outputs (+diagnostics).
- * `cancel` (may be NULL) is the CancellationToken (SampleBatchJob.cs:23,61): polled between
- * kernel chunks; when set the call returns RTB_ERR_CANCELLED promptly. */
+ * `cancel` (may be NULL) is the CancellationToken (SampleBatchJob.cs:23,61; the host flips it through a raw
+ * pointer, Raytracer.cs:189-192, then Complete()s, :512-515).  The batch is ONE kernel launch with or without a
+ * token: the kernel polls a flag in mapped pinned memory owned by the context (a volatile load whenever a warp
+ * claims a work tile; a CTA that saw it stops issuing samples), and the blocking call copies *cancel into that
+ * flag while it waits.  Once set, the call returns RTB_ERR_CANCELLED within a fraction of a millisecond
+ * (worlds with participating media: within one pixel's samples); outputs are then unspecified, as in the
+ * reference (the host discards them).
+ *
+ * Accumulation range.  Per pixel and batch the sums of colour, normal, albedo and sampleCountWeight are kept in
+ * signed 64-bit fixed point with 32 fraction bits (integer addition is associative: the image does not depend
+ * on the order in which paths retire, on tiling or on the GPU count).  Consequences, which the reference's
+ * float sums do not share: (1) a sample contributes round-to-nearest multiples of 2^-32 (components below 2^-33
+ * contribute 0); (2) a successful sample with a non-finite component or one of magnitude >= 1e9, or a batch
+ * whose per-pixel sum reaches 2^31, writes NaN to that pixel's out_color / out_normal / out_albedo /
+ * out_sample_count_weight (CombineJob turns NaN into black, CombineJob.cs:50-53) — it never wraps silently. */
 RTB_API int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params,
                              const rtb_batch_buffers* host_buffers,
                              const volatile uint8_t* cancel);
@@ -326,7 +339,11 @@ RTB_API int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params,
 /* Same batch on DEVICE-resident buffers, enqueued on `cuda_stream` (a cudaStream_t passed as
  * void*; NULL = the CUDA default stream) without synchronising: the caller owns the
  * buffers and the stream (used for multi-batch accumulation that never leaves HBM, and for
- * row-tile sharding where each rank renders into its slice of a gather buffer). */
+ * row-tile sharding where each rank renders into its slice of a frame).  The buffers may live on ANOTHER device
+ * that this context's device can reach (cudaDeviceEnablePeerAccess, or a CUDA IPC mapping from rtb_ipc_open):
+ * the kernel reads its rows' inputs and writes its rows' outputs over NVLink, so no gather follows it.
+ * All batches of one context may be enqueued on different streams concurrently (each launch takes its own work
+ * counter); instrumented batches (RTB_OPT_COUNTERS) must not overlap each other. */
 RTB_API int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params,
                                     const rtb_batch_buffers* device_buffers,
                                     void* cuda_stream);
@@ -383,8 +400,8 @@ RTB_API int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out);
 
 typedef enum rtb_option {
   RTB_OPT_COUNTERS = 1,         /* 0/1: run the instrumented kernel (slower) */
-  RTB_OPT_KERNEL = 2,           /* 0 = auto, 1 = simple (thread per pixel), 2 = persistent megakernel, 3 = warp-pool wavefront kernel */
-  RTB_OPT_CANCEL_CHUNK_ROWS = 3,/* rows per launch when a cancel token is passed (0 = auto) */
+  RTB_OPT_KERNEL = 2,           /* 0 = auto, 1 = simple (thread per pixel), 2 = persistent megakernel */
+  /* 3 was RTB_OPT_CANCEL_CHUNK_ROWS (ABI 1): the token is polled inside one launch now */
   RTB_OPT_LEAF_SPHERES = 4,     /* 1..15 (default 1): subtrees of the host's BVH holding at most this many spheres are
                                  * walked as one leaf on the device (results are identical for every value; takes effect
                                  * at the next rtb_upload_scene) */

@@ -70,7 +70,7 @@ MATERIAL_STANDARD, MATERIAL_DIELECTRIC, MATERIAL_PROBABILISTIC_VOLUME = 0, 1, 2
 SKY_NONE, SKY_GRADIENT, SKY_CUBEMAP = 0, 1, 2
 SCENE_THREE_SPHERES, SCENE_FINAL, SCENE_STRESS = 0, 1, 2
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 RTB_OK = 0
 RTB_ERR_INVALID_ARGUMENT = 1
 RTB_ERR_NO_SCENE = 2
@@ -79,9 +79,9 @@ RTB_ERR_UNSUPPORTED = 4
 RTB_ERR_OUT_OF_MEMORY = 5
 RTB_ERR_CUDA = 100
 
-OPT_COUNTERS, OPT_KERNEL, OPT_CANCEL_CHUNK_ROWS, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS, OPT_HOST_ACCESS, OPT_NOISE = 1, 2, 3, 4, 5, 6, 7
+OPT_COUNTERS, OPT_KERNEL, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS, OPT_HOST_ACCESS, OPT_NOISE = 1, 2, 4, 5, 6, 7
 NOISE_PHILOX, NOISE_WHITE = 0, 1
-KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA, KERNEL_POOL = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA = 0, 1, 2
 
 f32 = C.c_float
 f32x2 = C.c_float * 2

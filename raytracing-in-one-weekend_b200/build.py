@@ -21,7 +21,7 @@ HOST_SOURCES = [os.path.join(CSRC, "host", "rtb_host.cpp")]
 CUDA_SOURCES = [os.path.join(CSRC, "plugin.cu")]
 CUDA_DEPS = [
     os.path.join(CSRC, f)
-    for f in ("kernel_common.cuh", "sample_kernels.cuh", "pool_kernel.cuh", "volume_kernel.cuh", "aux_kernels.cuh")
+    for f in ("kernel_common.cuh", "sample_kernels.cuh", "volume_kernel.cuh", "aux_kernels.cuh")
 ] + [os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
 HOST_DEPS = [os.path.join(INCLUDE, "rtb_host.h"), os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
 

@@ -27,12 +27,12 @@ using um::f3;
 // shared memory by TMA bulk copies at CTA start (or read in place through the read-only
 // path when it does not fit).
 //
-//   inner nodes  : n_inner * 64 B   child boxes stored in the parent, 4 x float4:
+//   inner nodes  : n_inner * kNodeStride B   child boxes stored in the parent, 4 x float4 (+ padding up to the stride):
 //                    q0 = (Lmin.x, Lmin.y, Lmin.z, Lmax.x)
 //                    q1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
 //                    q2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)
 //                    q3 = (left_ref, right_ref, -, -) as int32
-//                  ref >= 0: inner node, byte offset of its record (index * 64);
+//                  ref >= 0: inner node, byte offset of its record (index * kNodeStride);
 //                  ref < 0: leaf, ~ref = byte offset of its first slot in `spheres` | (count - 1)
 //                  (count - 1 == 15: the count is leaf_count[first slot])
 //                  Entities are named by the byte offset of their slot ("slot" below) everywhere in the kernels.
@@ -94,7 +94,19 @@ struct SceneDesc {
   uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
   const uint32_t* chain_ref;    // per sphere: first chain box | box count << 24
   const float4* chain_boxes;    // 2 x float4 per box (min.xyz, max.xyz), tightest first
+  uint32_t* status;             // device word of sticky kStatus* bits a kernel raises (read back by the synchronising calls)
 };
+constexpr uint32_t kStatusHitListOverflow = 1u;   // sample_volumes: a ray met more entities than kMaxRayHits (volume_kernel.cuh)
+
+// Bytes between inner-node records.  The walk reads a node as four LDS.128 at [ref + 16 k]; with 64-byte records the
+// k-th quad of EVERY node starts in one of two 16-byte bank groups (64 B = 16 banks), so divergent lanes pile up on
+// 8 of the 32 banks (ncu, round 1: 31 % of the shared wavefronts were conflict replays).  An odd multiple of 16 bytes
+// spreads the same quad of different nodes over all eight bank groups; refs are byte offsets, so the walk is unchanged.
+#ifndef RTB_NODE_STRIDE
+#define RTB_NODE_STRIDE 80
+#endif
+constexpr uint32_t kNodeStride = RTB_NODE_STRIDE;
+static_assert(kNodeStride >= 64 && kNodeStride % 16 == 0, "node records are 4 x float4, 16-byte aligned");
 
 constexpr int kDefaultCollapse = 1;   // measured on B200 (profiles/README.md): single-sphere leaves are fastest for the staged-in-smem walk
 // Geometry of the guard that stands in for the skipped boxes (see chain_guard).
@@ -122,7 +134,11 @@ struct BatchArgs {
   int phase_size[3];
   uint32_t n_tiles;
   uint32_t refill_min;               // megakernel: free lanes a warp waits for before it refills them (plugin.cu: choose_tiles)
-  uint32_t* tile_counter;            // global work counter (zeroed before launch)
+  uint32_t* tile_counter;            // global work counter of THIS launch (zeroed before it; plugin.cu keeps a ring of them)
+  // CancellationToken (SampleBatchJob.cs:61 polls it per pixel): a word in mapped pinned host memory owned by the
+  // context; the blocking call copies the caller's token into it while the kernel runs, the kernel reads it with a
+  // volatile load whenever a warp claims a tile and stops issuing work once it is set (never NULL).
+  const uint32_t* cancel_flag;
   unsigned long long* counters;      // rtb_counters as 8 x u64, or nullptr
 };
 
@@ -242,6 +258,12 @@ struct WorkCounters {           // per-thread tallies of the instrumented build
 
 __device__ __forceinline__ f3 v3(const float* p) { return um::mk(p[0], p[1], p[2]); }
 
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // HitTests.Hit(this AxisAlignedBoundingBox) (HitTests.cs:9-21): returns the decision and tMin.
 // fminf/fmaxf agree with math.min/max ("isnan(y) || x < y ? x : y") on every input except
 // the sign of a zero result, which no comparison below can observe.
@@ -317,8 +339,17 @@ __device__ __forceinline__ void aabb_range(f3 mn, f3 mx, f3 o, f3 inv, float* t_
 // is hit nearer than best_t: the same record FindHits' sort would put first
 // (SampleBatchJob.cs:450-475) — a root is accepted iff 0 < t < +inf there, and the
 // second root is never nearer than the first, so clipping at best_t changes nothing.
-template <bool CHAINS>
-__device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a,
+//
+// DEFER (the lean sphere builds): the division by a = dot(d, d) is taken out of the walk.  Every ray of the job has
+// |d| = 1 up to rounding; when |a - 1| <= 1e-4 (`a_ok`, decided once per walk) candidates are compared by their
+// NUMERATORS x = -b -/+ sqrt(disc) and the walk's single winner is divided once, with the warp converged, after it:
+//   * x -> fl(x / a) is monotonic, so the smallest numerator has the smallest distance (numerators that differ and
+//     round to the same distance are a tie the reference's unstable sort does not define either);
+//   * fl(x / a) > 0 iff x > 0 (no float underflows when divided by a number in [0.9999, 1.0001]);
+//   * the prune limit best * kPruneMargin stays beyond the hit: fl(x / a) <= x * 1.00011 < x * kPruneMargin.
+// A ray with any other |d| divides every candidate as before (best_t then already holds distances).
+template <bool CHAINS, bool DEFER>
+__device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a, bool a_ok,
                                            float& best_t, int& best_idx) {
   f3 oc = o + um::mk(-s.x, -s.y, -s.z);
   float b = um::dot(oc, d);
@@ -332,17 +363,15 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
   //   c > 0, b >= 0 (outside, moving away):  -b - sq <= 0 and -b + sq <= 0: neither root is > 0            -> no hit
   //   c <= 0 (inside or on the sphere):      sq >= |b| so t1 <= 0: only t2 can be accepted
   //   c > 0, b < 0:                          0 <= t1 <= t2: if t1 > 0 it alone decides (t1 >= best_t implies t2 >= best_t)
-#if !defined(RTB_NO_ROOT_SHORTCUTS)
   if (disc > 0.0f && !(c > 0.0f && b >= 0.0f)) {
     const float sq = um::sqrt(disc);
-    float t = um::div(c > 0.0f ? -b - sq : -b + sq, a);
-    if (c > 0.0f && !(t > 0.0f)) t = um::div(-b + sq, a);      // t1 rounded to 0: the reference moves on to t2
-#else
-  if (disc > 0.0f) {
-    float sq = um::sqrt(disc);
-    float t = um::div(-b - sq, a);
-    if (!(t < best_t && t > 0.0f)) t = um::div(-b + sq, a);
-#endif
+    float t = c > 0.0f ? -b - sq : -b + sq;
+    if (DEFER && a_ok) {
+      if (c > 0.0f && !(t > 0.0f)) t = -b + sq;                  // t1 rounded to 0: the reference moves on to t2
+    } else {
+      t = um::div(t, a);
+      if (c > 0.0f && !(t > 0.0f)) t = um::div(-b + sq, a);
+    }
     if (t < best_t && t > 0.0f) {
       if (CHAINS && sd.has_chains && (sd.has_chains == 2u || !chain_guard(a, b, oc2, r2, disc)) && !chain_boxes_hit(sd, idx, o, inv)) return;
       best_t = t;
@@ -500,16 +529,8 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 // record while testing a fraction of the nodes.
 constexpr float kPruneMargin = 1.0005f;
 constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
-
-#ifndef RTB_LEAF_UNROLL
-#define RTB_LEAF_UNROLL 1
-#endif
-constexpr int kLeafUnroll = RTB_LEAF_UNROLL;   // unrolling of the multi-entity leaf loop (single-entity leaves have their own path)
-#ifndef RTB_SPLIT_TRIPS
-#define RTB_SPLIT_TRIPS 0   // 1: the lean builds also use one node (inner OR leaf) per trip
-#endif
-#ifndef RTB_TRAVERSAL
-#define RTB_TRAVERSAL 0   // 0: one node (inner or leaf) per loop trip (measured fastest on B200); 1: while-while (inner run, then leaf run)
+#ifndef RTB_DEFER_DIV
+#define RTB_DEFER_DIV 1   // lean sphere builds: divide the walk's winner once instead of every candidate (see sphere_hit)
 #endif
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
@@ -522,6 +543,8 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   f3 inv = um::rcp(d);
   inv = um::mk(um::isnan(inv.x) ? um::INF : inv.x, um::isnan(inv.y) ? um::INF : inv.y, um::isnan(inv.z) ? um::INF : inv.z);
   const float a = um::dot(d, d);
+  constexpr bool DEFER = RTB_DEFER_DIV && FLAVOR < kFlavorGeneral;
+  const bool a_ok = DEFER && um::abs(a - 1.0f) <= 1.0e-4f;
 
   float t_enter;
   if (COUNTERS) wc.node_tests++;
@@ -529,13 +552,12 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
 
   int stack[kStackMax];
   stack[0] = kTraversalDone;
-  int sp = 1;
   int cur = sd.root_ref;
   auto test_prim = [&](int slot) {
     const float4 prim = sv.sphere(slot);
     if (FLAVOR >= kFlavorPlaced && prim.w != prim.w && __float_as_uint(prim.y) != 0u) placed_hit(sv, __float_as_uint(prim.x), slot, o, d, clk, best_t, best_idx);
     else if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx);
-    else sphere_hit<(FLAVOR >= kFlavorChains)>(sd, prim, slot, o, d, inv, a, best_t, best_idx);
+    else sphere_hit<(FLAVOR >= kFlavorChains), DEFER>(sd, prim, slot, o, d, inv, a, a_ok, best_t, best_idx);
   };
   auto test_leaf = [&](int ref) {
     const uint32_t code = (uint32_t)~ref;
@@ -555,82 +577,11 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
         return;
       }
     }
-#pragma unroll kLeafUnroll
+#pragma unroll 1
     for (int i = 0; i < count; i++) test_prim(first + 16 * i);
     if (COUNTERS) wc.sphere_tests += count;
   };
-#if RTB_TRAVERSAL == 2
-  // Speculative while-while (Aila & Laine, HPG 2009), one step per trip with warp votes: a lane that
-  // reaches a leaf parks it in `leaf` and keeps walking inner nodes for as long as ANY lane of the warp
-  // is still looking for its first leaf; when nobody is, every lane tests the spheres of its parked
-  // leaf in the same trips.  Sphere tests therefore run with most of the warp instead of the one or
-  // two lanes that happen to sit on a leaf.  (Walking on with an untested leaf only delays pruning.)
-  const unsigned mask = __activemask();
-  int leaf = 0;                                   // parked leaf ref (negative) or 0
-  auto is_leaf = [](int r) { return r < 0 && r != kTraversalDone; };
-  for (;;) {
-    if (leaf == 0 && is_leaf(cur)) { leaf = cur; cur = stack[--sp]; }
-    const bool keep_walking = __any_sync(mask, cur >= 0 && leaf == 0);
-    if (keep_walking) {
-      if (cur >= 0) {
-        const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
-        float tl, tr;
-        bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
-        bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
-        if (COUNTERS) wc.node_tests += 2;
-        const float limit = best_t * kPruneMargin;
-        hl = hl && tl < limit;
-        hr = hr && tr < limit;
-        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
-        if (hl && hr) {
-          const bool left_first = tl <= tr;
-          stack[sp++] = left_first ? right : left;
-          cur = left_first ? left : right;
-        } else if (hl || hr) {
-          cur = hl ? left : right;
-        } else {
-          cur = stack[--sp];
-        }
-      }
-      continue;
-    }
-    if (!__any_sync(mask, leaf != 0)) break;      // nobody searching, nobody holding a leaf: every lane is done
-    if (leaf != 0) {
-      test_leaf(leaf);
-      leaf = 0;
-    }
-  }
-#elif RTB_TRAVERSAL == 1
-  while (cur != kTraversalDone) {
-    // inner nodes until this lane holds a leaf (or is done); the warp reconverges after the loop,
-    // so the sphere tests below run with every lane that found a leaf
-    while (cur >= 0) {
-      const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
-      float tl, tr;
-      bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
-      bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
-      if (COUNTERS) wc.node_tests += 2;
-      const float limit = best_t * kPruneMargin;
-      hl = hl && tl < limit;
-      hr = hr && tr < limit;
-      const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
-      if (hl && hr) {
-        const bool left_first = tl <= tr;
-        stack[sp++] = left_first ? right : left;
-        cur = left_first ? left : right;
-      } else if (hl || hr) {
-        cur = hl ? left : right;
-      } else {
-        cur = stack[--sp];
-      }
-    }
-    if (cur != kTraversalDone) {
-      test_leaf(cur);
-      cur = stack[--sp];
-    }
-  }
-#else
-  if (FLAVOR < kFlavorGeneral && !RTB_SPLIT_TRIPS) {
+  if (FLAVOR < kFlavorGeneral) {
   // The lean builds.  One trip = [box visit if the lane holds an inner node] -> [leaf test if it now holds a leaf] ->
   // [pop if it needs one]: a lane that descends into a leaf tests it in the same trip, and every lane passes the pop
   // once per trip (measured 131.4 -> 129.1 ms on config 3; the general flavour is faster with the split trips below).
@@ -668,40 +619,30 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       }
     }
   }
+    if (DEFER && a_ok && best_idx >= 0) {      // the winner's numerator -> its distance (HitTests.cs:33,45), once, converged
+      best_t = um::div(best_t, a);
+      if (!(best_t < um::INF)) best_idx = -1;  // "t < tMax" with tMax = +inf (SampleBatchJob.cs:457)
+    }
     return;
   }
-#ifndef RTB_INDEX_STACK
+  // The general and placed flavours: one node (inner OR leaf) per trip (measured faster for them: 72.8 vs 78.8 ms on the mesh world).
   int* top = stack + 1;
-#endif
   for (;;) {
     if (cur >= 0) {
       const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
-      float tl, tr;
-#ifndef RTB_NO_FUSED_LIMIT
       // "box hit (t_enter < t_exit) and not beyond the best hit (t_enter < limit)" as ONE comparison per child
       // against min(t_exit, limit) (t_exit is never NaN: fminf/fmaxf drop NaN operands)
-      float xl, xr;
+      float tl, tr, xl, xr;
       aabb_range(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl, &xl);
       aabb_range(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr, &xr);
       const float limit = best_t * kPruneMargin;
       const bool hl = tl < fminf(xl, limit);
       const bool hr = tr < fminf(xr, limit);
-#else
-      bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
-      bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
-      const float limit = best_t * kPruneMargin;
-      hl = hl && tl < limit;
-      hr = hr && tr < limit;
-#endif
       if (COUNTERS) wc.node_tests += 2;
       const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
       if (hl && hr) {
         const bool left_first = tl <= tr;
-#ifndef RTB_INDEX_STACK
         *top++ = left_first ? right : left;
-#else
-        stack[sp++] = left_first ? right : left;
-#endif
         cur = left_first ? left : right;
         continue;
       }
@@ -710,14 +651,9 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     } else {
       test_leaf(cur);
     }
-#ifndef RTB_INDEX_STACK
     cur = *--top;
-#else
-    cur = stack[--sp];
-#endif
     if (cur == kTraversalDone) break;
   }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------

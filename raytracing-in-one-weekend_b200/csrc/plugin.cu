@@ -9,6 +9,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -21,7 +24,6 @@
 
 #include "aux_kernels.cuh"
 #include "sample_kernels.cuh"
-#include "pool_kernel.cuh"
 #include "volume_kernel.cuh"
 
 using namespace rtbk;
@@ -65,15 +67,26 @@ struct rtb_ctx {
   bool has_scene = false;
 
   // work counters / options
-  uint32_t* d_tile_counter = nullptr;
+  // One tile counter per launch, taken round-robin from a ring: batches enqueued on different streams (or a device
+  // batch overlapping rtb_sample_batch) never share a counter.  (A counter is reused after kTileRing launches; that
+  // many batches of one context are never in flight at once.)
+  static constexpr uint32_t kTileRing = 256;
+  uint32_t* d_tile_ring = nullptr;
+  std::atomic<uint32_t> ring_next{0};
+  // CancellationToken relay: a word of mapped pinned host memory the kernels poll (BatchArgs::cancel_flag); the blocking
+  // call copies the caller's token into it while it waits for the kernel.
+  volatile uint32_t* h_cancel = nullptr;
+  uint32_t* d_cancel = nullptr;       // the same word through the device's mapping
+  uint32_t* d_status = nullptr;       // sticky kStatus* bits raised by kernels
+  cudaEvent_t ev_done = nullptr;
   unsigned long long* d_counters = nullptr;
+  cudaStream_t counters_stream = nullptr;   // stream of the last instrumented launch
   rtb_counters counters{};
   int default_kernel = 2;
-  int64_t opt_counters = 0, opt_kernel = 0, opt_cancel_rows = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0;
+  int64_t opt_counters = 0, opt_kernel = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0;
   bool last_in_place = false;
   float last_ms = 0.0f;
   bool smem_attr_set[2][10] = {};
-  bool pool_attr_set[2][2] = {{false, false}, {false, false}};
 
   DeviceBuffers buf;
   MetricsAcc* d_metrics_partial = nullptr;
@@ -261,7 +274,7 @@ struct Flattener {
       return leaf_ref(first, c);
     }
     const int32_t self = (int32_t)(inner.size() / 16);
-    if (self >= (1 << 24)) { error = "scene too large"; return 0; }
+    if (self >= (1 << 24) / (int32_t)(kNodeStride / 16)) { error = "scene too large"; return 0; }
     inner.resize(inner.size() + 16, 0.0f);
     const rtb_bvh_node& l = nodes[nd.left];
     const rtb_bvh_node& r = nodes[nd.right];
@@ -274,7 +287,7 @@ struct Flattener {
     q[8] = r.bounds_min[2]; q[9] = r.bounds_max[0]; q[10] = r.bounds_max[1]; q[11] = r.bounds_max[2];
     memcpy(&q[12], &lref, 4);
     memcpy(&q[13], &rref, 4);
-    return self * 64;                   // inner refs are BYTE offsets of the node record in the blob (inner_off == 0)
+    return self * (int32_t)kNodeStride; // inner refs are BYTE offsets of the node record in the blob (inner_off == 0)
   }
   // a chain holds at most 255 boxes
   bool path_len_ok(int32_t n) const {
@@ -377,7 +390,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t off = 0;
-  d.inner_off = (uint32_t)off; off = align16(off + (size_t)d.n_inner * 64);
+  d.inner_off = (uint32_t)off; off = align16(off + (size_t)d.n_inner * kNodeStride);
   d.sphere_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 16);
   d.leaf_count_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
   d.mat_index_off = (uint32_t)off; off = align16(off + (n_dev + 1) * 4);
@@ -402,7 +415,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
     memcpy(&f.inner[(size_t)i * 16 + 12], r, 8);
   }
   if (d.has_root) d.root_ref = patch(d.root_ref);
-  if (d.n_inner) memcpy(b + d.inner_off, f.inner.data(), (size_t)d.n_inner * 64);
+  for (uint32_t i = 0; i < d.n_inner; i++) memcpy(b + d.inner_off + (size_t)i * kNodeStride, &f.inner[(size_t)i * 16], 64);
   for (size_t i = 0; i < n_dev; i++) {
     const uint32_t h = f.order[i];
     float s[4] = {0, 0, 0, 0};
@@ -545,13 +558,14 @@ int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_
   choose_tiles(a, n_warps_full, max_spp);
   const uint32_t ctas_needed = (a.n_tiles + kMegaWarps - 1) / kMegaWarps;
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
+  a.tile_counter = ctx->d_tile_ring + (ctx->ring_next.fetch_add(1) % rtb_ctx::kTileRing);
   RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
   kernel<<<grid, kMegaBlock, smem, stream>>>(a);
   RTB_CUDA(ctx, cudaGetLastError());
   return RTB_OK;
 }
 
-// Tile size shared by the two persistent kernels: ~2048 samples per warp tile (measured best on B200, profiles/README.md), at least ~6 tiles per
+// Tile size of the persistent kernel: ~2048 samples per warp tile (measured best on B200, profiles/README.md), at least ~6 tiles per
 // resident warp when the image is small, never fewer than 1024 samples per tile unless the pixel count forces it.
 void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
   static const uint32_t target = [] { const char* e = getenv("RTB_TILE_SAMPLES"); return e ? (uint32_t)std::max(32, atoi(e)) : 2048u; }();
@@ -589,26 +603,6 @@ void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
   a.n_tiles = tile;
 }
 
-template <bool SMEM, bool COUNTERS>
-int launch_pool_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_spp) {
-  const size_t smem = pool_smem_bytes(a.scene.blob_bytes, SMEM);
-  auto kernel = sample_poolkernel<SMEM, COUNTERS>;
-  if (!ctx->pool_attr_set[SMEM][COUNTERS]) {
-    RTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    ctx->pool_attr_set[SMEM][COUNTERS] = true;
-  }
-  int blocks_per_sm = 0;
-  RTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kPoolBlock, smem));
-  if (blocks_per_sm < 1) return fail(ctx, RTB_ERR_CUDA, "pool kernel does not fit on an SM (smem %zu B)", smem);
-  choose_tiles(a, (uint32_t)(ctx->sm_count * blocks_per_sm * kPoolWarps), max_spp);
-  const uint32_t ctas_needed = (a.n_tiles + kPoolWarps - 1) / kPoolWarps;
-  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
-  RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
-  kernel<<<grid, kPoolBlock, smem, stream>>>(a);
-  RTB_CUDA(ctx, cudaGetLastError());
-  return RTB_OK;
-}
-
 int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffers& dev, int width, int height,
                  ActiveRows rows, cudaStream_t stream) {
   if (rows.n_rows <= 0) return RTB_OK;
@@ -629,7 +623,8 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   a.row_step = rows.row_step;
   a.n_rows = rows.n_rows;
   a.n_active_pixels = (uint32_t)rows.n_rows * (uint32_t)width;
-  a.tile_counter = ctx->d_tile_counter;
+  a.cancel_flag = ctx->d_cancel;
+  a.scene.status = ctx->d_status;
   const bool counters = ctx->opt_counters != 0;
   a.counters = counters ? ctx->d_counters : nullptr;
   const uint32_t max_spp = std::max(p.sample_count_range[0], p.sample_count_range[1]);
@@ -647,6 +642,7 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
       a.b.out_diagnostics = ctx->d_scratch_diag;
     }
     RTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+    ctx->counters_stream = stream;
   }
 
   int kernel_kind = (int)ctx->opt_kernel;
@@ -677,15 +673,6 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
       else sample_simple<false, false><<<grid, 128, 0, stream>>>(a);
     }
     RTB_CUDA(ctx, cudaGetLastError());
-  } else if (kernel_kind == 3) {
-    if (ctx->scene.n_placed || ctx->d_mat_textures)
-      return fail(ctx, RTB_ERR_UNSUPPORTED, "the experimental pool kernel does not handle placed entities or image textures");
-    const bool fits = pool_smem_bytes(ctx->scene.blob_bytes, true) <= (size_t)ctx->max_smem_optin &&
-                      ctx->scene.blob_bytes < (1u << 20);
-    int rc;
-    if (fits) rc = counters ? launch_pool_t<true, true>(ctx, a, stream, max_spp) : launch_pool_t<true, false>(ctx, a, stream, max_spp);
-    else rc = counters ? launch_pool_t<false, true>(ctx, a, stream, max_spp) : launch_pool_t<false, false>(ctx, a, stream, max_spp);
-    if (rc != RTB_OK) return rc;
   } else {
     // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
     const int flavor = ctx->scene.n_placed ? (ctx->d_mat_textures ? kFlavorPlacedTextured : kFlavorPlaced)
@@ -752,6 +739,23 @@ void drop_textures(rtb_ctx* ctx) {
   ctx->d_tri_uv = nullptr;
 }
 
+// cudaStreamSynchronize that keeps relaying the caller's CancellationToken into the flag the running kernel polls.
+cudaError_t wait_for_stream(rtb_ctx* ctx, cudaStream_t s, const volatile uint8_t* cancel) {
+  if (!cancel) return cudaStreamSynchronize(s);
+  cudaError_t e = cudaEventRecord(ctx->ev_done, s);
+  if (e != cudaSuccess) return e;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t spins = 0;; spins++) {
+    if (*cancel) *ctx->h_cancel = 1u;
+    e = cudaEventQuery(ctx->ev_done);
+    if (e != cudaErrorNotReady) return e;
+    // short batches: spin (like the runtime's own blocking wait); long ones: yield, then nap 20 us between polls
+    if (spins < 256) continue;
+    if (std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(2)) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(20));
+  }
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -788,7 +792,7 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* k = getenv("RTB_KERNEL")) {         // experiment knob; RTB_OPT_KERNEL is the API
     const long v = strtol(k, nullptr, 10);
-    if (v >= 1 && v <= 3) ctx->default_kernel = (int)v;
+    if (v >= 1 && v <= 2) ctx->default_kernel = (int)v;
   }
   if (const char* k = getenv("RTB_LEAF_SPHERES")) {   // experiment knob; RTB_OPT_LEAF_SPHERES is the API
     const long v = strtol(k, nullptr, 10);
@@ -803,7 +807,19 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess) return bail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess) return bail(e, "cudaEventCreate");
-  if ((e = cudaMalloc(&ctx->d_tile_counter, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaMalloc(&ctx->d_tile_ring, rtb_ctx::kTileRing * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&ctx->d_status, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
+  {
+    void* h = nullptr;
+    if ((e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+    ctx->h_cancel = static_cast<volatile uint32_t*>(h);
+    *ctx->h_cancel = 0u;
+    void* d = nullptr;
+    if ((e = cudaHostGetDevicePointer(&d, h, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
+    ctx->d_cancel = static_cast<uint32_t*>(d);
+  }
   if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
   if ((e = cudaMalloc(&ctx->d_metrics_partial, 1024 * sizeof(MetricsAcc))) != cudaSuccess) return bail(e, "cudaMalloc");
   *out_ctx = ctx;
@@ -818,8 +834,10 @@ int rtb_destroy(rtb_ctx* ctx) {
     for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
     DeviceBuffers& b = ctx->buf;
     void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
-                    b.diagnostics, ctx->d_sky, ctx->d_tex_pixels, ctx->d_tex_images, ctx->d_mat_textures, ctx->d_tri_uv, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_counter, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+                    b.diagnostics, ctx->d_sky, ctx->d_tex_pixels, ctx->d_tex_images, ctx->d_mat_textures, ctx->d_tri_uv, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_ring, ctx->d_status, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_cancel) cudaFreeHost(const_cast<uint32_t*>(ctx->h_cancel));
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1084,26 +1102,11 @@ int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_bat
     dev.out_diagnostics = host->out_diagnostics ? d.diagnostics : nullptr;
   }
 
+  // CancellationToken (SampleBatchJob.cs:61; the host flips it through a raw pointer, Raytracer.cs:189-192, then
+  // Complete()s, :512-515): ONE launch; the kernel polls the context's mapped flag, wait_for_stream relays the token into it.
+  *ctx->h_cancel = 0u;
   RTB_CUDA(ctx, cudaEventRecord(ctx->ev_start, s));
-  if (!cancel) {
-    if ((rc = launch_batch(ctx, *params, dev, width, height, all, s)) != RTB_OK) return rc;
-  } else {
-    // CancellationToken (SampleBatchJob.cs:61): the reference polls once per pixel; a kernel
-    // cannot be recalled, so the batch is issued in row chunks and the token is polled between them.
-    int chunk = ctx->opt_cancel_rows > 0 ? (int)ctx->opt_cancel_rows : std::max(1, height / 16);
-    if (ctx->opt_counters) chunk = height;  // counters describe one launch
-    int lo = params->row_end > params->row_begin ? params->row_begin : 0;
-    const int hi = params->row_end > params->row_begin ? params->row_end : height;
-    for (; lo < hi; lo += chunk) {
-      if (*cancel) {
-        cudaStreamSynchronize(s);
-        return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
-      }
-      const ActiveRows part = active_rows(*params, height, lo, std::min(hi, lo + chunk));
-      if ((rc = launch_batch(ctx, *params, dev, width, height, part, s)) != RTB_OK) return rc;
-      RTB_CUDA(ctx, cudaStreamSynchronize(s));
-    }
-  }
+  if ((rc = launch_batch(ctx, *params, dev, width, height, all, s)) != RTB_OK) return rc;
   RTB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, s));
 
   if (!in_place) {
@@ -1117,9 +1120,16 @@ int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_bat
   }
   if (ctx->opt_counters)
     RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
-  RTB_CUDA(ctx, cudaStreamSynchronize(s));
+  uint32_t status = 0;
+  if (ctx->scene.has_volumes) RTB_CUDA(ctx, cudaMemcpyAsync(&status, ctx->d_status, sizeof status, cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(ctx, wait_for_stream(ctx, s, cancel));
   RTB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
-  if (cancel && *cancel) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  if (*ctx->h_cancel || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  if (status & kStatusHitListOverflow) {
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), s);
+    return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met more than %d entities in a world with participating media (the reference's hit list grows, "
+                "HybridCollections.cs:65-71; this kernel's does not): outputs are not the reference's", kMaxRayHits);
+  }
   return RTB_OK;
 }
 
@@ -1212,9 +1222,10 @@ int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out) {
   if (!ctx || !out) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_get_counters: bad argument");
   if (!ctx->opt_counters) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "counters are disabled (rtb_set_option(RTB_OPT_COUNTERS, 1))");
   DeviceGuard g(ctx->device);
-  // device-buffer batches do not synchronise: fetch the counters of the last launch now
-  RTB_CUDA(ctx, cudaDeviceSynchronize());
-  RTB_CUDA(ctx, cudaMemcpy(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost));
+  // device-buffer batches do not synchronise: fetch the counters behind the last instrumented launch, on ITS stream
+  // (not a device-wide synchronisation: other streams of the process keep running)
+  RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, ctx->counters_stream));
+  RTB_CUDA(ctx, cudaStreamSynchronize(ctx->counters_stream));
   *out = ctx->counters;
   return RTB_OK;
 }
@@ -1224,7 +1235,7 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
   switch (option) {
     case RTB_OPT_COUNTERS: ctx->opt_counters = value ? 1 : 0; return RTB_OK;
     case RTB_OPT_KERNEL:
-      if (value < 0 || value > 3) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_KERNEL must be 0..3");
+      if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_KERNEL must be 0..2");
       ctx->opt_kernel = value;
       return RTB_OK;
     case RTB_OPT_LEAF_SPHERES:
@@ -1241,10 +1252,6 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
     case RTB_OPT_ALWAYS_WALK_CHAINS:
       ctx->opt_walk_chains = value ? 1 : 0;
       if (ctx->has_scene && ctx->scene.has_chains) ctx->scene.has_chains = value ? 2u : 1u;
-      return RTB_OK;
-    case RTB_OPT_CANCEL_CHUNK_ROWS:
-      if (value < 0) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_CANCEL_CHUNK_ROWS must be >= 0");
-      ctx->opt_cancel_rows = value;
       return RTB_OK;
   }
   return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "unknown option %d", option);

@@ -66,7 +66,10 @@ __device__ __forceinline__ void lane_add(WarpTile& t, int lane, int v, float x) 
   const unsigned long long sum = (((unsigned long long)cur.y << 32) | cur.x) + q;
   t.lane_acc[v][lane] = make_uint2((uint32_t)sum, (uint32_t)(sum >> 32));
 }
-// tile totals += this lane's partials; partials := 0
+// tile totals += this lane's partials; partials := 0.  A pixel total that leaves the signed 64-bit range (|sum| >= 2^31:
+// only emitters brighter than ~1e6 at hundreds of samples get there) marks the pixel instead of wrapping: the hi-word
+// add reports its old value, and two's-complement addition overflowed iff both operands have the sign the result lacks.
+// (A lane's own partial cannot overflow first: see finish_path.)
 __device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
 #pragma unroll
   for (int v = 0; v < kAccValues; v++) {
@@ -74,7 +77,10 @@ __device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
     if (cur.x | cur.y) {
       const uint32_t old = atomicAdd(&t.acc_lo[slot][v], cur.x);
       const uint32_t hi = cur.y + ((old + cur.x) < old ? 1u : 0u);
-      if (hi) atomicAdd(&t.acc_hi[slot][v], hi);
+      if (hi) {
+        const uint32_t old_hi = atomicAdd(&t.acc_hi[slot][v], hi);
+        if (~(old_hi ^ hi) & (old_hi ^ (old_hi + hi)) & 0x80000000u) t.non_finite[slot] = 1;
+      }
       t.lane_acc[v][lane] = make_uint2(0u, 0u);
     }
   }
@@ -109,6 +115,7 @@ template <bool SMEM, bool COUNTERS, int FLAVOR>
 __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  volatile uint32_t* cta_cancelled = reinterpret_cast<volatile uint32_t*>(smem + 8);   // set by the first warp that sees the token
   unsigned char* blob_smem = smem + 16;
   const size_t tiles_off = (16 + (SMEM ? a.scene.blob_bytes : 0) + 15) & ~(size_t)15;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
 
   // ---- stage the world into shared memory: TMA bulk copies signalled on one mbarrier ----
   SceneView<SMEM> sv;
+  if (threadIdx.x == 0) *cta_cancelled = 0u;
   if (SMEM) {
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
@@ -131,6 +139,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     mbar_wait(bar, 0);
     sv.bind(blob_smem, a.scene);
   } else {
+    __syncthreads();
     sv.bind(a.scene.blob, a.scene);
   }
 
@@ -177,23 +186,38 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     }
     // bounce-loop iterations of this path (SampleBatchJob.cs:203): every hit so far, plus the miss that ended it
     uint32_t counts = tile.lane_counts[lane] + (uint32_t)depth + (success ? 1u : 0u);
+    bool flush_now = false;
     if (success) {
       const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, tile.aov[0][lane], tile.aov[1][lane], tile.aov[2][lane],
                                       tile.aov[3][lane], tile.aov[4][lane], tile.aov[5][lane], events_acc};
-      bool finite = true;
+      // Range of the fixed-point sums (rtb.h "Accumulation range").  Ordinary samples (every component below 2^20): a lane's
+      // partial holds at most 1024 of them between flushes, so it stays below 2^30 and cannot wrap.  A brighter sample goes
+      // alone: partials out first, the sample in, out again — lane_flush sees the pixel total overflow if it does.
+      bool ordinary = true;
 #pragma unroll
-      for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
-      if (finite) {
+      for (int k = 0; k < kAccValues; k++) ordinary = ordinary && (um::abs(vals[k]) < 1048576.0f);
+      if (!ordinary) {
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
+        if (finite) {
+          lane_flush(tile, lane, acc_slot);
+          counts = (uint32_t)depth + 1u;
+          flush_now = true;
+        } else {
+          tile.non_finite[slot] = 1;
+        }
+        ordinary = finite;
+      }
+      if (ordinary) {
 #pragma unroll
         for (int k = 0; k < kAccValues; k++) lane_add(tile, lane, k, vals[k]);
-      } else {
-        tile.non_finite[slot] = 1;
       }
       counts += 1u << 20;
     }
     tile.lane_counts[lane] = counts;
     // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps
-    if ((counts >> 20) >= 2048u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
+    if (flush_now || (counts >> 20) >= 1024u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
   };
 
   // One trip of the loop, for every lane of the warp:
@@ -244,9 +268,14 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
           a.b.out_diagnostics[index] = dg;
         }
       }
-      // next tile
+      // next tile — unless the host's CancellationToken was set (SampleBatchJob.cs:61 polls it per pixel; here the warp
+      // that claims a tile reads the mapped flag, and tells the CTA's other warps to stop issuing samples)
       uint32_t t = 0;
-      if (lane == 0) t = atomicAdd(a.tile_counter, 1u);
+      if (lane == 0) {
+        const uint32_t cancelled = ld_volatile_u32(a.cancel_flag);
+        t = atomicAdd(a.tile_counter, 1u);
+        if (cancelled) { *cta_cancelled = 1u; t = 0xffffffffu; }
+      }
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= a.n_tiles) break;
       tile_range(a, t, &tile_base, &tile_n);
@@ -334,6 +363,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     // 122.7 / 123.7 / 132.3 ms, mesh world 70.2 -> 67.1 ms; on the linear list (converged walk: an idle lane is pure loss)
     // and on worlds of a dozen entities 1 is best — the plugin picks 8 for trees of >= 64 inner nodes.
     if (need && ((uint32_t)__popc(need) >= a.refill_min || need == 0xffffffffu)) {
+      if (*cta_cancelled) next_item = total_items;      // cancelled: the tile's remaining samples are not started
       const uint32_t my_item = next_item + __popc(need & lt_mask);
       if (!alive && my_item < total_items) {
         // item -> (pixel slot, sample) through the tile's prefix table
@@ -464,6 +494,7 @@ template <bool COUNTERS, bool WHITE>
 __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ BatchArgs a) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.n_active_pixels) return;
+  if (ld_volatile_u32(a.cancel_flag)) return;          // CancellationToken (SampleBatchJob.cs:61): pixels not yet started are skipped
   const rtb_batch_params& p = a.p;
   SceneView<false> sv;
   sv.bind(a.scene.blob, a.scene);

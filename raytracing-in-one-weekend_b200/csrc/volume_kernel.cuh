@@ -13,8 +13,9 @@
 namespace rtbk {
 
 constexpr uint32_t kLaneSamples = 8;  // samples a lane traces back to back before the warp accumulates (Philox mode)
-constexpr int kMaxRayHits = 48;     // hit records kept per ray (the reference's list starts at 32 and grows, SampleBatchJob.cs:21);
-                                    // beyond this the farthest hits are dropped
+constexpr int kMaxRayHits = 48;     // hit records kept per ray (the reference's list starts at 32 and grows, SampleBatchJob.cs:21;
+                                    // HybridCollections.cs:65-71).  A ray that meets more raises kStatusHitListOverflow and the
+                                    // batch fails with RTB_ERR_UNSUPPORTED: never a silently different image
 
 struct RayHits {                    // FindHits' sorted hitBuffer
   float t[kMaxRayHits];
@@ -90,6 +91,7 @@ __device__ __noinline__ bool collect_hits(const int MODE, const SceneView<false>
   auto insert = [&](float t, int slot, f3 n) {
     int pos = 0;
     while (pos < hits->count && hits->t[pos] < t) pos++;       // before the first record that is not nearer
+    if (hits->count >= kMaxRayHits && sd.status) atomicOr(sd.status, kStatusHitListOverflow);   // a record is about to be lost
     if (pos >= kMaxRayHits) return;
     const int last = hits->count < kMaxRayHits ? hits->count : kMaxRayHits - 1;
     for (int k = last; k > pos; k--) { hits->t[k] = hits->t[k - 1]; hits->slot[k] = hits->slot[k - 1]; hits->n[k] = hits->n[k - 1]; }
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ Ba
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t k = WHITE ? blockIdx.x * blockDim.x + threadIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= a.n_active_pixels) return;
+  if (ld_volatile_u32(a.cancel_flag)) return;          // CancellationToken (SampleBatchJob.cs:61): pixels not yet started are skipped
   const rtb_batch_params& p = a.p;
   SceneView<false> sv;
   sv.bind(a.scene.blob, a.scene);

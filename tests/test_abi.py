@@ -34,7 +34,7 @@ def test_struct_sizes_match_the_headers(rtb, tmp_path):
 
 def test_headers_compile_as_c(tmp_path):
     src = tmp_path / "c.c"
-    src.write_text('#include "rtb.h"\n#include "rtb_host.h"\nint main(void){return RTB_ABI_VERSION == 1 ? 0 : 1;}\n')
+    src.write_text('#include "rtb.h"\n#include "rtb_host.h"\nint main(void){return RTB_ABI_VERSION == 2 ? 0 : 1;}\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", INCLUDE, "-o", str(tmp_path / "c"), str(src)], check=True)
 
 
@@ -47,7 +47,7 @@ def test_plugin_exports_every_declared_symbol(rtb):
     L = C.CDLL(path)
     for n in names:
         assert hasattr(L, n), n
-    assert rtb.plugin.lib().rtb_abi_version() == 1
+    assert rtb.plugin.lib().rtb_abi_version() == rtb.abi.ABI_VERSION == 2
 
 
 def test_host_lib_exports_every_declared_symbol(rtb):

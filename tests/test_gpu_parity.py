@@ -61,7 +61,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-bvh{c[1]}-{c[2]}x{c[3]}x{c[4]}-d{c[5]}")
 def test_sample_batch_matches_the_oracle(rtb, oracle, ctx, case, kernel):
     name, depth, W, H, spp, td, ap, jitter = case
@@ -69,7 +69,7 @@ def test_sample_batch_matches_the_oracle(rtb, oracle, ctx, case, kernel):
     p = rtb.host.make_params(scene, W, H, spp, td, aperture=ap, jitter=jitter)
     ref = oracle.Buffers(W, H)
     oracle.sample_batch(scene, p, ref)
-    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
     got = render_gpu(rtb, ctx, scene, p, W, H, k)
     assert_parity(ref, got, exact=(kernel == "simple"))
 
@@ -126,11 +126,6 @@ def test_gpu_matches_golden_fixtures(rtb, ctx, case):
     assert np.array_equal(mega.diagnostics["ray_count"], g["ray_count"])
     n = np.maximum(g["color"][:, 3:4], 1)
     assert np.abs(mega.out_color[:, :3] / n - g["color"][:, :3] / n).max() <= RGB_TOL
-    # the two persistent kernels share the per-path arithmetic and the order-independent sums: same bits
-    pool = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_POOL)
-    for x, y in ((mega.out_color, pool.out_color), (mega.out_normal, pool.out_normal), (mega.out_albedo, pool.out_albedo),
-                 (mega.out_weight, pool.out_weight), (mega.diagnostics["ray_count"], pool.diagnostics["ray_count"])):
-        assert x.tobytes() == y.tobytes()
 
 
 @pytest.mark.parametrize("name,depth,td,ap", [("final", 16, 50, 0.1), ("final", 32, 50, 0.0), ("three_spheres", 2, 50, 0.2)])
@@ -168,7 +163,7 @@ def test_image_does_not_depend_on_the_device_tree(rtb, oracle, ctx, name, depth,
         ctx.set_option(rtb.abi.OPT_ALWAYS_WALK_CHAINS, 0)
 
 
-@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
 def test_stress_scene_walks_the_world_in_hbm(rtb, oracle, ctx, kernel):
     """BASELINE config 5's world (10 000 dart-thrown spheres, BVH depth 16): the flattened world (~0.9 MB) does
     not fit shared memory, so the kernels read it in place through the read-only path — same decisions."""
@@ -179,12 +174,12 @@ def test_stress_scene_walks_the_world_in_hbm(rtb, oracle, ctx, kernel):
     p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
     ref = oracle.Buffers(W, H)
     oracle.sample_batch(scene, p, ref)
-    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
     got = render_gpu(rtb, ctx, scene, p, W, H, k)
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
-@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
 @pytest.mark.parametrize("depth,aperture", [(16, 0.0), (2, 0.15), (0, 0.0)])
 def test_mesh_world_matches_the_oracle(rtb, oracle, ctx, kernel, depth, aperture):
     """rtb_upload_world: EntityType.Triangle entities (what the reference's host ingests at HEAD,
@@ -194,7 +189,7 @@ def test_mesh_world_matches_the_oracle(rtb, oracle, ctx, kernel, depth, aperture
     p = rtb.host.make_params(scene, W, H, spp, 50, aperture=aperture)
     ref = oracle.Buffers(W, H)
     oracle.sample_batch(scene, p, ref)
-    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
     got = render_gpu(rtb, ctx, scene, p, W, H, k)
     assert_parity(ref, got, exact=(kernel == "simple"))
 
@@ -328,14 +323,12 @@ def test_textures_on_a_sphere_world_and_argument_checks(rtb, oracle, ctx):
     bad[1]["glossiness_image"], bad[1]["glossiness_channel"] = 0, 3            # alpha of an RGB24 image
     with pytest.raises(rtb.plugin.RtbError):
         ctx.upload_textures([img], bad)
-    ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_POOL)
-    ctx.upload(scene)
     with pytest.raises(rtb.plugin.RtbError):
-        ctx.sample_batch(p, rtb.plugin.HostBuffers(W, H))                      # the experimental kernel refuses textures
+        ctx.set_option(rtb.abi.OPT_KERNEL, 3)                                  # the rejected wavefront kernel is gone
     ctx.set_option(rtb.abi.OPT_KERNEL, 0)
 
 
-@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
 def test_emissive_panel_without_sky(rtb, oracle, ctx, kernel):
     """Material.Emit (Material.cs:175-179) + SkyType.None: the overhead panel is the only light, so every pixel's
     radiance is emission carried down the path by the attenuation product (SampleBatchJob.cs:383-396)."""
@@ -345,12 +338,12 @@ def test_emissive_panel_without_sky(rtb, oracle, ctx, kernel):
     ref = oracle.Buffers(W, H)
     oracle.sample_batch(scene, p, ref)
     assert ref.rgb().max() > 0.5 and (ref.rgb().reshape(-1, 3).max(axis=1) == 0).mean() > 0.05   # lit floor, black sky
-    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
     got = render_gpu(rtb, ctx, scene, p, W, H, k)
     assert_parity(ref, got, exact=(kernel == "simple"))
 
 
-@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
 def test_emissive_sphere_in_a_sphere_world(rtb, oracle, ctx, kernel):
     """Material.Emit on sphere entities (the lean sphere build carries radiance along the path too)."""
     W, H, spp = 80, 45, 16
@@ -364,7 +357,7 @@ def test_emissive_sphere_in_a_sphere_world(rtb, oracle, ctx, kernel):
     base = oracle.Buffers(W, H)
     oracle.sample_batch(dark, p, base)
     assert np.abs(ref.rgb() - base.rgb()).max() > 0.5            # the emitters are visible
-    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
     got = render_gpu(rtb, ctx, scene, p, W, H, k)
     assert_parity(ref, got, exact=(kernel == "simple"))
 
@@ -382,7 +375,7 @@ def _test_cubemap(size=16):
     return faces.astype(np.float16)
 
 
-@pytest.mark.parametrize("kernel", ["simple", "mega", "pool"])
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
 @pytest.mark.parametrize("world", ["mesh", "final"])
 def test_cubemap_sky(rtb, oracle, ctx, kernel, world):
     """SkyType.CubeMap (Environment.cs, Texture.cs:141-211) — the sky the reference's host builds from the scene's HDRI
@@ -398,7 +391,7 @@ def test_cubemap_sky(rtb, oracle, ctx, kernel, world):
         ref = oracle.Buffers(W, H)
         oracle.sample_batch(scene, p, ref)
         assert ref.rgb().max() > 2.0                            # the sun texel is seen (directly or in a reflection)
-        k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA, "pool": rtb.abi.KERNEL_POOL}[kernel]
+        k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
         got = render_gpu(rtb, ctx, scene, p, W, H, k)
         assert_parity(ref, got, exact=(kernel == "simple"))
     finally:
@@ -684,7 +677,7 @@ def test_error_behaviour(rtb):
             c.sample_batch(p, b, cancel=cancel)
         assert e.value.code == abi.RTB_ERR_CANCELLED
         cancel[0] = 0
-        c.sample_batch(p, b, cancel=cancel)          # chunked launches, token never set: same image as unchunked
+        c.sample_batch(p, b, cancel=cancel)          # a live token that is never set: the same single launch, the same image
         b2 = rtb.plugin.HostBuffers(16, 9)
         c.sample_batch(p, b2)
         assert b.out_color.tobytes() == b2.out_color.tobytes()
@@ -921,7 +914,7 @@ def test_random_small_batches_agree_across_kernels_and_with_the_oracle(rtb, orac
         ref = oracle.Buffers(W, H)
         ref.in_color[:], ref.in_weight[:], ref.in_normal[:], ref.in_albedo[:] = inputs
         oracle.sample_batch(scene, p, ref)
-        for kernel, exact in ((rtb.abi.KERNEL_SIMPLE, True), (rtb.abi.KERNEL_MEGA, False), (rtb.abi.KERNEL_POOL, False)):
+        for kernel, exact in ((rtb.abi.KERNEL_SIMPLE, True), (rtb.abi.KERNEL_MEGA, False)):
             got = render_gpu(rtb, ctx, scene, p, W, H, kernel, inputs=inputs)
             try:
                 assert np.array_equal(ref.out_color[:, 3], got.out_color[:, 3])
@@ -1022,3 +1015,117 @@ def test_an_unused_volume_material_does_not_change_the_kernel(rtb, ctx):
                                                                 dtype=rtb.abi.MATERIAL_DTYPE)])
     b = render_gpu(rtb, ctx, extra, p, W, H, rtb.abi.KERNEL_MEGA)
     assert a.out_color.tobytes() == b.out_color.tobytes() and a.out_weight.tobytes() == b.out_weight.tobytes()
+
+
+def test_cancellation_token_set_mid_flight(rtb):
+    """CancellationToken (SampleBatchJob.cs:61; Raytracer.cs:189-192 flips it through a raw pointer while the job runs): the
+    batch is ONE launch whether or not a token is passed; the kernel polls the context's mapped flag when a warp claims a tile.
+    A token set from another thread in the middle of a ~120 ms batch ends the call within 5 ms with RTB_ERR_CANCELLED; a live
+    token that is never set costs nothing measurable (same kernel, same launch)."""
+    import threading
+    import time
+
+    abi = rtb.abi
+    W, H, spp = 1920, 1080, 256
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    c = rtb.plugin.Context(0)
+    try:
+        c.upload(scene)
+        b = rtb.plugin.HostBuffers(W, H, diagnostics=False)
+        c.register_host_buffers(b)
+        c.sample_batch(p, b)                                   # warm-up, and the time of an undisturbed batch
+        t_plain = []
+        for _ in range(2):
+            t = time.perf_counter()
+            c.sample_batch(p, b)
+            t_plain.append(time.perf_counter() - t)
+        cancel = np.zeros(1, np.uint8)
+        t_token = []
+        for _ in range(2):
+            t = time.perf_counter()
+            c.sample_batch(p, b, cancel=cancel)                # live token, never set
+            t_token.append(time.perf_counter() - t)
+        assert min(t_token) <= min(t_plain) * 1.02, (t_token, t_plain)
+        full = min(t_plain)
+        for delay in (0.010, 0.040):
+            cancel[0] = 0
+            set_at = [0.0]
+
+            def fire():
+                time.sleep(delay)
+                set_at[0] = time.perf_counter()
+                cancel[0] = 1
+
+            th = threading.Thread(target=fire)
+            th.start()
+            with pytest.raises(rtb.plugin.RtbError) as e:
+                c.sample_batch(p, b, cancel=cancel)
+            returned = time.perf_counter()
+            th.join()
+            assert e.value.code == abi.RTB_ERR_CANCELLED
+            assert returned - set_at[0] < 0.005, f"cancel took {1e3 * (returned - set_at[0]):.2f} ms"
+            assert returned - set_at[0] + delay < 0.8 * full          # it really stopped early
+        cancel[0] = 0
+        c.sample_batch(p, b, cancel=cancel)                    # and the context is usable afterwards
+        assert b.out_color[:, 3].min() > 0
+    finally:
+        c.close()
+
+
+def test_accumulator_range_is_loud(rtb, oracle, ctx):
+    """rtb.h "Accumulation range": the megakernel's per-pixel sums are 64-bit fixed point with 32 fraction bits.  Emitters far
+    brighter than any display range still add up like the reference's floats (2^20 <= sample < 1e9 takes the one-at-a-time
+    path); a pixel whose batch total reaches 2^31 is written as NaN — never a wrapped, sign-flipped value."""
+    W, H, spp = 32, 18, 64
+    for emission, overflow in ((3.0e6, False), (9.0e7, True)):
+        scene = rtb.host.make_scene("three_spheres", max_bvh_depth=2)
+        scene.materials = scene.materials.copy()
+        scene.materials["albedo"][:] = 0.0
+        scene.materials["emission"][:] = emission
+        p = rtb.host.make_params(scene, W, H, spp, 8)
+        ref = oracle.Buffers(W, H)
+        oracle.sample_batch(scene, p, ref)
+        got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+        assert np.array_equal(ref.out_color[:, 3], got.out_color[:, 3])
+        big = ref.out_color[:, 0] >= 2.0 ** 31
+        assert big.any() == overflow
+        assert np.isnan(got.out_color[big, :3]).all()
+        ok = ~big
+        assert np.isfinite(got.out_color[ok]).all()
+        np.testing.assert_allclose(got.out_color[ok, :3], ref.out_color[ok, :3], rtol=2e-6)
+        assert (got.out_color[ok, :3] >= 0).all()
+
+
+def test_media_hit_list_overflow_is_an_error(rtb, ctx):
+    """The reference's HybridList<HitRecord> starts at 32 records and grows (HybridCollections.cs:65-71); the volume kernel keeps
+    48.  A ray through more media boundaries than that must fail the batch (RTB_ERR_UNSUPPORTED), not render something else."""
+    abi = rtb.abi
+    n = 40                                   # 40 nested fog shells along every camera ray: 3 records each (entry, exit, injected exit)
+    materials = np.array([rtb.host._material(abi.MATERIAL_PROBABILISTIC_VOLUME, (0.9, 0.9, 0.9), ior=0.01)], dtype=abi.MATERIAL_DTYPE)
+    spheres = np.zeros(n, dtype=abi.SPHERE_DTYPE)
+    for i in range(n):
+        spheres[i] = ((0.0, 0.0, 0.0), 1.0 + 0.05 * i, 0, (0, 0, 0))
+    cam = abi.Camera()
+    cam.position[:] = (0.0, 0.0, -8.0)
+    cam.target[:] = (0.0, 0.0, 0.0)
+    cam.aperture = 0.0
+    cam.vertical_fov = 20.0
+    env = abi.Environment()
+    env.sky_type = abi.SKY_GRADIENT
+    env.sky_bottom_color[:] = (1, 1, 1)
+    env.sky_top_color[:] = (0.5, 0.7, 1.0)
+    scene = rtb.host.build_world(spheres, [], materials, 4, cam, env, 8.0, name="shells")
+    p = rtb.host.make_params(scene, 16, 9, 2, 8)
+    c = rtb.plugin.Context(0)
+    try:
+        c.upload(scene)
+        with pytest.raises(rtb.plugin.RtbError) as e:
+            c.sample_batch(p, rtb.plugin.HostBuffers(16, 9))
+        assert e.value.code == abi.RTB_ERR_UNSUPPORTED
+        # fewer shells fit: the same world with 10 of them renders
+        scene = rtb.host.build_world(spheres[:10], [], materials, 4, cam, env, 8.0, name="shells")
+        c.upload(scene)
+        c.sample_batch(p, rtb.plugin.HostBuffers(16, 9))
+    finally:
+        c.close()

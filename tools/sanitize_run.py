@@ -20,7 +20,7 @@ for scene, ap, k in cases:
     ctx.set_option(abi.OPT_LEAF_SPHERES, k)
     ctx.upload(scene)
     p = rtb.host.make_params(scene, W, H, spp, 50, aperture=ap)
-    for kernel in ((abi.KERNEL_SIMPLE, abi.KERNEL_MEGA) if wide else (abi.KERNEL_SIMPLE, abi.KERNEL_MEGA, abi.KERNEL_POOL)):
+    for kernel in (abi.KERNEL_SIMPLE, abi.KERNEL_MEGA):
         for counters in (0, 1):
             ctx.set_option(abi.OPT_KERNEL, kernel)
             ctx.set_option(abi.OPT_COUNTERS, counters)
