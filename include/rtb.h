@@ -355,6 +355,73 @@ RTB_API int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params
 RTB_API int rtb_register_host_buffer(rtb_ctx* ctx, void* ptr, size_t bytes);
 RTB_API int rtb_unregister_host_buffer(rtb_ctx* ctx, void* ptr);
 
+/* ---- one host, N GPUs ------------------------------------------------------
+ * The reference schedules ONE job over W*H pixels (Raytracer.cs:730); a host with several GPUs keeps that one call
+ * site: an rtb_multi handle owns one context per device and renders one batch of the frame with all of them.  Every
+ * pixel is independent and the Philox stream is keyed by the global pixel index, so device g simply takes the rows
+ * [bounds[g], bounds[g + 1]) of the SAME buffers and the image is bit-identical for any device count.  There is no
+ * gather: host arrays are written in place by every device over its own PCIe link (pinned) or staged per device
+ * (pageable); device arrays live on one GPU and the others write their rows into them over NVLink peer access.
+ * Row tiles are balanced inside the plugin: an instrumented probe batch (a few samples per pixel, split over the
+ * devices) gives a per-row cost model whenever the world, the size or the view changes, and every batch's measured
+ * per-device kernel times correct it (sky rows are cheap, glass is dear). */
+#define RTB_MULTI_MAX_DEVICES 16
+typedef struct rtb_multi rtb_multi;
+/* `devices`: CUDA device ordinals.  (An ordinal may repeat: two contexts then share that GPU — of use on a one-GPU box
+ * to exercise the tiling.) */
+RTB_API int rtb_multi_create(const int* devices, int device_count, rtb_multi** out_multi);
+RTB_API int rtb_multi_destroy(rtb_multi* m);
+RTB_API int rtb_multi_device_count(const rtb_multi* m);
+/* The context of device `index` of the handle (options, counters, rtb_last_kernel_ms); owned by the handle. */
+RTB_API rtb_ctx* rtb_multi_context(rtb_multi* m, int index);
+RTB_API const char* rtb_multi_last_error(const rtb_multi* m);
+/* rtb_set_option on every device; RTB_OPT_BALANCE_TILES belongs to the handle itself. */
+RTB_API int rtb_multi_set_option(rtb_multi* m, int option, int64_t value);
+/* The rtb_upload_* calls, replicated to every device (the world is <= a few MB). */
+RTB_API int rtb_multi_upload_scene(rtb_multi* m, const rtb_sphere* spheres, size_t sphere_count,
+                                   const rtb_material* materials, size_t material_count,
+                                   const rtb_bvh_node* nodes, size_t node_count);
+RTB_API int rtb_multi_upload_placed_world(rtb_multi* m, const rtb_entity* entities, size_t entity_count,
+                                          const rtb_sphere* spheres, size_t sphere_count,
+                                          const rtb_triangle* triangles, size_t triangle_count,
+                                          const rtb_placed_entity* placed, size_t placed_count,
+                                          const rtb_material* materials, size_t material_count,
+                                          const rtb_bvh_node* nodes, size_t node_count);
+RTB_API int rtb_multi_upload_textures(rtb_multi* m, const rtb_image* images, size_t image_count,
+                                      const rtb_material_textures* material_textures, size_t material_count,
+                                      const float* triangle_uvs, size_t triangle_count);
+RTB_API int rtb_multi_upload_sky_cubemap(rtb_multi* m, const uint16_t* half_rgba, int face_width, int face_height);
+/* Pins a pooled host array once for every device of the handle (see rtb_register_host_buffer). */
+RTB_API int rtb_multi_register_host_buffer(rtb_multi* m, void* ptr, size_t bytes);
+RTB_API int rtb_multi_unregister_host_buffer(rtb_multi* m, void* ptr);
+/* rtb_sample_batch over every device of the handle: blocking, HOST buffers, the same CancellationToken contract
+ * (the token is relayed to every device's kernel).  params->row_begin/row_end restrict the batch as usual. */
+RTB_API int rtb_multi_sample_batch(rtb_multi* m, const rtb_batch_params* params,
+                                   const rtb_batch_buffers* host_buffers, const volatile uint8_t* cancel);
+/* rtb_sample_batch_device over every device of the handle: the buffers live on device `owner_index` (index into the
+ * handle's device list) and the batch is ordered on `owner_stream` of that device like any other work enqueued
+ * there: it starts when the stream reaches it and the stream continues when every device's rows have landed.  The
+ * other devices read and write the owner's memory over peer access (fails with RTB_ERR_UNSUPPORTED without a peer
+ * path).  Does not synchronise. */
+RTB_API int rtb_multi_sample_batch_device(rtb_multi* m, const rtb_batch_params* params,
+                                          const rtb_batch_buffers* device_buffers, int owner_index, void* owner_stream);
+/* Row bounds (device_count + 1 ints) and kernel milliseconds (device_count floats) of the last batch; either may be
+ * NULL.  Kernel times of a device-buffer batch are available once the owner's stream has passed it. */
+RTB_API int rtb_multi_get_tiles(rtb_multi* m, int* out_bounds, float* out_kernel_ms);
+/* The balancer's partition, exposed for tests and for hosts that shard by themselves: bounds of `device_count` row
+ * tiles of [row_begin, row_end) with near-equal sums of row_cost (indexed by absolute row; NULL = equal rows). */
+RTB_API int rtb_balance_rows(const double* row_cost, int row_begin, int row_end, int device_count, int* out_bounds);
+
+/* One process per GPU (torch.distributed-style hosts): device memory one process allocates and the other ranks map,
+ * so that every rank's kernel writes its row tile straight into rank 0's frame over NVLink (the buffers of
+ * rtb_sample_batch_device may be such a mapping).  Thin wrappers over cudaMalloc / cudaIpc*. */
+typedef struct rtb_ipc_handle { unsigned char bytes[64]; } rtb_ipc_handle;
+RTB_API int rtb_device_alloc(rtb_ctx* ctx, size_t bytes, void** out_device_ptr);     /* zero-filled */
+RTB_API int rtb_device_free(rtb_ctx* ctx, void* device_ptr);
+RTB_API int rtb_ipc_export(rtb_ctx* ctx, void* device_ptr, rtb_ipc_handle* out_handle);
+RTB_API int rtb_ipc_open(rtb_ctx* ctx, const rtb_ipc_handle* handle, void** out_device_ptr);
+RTB_API int rtb_ipc_close(rtb_ctx* ctx, void* device_ptr);
+
 /* ---- adjacent jobs, device-side ("next" rows f1/f2 of SURVEY.md §8) --------------------- */
 /* CombineJob (CombineJob.cs:29-71): rgb = color.xyz / (int)color.w with the interlace
  * look-around, NaN -> 0, albedo / max(n,1), normalizesafe(normal / max(n,1)).
@@ -411,6 +478,7 @@ typedef enum rtb_option {
                                  * (NoiseColor.White: one sequential Unity.Mathematics.Random xorshift32 stream per pixel per batch,
                                  * SampleBatchJob.cs:91) — validation only, needs RTB_OPT_KERNEL = 1 (a sequential stream cannot be
                                  * split over lanes) */
+  RTB_OPT_BALANCE_TILES = 8,    /* rtb_multi only. 1 (default): cost-model + kernel-time balanced row tiles; 0: equal row counts */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
                                  * instead of only when the hit geometry does not already prove them (same results, slower) */
 } rtb_option;

@@ -119,6 +119,28 @@ __global__ void reduce_metrics_kernel(int n, const rtb_diagnostics* __restrict__
   }
 }
 
+// Row costs for the multi-GPU tile balancer (plugin.cu: rtb_multi): per image row, the instruction-weighted work of an
+// instrumented probe batch — rays, executed box tests and executed entity tests per pixel (the reference's FULL_DIAGNOSTICS
+// fields, Raytracer.cs:56-60), weighted by what each costs the walk.  One block per row of [row_begin, row_end).
+__global__ void __launch_bounds__(256) row_cost_kernel(const rtb_diagnostics* __restrict__ diag, int width, int row_begin,
+                                                       float* __restrict__ row_cost) {
+  const int row = row_begin + (int)blockIdx.x;
+  float s = 0.0f;
+  for (int x = threadIdx.x; x < width; x += blockDim.x) {
+    const rtb_diagnostics d = diag[(size_t)row * (size_t)width + (size_t)x];
+    s += 450.0f * d.ray_count + 35.0f * d.bounds_hit_count + 40.0f * d.candidate_count;
+  }
+  __shared__ float sh[8];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    row_cost[row] = t;
+  }
+}
+
 // FP32-pipe roofline microbenchmark: 16 independent FMA chains per thread, register operands.
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float b, float c) {
   float a[16];

@@ -739,23 +739,6 @@ void drop_textures(rtb_ctx* ctx) {
   ctx->d_tri_uv = nullptr;
 }
 
-// cudaStreamSynchronize that keeps relaying the caller's CancellationToken into the flag the running kernel polls.
-cudaError_t wait_for_stream(rtb_ctx* ctx, cudaStream_t s, const volatile uint8_t* cancel) {
-  if (!cancel) return cudaStreamSynchronize(s);
-  cudaError_t e = cudaEventRecord(ctx->ev_done, s);
-  if (e != cudaSuccess) return e;
-  const auto t0 = std::chrono::steady_clock::now();
-  for (uint32_t spins = 0;; spins++) {
-    if (*cancel) *ctx->h_cancel = 1u;
-    e = cudaEventQuery(ctx->ev_done);
-    if (e != cudaErrorNotReady) return e;
-    // short batches: spin (like the runtime's own blocking wait); long ones: yield, then nap 20 us between polls
-    if (spins < 256) continue;
-    if (std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(2)) std::this_thread::yield();
-    else std::this_thread::sleep_for(std::chrono::microseconds(20));
-  }
-}
-
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -767,6 +750,346 @@ struct DeviceGuard {
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
+
+// cudaStreamSynchronize of every context's stream that keeps relaying the caller's CancellationToken into the flags the
+// running kernels poll.
+cudaError_t wait_for_streams(rtb_ctx* const* ctxs, int n, const volatile uint8_t* cancel) {
+  DeviceGuard restore(ctxs[0]->device);
+  if (!cancel) {
+    for (int i = 0; i < n; i++) {
+      cudaError_t e = cudaSetDevice(ctxs[i]->device);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctxs[i]->stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  for (int i = 0; i < n; i++) {
+    cudaError_t e = cudaSetDevice(ctxs[i]->device);
+    if (e == cudaSuccess) e = cudaEventRecord(ctxs[i]->ev_done, ctxs[i]->stream);
+    if (e != cudaSuccess) return e;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  int pending = n;
+  std::vector<char> done((size_t)n, 0);
+  for (uint32_t spins = 0; pending > 0; spins++) {
+    if (*cancel)
+      for (int i = 0; i < n; i++) *ctxs[i]->h_cancel = 1u;
+    for (int i = 0; i < n; i++) {
+      if (done[i]) continue;
+      const cudaError_t e = cudaEventQuery(ctxs[i]->ev_done);
+      if (e == cudaErrorNotReady) continue;
+      if (e != cudaSuccess) return e;
+      done[i] = 1;
+      pending--;
+    }
+    // short batches: spin (like the runtime's own blocking wait); long ones: yield, then nap 20 us between polls
+    if (pending == 0 || spins < 256) continue;
+    if (std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(2)) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(20));
+  }
+  return cudaSuccess;
+}
+
+
+
+// One host-buffer batch of one context in three phases, so that a multi-device batch (rtb_multi_sample_batch) can start
+// every device before it waits for any:  begin = validate, stage the inputs (pageable hosts only), launch;
+// drain = queue the read-back of the outputs (pageable hosts only), the counters and the status word; then the caller
+// waits for the stream(s); end = kernel time, cancellation and status verdicts.  The caller holds ctx->mu throughout.
+struct HostBatch {
+  bool empty = true, in_place = false;
+  int width = 0, height = 0;
+  ActiveRows all{};
+  const rtb_batch_buffers* host = nullptr;
+  uint32_t status = 0;
+};
+
+int host_batch_begin(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_batch_buffers* host, HostBatch* st) {
+  int width, height;
+  int rc = validate_params(ctx, params, &width, &height);
+  if (rc != RTB_OK) return rc;
+  if (!ctx->has_scene) return fail(ctx, RTB_ERR_NO_SCENE, "rtb_upload_scene has not been called");
+  if (!host || !host->in_color || !host->in_sample_count_weight || !host->in_normal || !host->in_albedo || !host->out_color ||
+      !host->out_sample_count_weight || !host->out_normal || !host->out_albedo)
+    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "a batch buffer pointer is NULL");
+  DeviceGuard g(ctx->device);
+  const size_t pixels = (size_t)width * height;
+  cudaStream_t s = ctx->stream;
+  const ActiveRows all = active_rows(*params, height, 0, 0);
+  st->empty = all.n_rows <= 0;
+  st->width = width; st->height = height; st->all = all; st->host = host;
+  if (st->empty) return RTB_OK;
+
+  // Pinned host arrays (rtb_register_host_buffer, or any cudaHostAlloc'd memory) are read and written IN PLACE by the
+  // kernel over PCIe: each accumulator crosses the bus once, inside the kernel, overlapped with tracing, instead of in
+  // eight staged copies around it.  Pageable arrays take the staged path.
+  rtb_batch_buffers dev{};
+  bool in_place = ctx->opt_host_access != 0;
+  if (in_place) {
+    const void* hp[9] = {host->in_color, host->in_sample_count_weight, host->in_normal, host->in_albedo, host->out_color,
+                         host->out_sample_count_weight, host->out_normal, host->out_albedo, host->out_diagnostics};
+    void* dp[9] = {};
+    for (int i = 0; i < 9 && in_place; i++) {
+      if (!hp[i]) continue;             // diagnostics may be NULL
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        in_place = false;
+      } else {
+        dp[i] = at.devicePointer;
+      }
+    }
+    if (in_place) {
+      dev.in_color = (const float*)dp[0]; dev.in_sample_count_weight = (const float*)dp[1];
+      dev.in_normal = (const float*)dp[2]; dev.in_albedo = (const float*)dp[3];
+      dev.out_color = (float*)dp[4]; dev.out_sample_count_weight = (float*)dp[5];
+      dev.out_normal = (float*)dp[6]; dev.out_albedo = (float*)dp[7];
+      dev.out_diagnostics = (rtb_diagnostics*)dp[8];
+    }
+  }
+  ctx->last_in_place = st->in_place = in_place;
+  if (!in_place) {
+    if ((rc = ensure_buffers(ctx, pixels)) != RTB_OK) return rc;
+    DeviceBuffers& d = ctx->buf;
+    RTB_CUDA(ctx, copy_rows(d.in_color, host->in_color, 16, width, all, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(ctx, copy_rows(d.in_weight, host->in_sample_count_weight, 4, width, all, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(ctx, copy_rows(d.in_normal, host->in_normal, 12, width, all, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(ctx, copy_rows(d.in_albedo, host->in_albedo, 12, width, all, cudaMemcpyHostToDevice, s));
+    dev.in_color = d.in_color; dev.in_sample_count_weight = d.in_weight; dev.in_normal = d.in_normal; dev.in_albedo = d.in_albedo;
+    dev.out_color = d.out_color; dev.out_sample_count_weight = d.out_weight; dev.out_normal = d.out_normal; dev.out_albedo = d.out_albedo;
+    dev.out_diagnostics = host->out_diagnostics ? d.diagnostics : nullptr;
+  }
+
+  // CancellationToken (SampleBatchJob.cs:61; the host flips it through a raw pointer, Raytracer.cs:189-192, then
+  // Complete()s, :512-515): ONE launch; the kernel polls the context's mapped flag, wait_for_streams relays the token into it.
+  *ctx->h_cancel = 0u;
+  RTB_CUDA(ctx, cudaEventRecord(ctx->ev_start, s));
+  if ((rc = launch_batch(ctx, *params, dev, width, height, all, s)) != RTB_OK) return rc;
+  RTB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, s));
+  return RTB_OK;
+}
+
+int host_batch_drain(rtb_ctx* ctx, HostBatch* st) {
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const rtb_batch_buffers* host = st->host;
+  if (!st->in_place) {
+    DeviceBuffers& d = ctx->buf;
+    RTB_CUDA(ctx, copy_rows(host->out_color, d.out_color, 16, st->width, st->all, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, copy_rows(host->out_sample_count_weight, d.out_weight, 4, st->width, st->all, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, copy_rows(host->out_normal, d.out_normal, 12, st->width, st->all, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, copy_rows(host->out_albedo, d.out_albedo, 12, st->width, st->all, cudaMemcpyDeviceToHost, s));
+    if (host->out_diagnostics)
+      RTB_CUDA(ctx, copy_rows(host->out_diagnostics, d.diagnostics, sizeof(rtb_diagnostics), st->width, st->all, cudaMemcpyDeviceToHost, s));
+  }
+  if (ctx->opt_counters)
+    RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
+  if (ctx->scene.has_volumes) RTB_CUDA(ctx, cudaMemcpyAsync(&st->status, ctx->d_status, sizeof st->status, cudaMemcpyDeviceToHost, s));
+  return RTB_OK;
+}
+
+int host_batch_end(rtb_ctx* ctx, HostBatch* st, const volatile uint8_t* cancel) {
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
+  if (*ctx->h_cancel || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  if (st->status & kStatusHitListOverflow) {
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
+    return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met more than %d entities in a world with participating media (the reference's hit list grows, "
+                "HybridCollections.cs:65-71; this kernel's does not): outputs are not the reference's", kMaxRayHits);
+  }
+  return RTB_OK;
+}
+
+
+// ---- one host, N GPUs ------------------------------------------------------------------------
+// Row tiles with near-equal modelled cost: bounds[g] = first row of device g's tile, bounds[n] = hi.  Every tile of a
+// non-empty range gets at least one row while rows last.
+void balance_rows(const double* cost, int lo, int hi, int n, int* bounds) {
+  const int rows = std::max(0, hi - lo);
+  std::vector<double> cum((size_t)rows + 1, 0.0);
+  for (int r = 0; r < rows; r++) cum[(size_t)r + 1] = cum[(size_t)r] + std::max(cost ? cost[lo + r] : 1.0, 1e-12);
+  bounds[0] = lo;
+  for (int g = 1; g < n; g++) {
+    const double target = cum[(size_t)rows] * (double)g / (double)n;
+    int b = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+    b = std::max(b, bounds[g - 1] - lo + 1);
+    b = std::min(b, rows - (n - g));
+    b = std::max(b, bounds[g - 1] - lo);       // more devices than rows: empty tiles at the end
+    bounds[g] = lo + std::min(std::max(b, 0), rows);
+  }
+  bounds[n] = hi;
+}
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t bytes) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+}  // namespace
+
+// rtb_multi: the frame of ONE sample job rendered by every GPU of the box behind one call — what the reference's single
+// call site (Raytracer.cs:671-736) needs when the host has N devices.  Every pixel is independent and the Philox stream
+// is keyed by the global pixel index, so device g renders rows [bounds[g], bounds[g + 1]) of the SAME
+// buffers: host arrays in place (pinned) or staged per device (pageable), or device arrays on one GPU that the others
+// reach over NVLink peer access.  No gather, no collective: the tiles land where the consumer reads them.
+struct rtb_multi {
+  std::vector<rtb_ctx*> ctx;
+  std::string last_error;
+  std::mutex mu;
+  // tile balancer: per-row cost model (instrumented probe batch) corrected by measured kernel times
+  std::vector<double> row_cost;
+  uint64_t model_key = 0;
+  uint64_t scene_generation = 1;
+  std::vector<int> bounds;              // n + 1 row bounds of the last batch
+  std::vector<float> kernel_ms;         // per device, last batch
+  bool times_pending = false;           // device-buffer batches: kernel times are read when their events have completed
+  std::vector<char> peer_enabled;       // [from * n + to]
+  int64_t opt_balance = 1;
+  std::vector<cudaEvent_t> ev_join;     // per device: end of its part of a device-buffer batch
+  cudaEvent_t ev_fork = nullptr;        // on the owner's stream: inputs ready
+};
+
+namespace {
+
+int mfail(rtb_multi* m, int code, const char* fmt, ...) {
+  char msg[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof msg, fmt, ap);
+  va_end(ap);
+  if (m) m->last_error = msg;
+  g_thread_error = msg;
+  return code;
+}
+
+int mforward(rtb_multi* m, int i, int rc) {     // a per-device failure becomes the multi handle's error
+  if (rc != RTB_OK) m->last_error = "device " + std::to_string(m->ctx[i]->device) + ": " + m->ctx[i]->last_error;
+  return rc;
+}
+
+// The cost model of the rows [lo, hi) for this (world, size, view): each device probes an equal share of the rows with
+// the instrumented kernel at a few samples per pixel and reduces its diagnostics to per-row costs.
+int multi_probe(rtb_multi* m, const rtb_batch_params& params, int width, int height, int lo, int hi) {
+  const int n = (int)m->ctx.size();
+  m->row_cost.assign((size_t)height, 0.0);
+  std::vector<int> eq((size_t)n + 1);
+  balance_rows(nullptr, lo, hi, n, eq.data());
+  std::vector<std::vector<float>> part((size_t)n);
+  std::vector<float*> d_cost((size_t)n, nullptr);
+  int rc = RTB_OK;
+  for (int g = 0; g < n && rc == RTB_OK; g++) {
+    rtb_ctx* c = m->ctx[g];
+    if (eq[g + 1] <= eq[g]) continue;
+    DeviceGuard dg(c->device);
+    if ((rc = ensure_buffers(c, (size_t)width * height)) != RTB_OK) break;
+    rtb_batch_params p = params;
+    p.seed = 12345u;
+    const uint32_t k = std::max(1u, std::min(8u, std::max(params.sample_count_range[0], params.sample_count_range[1])));
+    p.sample_count_range[0] = p.sample_count_range[1] = k;
+    p.row_begin = eq[g];
+    p.row_end = eq[g + 1];
+    DeviceBuffers& d = c->buf;
+    const size_t off = (size_t)eq[g] * width, cnt = (size_t)(eq[g + 1] - eq[g]) * width;
+    cudaMemsetAsync(d.in_color + 4 * off, 0, cnt * 16, c->stream);
+    cudaMemsetAsync(d.in_weight + off, 0, cnt * 4, c->stream);
+    cudaMemsetAsync(d.in_normal + 3 * off, 0, cnt * 12, c->stream);
+    cudaMemsetAsync(d.in_albedo + 3 * off, 0, cnt * 12, c->stream);
+    rtb_batch_buffers dev{};
+    dev.in_color = d.in_color; dev.in_sample_count_weight = d.in_weight; dev.in_normal = d.in_normal; dev.in_albedo = d.in_albedo;
+    dev.out_color = d.out_color; dev.out_sample_count_weight = d.out_weight; dev.out_normal = d.out_normal; dev.out_albedo = d.out_albedo;
+    dev.out_diagnostics = d.diagnostics;
+    const int64_t was = c->opt_counters;
+    c->opt_counters = 1;
+    rc = launch_batch(c, p, dev, width, height, active_rows(p, height, 0, 0), c->stream);
+    c->opt_counters = was;
+    if (rc != RTB_OK) { mforward(m, g, rc); break; }
+    if (cudaMalloc(&d_cost[g], (size_t)height * sizeof(float)) != cudaSuccess) { rc = mfail(m, RTB_ERR_OUT_OF_MEMORY, "out of device memory"); break; }
+    row_cost_kernel<<<(unsigned)(eq[g + 1] - eq[g]), 256, 0, c->stream>>>(d.diagnostics, width, eq[g], d_cost[g]);
+    part[g].resize((size_t)height);
+    cudaMemcpyAsync(part[g].data() + eq[g], d_cost[g] + eq[g], (size_t)(eq[g + 1] - eq[g]) * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  }
+  for (int g = 0; g < n; g++) {
+    rtb_ctx* c = m->ctx[g];
+    DeviceGuard dg(c->device);
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (d_cost[g]) cudaFree(d_cost[g]);
+    if (e != cudaSuccess && rc == RTB_OK) rc = mfail(m, RTB_ERR_CUDA + (int)e, "probe batch: %s", cudaGetErrorString(e));
+    if (rc == RTB_OK && !part[g].empty())
+      for (int r = eq[g]; r < eq[g + 1]; r++) m->row_cost[(size_t)r] = (double)part[g][(size_t)r];
+  }
+  return rc;
+}
+
+// Row bounds of this batch: probe when the model does not describe this (world, size, view, slice), else reuse the model
+// the last batches' kernel times corrected.
+int multi_tiles(rtb_multi* m, const rtb_batch_params& params, int width, int height, int* lo_out, int* hi_out) {
+  const int n = (int)m->ctx.size();
+  int lo = 0, hi = height;
+  if (params.row_end > params.row_begin) { lo = std::max(lo, params.row_begin); hi = std::min(hi, params.row_end); }
+  *lo_out = lo; *hi_out = hi;
+  m->bounds.assign((size_t)n + 1, lo);
+  if (!m->opt_balance || n == 1) {
+    balance_rows(nullptr, lo, hi, n, m->bounds.data());
+    return RTB_OK;
+  }
+  uint64_t key = 1469598103934665603ull;
+  key = fnv1a(key, &m->scene_generation, sizeof m->scene_generation);
+  key = fnv1a(key, params.size, sizeof params.size);
+  key = fnv1a(key, &params.view, sizeof params.view);
+  key = fnv1a(key, &params.trace_depth, sizeof params.trace_depth);
+  const int range[2] = {lo, hi};
+  key = fnv1a(key, range, sizeof range);
+  if (key != m->model_key || m->row_cost.size() != (size_t)height) {
+    const int rc = multi_probe(m, params, width, height, lo, hi);
+    if (rc != RTB_OK) return rc;
+    m->model_key = key;
+  }
+  // rows the interlace test skips cost nothing
+  std::vector<double> cost(m->row_cost);
+  if (params.slice_divider > 1)
+    for (int r = 0; r < height; r++)
+      if (r % params.slice_divider != params.slice_offset) cost[(size_t)r] = 0.0;
+  balance_rows(cost.data(), lo, hi, n, m->bounds.data());
+  return RTB_OK;
+}
+
+// measured kernel time of each tile -> the model: scale the tile's rows so that they sum to the time it took
+void multi_feedback(rtb_multi* m) {
+  const int n = (int)m->ctx.size();
+  if (!m->opt_balance || n == 1 || m->row_cost.empty()) return;
+  for (int g = 0; g < n; g++) {
+    double c = 0.0;
+    for (int r = m->bounds[g]; r < m->bounds[g + 1]; r++) c += m->row_cost[(size_t)r];
+    if (c > 0.0 && m->kernel_ms[g] > 0.0f)
+      for (int r = m->bounds[g]; r < m->bounds[g + 1]; r++) m->row_cost[(size_t)r] *= (double)m->kernel_ms[g] / c;
+  }
+}
+
+void multi_collect_pending_times(rtb_multi* m) {
+  if (!m->times_pending) return;
+  const int n = (int)m->ctx.size();
+  for (int g = 0; g < n; g++)
+    if (m->bounds[g + 1] > m->bounds[g] && cudaEventQuery(m->ctx[g]->ev_stop) != cudaSuccess) { cudaGetLastError(); return; }
+  for (int g = 0; g < n; g++) {
+    m->kernel_ms[g] = 0.0f;
+    if (m->bounds[g + 1] > m->bounds[g]) cudaEventElapsedTime(&m->kernel_ms[g], m->ctx[g]->ev_start, m->ctx[g]->ev_stop);
+  }
+  m->times_pending = false;
+  multi_feedback(m);
+}
+
+template <typename F>
+int multi_each(rtb_multi* m, F f) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  std::lock_guard<std::mutex> lock(m->mu);
+  for (size_t i = 0; i < m->ctx.size(); i++) {
+    const int rc = f(m->ctx[i]);
+    if (rc != RTB_OK) return mforward(m, (int)i, rc);
+  }
+  m->scene_generation++;
+  return RTB_OK;
+}
 
 }  // namespace
 
@@ -1047,90 +1370,15 @@ int rtb_sample_batch_device(rtb_ctx* ctx, const rtb_batch_params* params, const 
 
 int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_batch_buffers* host, const volatile uint8_t* cancel) {
   if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  int width, height;
-  int rc = validate_params(ctx, params, &width, &height);
-  if (rc != RTB_OK) return rc;
-  if (!ctx->has_scene) return fail(ctx, RTB_ERR_NO_SCENE, "rtb_upload_scene has not been called");
-  if (!host || !host->in_color || !host->in_sample_count_weight || !host->in_normal || !host->in_albedo || !host->out_color ||
-      !host->out_sample_count_weight || !host->out_normal || !host->out_albedo)
-    return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "a batch buffer pointer is NULL");
   if (cancel && *cancel) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
   std::lock_guard<std::mutex> lock(ctx->mu);
-  DeviceGuard g(ctx->device);
-  const size_t pixels = (size_t)width * height;
-  cudaStream_t s = ctx->stream;
-  const ActiveRows all = active_rows(*params, height, 0, 0);
-  if (all.n_rows <= 0) return RTB_OK;
-
-  // Pinned host arrays (rtb_register_host_buffer, or any cudaHostAlloc'd memory) are read and written IN PLACE by the
-  // kernel over PCIe: each accumulator crosses the bus once, inside the kernel, overlapped with tracing, instead of in
-  // eight staged copies around it.  Pageable arrays take the staged path.
-  rtb_batch_buffers dev{};
-  bool in_place = ctx->opt_host_access != 0;
-  if (in_place) {
-    const void* hp[9] = {host->in_color, host->in_sample_count_weight, host->in_normal, host->in_albedo, host->out_color,
-                         host->out_sample_count_weight, host->out_normal, host->out_albedo, host->out_diagnostics};
-    void* dp[9] = {};
-    for (int i = 0; i < 9 && in_place; i++) {
-      if (!hp[i]) continue;             // diagnostics may be NULL
-      cudaPointerAttributes at{};
-      if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-        cudaGetLastError();
-        in_place = false;
-      } else {
-        dp[i] = at.devicePointer;
-      }
-    }
-    if (in_place) {
-      dev.in_color = (const float*)dp[0]; dev.in_sample_count_weight = (const float*)dp[1];
-      dev.in_normal = (const float*)dp[2]; dev.in_albedo = (const float*)dp[3];
-      dev.out_color = (float*)dp[4]; dev.out_sample_count_weight = (float*)dp[5];
-      dev.out_normal = (float*)dp[6]; dev.out_albedo = (float*)dp[7];
-      dev.out_diagnostics = (rtb_diagnostics*)dp[8];
-    }
-  }
-  ctx->last_in_place = in_place;
-  if (!in_place) {
-    if ((rc = ensure_buffers(ctx, pixels)) != RTB_OK) return rc;
-    DeviceBuffers& d = ctx->buf;
-    RTB_CUDA(ctx, copy_rows(d.in_color, host->in_color, 16, width, all, cudaMemcpyHostToDevice, s));
-    RTB_CUDA(ctx, copy_rows(d.in_weight, host->in_sample_count_weight, 4, width, all, cudaMemcpyHostToDevice, s));
-    RTB_CUDA(ctx, copy_rows(d.in_normal, host->in_normal, 12, width, all, cudaMemcpyHostToDevice, s));
-    RTB_CUDA(ctx, copy_rows(d.in_albedo, host->in_albedo, 12, width, all, cudaMemcpyHostToDevice, s));
-    dev.in_color = d.in_color; dev.in_sample_count_weight = d.in_weight; dev.in_normal = d.in_normal; dev.in_albedo = d.in_albedo;
-    dev.out_color = d.out_color; dev.out_sample_count_weight = d.out_weight; dev.out_normal = d.out_normal; dev.out_albedo = d.out_albedo;
-    dev.out_diagnostics = host->out_diagnostics ? d.diagnostics : nullptr;
-  }
-
-  // CancellationToken (SampleBatchJob.cs:61; the host flips it through a raw pointer, Raytracer.cs:189-192, then
-  // Complete()s, :512-515): ONE launch; the kernel polls the context's mapped flag, wait_for_stream relays the token into it.
-  *ctx->h_cancel = 0u;
-  RTB_CUDA(ctx, cudaEventRecord(ctx->ev_start, s));
-  if ((rc = launch_batch(ctx, *params, dev, width, height, all, s)) != RTB_OK) return rc;
-  RTB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, s));
-
-  if (!in_place) {
-    DeviceBuffers& d = ctx->buf;
-    RTB_CUDA(ctx, copy_rows(host->out_color, d.out_color, 16, width, all, cudaMemcpyDeviceToHost, s));
-    RTB_CUDA(ctx, copy_rows(host->out_sample_count_weight, d.out_weight, 4, width, all, cudaMemcpyDeviceToHost, s));
-    RTB_CUDA(ctx, copy_rows(host->out_normal, d.out_normal, 12, width, all, cudaMemcpyDeviceToHost, s));
-    RTB_CUDA(ctx, copy_rows(host->out_albedo, d.out_albedo, 12, width, all, cudaMemcpyDeviceToHost, s));
-    if (host->out_diagnostics)
-      RTB_CUDA(ctx, copy_rows(host->out_diagnostics, d.diagnostics, sizeof(rtb_diagnostics), width, all, cudaMemcpyDeviceToHost, s));
-  }
-  if (ctx->opt_counters)
-    RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
-  uint32_t status = 0;
-  if (ctx->scene.has_volumes) RTB_CUDA(ctx, cudaMemcpyAsync(&status, ctx->d_status, sizeof status, cudaMemcpyDeviceToHost, s));
-  RTB_CUDA(ctx, wait_for_stream(ctx, s, cancel));
-  RTB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
-  if (*ctx->h_cancel || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
-  if (status & kStatusHitListOverflow) {
-    cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), s);
-    return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met more than %d entities in a world with participating media (the reference's hit list grows, "
-                "HybridCollections.cs:65-71; this kernel's does not): outputs are not the reference's", kMaxRayHits);
-  }
-  return RTB_OK;
+  HostBatch st;
+  int rc = host_batch_begin(ctx, params, host, &st);
+  if (rc != RTB_OK || st.empty) return rc;
+  if ((rc = host_batch_drain(ctx, &st)) != RTB_OK) return rc;
+  rtb_ctx* one[1] = {ctx};
+  RTB_CUDA(ctx, wait_for_streams(one, 1, cancel));
+  return host_batch_end(ctx, &st, cancel);
 }
 
 int rtb_register_host_buffer(rtb_ctx* ctx, void* ptr, size_t bytes) {
@@ -1290,6 +1538,266 @@ int rtb_last_batch_in_place(rtb_ctx* ctx, int* out_in_place) {
 int rtb_last_kernel_ms(rtb_ctx* ctx, float* out_ms) {
   if (!ctx || !out_ms) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_last_kernel_ms: bad argument");
   *out_ms = ctx->last_ms;
+  return RTB_OK;
+}
+
+
+// ---- one host, N GPUs (include/rtb.h "multi-device") -------------------------------------------
+
+int rtb_balance_rows(const double* row_cost, int row_begin, int row_end, int device_count, int* out_bounds) {
+  if (!out_bounds || device_count < 1 || row_begin < 0 || row_end < row_begin)
+    return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "rtb_balance_rows: bad argument");
+  balance_rows(row_cost, row_begin, row_end, device_count, out_bounds);
+  return RTB_OK;
+}
+
+int rtb_multi_create(const int* devices, int device_count, rtb_multi** out) {
+  if (!out) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (!devices || device_count < 1 || device_count > RTB_MULTI_MAX_DEVICES)
+    return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "rtb_multi_create: 1..%d devices", RTB_MULTI_MAX_DEVICES);
+  rtb_multi* m = new (std::nothrow) rtb_multi();
+  if (!m) return mfail(nullptr, RTB_ERR_OUT_OF_MEMORY, "out of host memory");
+  for (int i = 0; i < device_count; i++) {
+    rtb_ctx* c = nullptr;
+    const int rc = rtb_create(devices[i], &c);
+    if (rc != RTB_OK) {
+      const std::string why = g_thread_error;
+      rtb_multi_destroy(m);
+      return mfail(nullptr, rc, "%s", why.c_str());
+    }
+    m->ctx.push_back(c);
+  }
+  m->kernel_ms.assign((size_t)device_count, 0.0f);
+  m->bounds.assign((size_t)device_count + 1, 0);
+  m->peer_enabled.assign((size_t)device_count * device_count, 0);
+  m->ev_join.assign((size_t)device_count, nullptr);
+  for (int i = 0; i < device_count; i++) {
+    DeviceGuard g(devices[i]);
+    cudaEventCreateWithFlags(&m->ev_join[(size_t)i], cudaEventDisableTiming);
+  }
+  *out = m;
+  return RTB_OK;
+}
+
+int rtb_multi_destroy(rtb_multi* m) {
+  if (!m) return RTB_OK;
+  for (size_t i = 0; i < m->ctx.size(); i++) {
+    DeviceGuard g(m->ctx[i]->device);
+    cudaStreamSynchronize(m->ctx[i]->stream);
+    if (i < m->ev_join.size() && m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (rtb_ctx* c : m->ctx) rtb_destroy(c);
+  delete m;
+  return RTB_OK;
+}
+
+int rtb_multi_device_count(const rtb_multi* m) { return m ? (int)m->ctx.size() : 0; }
+rtb_ctx* rtb_multi_context(rtb_multi* m, int index) { return m && index >= 0 && (size_t)index < m->ctx.size() ? m->ctx[(size_t)index] : nullptr; }
+const char* rtb_multi_last_error(const rtb_multi* m) { return m ? m->last_error.c_str() : g_thread_error.c_str(); }
+
+int rtb_multi_set_option(rtb_multi* m, int option, int64_t value) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  std::lock_guard<std::mutex> lock(m->mu);
+  if (option == RTB_OPT_BALANCE_TILES) {
+    m->opt_balance = value ? 1 : 0;
+    m->model_key = 0;
+    return RTB_OK;
+  }
+  for (size_t i = 0; i < m->ctx.size(); i++) {
+    const int rc = rtb_set_option(m->ctx[i], option, value);
+    if (rc != RTB_OK) return mforward(m, (int)i, rc);
+  }
+  return RTB_OK;
+}
+
+int rtb_multi_upload_scene(rtb_multi* m, const rtb_sphere* spheres, size_t sphere_count, const rtb_material* materials,
+                           size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
+  return multi_each(m, [&](rtb_ctx* c) { return rtb_upload_scene(c, spheres, sphere_count, materials, material_count, nodes, node_count); });
+}
+
+int rtb_multi_upload_placed_world(rtb_multi* m, const rtb_entity* entities, size_t entity_count, const rtb_sphere* spheres,
+                                  size_t sphere_count, const rtb_triangle* triangles, size_t triangle_count,
+                                  const rtb_placed_entity* placed, size_t placed_count, const rtb_material* materials,
+                                  size_t material_count, const rtb_bvh_node* nodes, size_t node_count) {
+  return multi_each(m, [&](rtb_ctx* c) {
+    return rtb_upload_placed_world(c, entities, entity_count, spheres, sphere_count, triangles, triangle_count, placed, placed_count,
+                                   materials, material_count, nodes, node_count);
+  });
+}
+
+int rtb_multi_upload_textures(rtb_multi* m, const rtb_image* images, size_t image_count, const rtb_material_textures* mt,
+                              size_t material_count, const float* triangle_uvs, size_t triangle_count) {
+  return multi_each(m, [&](rtb_ctx* c) { return rtb_upload_textures(c, images, image_count, mt, material_count, triangle_uvs, triangle_count); });
+}
+
+int rtb_multi_upload_sky_cubemap(rtb_multi* m, const uint16_t* half_rgba, int face_width, int face_height) {
+  return multi_each(m, [&](rtb_ctx* c) { return rtb_upload_sky_cubemap(c, half_rgba, face_width, face_height); });
+}
+
+int rtb_multi_register_host_buffer(rtb_multi* m, void* ptr, size_t bytes) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  std::lock_guard<std::mutex> lock(m->mu);
+  // one registration (portable + mapped) serves every device of the process
+  return mforward(m, 0, rtb_register_host_buffer(m->ctx[0], ptr, bytes));
+}
+
+int rtb_multi_unregister_host_buffer(rtb_multi* m, void* ptr) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  std::lock_guard<std::mutex> lock(m->mu);
+  return mforward(m, 0, rtb_unregister_host_buffer(m->ctx[0], ptr));
+}
+
+int rtb_multi_sample_batch(rtb_multi* m, const rtb_batch_params* params, const rtb_batch_buffers* host, const volatile uint8_t* cancel) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  if (cancel && *cancel) return mfail(m, RTB_ERR_CANCELLED, "cancelled");
+  std::lock_guard<std::mutex> lock(m->mu);
+  const int n = (int)m->ctx.size();
+  int width, height, lo, hi;
+  int rc = validate_params(m->ctx[0], params, &width, &height);
+  if (rc != RTB_OK) return mforward(m, 0, rc);
+  multi_collect_pending_times(m);
+  if ((rc = multi_tiles(m, *params, width, height, &lo, &hi)) != RTB_OK) return rc;
+
+  std::vector<std::unique_lock<std::mutex>> locks;
+  for (rtb_ctx* c : m->ctx) locks.emplace_back(c->mu);
+  std::vector<HostBatch> st((size_t)n);
+  std::vector<rtb_ctx*> busy;
+  int first_rc = RTB_OK;
+  for (int g = 0; g < n; g++) {                      // every device starts before any is waited for
+    m->kernel_ms[g] = 0.0f;
+    if (m->bounds[g + 1] <= m->bounds[g]) continue;
+    rtb_batch_params p = *params;
+    p.row_begin = m->bounds[g];
+    p.row_end = m->bounds[g + 1];
+    rc = host_batch_begin(m->ctx[g], &p, host, &st[g]);
+    if (rc != RTB_OK) { first_rc = mforward(m, g, rc); break; }
+    if (!st[g].empty) busy.push_back(m->ctx[g]);
+  }
+  if (first_rc != RTB_OK)                            // stop what was started
+    for (rtb_ctx* c : busy) *c->h_cancel = 1u;
+  for (int g = 0; g < n && first_rc == RTB_OK; g++)
+    if (!st[g].empty && (rc = host_batch_drain(m->ctx[g], &st[g])) != RTB_OK) first_rc = mforward(m, g, rc);
+  if (!busy.empty()) {
+    const cudaError_t e = wait_for_streams(busy.data(), (int)busy.size(), cancel);
+    if (e != cudaSuccess && first_rc == RTB_OK) first_rc = mfail(m, RTB_ERR_CUDA + (int)e, "waiting for the devices: %s", cudaGetErrorString(e));
+  }
+  if (first_rc != RTB_OK) return first_rc;
+  for (int g = 0; g < n; g++) {
+    if (st[g].empty) continue;
+    rc = host_batch_end(m->ctx[g], &st[g], cancel);
+    m->kernel_ms[g] = m->ctx[g]->last_ms;
+    if (rc != RTB_OK && first_rc == RTB_OK) first_rc = mforward(m, g, rc);
+  }
+  if (first_rc == RTB_OK) multi_feedback(m);
+  return first_rc;
+}
+
+int rtb_multi_sample_batch_device(rtb_multi* m, const rtb_batch_params* params, const rtb_batch_buffers* dev, int owner_index,
+                                  void* owner_stream) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  std::lock_guard<std::mutex> lock(m->mu);
+  const int n = (int)m->ctx.size();
+  if (owner_index < 0 || owner_index >= n) return mfail(m, RTB_ERR_INVALID_ARGUMENT, "owner_index out of range");
+  int width, height, lo, hi;
+  int rc = validate_params(m->ctx[0], params, &width, &height);
+  if (rc != RTB_OK) return mforward(m, 0, rc);
+  rtb_ctx* owner = m->ctx[(size_t)owner_index];
+  // the other devices reach the owner's memory over NVLink peer access
+  for (int g = 0; g < n; g++) {
+    if (g == owner_index || m->ctx[g]->device == owner->device || m->peer_enabled[(size_t)g * n + owner_index]) continue;
+    DeviceGuard dg(m->ctx[g]->device);
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, m->ctx[g]->device, owner->device);
+    if (!can) return mfail(m, RTB_ERR_UNSUPPORTED, "device %d cannot access device %d's memory (no peer path)", m->ctx[g]->device, owner->device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return mfail(m, RTB_ERR_CUDA + (int)e, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    m->peer_enabled[(size_t)g * n + owner_index] = 1;
+  }
+  multi_collect_pending_times(m);
+  if ((rc = multi_tiles(m, *params, width, height, &lo, &hi)) != RTB_OK) return rc;
+  cudaStream_t os = (cudaStream_t)owner_stream;
+  {
+    DeviceGuard dg(owner->device);
+    if (!m->ev_fork) cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
+    cudaEventRecord(m->ev_fork, os);                 // the inputs are ready when the owner's stream gets here
+  }
+  for (int g = 0; g < n; g++) {
+    if (m->bounds[g + 1] <= m->bounds[g]) continue;
+    rtb_ctx* c = m->ctx[g];
+    DeviceGuard dg(c->device);
+    cudaStream_t s = g == owner_index ? os : c->stream;
+    if (g != owner_index) cudaStreamWaitEvent(s, m->ev_fork, 0);
+    rtb_batch_params p = *params;
+    p.row_begin = m->bounds[g];
+    p.row_end = m->bounds[g + 1];
+    cudaEventRecord(c->ev_start, s);
+    rc = rtb_sample_batch_device(c, &p, dev, s);
+    cudaEventRecord(c->ev_stop, s);
+    if (rc != RTB_OK) return mforward(m, g, rc);
+    if (g != owner_index) {
+      cudaEventRecord(m->ev_join[(size_t)g], s);
+      DeviceGuard og(owner->device);
+      cudaStreamWaitEvent(os, m->ev_join[(size_t)g], 0);   // the owner's stream continues when every tile has landed
+    }
+  }
+  m->times_pending = true;
+  return RTB_OK;
+}
+
+int rtb_multi_get_tiles(rtb_multi* m, int* out_bounds, float* out_kernel_ms) {
+  if (!m) return mfail(nullptr, RTB_ERR_INVALID_ARGUMENT, "multi handle is NULL");
+  std::lock_guard<std::mutex> lock(m->mu);
+  multi_collect_pending_times(m);
+  const int n = (int)m->ctx.size();
+  if (out_bounds) for (int g = 0; g <= n; g++) out_bounds[g] = m->bounds[(size_t)g];
+  if (out_kernel_ms) for (int g = 0; g < n; g++) out_kernel_ms[g] = m->kernel_ms[(size_t)g];
+  return RTB_OK;
+}
+
+// ---- device memory a peer process can map (one process per GPU: every rank writes its tile into rank 0's frame) ----
+
+int rtb_device_alloc(rtb_ctx* ctx, size_t bytes, void** out_ptr) {
+  if (!ctx || !out_ptr || !bytes) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_device_alloc: bad argument");
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaMalloc(out_ptr, bytes));
+  RTB_CUDA(ctx, cudaMemset(*out_ptr, 0, bytes));
+  return RTB_OK;
+}
+
+int rtb_device_free(rtb_ctx* ctx, void* ptr) {
+  if (!ctx) return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  if (ptr) RTB_CUDA(ctx, cudaFree(ptr));
+  return RTB_OK;
+}
+
+int rtb_ipc_export(rtb_ctx* ctx, void* device_ptr, rtb_ipc_handle* out) {
+  if (!ctx || !device_ptr || !out) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_ipc_export: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(rtb_ipc_handle), "handle size");
+  DeviceGuard g(ctx->device);
+  cudaIpcMemHandle_t h;
+  RTB_CUDA(ctx, cudaIpcGetMemHandle(&h, device_ptr));
+  memset(out, 0, sizeof *out);
+  memcpy(out->bytes, &h, sizeof h);
+  return RTB_OK;
+}
+
+int rtb_ipc_open(rtb_ctx* ctx, const rtb_ipc_handle* handle, void** out_ptr) {
+  if (!ctx || !handle || !out_ptr) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_ipc_open: bad argument");
+  DeviceGuard g(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle->bytes, sizeof h);
+  RTB_CUDA(ctx, cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RTB_OK;
+}
+
+int rtb_ipc_close(rtb_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_ipc_close: bad argument");
+  DeviceGuard g(ctx->device);
+  RTB_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
   return RTB_OK;
 }
 

@@ -19,7 +19,13 @@ EXPORTS = [
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_finalize_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
+    "rtb_multi_create", "rtb_multi_destroy", "rtb_multi_device_count", "rtb_multi_context", "rtb_multi_last_error", "rtb_multi_set_option",
+    "rtb_multi_upload_scene", "rtb_multi_upload_placed_world", "rtb_multi_upload_textures", "rtb_multi_upload_sky_cubemap",
+    "rtb_multi_register_host_buffer", "rtb_multi_unregister_host_buffer", "rtb_multi_sample_batch", "rtb_multi_sample_batch_device",
+    "rtb_multi_get_tiles", "rtb_balance_rows",
+    "rtb_device_alloc", "rtb_device_free", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close",
 ]
+_NOT_INT = ("rtb_last_error", "rtb_multi_last_error", "rtb_multi_context")
 
 _lib = None
 
@@ -66,8 +72,31 @@ def lib():
         L.rtb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.rtb_last_batch_in_place.argtypes = [vp, C.POINTER(C.c_int)]
         L.rtb_measure_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+        L.rtb_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        L.rtb_multi_destroy.argtypes = [vp]
+        L.rtb_multi_device_count.argtypes = [vp]
+        L.rtb_multi_context.argtypes = [vp, C.c_int]
+        L.rtb_multi_context.restype = vp
+        L.rtb_multi_last_error.argtypes = [vp]
+        L.rtb_multi_last_error.restype = C.c_char_p
+        L.rtb_multi_set_option.argtypes = [vp, C.c_int, C.c_int64]
+        L.rtb_multi_upload_scene.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+        L.rtb_multi_upload_placed_world.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
+        L.rtb_multi_upload_textures.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+        L.rtb_multi_upload_sky_cubemap.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.rtb_multi_register_host_buffer.argtypes = [vp, vp, sz]
+        L.rtb_multi_unregister_host_buffer.argtypes = [vp, vp]
+        L.rtb_multi_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
+        L.rtb_multi_sample_batch_device.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), C.c_int, vp]
+        L.rtb_multi_get_tiles.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.rtb_balance_rows.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.rtb_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+        L.rtb_device_free.argtypes = [vp, vp]
+        L.rtb_ipc_export.argtypes = [vp, vp, vp]
+        L.rtb_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+        L.rtb_ipc_close.argtypes = [vp, vp]
         for name in EXPORTS:
-            if name != "rtb_last_error":
+            if name not in _NOT_INT:
                 getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -342,3 +371,115 @@ class Context:
         ms = C.c_float(0)
         self._check(self._L.rtb_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+    # ---- device memory other rank processes can map (one process per GPU) -----------------------
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._L.rtb_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self._L.rtb_device_free(self._h, ptr))
+
+    def ipc_export(self, ptr):
+        """-> 64 bytes another process of this box hands to `ipc_open`."""
+        h = (C.c_ubyte * 64)()
+        self._check(self._L.rtb_ipc_export(self._h, ptr, h))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self._L.rtb_ipc_open(self._h, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self._L.rtb_ipc_close(self._h, ptr))
+
+
+def balance_rows(row_cost, row_begin, row_end, device_count):
+    """rtb_balance_rows: the plugin's row-tile partition (host-side only, no GPU needed)."""
+    cost = None if row_cost is None else np.ascontiguousarray(row_cost, dtype=np.float64)
+    out = (C.c_int * (device_count + 1))()
+    rc = lib().rtb_balance_rows(None if cost is None else cost.ctypes.data_as(C.POINTER(C.c_double)), row_begin, row_end, device_count, out)
+    if rc != 0:
+        raise RtbError(rc, (lib().rtb_last_error(None) or b"").decode())
+    return list(out)
+
+
+class MultiContext:
+    """One rtb_multi: the frame of one sample job rendered by several GPUs of the box behind one call (no gather)."""
+
+    def __init__(self, devices):
+        self._L = lib()
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self._L.rtb_multi_create(arr, len(devices), C.byref(self._h))
+        if rc != 0:
+            raise RtbError(rc, (self._L.rtb_multi_last_error(None) or b"").decode())
+        self.devices = list(devices)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RtbError(rc, (self._L.rtb_multi_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            self._L.rtb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option, value):
+        self._check(self._L.rtb_multi_set_option(self._h, option, value))
+
+    def upload(self, scene):
+        def arr(a, dt):
+            a = np.ascontiguousarray(a if a is not None else [], dtype=dt)
+            return a, (a.ctypes.data if len(a) else None), len(a)
+        sp, sp_p, sp_n = arr(scene.spheres, abi.SPHERE_DTYPE)
+        ma, ma_p, ma_n = arr(scene.materials, abi.MATERIAL_DTYPE)
+        no, no_p, no_n = arr(scene.nodes, abi.BVH_NODE_DTYPE)
+        if getattr(scene, "entities", None) is not None:
+            en, en_p, en_n = arr(scene.entities, abi.ENTITY_DTYPE)
+            tr, tr_p, tr_n = arr(scene.triangles, abi.TRIANGLE_DTYPE)
+            pl, pl_p, pl_n = arr(getattr(scene, "placed", None), abi.PLACED_DTYPE)
+            self._check(self._L.rtb_multi_upload_placed_world(self._h, en_p, en_n, sp_p, sp_n, tr_p, tr_n, pl_p, pl_n, ma_p, ma_n, no_p, no_n))
+        else:
+            self._check(self._L.rtb_multi_upload_scene(self._h, sp_p, sp_n, ma_p, ma_n, no_p, no_n))
+        if getattr(scene, "material_textures", None) is not None:
+            imgs, keep = image_structs(scene.images)
+            mt = np.ascontiguousarray(scene.material_textures, dtype=abi.MATERIAL_TEXTURES_DTYPE)
+            uv = None if scene.triangle_uvs is None else np.ascontiguousarray(scene.triangle_uvs, dtype=np.float32)
+            self._check(self._L.rtb_multi_upload_textures(self._h, C.addressof(imgs) if len(keep) else None, len(keep),
+                                                          mt.ctypes.data if len(mt) else None, len(mt),
+                                                          uv.ctypes.data if uv is not None and uv.size else None, 0 if uv is None else uv.size // 6))
+
+    def register_host_buffers(self, buffers):
+        for a in buffers.arrays():
+            self._check(self._L.rtb_multi_register_host_buffer(self._h, a.ctypes.data, a.nbytes))
+
+    def unregister_host_buffers(self, buffers):
+        for a in buffers.arrays():
+            self._check(self._L.rtb_multi_unregister_host_buffer(self._h, a.ctypes.data))
+
+    def sample_batch(self, params, buffers, cancel=None):
+        b = buffers.as_struct()
+        self._check(self._L.rtb_multi_sample_batch(self._h, C.byref(params), C.byref(b), cancel.ctypes.data if cancel is not None else None))
+        return buffers
+
+    def sample_batch_device(self, params, device_buffers, owner_index=0, stream=None):
+        self._check(self._L.rtb_multi_sample_batch_device(self._h, C.byref(params), C.byref(device_buffers), owner_index, stream))
+
+    def tiles(self):
+        """-> (row bounds [n + 1], kernel ms per device [n]) of the last batch."""
+        n = len(self.devices)
+        b = (C.c_int * (n + 1))()
+        ms = (C.c_float * n)()
+        self._check(self._L.rtb_multi_get_tiles(self._h, b, ms))
+        return list(b), list(ms)

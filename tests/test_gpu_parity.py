@@ -1129,3 +1129,105 @@ def test_media_hit_list_overflow_is_an_error(rtb, ctx):
         c.sample_batch(p, rtb.plugin.HostBuffers(16, 9))
     finally:
         c.close()
+
+
+def _multi_devices():
+    import torch
+
+    n = torch.cuda.device_count()
+    return [0, 1] if n >= 2 else [0, 0]          # one GPU: two contexts share it, the tiling logic is the same
+
+
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned-in-place"])
+def test_multi_device_host_batch_is_bit_identical(rtb, ctx, pinned):
+    """rtb_multi_sample_batch: ONE call renders the frame with every device of the handle (row tiles balanced inside the plugin,
+    no gather).  Every output equals the single-device render bit for bit (order-independent sums, Philox keyed by the global
+    pixel index), for pageable host arrays (staged per device) and pinned ones (written in place by every device)."""
+    W, H, spp = 96, 54, 16
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    one = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    m = rtb.plugin.MultiContext(_multi_devices())
+    try:
+        m.upload(scene)
+        b = rtb.plugin.HostBuffers(W, H)
+        if pinned:
+            m.register_host_buffers(b)
+        for balance in (1, 0):
+            m.set_option(rtb.abi.OPT_BALANCE_TILES, balance)
+            for _ in range(3):                           # the third batch runs on tiles corrected by measured kernel times
+                for a in b.arrays():
+                    a[...] = 0
+                m.sample_batch(p, b)
+                bounds, ms = m.tiles()
+                assert bounds[0] == 0 and bounds[-1] == H and all(bounds[g + 1] > bounds[g] for g in range(2))
+                assert all(t > 0 for t in ms)
+                for x, y in ((one.out_color, b.out_color), (one.out_normal, b.out_normal), (one.out_albedo, b.out_albedo),
+                             (one.out_weight, b.out_weight), (one.diagnostics["ray_count"], b.diagnostics["ray_count"])):
+                    assert x.tobytes() == y.tobytes()
+        # interlaced rows and a row range compose with the tiling
+        p2 = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1, slice_offset=1, slice_divider=3)
+        p2.row_begin, p2.row_end = 5, 40
+        ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_MEGA)
+        ref = rtb.plugin.HostBuffers(W, H)
+        ctx.sample_batch(p2, ref)
+        for a in b.arrays():
+            a[...] = 0
+        m.sample_batch(p2, b)
+        assert ref.out_color.tobytes() == b.out_color.tobytes()
+        # the token reaches every device
+        cancel = np.ones(1, np.uint8)
+        with pytest.raises(rtb.plugin.RtbError) as e:
+            m.sample_batch(p, b, cancel=cancel)
+        assert e.value.code == rtb.abi.RTB_ERR_CANCELLED
+        if pinned:
+            m.unregister_host_buffers(b)
+    finally:
+        m.close()
+
+
+def test_multi_device_batch_on_device_buffers(rtb, ctx):
+    """rtb_multi_sample_batch_device: the accumulation buffers live on ONE device; the others write their row tiles into them
+    over peer access (NVLink), ordered on the owner's stream — no gather, no collective.  Bit-identical to one device."""
+    import torch
+
+    W, H, spp = 96, 54, 16
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    one = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    m = rtb.plugin.MultiContext(_multi_devices())
+    try:
+        m.upload(scene)
+        dev = torch.device("cuda:0")
+        n = W * H
+        z = lambda c: torch.zeros(n, c, device=dev, dtype=torch.float32)   # noqa: E731
+        inp = [z(4), torch.zeros(n, device=dev), z(3), z(3)]
+        out = [z(4), torch.zeros(n, device=dev), z(3), z(3)]
+        diag = z(4)
+        bufs = rtb.plugin.device_buffers_struct(*inp, *out, diag)
+        stream = torch.cuda.current_stream(dev)
+        for _ in range(3):
+            for t in out:
+                t.zero_()
+            m.sample_batch_device(p, bufs, owner_index=0, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            assert out[0].cpu().numpy().tobytes() == one.out_color.tobytes()
+            assert out[2].cpu().numpy().tobytes() == one.out_normal.tobytes()
+            assert out[3].cpu().numpy().tobytes() == one.out_albedo.tobytes()
+            assert out[1].cpu().numpy().tobytes() == one.out_weight.tobytes()
+            assert np.array_equal(diag.cpu().numpy()[:, 0], one.diagnostics["ray_count"])
+        bounds, ms = m.tiles()
+        assert bounds[0] == 0 and bounds[-1] == H and all(t > 0 for t in ms)
+    finally:
+        m.close()
+
+
+def test_peer_process_frame_mapping(rtb, ctx):
+    """rtb_device_alloc / rtb_ipc_export: memory another rank process maps to write its tile into (the export side; the
+    open side needs a second process and is exercised by bench.py --gpus N)."""
+    ptr = ctx.device_alloc(1 << 20)
+    try:
+        h = ctx.ipc_export(ptr)
+        assert len(h) == 64 and any(h)
+    finally:
+        ctx.device_free(ptr)

@@ -115,3 +115,29 @@ def test_add_mesh_bakes_the_transform_and_rotates_normals(rtb):
     assert flat[0].tobytes() == want.tobytes()
     with pytest.raises(ValueError):
         host.add_mesh(v, [0, 1, 9], 0)                                        # index past the vertex array
+
+
+def test_plugin_row_balancer_matches_the_python_partition(rtb):
+    """rtb_balance_rows (the C++ balancer behind rtb_multi_sample_batch) against sharding.balanced_row_tiles, the partition the
+    one-process-per-GPU driver uses: same bounds on random cost profiles, every tile non-empty, ranges respected."""
+    from importlib import import_module
+
+    sh = import_module("raytracing-in-one-weekend_b200.sharding")
+    rng = np.random.default_rng(7)
+    for height in (8, 27, 1080, 2160):
+        for world in (1, 2, 3, 4, 8):
+            if world > height:
+                continue
+            cost = rng.random(height) ** 3 + 1e-3
+            cost[: height // 3] *= 0.05                     # cheap sky rows at one end, as in the final scene
+            want = sh.balanced_row_tiles(cost, world)
+            got = rtb.plugin.balance_rows(cost, 0, height, world)
+            assert got == [b for b, _ in want] + [height]
+            assert all(got[g + 1] > got[g] for g in range(world))
+            sums = [cost[got[g]:got[g + 1]].sum() for g in range(world)]
+            assert max(sums) <= cost.sum() / world + cost.max() + 1e-9
+    # a sub-range, equal rows without a model, more devices than rows
+    assert rtb.plugin.balance_rows(None, 10, 20, 2) == [10, 15, 20]
+    assert rtb.plugin.balance_rows(np.ones(100), 40, 60, 4) == [40, 45, 50, 55, 60]
+    b = rtb.plugin.balance_rows(None, 0, 2, 4)
+    assert b[0] == 0 and b[-1] == 2 and all(b[g + 1] >= b[g] for g in range(4)) and sum(b[g + 1] - b[g] for g in range(4)) == 2
