@@ -319,9 +319,9 @@ RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
  * through device copies of the four inputs and the four outputs (+diagnostics).
  * `cancel` (may be NULL) is the CancellationToken (SampleBatchJob.cs:23,61; the host flips it through a raw
  * pointer, Raytracer.cs:189-192, then Complete()s, :512-515).  The batch is ONE kernel launch with or without a
- * token: the kernel polls a flag in mapped pinned memory owned by the context (a volatile load whenever a warp
- * claims a work tile; a CTA that saw it stops issuing samples), and the blocking call copies *cancel into that
- * flag while it waits.  Once set, the call returns RTB_ERR_CANCELLED within a fraction of a millisecond
+ * token: the kernel polls a word in device memory owned by the context (a volatile load whenever a warp claims a
+ * work tile; a CTA that saw it stops issuing samples), and the blocking call watches *cancel while it waits and
+ * writes that word from a second stream when the token is set.  Once set, the call returns RTB_ERR_CANCELLED within a fraction of a millisecond
  * (worlds with participating media: within one pixel's samples); outputs are then unspecified, as in the
  * reference (the host discards them).
  *
@@ -478,6 +478,14 @@ typedef enum rtb_option {
                                  * (NoiseColor.White: one sequential Unity.Mathematics.Random xorshift32 stream per pixel per batch,
                                  * SampleBatchJob.cs:91) — validation only, needs RTB_OPT_KERNEL = 1 (a sequential stream cannot be
                                  * split over lanes) */
+  RTB_OPT_MATH = 9,             /* 0 (default): the parity build — strict IEEE evaluation with FMAs only where written, every path
+                                 * decision checkable bit for bit against the CPU restatement.  1: the fast build of the sphere
+                                 * megakernel, compiled the way the reference's own [BurstCompile(FloatPrecision.Medium,
+                                 * FloatMode.Fast)] (SampleBatchJob.cs:16) allows: FMA contraction, hardware sqrt / divide / sincos
+                                 * approximations, one-FMA slab planes.  Same estimator and random numbers; images differ from the
+                                 * parity build by a few flipped decisions per million paths (tools/fast_math_report.py).  Worlds
+                                 * with triangles, placed entities, textures or media, and instrumented batches, keep the parity
+                                 * kernels whatever this says. */
   RTB_OPT_BALANCE_TILES = 8,    /* rtb_multi only. 1 (default): cost-model + kernel-time balanced row tiles; 0: equal row counts */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
                                  * instead of only when the hit geometry does not already prove them (same results, slower) */

@@ -65,22 +65,37 @@ UM_HD float fma(float a, float b, float c) {
   return __builtin_fmaf(a, b, c);
 #endif
 }
+/* RTB_FAST_MATH (device only; csrc/fast_kernels.cu): the opt-in build in the spirit of the reference's own
+ * [BurstCompile(FloatPrecision.Medium, FloatMode.Fast)] (SampleBatchJob.cs:16) — hardware approximations for sqrt,
+ * division, sincos and log (MUFU.RSQ/RCP/SIN/COS/LG2, ~2 ulp), FMA contraction everywhere (-fmad=true).  Its images
+ * equal the parity build's statistically, not bitwise; tools/fast_math_report.py measures by how much. */
 UM_HD float sqrt(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(RTB_FAST_MATH)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#elif defined(__CUDA_ARCH__)
   return __fsqrt_rn(x);
 #else
   return __builtin_sqrtf(x);
 #endif
 }
 UM_HD float div(float a, float b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(RTB_FAST_MATH)
+  return __fdividef(a, b);
+#elif defined(__CUDA_ARCH__)
   return __fdiv_rn(a, b);
 #else
   return a / b;
 #endif
 }
+#if defined(__CUDA_ARCH__) && defined(RTB_FAST_MATH)
+UM_HD float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+UM_HD float rsqrt(float x) { return rsqrtf(x); }
+#else
 UM_HD float rcp(float x) { return div(1.0f, x); }          /* math.rcp = 1/x */
 UM_HD float rsqrt(float x) { return div(1.0f, um::sqrt(x)); } /* math.rsqrt = 1/sqrt(x) */
+#endif
 UM_HD bool isnan(float x) { return x != x; }
 UM_HD bool isinf(float x) { return (asuint(x) & 0x7fffffffu) == 0x7f800000u; }
 UM_HD float abs(float x) { return asfloat(asuint(x) & 0x7fffffffu); }
@@ -161,6 +176,10 @@ UM_HD rigid inverse(rigid a) {
  * constant, then the Cephes single-precision minimax polynomials on [-pi/4, pi/4].
  * Max error vs correctly-rounded: < 2 ULP on [0, 2pi] (tests/test_umath.py pins this). */
 UM_HD void sincos(float theta, float* s, float* c) {
+#if defined(__CUDA_ARCH__) && defined(RTB_FAST_MATH)
+  __sincosf(theta, s, c);
+  return;
+#endif
   const float TWO_OVER_PI = 0.636619772f;
   const float PIO2_HI = 1.57079637050628662109375f; /* float(pi/2) = 0x3FC90FDB */
   const float PIO2_LO = -4.371139000186241e-08f;    /* pi/2 - PIO2_HI */
@@ -189,6 +208,9 @@ UM_HD float tan(float x) { float s, c; um::sincos(x, &s, &c); return um::div(s, 
 /* log(x) for normal positive x (Cephes logf layout).  Used by RoughnessToAlpha
  * (Microfacet.cs:71-80) on [1e-3, 1].  < 2 ULP. */
 UM_HD float log(float x) {
+#if defined(__CUDA_ARCH__) && defined(RTB_FAST_MATH)
+  return __logf(x);
+#endif
   uint32_t u = asuint(x);
   int e = (int)(u >> 23) - 126;                     /* x = m * 2^e, m in [0.5, 1) */
   float m = asfloat((u & 0x007fffffu) | 0x3f000000u);

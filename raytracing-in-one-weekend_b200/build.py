@@ -19,21 +19,24 @@ INCLUDE = os.path.join(ROOT, "include")
 
 HOST_SOURCES = [os.path.join(CSRC, "host", "rtb_host.cpp")]
 CUDA_SOURCES = [os.path.join(CSRC, "plugin.cu")]
+FAST_SOURCES = [os.path.join(CSRC, "fast_kernels.cu")]       # the opt-in fast-arithmetic build of the sphere megakernel
 CUDA_DEPS = [
     os.path.join(CSRC, f)
     for f in ("kernel_common.cuh", "sample_kernels.cuh", "volume_kernel.cuh", "aux_kernels.cuh")
 ] + [os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
 HOST_DEPS = [os.path.join(INCLUDE, "rtb_host.h"), os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
 
-# -fmad=false: the parity contract of include/rtb/umath.h (FMAs only where written).
-NVCC_FLAGS = [
+NVCC_COMMON = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",
-    "-fmad=false",
-    "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
     "-I", INCLUDE, "-I", CSRC,
 ]
+# -fmad=false: the parity contract of include/rtb/umath.h (FMAs only where written).  fast_kernels.cu is the one
+# translation unit compiled with contraction on (RTB_OPT_MATH = 1).
+NVCC_PARITY = ["-fmad=false"]
+NVCC_FAST = ["-fmad=true"]
+NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static"]
 GXX_FLAGS = [
     "-std=c++17", "-O2", "-ffp-contract=off", "-march=x86-64-v3",
     "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra",
@@ -76,12 +79,24 @@ def build_host(force=False, verbose=False):
     return out
 
 
+def _compile_and_link(out, objdir, extra_flags, verbose):
+    """plugin.cu (parity flags) and fast_kernels.cu (fast flags) -> objects, in parallel, then one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [(CUDA_SOURCES[0], NVCC_PARITY, os.path.join(objdir, "plugin.o")),
+            (FAST_SOURCES[0], NVCC_FAST, os.path.join(objdir, "fast_kernels.o"))]
+    with ThreadPoolExecutor(2) as ex:
+        list(ex.map(lambda j: _run([nvcc] + NVCC_COMMON + j[1] + list(extra_flags) + ["-c", j[0], "-o", j[2]], verbose), jobs))
+    _run([nvcc] + NVCC_LINK + ["-o", out] + [j[2] for j in jobs], verbose)
+
+
 def build_plugin(force=False, verbose=False, extra_flags=()):
     os.makedirs(LIB, exist_ok=True)
     out = plugin_lib_path()
-    if force or _stale(out, CUDA_SOURCES + CUDA_DEPS):
-        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        _run([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + CUDA_SOURCES, verbose)
+    if force or _stale(out, CUDA_SOURCES + FAST_SOURCES + CUDA_DEPS):
+        _compile_and_link(out, os.path.join(PKG, "build"), extra_flags, verbose)
     return out
 
 
@@ -91,8 +106,7 @@ def build_variant(tag, defines, verbose=False):
     d = os.path.join(LIB, "variants")
     os.makedirs(d, exist_ok=True)
     out = os.path.join(d, f"librtb_{tag}.so")
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    _run([nvcc] + NVCC_FLAGS + [f"-D{x}" for x in defines] + ["-o", out] + CUDA_SOURCES, verbose)
+    _compile_and_link(out, os.path.join(PKG, "build", "variant_" + tag), [f"-D{x}" for x in defines], verbose)
     return out
 
 

@@ -28,6 +28,10 @@
 
 using namespace rtbk;
 
+// csrc/fast_kernels.cu: the lean sphere megakernel compiled with fast arithmetic (RTB_OPT_MATH = 1)
+extern "C" int rtb_fast_launch_spheres(const void* args, size_t args_bytes, int scene_in_smem, unsigned grid, size_t smem,
+                                       int max_smem_optin, void* stream);
+
 namespace {
 
 thread_local std::string g_thread_error;
@@ -73,17 +77,20 @@ struct rtb_ctx {
   static constexpr uint32_t kTileRing = 256;
   uint32_t* d_tile_ring = nullptr;
   std::atomic<uint32_t> ring_next{0};
-  // CancellationToken relay: a word of mapped pinned host memory the kernels poll (BatchArgs::cancel_flag); the blocking
-  // call copies the caller's token into it while it waits for the kernel.
-  volatile uint32_t* h_cancel = nullptr;
-  uint32_t* d_cancel = nullptr;       // the same word through the device's mapping
+  // CancellationToken relay (BatchArgs::cancel_flag / cancel_epoch): the kernels poll a device word; the blocking call
+  // watches the caller's token while it waits and, when it is set, copies the batch's epoch into that word on cancel_stream.
+  uint32_t* d_cancel = nullptr;       // device word
+  uint32_t* h_epoch = nullptr;        // pinned source of the cancel copy
+  uint32_t cancel_epoch = 0;          // epoch of the batch in flight (never 0: the word starts as 0)
+  bool cancel_sent = false;           // this batch's cancel copy was issued
+  cudaStream_t cancel_stream = nullptr;
   uint32_t* d_status = nullptr;       // sticky kStatus* bits raised by kernels
   cudaEvent_t ev_done = nullptr;
   unsigned long long* d_counters = nullptr;
   cudaStream_t counters_stream = nullptr;   // stream of the last instrumented launch
   rtb_counters counters{};
   int default_kernel = 2;
-  int64_t opt_counters = 0, opt_kernel = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0;
+  int64_t opt_counters = 0, opt_kernel = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0, opt_math = 0;
   bool last_in_place = false;
   float last_ms = 0.0f;
   bool smem_attr_set[2][10] = {};
@@ -560,6 +567,12 @@ int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
   a.tile_counter = ctx->d_tile_ring + (ctx->ring_next.fetch_add(1) % rtb_ctx::kTileRing);
   RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
+  if (FLAVOR == kFlavorSpheres && !COUNTERS && ctx->opt_math == 1) {
+    // the same kernel source built with fast arithmetic (fast_kernels.cu); same launch geometry
+    const int e = rtb_fast_launch_spheres(&a, sizeof a, SMEM ? 1 : 0, grid, smem, ctx->max_smem_optin, stream);
+    if (e != 0) return fail(ctx, RTB_ERR_CUDA + e, "fast-math megakernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return RTB_OK;
+  }
   kernel<<<grid, kMegaBlock, smem, stream>>>(a);
   RTB_CUDA(ctx, cudaGetLastError());
   return RTB_OK;
@@ -623,7 +636,10 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   a.row_step = rows.row_step;
   a.n_rows = rows.n_rows;
   a.n_active_pixels = (uint32_t)rows.n_rows * (uint32_t)width;
+  // every launch gets a fresh epoch: the word the kernels poll can only equal it after send_cancel for THIS launch
+  if (++ctx->cancel_epoch == 0u) ctx->cancel_epoch = 1u;
   a.cancel_flag = ctx->d_cancel;
+  a.cancel_epoch = ctx->cancel_epoch;
   a.scene.status = ctx->d_status;
   const bool counters = ctx->opt_counters != 0;
   a.counters = counters ? ctx->d_counters : nullptr;
@@ -751,6 +767,15 @@ struct DeviceGuard {
   }
 };
 
+// Tells the kernels of the context's current batch to stop: the batch's epoch goes into the word they poll.
+void send_cancel(rtb_ctx* ctx) {
+  if (ctx->cancel_sent) return;
+  ctx->cancel_sent = true;
+  DeviceGuard g(ctx->device);
+  *ctx->h_epoch = ctx->cancel_epoch;
+  cudaMemcpyAsync(ctx->d_cancel, ctx->h_epoch, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->cancel_stream);
+}
+
 // cudaStreamSynchronize of every context's stream that keeps relaying the caller's CancellationToken into the flags the
 // running kernels poll.
 cudaError_t wait_for_streams(rtb_ctx* const* ctxs, int n, const volatile uint8_t* cancel) {
@@ -773,7 +798,7 @@ cudaError_t wait_for_streams(rtb_ctx* const* ctxs, int n, const volatile uint8_t
   std::vector<char> done((size_t)n, 0);
   for (uint32_t spins = 0; pending > 0; spins++) {
     if (*cancel)
-      for (int i = 0; i < n; i++) *ctxs[i]->h_cancel = 1u;
+      for (int i = 0; i < n; i++) send_cancel(ctxs[i]);
     for (int i = 0; i < n; i++) {
       if (done[i]) continue;
       const cudaError_t e = cudaEventQuery(ctxs[i]->ev_done);
@@ -862,7 +887,7 @@ int host_batch_begin(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_bat
 
   // CancellationToken (SampleBatchJob.cs:61; the host flips it through a raw pointer, Raytracer.cs:189-192, then
   // Complete()s, :512-515): ONE launch; the kernel polls the context's mapped flag, wait_for_streams relays the token into it.
-  *ctx->h_cancel = 0u;
+  ctx->cancel_sent = false;
   RTB_CUDA(ctx, cudaEventRecord(ctx->ev_start, s));
   if ((rc = launch_batch(ctx, *params, dev, width, height, all, s)) != RTB_OK) return rc;
   RTB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, s));
@@ -891,7 +916,8 @@ int host_batch_drain(rtb_ctx* ctx, HostBatch* st) {
 int host_batch_end(rtb_ctx* ctx, HostBatch* st, const volatile uint8_t* cancel) {
   DeviceGuard g(ctx->device);
   RTB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
-  if (*ctx->h_cancel || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  if (ctx->cancel_sent) cudaStreamSynchronize(ctx->cancel_stream);   // the pinned source is reused by the next batch
+  if (ctx->cancel_sent || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
   if (st->status & kStatusHitListOverflow) {
     cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
     return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met more than %d entities in a world with participating media (the reference's hit list grows, "
@@ -1134,17 +1160,10 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   if ((e = cudaMalloc(&ctx->d_tile_ring, rtb_ctx::kTileRing * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
   if ((e = cudaMalloc(&ctx->d_status, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
   if ((e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
-  {
-    void* h = nullptr;
-    if ((e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) return bail(e, "cudaHostAlloc");
-    ctx->h_cancel = static_cast<volatile uint32_t*>(h);
-    *ctx->h_cancel = 0u;
-    void* d = nullptr;
-    if ((e = cudaHostGetDevicePointer(&d, h, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
-    ctx->d_cancel = static_cast<uint32_t*>(d);
-  }
-  if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-  if ((e = cudaMalloc(&ctx->d_metrics_partial, 1024 * sizeof(MetricsAcc))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&ctx->d_cancel, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMemset(ctx->d_cancel, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
+  if ((e = cudaHostAlloc((void**)&ctx->h_epoch, 64, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+  if ((e = cudaStreamCreateWithFlags(&ctx->cancel_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   *out_ctx = ctx;
   return RTB_OK;
 }
@@ -1157,9 +1176,10 @@ int rtb_destroy(rtb_ctx* ctx) {
     for (auto& kv : ctx->registered) cudaHostUnregister(kv.first);
     DeviceBuffers& b = ctx->buf;
     void* ptrs[] = {b.in_color, b.in_weight, b.in_normal, b.in_albedo, b.out_color, b.out_weight, b.out_normal, b.out_albedo,
-                    b.diagnostics, ctx->d_sky, ctx->d_tex_pixels, ctx->d_tex_images, ctx->d_mat_textures, ctx->d_tri_uv, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_ring, ctx->d_status, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
+                    b.diagnostics, ctx->d_sky, ctx->d_tex_pixels, ctx->d_tex_images, ctx->d_mat_textures, ctx->d_tri_uv, ctx->d_blob, ctx->d_materials, ctx->d_chain_ref, ctx->d_chain_boxes, ctx->d_tile_ring, ctx->d_status, ctx->d_cancel, ctx->d_counters, ctx->d_metrics_partial, ctx->d_scratch_diag};
     for (void* p : ptrs) if (p) cudaFree(p);
-    if (ctx->h_cancel) cudaFreeHost(const_cast<uint32_t*>(ctx->h_cancel));
+    if (ctx->cancel_stream) { cudaStreamSynchronize(ctx->cancel_stream); cudaStreamDestroy(ctx->cancel_stream); }
+    if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -1497,6 +1517,10 @@ int rtb_set_option(rtb_ctx* ctx, int option, int64_t value) {
     case RTB_OPT_HOST_ACCESS:
       ctx->opt_host_access = value ? 1 : 0;
       return RTB_OK;
+    case RTB_OPT_MATH:
+      if (value < 0 || value > 1) return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "RTB_OPT_MATH must be 0 (parity) or 1 (fast)");
+      ctx->opt_math = value;
+      return RTB_OK;
     case RTB_OPT_ALWAYS_WALK_CHAINS:
       ctx->opt_walk_chains = value ? 1 : 0;
       if (ctx->has_scene && ctx->scene.has_chains) ctx->scene.has_chains = value ? 2u : 1u;
@@ -1676,7 +1700,7 @@ int rtb_multi_sample_batch(rtb_multi* m, const rtb_batch_params* params, const r
     if (!st[g].empty) busy.push_back(m->ctx[g]);
   }
   if (first_rc != RTB_OK)                            // stop what was started
-    for (rtb_ctx* c : busy) *c->h_cancel = 1u;
+    for (rtb_ctx* c : busy) send_cancel(c);
   for (int g = 0; g < n && first_rc == RTB_OK; g++)
     if (!st[g].empty && (rc = host_batch_drain(m->ctx[g], &st[g])) != RTB_OK) first_rc = mforward(m, g, rc);
   if (!busy.empty()) {

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       // that claims a tile reads the mapped flag, and tells the CTA's other warps to stop issuing samples)
       uint32_t t = 0;
       if (lane == 0) {
-        const uint32_t cancelled = ld_volatile_u32(a.cancel_flag);
+        const bool cancelled = cancel_requested(a.cancel_flag, a.cancel_epoch);
         t = atomicAdd(a.tile_counter, 1u);
         if (cancelled) { *cta_cancelled = 1u; t = 0xffffffffu; }
       }
@@ -494,7 +494,7 @@ template <bool COUNTERS, bool WHITE>
 __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ BatchArgs a) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.n_active_pixels) return;
-  if (ld_volatile_u32(a.cancel_flag)) return;          // CancellationToken (SampleBatchJob.cs:61): pixels not yet started are skipped
+  if (cancel_requested(a.cancel_flag, a.cancel_epoch)) return;          // CancellationToken (SampleBatchJob.cs:61): pixels not yet started are skipped
   const rtb_batch_params& p = a.p;
   SceneView<false> sv;
   sv.bind(a.scene.blob, a.scene);

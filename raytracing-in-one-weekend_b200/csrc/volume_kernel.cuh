@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ Ba
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t k = WHITE ? blockIdx.x * blockDim.x + threadIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= a.n_active_pixels) return;
-  if (ld_volatile_u32(a.cancel_flag)) return;          // CancellationToken (SampleBatchJob.cs:61): pixels not yet started are skipped
+  if (cancel_requested(a.cancel_flag, a.cancel_epoch)) return;          // CancellationToken (SampleBatchJob.cs:61): pixels not yet started are skipped
   const rtb_batch_params& p = a.p;
   SceneView<false> sv;
   sv.bind(a.scene.blob, a.scene);

@@ -38,6 +38,13 @@ for name, depth, W, H, spp, td, ap, key in [("final", 16, 1920, 1080, 256, 50, 0
         ctx.sample_batch(p, b); ms.append(ctx.last_kernel_ms())
     res[key + "_ms"] = min(ms); res[key + "_msamples"] = W * H * spp / min(ms) / 1e3
     res[key + "_checksum"] = float(b.out_color.astype(np.float64).sum())
+    if %(fast)r:
+        ctx.set_option(abi.OPT_MATH, abi.MATH_FAST)
+        ms = []
+        for _ in range(3):
+            ctx.sample_batch(p, b); ms.append(ctx.last_kernel_ms())
+        ctx.set_option(abi.OPT_MATH, abi.MATH_PARITY)
+        res[key + "_fast_ms"] = min(ms); res[key + "_fast_checksum"] = float(b.out_color.astype(np.float64).sum())
 print("RESULT " + json.dumps(res))
 '''
 
@@ -65,7 +72,7 @@ def main():
         env.update(extra)
         if path:
             env["RTB_PLUGIN_LIB"] = path
-        r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "tag": tag, "cfgs": cfgs}], env=env, capture_output=True, text=True, timeout=900)
+        r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "tag": tag, "cfgs": cfgs, "fast": "--fast" in sys.argv}], env=env, capture_output=True, text=True, timeout=900)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")]
         if line:
             out.append(json.loads(line[0][7:]))
