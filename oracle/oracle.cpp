@@ -1162,4 +1162,41 @@ ORACLE_API void oracle_umath_pow(const float* x, float e, float* y, int n) {
   for (int i = 0; i < n; i++) y[i] = um::pow_pos(x[i], e);
 }
 
+// The vector / quaternion functions of include/rtb/umath.h, one record per call, so that tests can pin the header both
+// consumers share (this oracle and the CUDA kernels) against an INDEPENDENT float64 restatement of the
+// Unity.Mathematics formulas instead of against each other.  `in` / `out` record sizes per op:
+//   0 reflect(i, n)            6 -> 3      1 rotate(q, v)             7 -> 3      2 inverse(RigidTransform(q, p))  7 -> 7
+//   3 transform(rt(q, p), x)  10 -> 3      4 lerp(a, b, s) (float3)   7 -> 3      5 normalize(v)                   3 -> 3
+//   6 cross(a, b)              6 -> 3      7 mul(float3x3(c0,c1,c2), v) 12 -> 3   8 dot(a, b)                      6 -> 1
+//   9 scalars (x, y, z) -> min(x,y), max(x,y), saturate(x), round(x), unlerp(x,y,z), lerp(x,y,z), rcp(x), rsqrt(|x|)   3 -> 8
+ORACLE_API int oracle_umath_vec(int op, const float* in, float* out, int n) {
+  static const int in_size[10] = {6, 7, 7, 10, 7, 3, 6, 12, 6, 3}, out_size[10] = {3, 3, 7, 3, 3, 3, 3, 3, 1, 8};
+  if (op < 0 || op > 9) return -1;
+  auto put = [](float* o, f3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; };
+  for (int r = 0; r < n; r++) {
+    const float* a = in + (size_t)r * in_size[op];
+    float* o = out + (size_t)r * out_size[op];
+    switch (op) {
+      case 0: put(o, um::reflect(um::mk(a[0], a[1], a[2]), um::mk(a[3], a[4], a[5]))); break;
+      case 1: put(o, um::rotate(um::quat{a[0], a[1], a[2], a[3]}, um::mk(a[4], a[5], a[6]))); break;
+      case 2: {
+        const um::rigid inv = um::inverse(um::rigid{um::quat{a[0], a[1], a[2], a[3]}, um::mk(a[4], a[5], a[6])});
+        o[0] = inv.rot.x; o[1] = inv.rot.y; o[2] = inv.rot.z; o[3] = inv.rot.w; put(o + 4, inv.pos);
+        break;
+      }
+      case 3: put(o, um::transform(um::rigid{um::quat{a[0], a[1], a[2], a[3]}, um::mk(a[4], a[5], a[6])}, um::mk(a[7], a[8], a[9]))); break;
+      case 4: put(o, um::lerp(um::mk(a[0], a[1], a[2]), um::mk(a[3], a[4], a[5]), a[6])); break;
+      case 5: put(o, um::normalize(um::mk(a[0], a[1], a[2]))); break;
+      case 6: put(o, um::cross(um::mk(a[0], a[1], a[2]), um::mk(a[3], a[4], a[5]))); break;
+      case 7: put(o, um::mul_cols(um::mk(a[0], a[1], a[2]), um::mk(a[3], a[4], a[5]), um::mk(a[6], a[7], a[8]), um::mk(a[9], a[10], a[11]))); break;
+      case 8: o[0] = um::dot(um::mk(a[0], a[1], a[2]), um::mk(a[3], a[4], a[5])); break;
+      default:
+        o[0] = um::min(a[0], a[1]); o[1] = um::max(a[0], a[1]); o[2] = um::saturate(a[0]); o[3] = um::round(a[0]);
+        o[4] = um::unlerp(a[0], a[1], a[2]); o[5] = um::lerp(a[0], a[1], a[2]); o[6] = um::rcp(a[0]); o[7] = um::rsqrt(um::abs(a[0]));
+        break;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

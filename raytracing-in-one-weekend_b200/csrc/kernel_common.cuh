@@ -358,16 +358,18 @@ __device__ __forceinline__ void aabb_range_fast(f3 mn, f3 mx, f3 inv, f3 noi, fl
 // (SampleBatchJob.cs:450-475) — a root is accepted iff 0 < t < +inf there, and the
 // second root is never nearer than the first, so clipping at best_t changes nothing.
 //
-// DEFER (the lean sphere builds): the division by a = dot(d, d) is taken out of the walk.  Every ray of the job has
-// |d| = 1 up to rounding; when |a - 1| <= 1e-4 (`a_ok`, decided once per walk) candidates are compared by their
-// NUMERATORS x = -b -/+ sqrt(disc) and the walk's single winner is divided once, with the warp converged, after it:
+// DEFER (big leaves of the lean sphere builds — a linear hit list is one): the division by a = dot(d, d) is taken out of
+// the leaf's loop.  Every ray of the job has |d| = 1 up to rounding; when |a - 1| <= 1e-4 (`a_ok`, decided once per walk)
+// and nothing was hit before the leaf, its candidates are compared by their NUMERATORS x = -b -/+ sqrt(disc) and the
+// leaf's single winner is divided once after the loop (measured on the linear list of config 2: 57.7 -> 52.1 ms; in
+// single-sphere leaves of a tree the same trick LOST 16 %, so those keep dividing per candidate):
 //   * x -> fl(x / a) is monotonic, so the smallest numerator has the smallest distance (numerators that differ and
 //     round to the same distance are a tie the reference's unstable sort does not define either);
 //   * fl(x / a) > 0 iff x > 0 (no float underflows when divided by a number in [0.9999, 1.0001]);
 //   * the prune limit best * kPruneMargin stays beyond the hit: fl(x / a) <= x * 1.00011 < x * kPruneMargin.
-// A ray with any other |d| divides every candidate as before (best_t then already holds distances).
+// A ray with any other |d|, or one that already holds a hit, divides every candidate as before.
 template <bool CHAINS, bool DEFER>
-__device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a, bool a_ok,
+__device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a,
                                            float& best_t, int& best_idx) {
   f3 oc = o + um::mk(-s.x, -s.y, -s.z);
   float b = um::dot(oc, d);
@@ -384,7 +386,7 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
   if (disc > 0.0f && !(c > 0.0f && b >= 0.0f)) {
     const float sq = um::sqrt(disc);
     float t = c > 0.0f ? -b - sq : -b + sq;
-    if (DEFER && a_ok) {
+    if (DEFER) {
       if (c > 0.0f && !(t > 0.0f)) t = -b + sq;                  // t1 rounded to 0: the reference moves on to t2
     } else {
       t = um::div(t, a);
@@ -548,7 +550,7 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 constexpr float kPruneMargin = 1.0005f;
 constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
 #ifndef RTB_DEFER_DIV
-#define RTB_DEFER_DIV 1   // lean sphere builds: divide the walk's winner once instead of every candidate (see sphere_hit)
+#define RTB_DEFER_DIV 1   // lean sphere builds: a big leaf divides its winner once instead of every candidate (see sphere_hit)
 #endif
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
@@ -575,7 +577,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     const float4 prim = sv.sphere(slot);
     if (FLAVOR >= kFlavorPlaced && prim.w != prim.w && __float_as_uint(prim.y) != 0u) placed_hit(sv, __float_as_uint(prim.x), slot, o, d, clk, best_t, best_idx);
     else if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx);
-    else sphere_hit<(FLAVOR >= kFlavorChains), DEFER>(sd, prim, slot, o, d, inv, a, a_ok, best_t, best_idx);
+    else sphere_hit<(FLAVOR >= kFlavorChains), false>(sd, prim, slot, o, d, inv, a, best_t, best_idx);
   };
   auto test_leaf = [&](int ref) {
     const uint32_t code = (uint32_t)~ref;
@@ -589,9 +591,23 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     if (count == 16) {                   // a big leaf (a "linear hit list" is one leaf holding the world): unrolled in the lean builds
       count = (int)sv.leaf_count(first);
       if (FLAVOR < kFlavorGeneral) {
+        if (COUNTERS) wc.sphere_tests += count;
+        // Deferred division (see sphere_hit) for a big leaf reached before any hit — always the case for a linear list:
+        // its candidates are compared by their numerators and the leaf's winner is divided once after the loop.
+        if (DEFER && a_ok && best_idx < 0) {
+#pragma unroll 4
+          for (int i = 0; i < count; i++) {
+            const int slot = first + 16 * i;
+            sphere_hit<(FLAVOR >= kFlavorChains), true>(sd, sv.sphere(slot), slot, o, d, inv, a, best_t, best_idx);
+          }
+          if (best_idx >= 0) {
+            best_t = um::div(best_t, a);   // the winner's numerator -> its distance (HitTests.cs:33,45)
+            if (!(best_t < um::INF)) { best_idx = -1; best_t = um::INF; }   // "t < tMax" with tMax = +inf (SampleBatchJob.cs:457)
+          }
+          return;
+        }
 #pragma unroll 4
         for (int i = 0; i < count; i++) test_prim(first + 16 * i);
-        if (COUNTERS) wc.sphere_tests += count;
         return;
       }
     }
@@ -647,10 +663,6 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       }
     }
   }
-    if (DEFER && a_ok && best_idx >= 0) {      // the winner's numerator -> its distance (HitTests.cs:33,45), once, converged
-      best_t = um::div(best_t, a);
-      if (!(best_t < um::INF)) best_idx = -1;  // "t < tMax" with tMax = +inf (SampleBatchJob.cs:457)
-    }
     return;
   }
   // The general and placed flavours: one node (inner OR leaf) per trip (measured faster for them: 72.8 vs 78.8 ms on the mesh world).

@@ -1164,6 +1164,8 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   if ((e = cudaMemset(ctx->d_cancel, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
   if ((e = cudaHostAlloc((void**)&ctx->h_epoch, 64, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc");
   if ((e = cudaStreamCreateWithFlags(&ctx->cancel_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&ctx->d_metrics_partial, 1024 * sizeof(MetricsAcc))) != cudaSuccess) return bail(e, "cudaMalloc");
   *out_ctx = ctx;
   return RTB_OK;
 }

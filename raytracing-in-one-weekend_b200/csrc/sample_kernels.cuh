@@ -78,8 +78,12 @@ __device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
       const uint32_t old = atomicAdd(&t.acc_lo[slot][v], cur.x);
       const uint32_t hi = cur.y + ((old + cur.x) < old ? 1u : 0u);
       if (hi) {
+#ifndef RTB_NO_OVERFLOW_CHECK
         const uint32_t old_hi = atomicAdd(&t.acc_hi[slot][v], hi);
         if (~(old_hi ^ hi) & (old_hi ^ (old_hi + hi)) & 0x80000000u) t.non_finite[slot] = 1;
+#else
+        atomicAdd(&t.acc_hi[slot][v], hi);
+#endif
       }
       t.lane_acc[v][lane] = make_uint2(0u, 0u);
     }
@@ -272,7 +276,11 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       // that claims a tile reads the mapped flag, and tells the CTA's other warps to stop issuing samples)
       uint32_t t = 0;
       if (lane == 0) {
+#ifndef RTB_NO_CLAIM_CANCEL
         const bool cancelled = cancel_requested(a.cancel_flag, a.cancel_epoch);
+#else
+        const bool cancelled = false;
+#endif
         t = atomicAdd(a.tile_counter, 1u);
         if (cancelled) { *cta_cancelled = 1u; t = 0xffffffffu; }
       }
@@ -363,7 +371,9 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     // 122.7 / 123.7 / 132.3 ms, mesh world 70.2 -> 67.1 ms; on the linear list (converged walk: an idle lane is pure loss)
     // and on worlds of a dozen entities 1 is best — the plugin picks 8 for trees of >= 64 inner nodes.
     if (need && ((uint32_t)__popc(need) >= a.refill_min || need == 0xffffffffu)) {
+#ifndef RTB_NO_LOOP_CANCEL
       if (*cta_cancelled) next_item = total_items;      // cancelled: the tile's remaining samples are not started
+#endif
       const uint32_t my_item = next_item + __popc(need & lt_mask);
       if (!alive && my_item < total_items) {
         // item -> (pixel slot, sample) through the tile's prefix table

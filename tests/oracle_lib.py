@@ -76,6 +76,8 @@ def lib(fast=False):
         L.oracle_umath_sincos.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_umath_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_umath_pow.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_int]
+        L.oracle_umath_vec.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_umath_vec.restype = C.c_int
         _libs[name] = L
     return _libs[name]
 
@@ -192,3 +194,16 @@ def sample_batch(scene, params, buffers, noise=NOISE_PHILOX, threads=None, fast=
     if rc != 0:
         raise RuntimeError(f"oracle_sample_batch failed: {rc}")
     return buffers
+
+
+UMATH_VEC_SIZES = {0: (6, 3), 1: (7, 3), 2: (7, 7), 3: (10, 3), 4: (7, 3), 5: (3, 3), 6: (6, 3), 7: (12, 3), 8: (6, 1), 9: (3, 8)}
+
+
+def umath_vec(op, records):
+    """include/rtb/umath.h's vector / quaternion functions on float32 records [n, in_size] -> [n, out_size]."""
+    a = np.ascontiguousarray(records, dtype=np.float32)
+    n_in, n_out = UMATH_VEC_SIZES[op]
+    assert a.ndim == 2 and a.shape[1] == n_in
+    out = np.zeros((len(a), n_out), np.float32)
+    assert lib().oracle_umath_vec(op, a.ctypes.data, out.ctypes.data, len(a)) == 0
+    return out
