@@ -549,9 +549,36 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 // record while testing a fraction of the nodes.
 constexpr float kPruneMargin = 1.0005f;
 constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
+
 #ifndef RTB_DEFER_DIV
 #define RTB_DEFER_DIV 1   // lean sphere builds: a big leaf divides its winner once instead of every candidate (see sphere_hit)
 #endif
+// A leaf of 16 or more spheres in the lean builds (a linear hit list is one such leaf holding the world), out of line so
+// that the tree walk's own code stays small (the megakernel is instruction-fetch sensitive: every few hundred instructions
+// inlined into the walk cost milliseconds).  Deferred division (see sphere_hit) when the ray's |d|^2 is 1 to 1e-4 and nothing
+// was hit before the leaf: candidates are compared by their numerators and the leaf's winner is divided once.
+template <bool SMEM, bool CHAINS>
+__device__ __noinline__ float2 big_leaf_hit(SceneView<SMEM> sv, const SceneDesc& sd, int first, int count, f3 o, f3 d, f3 inv, float a,
+                                            float best_t, int best_idx) {
+  if (RTB_DEFER_DIV && best_idx < 0 && um::abs(a - 1.0f) <= 1.0e-4f) {
+#pragma unroll 4
+    for (int i = 0; i < count; i++) {
+      const int slot = first + 16 * i;
+      sphere_hit<CHAINS, true>(sd, sv.sphere(slot), slot, o, d, inv, a, best_t, best_idx);
+    }
+    if (best_idx >= 0) {
+      best_t = um::div(best_t, a);       // the winner's numerator -> its distance (HitTests.cs:33,45)
+      if (!(best_t < um::INF)) { best_idx = -1; best_t = um::INF; }   // "t < tMax" with tMax = +inf (SampleBatchJob.cs:457)
+    }
+  } else {
+#pragma unroll 4
+    for (int i = 0; i < count; i++) {
+      const int slot = first + 16 * i;
+      sphere_hit<CHAINS, false>(sd, sv.sphere(slot), slot, o, d, inv, a, best_t, best_idx);
+    }
+  }
+  return make_float2(best_t, __int_as_float(best_idx));
+}
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
 __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
@@ -563,8 +590,6 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   f3 inv = um::rcp(d);
   inv = um::mk(um::isnan(inv.x) ? um::INF : inv.x, um::isnan(inv.y) ? um::INF : inv.y, um::isnan(inv.z) ? um::INF : inv.z);
   const float a = um::dot(d, d);
-  constexpr bool DEFER = RTB_DEFER_DIV && FLAVOR < kFlavorGeneral;
-  const bool a_ok = DEFER && um::abs(a - 1.0f) <= 1.0e-4f;
 
   float t_enter;
   if (COUNTERS) wc.node_tests++;
@@ -588,26 +613,13 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       return;
     }
     int count = (int)(code & 15u) + 1;
-    if (count == 16) {                   // a big leaf (a "linear hit list" is one leaf holding the world): unrolled in the lean builds
+    if (count == 16) {                   // a big leaf (a "linear hit list" is one leaf holding the world)
       count = (int)sv.leaf_count(first);
-      if (FLAVOR < kFlavorGeneral) {
+      if (FLAVOR < kFlavorGeneral) {     // out of line: a tree of small leaves never gets here, and the walk's code stays short
         if (COUNTERS) wc.sphere_tests += count;
-        // Deferred division (see sphere_hit) for a big leaf reached before any hit — always the case for a linear list:
-        // its candidates are compared by their numerators and the leaf's winner is divided once after the loop.
-        if (DEFER && a_ok && best_idx < 0) {
-#pragma unroll 4
-          for (int i = 0; i < count; i++) {
-            const int slot = first + 16 * i;
-            sphere_hit<(FLAVOR >= kFlavorChains), true>(sd, sv.sphere(slot), slot, o, d, inv, a, best_t, best_idx);
-          }
-          if (best_idx >= 0) {
-            best_t = um::div(best_t, a);   // the winner's numerator -> its distance (HitTests.cs:33,45)
-            if (!(best_t < um::INF)) { best_idx = -1; best_t = um::INF; }   // "t < tMax" with tMax = +inf (SampleBatchJob.cs:457)
-          }
-          return;
-        }
-#pragma unroll 4
-        for (int i = 0; i < count; i++) test_prim(first + 16 * i);
+        const float2 r = big_leaf_hit<SMEM, (FLAVOR >= kFlavorChains)>(sv, sd, first, count, o, d, inv, a, best_t, best_idx);
+        best_t = r.x;
+        best_idx = __float_as_int(r.y);
         return;
       }
     }

@@ -70,7 +70,13 @@ __device__ __forceinline__ void lane_add(WarpTile& t, int lane, int v, float x) 
 // only emitters brighter than ~1e6 at hundreds of samples get there) marks the pixel instead of wrapping: the hi-word
 // add reports its old value, and two's-complement addition overflowed iff both operands have the sign the result lacks.
 // (A lane's own partial cannot overflow first: see finish_path.)
-__device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
+// Out of line: it runs when a lane moves to another pixel (every few paths), from four places of the kernel.
+#ifdef RTB_FLUSH_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void lane_flush(WarpTile& t, int lane, int slot) {
 #pragma unroll
   for (int v = 0; v < kAccValues; v++) {
     const uint2 cur = t.lane_acc[v][lane];
@@ -327,9 +333,10 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     float4 m0 = make_float4(0, 0, 0, 0), m1 = m0, m2 = m0, m3 = m0;
     f3 N = um::mk(0.0f), P = um::mk(0.0f);
     if (alive) {
-      int hit_idx;
+      int hit_idx = -1;
       const RayClock clk{pixel, sample, p.seed, 0.0f, false};
-      closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
+      const bool exhausted = depth == p.trace_depth;      // a failed sample (SampleBatchJob.cs:379-381), found at the end of the last trip
+      if (!exhausted) closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
       if (hit_idx >= 0) {
         hit = true;
         const float4 s = sv.sphere(hit_idx);
@@ -346,18 +353,20 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         N = hit_normal<SMEM, FLAVOR>(sv, s, ray.o, ray.d, t_hit, clk);
         P = um::mad(ray.d, t_hit, ray.o);
       } else {
-        const f3 sky = sky_color(p.environment, a.scene, ray.d);
-        radiance = um::mad(throughput, sky, radiance);
-        if (!first_non_specular) {
-          const f3 s_normal = -ray.d;
-          set_albedo(sky);
-          set_normal(s_normal);
-          if (sample == 0) {
-            tile.fallback[slot][0] = s_normal.x; tile.fallback[slot][1] = s_normal.y; tile.fallback[slot][2] = s_normal.z;
-            tile.fallback[slot][3] = sky.x; tile.fallback[slot][4] = sky.y; tile.fallback[slot][5] = sky.z;
+        if (!exhausted) {
+          const f3 sky = sky_color(p.environment, a.scene, ray.d);
+          radiance = um::mad(throughput, sky, radiance);
+          if (!first_non_specular) {
+            const f3 s_normal = -ray.d;
+            set_albedo(sky);
+            set_normal(s_normal);
+            if (sample == 0) {
+              tile.fallback[slot][0] = s_normal.x; tile.fallback[slot][1] = s_normal.y; tile.fallback[slot][2] = s_normal.z;
+              tile.fallback[slot][3] = sky.x; tile.fallback[slot][4] = sky.y; tile.fallback[slot][5] = sky.z;
+            }
           }
         }
-        finish_path(true);
+        finish_path(!exhausted);        // the kernel's ONE copy of the accumulation code
       }
     }
 
@@ -449,8 +458,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       const f3 off_n = um::dot(sc.dir, N) >= 0 ? N : -N;
       ray.o = um::mad(off_n, 0.001f, P);
       ray.d = sc.dir;
-      depth++;
-      if (depth == p.trace_depth) finish_path(false);   // failed sample (:379-381)
+      depth++;                          // depth == TraceDepth: the sample failed (:379-381); the next trip's step (1) retires it
     } else if (fresh) {
       ray = camera_ray_finish(p, cx, cy, r, sn, cs);
       alive = true;

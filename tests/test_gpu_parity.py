@@ -1231,3 +1231,67 @@ def test_peer_process_frame_mapping(rtb, ctx):
         assert len(h) == 64 and any(h)
     finally:
         ctx.device_free(ptr)
+
+
+@pytest.mark.parametrize("name,depth", [("three_spheres", 0), ("final", 16)])
+def test_white_furnace_on_the_gpu(rtb, ctx, name, depth):
+    """tests/test_oracle_kat.py::test_white_furnace_radiance_is_exactly_one, on every kernel: albedo 1 under a sky of radiance 1
+    gives pixel sums EQUAL to the sample counts — a check that needs no oracle at all."""
+    from test_oracle_kat import furnace_scene
+
+    W, H, spp = 96, 54, 16
+    scene = furnace_scene(rtb, name, depth)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    for kernel in (rtb.abi.KERNEL_SIMPLE, rtb.abi.KERNEL_MEGA):
+        b = render_gpu(rtb, ctx, scene, p, W, H, kernel)
+        n = b.out_color[:, 3]
+        assert n.max() == spp and n.min() >= spp - 2
+        for c in range(3):
+            assert np.array_equal(b.out_color[:, c], n)
+    ctx.set_option(rtb.abi.OPT_KERNEL, rtb.abi.KERNEL_MEGA)
+    ctx.set_option(rtb.abi.OPT_MATH, rtb.abi.MATH_FAST)      # the fast-arithmetic build conserves energy exactly too
+    try:
+        b = rtb.plugin.HostBuffers(W, H)
+        ctx.sample_batch(p, b)
+        n = b.out_color[:, 3]
+        for c in range(3):
+            assert np.array_equal(b.out_color[:, c], n)
+    finally:
+        ctx.set_option(rtb.abi.OPT_MATH, rtb.abi.MATH_PARITY)
+
+
+def test_lambertian_albedo_series_on_the_gpu(rtb, ctx):
+    """colour == a^(RayCount - 1) at one sample per pixel (see test_oracle_kat.py::test_lambertian_albedo_series)."""
+    from test_oracle_kat import furnace_scene
+
+    W, H = 128, 72
+    scene = furnace_scene(rtb, "final", 16, albedo=0.5, lambertian_only=True)
+    p = rtb.host.make_params(scene, W, H, 1, 30, aperture=0.0)
+    for kernel in (rtb.abi.KERNEL_SIMPLE, rtb.abi.KERNEL_MEGA):
+        b = render_gpu(rtb, ctx, scene, p, W, H, kernel)
+        ok = b.out_color[:, 3] == 1
+        assert ok.mean() > 0.99
+        rays = b.diagnostics["ray_count"][ok].astype(np.int32)
+        want = np.ldexp(np.float32(1.0), -(rays - 1)).astype(np.float32)
+        for c in range(3):
+            assert np.array_equal(b.out_color[ok, c], want)
+
+
+def test_fast_math_build_agrees_statistically(rtb, ctx):
+    """RTB_OPT_MATH = 1 (fast_kernels.cu): same estimator, same random numbers, approximate arithmetic.  Against the parity
+    build at 64 spp: most pixels identical to 1e-4, the image mean within 1e-4, sample counts equal almost everywhere."""
+    W, H, spp = 160, 90, 64
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    strict = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    ctx.set_option(rtb.abi.OPT_MATH, rtb.abi.MATH_FAST)
+    try:
+        fast = rtb.plugin.HostBuffers(W, H)
+        ctx.sample_batch(p, fast)
+    finally:
+        ctx.set_option(rtb.abi.OPT_MATH, rtb.abi.MATH_PARITY)
+    assert fast.out_color.tobytes() != strict.out_color.tobytes()           # it really is another build
+    d = np.abs(strict.rgb() - fast.rgb()).reshape(-1, 3).max(axis=1)
+    assert (d > 1e-4).mean() < 0.10
+    assert abs(float(strict.rgb().mean()) - float(fast.rgb().mean())) < 1e-4
+    assert (strict.out_color[:, 3] != fast.out_color[:, 3]).mean() < 0.01
