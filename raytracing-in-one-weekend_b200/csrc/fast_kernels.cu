@@ -17,9 +17,9 @@
 
 namespace rtbk_fast {
 
-template <bool SMEM>
+template <bool SMEM, int FLAVOR>
 cudaError_t launch(const BatchArgs& a, unsigned grid, size_t smem, int max_smem_optin, cudaStream_t stream) {
-  auto kernel = sample_megakernel<SMEM, false, kFlavorSpheres>;
+  auto kernel = sample_megakernel<SMEM, false, FLAVOR>;
   static bool attr_set = false;          // per process and instantiation; cudaFuncSetAttribute applies to every device's copy
   cudaError_t e = cudaSuccess;
   int dev = 0;
@@ -31,19 +31,23 @@ cudaError_t launch(const BatchArgs& a, unsigned grid, size_t smem, int max_smem_
     attr_set = true;
     attr_dev_mask |= 1 << dev;
   }
-  kernel<<<grid, mega_block(kFlavorSpheres), smem, stream>>>(a);
+  kernel<<<grid, mega_block(FLAVOR), smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 }  // namespace rtbk_fast
 
 // `args`: the parity build's rtbk::BatchArgs (same layout: same header, same compiler) passed as bytes.
+// `flavor`: kFlavorSpheres (trees of small leaves) or kFlavorChains (collapsed or big leaves: linear hit lists).
 extern "C" __attribute__((visibility("hidden"))) int rtb_fast_launch_spheres(const void* args, size_t args_bytes, int scene_in_smem,
-                                                                             unsigned grid, size_t smem, int max_smem_optin,
-                                                                             void* stream) {
-  rtbk_fast::BatchArgs a;
-  if (args_bytes != sizeof a) return (int)cudaErrorInvalidValue;
+                                                                             int flavor, unsigned grid, size_t smem,
+                                                                             int max_smem_optin, void* stream) {
+  using namespace rtbk_fast;
+  BatchArgs a;
+  if (args_bytes != sizeof a || (flavor != kFlavorSpheres && flavor != kFlavorChains)) return (int)cudaErrorInvalidValue;
   memcpy(&a, args, sizeof a);
-  return (int)(scene_in_smem ? rtbk_fast::launch<true>(a, grid, smem, max_smem_optin, (cudaStream_t)stream)
-                             : rtbk_fast::launch<false>(a, grid, smem, max_smem_optin, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flavor == kFlavorSpheres)
+    return (int)(scene_in_smem ? launch<true, kFlavorSpheres>(a, grid, smem, max_smem_optin, s) : launch<false, kFlavorSpheres>(a, grid, smem, max_smem_optin, s));
+  return (int)(scene_in_smem ? launch<true, kFlavorChains>(a, grid, smem, max_smem_optin, s) : launch<false, kFlavorChains>(a, grid, smem, max_smem_optin, s));
 }

@@ -91,6 +91,7 @@ struct SceneDesc {
   const uint16_t* sky_faces;    // Environment.SkyCubemap texels (6 faces of RGBA halves) or nullptr
   int sky_w, sky_h;
   uint32_t has_volumes;         // some material is a ProbabilisticVolume: batches run sample_volumes (volume_kernel.cuh)
+  uint32_t has_big_leaves;      // some leaf holds 16 or more entities (count code 15: the count is in leaf_count)
   uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
   const uint32_t* chain_ref;    // per sphere: first chain box | box count << 24
   const float4* chain_boxes;    // 2 x float4 per box (min.xyz, max.xyz), tightest first
@@ -284,8 +285,11 @@ __device__ __forceinline__ bool aabb_hit(f3 mn, f3 mx, f3 o, f3 inv, float* t_en
 }
 
 // Kernel flavours (template int FLAVOR): what the walk has to handle beyond single-sphere leaves of spheres.
-constexpr int kFlavorSpheres = 0;        // spheres only, no collapsed leaves (the fast build)
-constexpr int kFlavorChains = 1;         // + collapsed leaves: accepted hits go through chain_guard
+constexpr int kFlavorSpheres = 0;        // spheres only, no collapsed leaves, every leaf < 16 spheres (the fast build of tree worlds)
+constexpr int kFlavorChains = 1;         // + collapsed leaves: accepted hits go through chain_guard; + leaves of 16 or more spheres
+                                         // (a linear hit list is ONE such leaf).  Its own build because the tree walk sits on a
+                                         // register / instruction-fetch cliff: the big-leaf code merely being present cost the
+                                         // tree worlds 16 % (130 -> 151 ms on config 3, measured; profiles/README.md)
 constexpr int kFlavorGeneral = 2;        // + EntityType.Triangle entities
 constexpr int kFlavorPlaced = 3;         // + placed entities: rotation, motion (Ray.Time), EntityType.Rect, EntityType.Box
 constexpr int kFlavorPlacedTextured = 4; // the same with image textures (the general flavour always has them; here the
@@ -558,7 +562,12 @@ constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an 
 // inlined into the walk cost milliseconds).  Deferred division (see sphere_hit) when the ray's |d|^2 is 1 to 1e-4 and nothing
 // was hit before the leaf: candidates are compared by their numerators and the leaf's winner is divided once.
 template <bool SMEM, bool CHAINS>
-__device__ __noinline__ float2 big_leaf_hit(SceneView<SMEM> sv, const SceneDesc& sd, int first, int count, f3 o, f3 d, f3 inv, float a,
+#ifdef RTB_BIG_LEAF_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+float2 big_leaf_hit(SceneView<SMEM> sv, const SceneDesc& sd, int first, int count, f3 o, f3 d, f3 inv, float a,
                                             float best_t, int best_idx) {
   if (RTB_DEFER_DIV && best_idx < 0 && um::abs(a - 1.0f) <= 1.0e-4f) {
 #pragma unroll 4
@@ -613,9 +622,9 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       return;
     }
     int count = (int)(code & 15u) + 1;
-    if (count == 16) {                   // a big leaf (a "linear hit list" is one leaf holding the world)
+    if (FLAVOR != kFlavorSpheres && count == 16) {   // a big leaf (upload sends worlds that have one to the other flavours)
       count = (int)sv.leaf_count(first);
-      if (FLAVOR < kFlavorGeneral) {     // out of line: a tree of small leaves never gets here, and the walk's code stays short
+      if (FLAVOR < kFlavorGeneral) {
         if (COUNTERS) wc.sphere_tests += count;
         const float2 r = big_leaf_hit<SMEM, (FLAVOR >= kFlavorChains)>(sv, sd, first, count, o, d, inv, a, best_t, best_idx);
         best_t = r.x;

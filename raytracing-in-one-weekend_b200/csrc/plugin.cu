@@ -29,7 +29,7 @@
 using namespace rtbk;
 
 // csrc/fast_kernels.cu: the lean sphere megakernel compiled with fast arithmetic (RTB_OPT_MATH = 1)
-extern "C" int rtb_fast_launch_spheres(const void* args, size_t args_bytes, int scene_in_smem, unsigned grid, size_t smem,
+extern "C" int rtb_fast_launch_spheres(const void* args, size_t args_bytes, int scene_in_smem, int flavor, unsigned grid, size_t smem,
                                        int max_smem_optin, void* stream);
 
 namespace {
@@ -165,6 +165,7 @@ struct Flattener {
   std::vector<int32_t> path;               // reference nodes below the current collapse root
   uint32_t max_depth = 0;
   bool collapsed_any = false;
+  bool count_table_used = false;           // some leaf's count is not in its ref (16 or more entities, or none): not the lean tree build
   const char* error = nullptr;
 
   // pass 1: validate (tree-ness, ranges) and count spheres per subtree
@@ -268,6 +269,7 @@ struct Flattener {
     const bool is_leaf = nd.first_entity >= 0;
     if (is_leaf || (c <= collapse_k && c <= 15 && path_len_ok(n) && collapsible(n, true))) {
       if (!is_leaf) collapsed_any = true;
+      if (c == 0 || c >= 16) count_table_used = true;
       const uint32_t first = (uint32_t)order.size();
       if (first + c >= (1u << 27)) { error = "scene too large"; return 0; }
       if (c == 0) {                       // empty leaf: a slot whose leaf_count is 0
@@ -391,6 +393,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   d.n_spheres = (uint32_t)n_dev;
   d.n_materials = (uint32_t)material_count;
   d.has_chains = f.collapsed_any ? 1 : 0;
+  d.has_big_leaves = f.count_table_used ? 1 : 0;
   d.n_triangles = (uint32_t)triangle_count;
   d.n_placed = (uint32_t)placed_count;
   d.has_volumes = has_volumes ? 1u : 0u;
@@ -567,9 +570,9 @@ int launch_mega_t(rtb_ctx* ctx, BatchArgs& a, cudaStream_t stream, uint32_t max_
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(ctx->sm_count * blocks_per_sm), ctas_needed));
   a.tile_counter = ctx->d_tile_ring + (ctx->ring_next.fetch_add(1) % rtb_ctx::kTileRing);
   RTB_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), stream));
-  if (FLAVOR == kFlavorSpheres && !COUNTERS && ctx->opt_math == 1) {
+  if (FLAVOR <= kFlavorChains && !COUNTERS && ctx->opt_math == 1) {
     // the same kernel source built with fast arithmetic (fast_kernels.cu); same launch geometry
-    const int e = rtb_fast_launch_spheres(&a, sizeof a, SMEM ? 1 : 0, grid, smem, ctx->max_smem_optin, stream);
+    const int e = rtb_fast_launch_spheres(&a, sizeof a, SMEM ? 1 : 0, FLAVOR, grid, smem, ctx->max_smem_optin, stream);
     if (e != 0) return fail(ctx, RTB_ERR_CUDA + e, "fast-math megakernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     return RTB_OK;
   }
@@ -692,7 +695,7 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
   } else {
     // the instrumented build and worlds with triangles take the general flavour; sphere worlds take the lean ones
     const int flavor = ctx->scene.n_placed ? (ctx->d_mat_textures ? kFlavorPlacedTextured : kFlavorPlaced)
-                       : (counters || ctx->scene.n_triangles || ctx->d_mat_textures) ? kFlavorGeneral : (ctx->scene.has_chains ? kFlavorChains : kFlavorSpheres);
+                       : (counters || ctx->scene.n_triangles || ctx->d_mat_textures) ? kFlavorGeneral : (ctx->scene.has_chains || ctx->scene.has_big_leaves ? kFlavorChains : kFlavorSpheres);
     const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true, flavor) <= (size_t)ctx->max_smem_optin &&
                       ctx->scene.blob_bytes < (1u << 20);
     int rc;
