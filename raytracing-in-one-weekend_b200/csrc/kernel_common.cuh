@@ -551,6 +551,20 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 // skips a box whose entry distance lies beyond the best hit so far (with a safety margin
 // far larger than the rounding error of either distance), so it returns the same nearest
 // record while testing a fraction of the nodes.
+// The lanes of a warp must meet at the top of EVERY trip of the walk loop.  Whether they do is the compiler's choice of loop
+// structure — the same source has compiled into one loop (box visit executed with 20.3 of 32 lanes on config 3) and into a
+// loop nest in which lanes iterate "visits that need no pop" on their own (13.8 lanes, +17 % kernel time), flipped by
+// unrelated edits elsewhere in the kernel (profiles/README.md, round 2).  A convergent operation at the loop top pins the
+// one-loop form: 4 instructions per trip (VOTE, R2UR, BRA.DIV, NOP).
+#ifndef RTB_WALK_SYNC
+#define RTB_WALK_SYNC 1
+#endif
+__device__ __forceinline__ void walk_converge() {
+#if RTB_WALK_SYNC
+  __syncwarp(__activemask());
+#endif
+}
+
 constexpr float kPruneMargin = 1.0005f;
 constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
 
@@ -648,6 +662,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
     const f3 noi = um::mk(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
 #endif
     for (;;) {
+      walk_converge();
       bool need_pop = false;
       if (cur >= 0) {
         const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
@@ -689,6 +704,9 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   // The general and placed flavours: one node (inner OR leaf) per trip (measured faster for them: 72.8 vs 78.8 ms on the mesh world).
   int* top = stack + 1;
   for (;;) {
+#ifndef RTB_NO_GENERAL_WALK_SYNC
+    walk_converge();
+#endif
     if (cur >= 0) {
       const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
       // "box hit (t_enter < t_exit) and not beyond the best hit (t_enter < limit)" as ONE comparison per child
