@@ -329,8 +329,8 @@ RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
  * signed 64-bit fixed point with 32 fraction bits (integer addition is associative: the image does not depend
  * on the order in which paths retire, on tiling or on the GPU count).  Consequences, which the reference's
  * float sums do not share: (1) a sample contributes round-to-nearest multiples of 2^-32 (components below 2^-33
- * contribute 0); (2) a successful sample with a non-finite component or one of magnitude >= 1e9, or a batch
- * whose per-pixel sum reaches 2^31, writes NaN to that pixel's out_color / out_normal / out_albedo /
+ * contribute 0); (2) a successful sample with a non-finite component or one of magnitude >= 2^25 (3.3e7), or a
+ * batch whose per-pixel sum reaches 2^30 (1.07e9) in magnitude, writes NaN to that pixel's out_color / out_normal / out_albedo /
  * out_sample_count_weight (CombineJob turns NaN into black, CombineJob.cs:50-53) — it never wraps silently. */
 RTB_API int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params,
                              const rtb_batch_buffers* host_buffers,

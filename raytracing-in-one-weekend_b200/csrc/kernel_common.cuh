@@ -576,12 +576,7 @@ constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an 
 // inlined into the walk cost milliseconds).  Deferred division (see sphere_hit) when the ray's |d|^2 is 1 to 1e-4 and nothing
 // was hit before the leaf: candidates are compared by their numerators and the leaf's winner is divided once.
 template <bool SMEM, bool CHAINS>
-#ifdef RTB_BIG_LEAF_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-float2 big_leaf_hit(SceneView<SMEM> sv, const SceneDesc& sd, int first, int count, f3 o, f3 d, f3 inv, float a,
+__device__ __noinline__ float2 big_leaf_hit(SceneView<SMEM> sv, const SceneDesc& sd, int first, int count, f3 o, f3 d, f3 inv, float a,
                                             float best_t, int best_idx) {
   if (RTB_DEFER_DIV && best_idx < 0 && um::abs(a - 1.0f) <= 1.0e-4f) {
 #pragma unroll 4
@@ -704,9 +699,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   // The general and placed flavours: one node (inner OR leaf) per trip (measured faster for them: 72.8 vs 78.8 ms on the mesh world).
   int* top = stack + 1;
   for (;;) {
-#ifndef RTB_NO_GENERAL_WALK_SYNC
     walk_converge();
-#endif
     if (cur >= 0) {
       const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
       // "box hit (t_enter < t_exit) and not beyond the best hit (t_enter < limit)" as ONE comparison per child

@@ -66,34 +66,33 @@ __device__ __forceinline__ void lane_add(WarpTile& t, int lane, int v, float x) 
   const unsigned long long sum = (((unsigned long long)cur.y << 32) | cur.x) + q;
   t.lane_acc[v][lane] = make_uint2((uint32_t)sum, (uint32_t)(sum >> 32));
 }
-// tile totals += this lane's partials; partials := 0.  A pixel total that leaves the signed 64-bit range (|sum| >= 2^31:
-// only emitters brighter than ~1e6 at hundreds of samples get there) marks the pixel instead of wrapping: the hi-word
-// add reports its old value, and two's-complement addition overflowed iff both operands have the sign the result lacks.
-// (A lane's own partial cannot overflow first: see finish_path.)
-// Out of line: it runs when a lane moves to another pixel (every few paths), from four places of the kernel.
-#ifdef RTB_FLUSH_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-void lane_flush(WarpTile& t, int lane, int slot) {
+// tile totals += this lane's partials; partials := 0.
+//
+// Range (rtb.h "Accumulation range"): a pixel total must stay below 2^30 in magnitude.  A total whose two top bits differ
+// (|sum| in [2^30, 2^31)) marks the pixel instead of ever wrapping.  The window cannot be jumped: ordinary samples are below
+// 2^20 and a lane's partial holds at most 1024 of them (< 2^30 ... flushed long before: see finish_path), a sample of 2^20
+// or more is added alone (and is below 2^25, or the pixel is marked without adding it), and the totals are read back AFTER
+// this lane's own adds, so the lane whose add carries a total across 2^30 sees it there (the concurrent flushes of the 31
+// other lanes move it by < 31 * 2^25 < 2^30 meanwhile).  The hi-word add itself stays a fire-and-forget shared atomic: waiting for its result
+// (ten dependent round trips per flush) cost the 64-spp configs up to 10 % (measured on the Cornell world).
+__device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
 #pragma unroll
   for (int v = 0; v < kAccValues; v++) {
     const uint2 cur = t.lane_acc[v][lane];
     if (cur.x | cur.y) {
       const uint32_t old = atomicAdd(&t.acc_lo[slot][v], cur.x);
       const uint32_t hi = cur.y + ((old + cur.x) < old ? 1u : 0u);
-      if (hi) {
-#ifndef RTB_NO_OVERFLOW_CHECK
-        const uint32_t old_hi = atomicAdd(&t.acc_hi[slot][v], hi);
-        if (~(old_hi ^ hi) & (old_hi ^ (old_hi + hi)) & 0x80000000u) t.non_finite[slot] = 1;
-#else
-        atomicAdd(&t.acc_hi[slot][v], hi);
-#endif
-      }
+      if (hi) atomicAdd(&t.acc_hi[slot][v], hi);
       t.lane_acc[v][lane] = make_uint2(0u, 0u);
     }
   }
+  uint32_t window = 0u;
+#pragma unroll
+  for (int v = 0; v < kAccValues; v++) {
+    const uint32_t h = t.acc_hi[slot][v];
+    window |= h ^ (h << 1);
+  }
+  if (window & 0x80000000u) t.non_finite[slot] = 1;
   const uint32_t c = t.lane_counts[lane];
   if (c) {
     if (c >> 20) atomicAdd(&t.successes[slot], c >> 20);
@@ -201,15 +200,15 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       const float vals[kAccValues] = {radiance.x, radiance.y, radiance.z, tile.aov[0][lane], tile.aov[1][lane], tile.aov[2][lane],
                                       tile.aov[3][lane], tile.aov[4][lane], tile.aov[5][lane], events_acc};
       // Range of the fixed-point sums (rtb.h "Accumulation range").  Ordinary samples (every component below 2^20): a lane's
-      // partial holds at most 1024 of them between flushes, so it stays below 2^30 and cannot wrap.  A brighter sample goes
-      // alone: partials out first, the sample in, out again — lane_flush sees the pixel total overflow if it does.
+      // partial holds at most 32 of them between flushes (see below), so it stays below 2^25.  A brighter sample goes alone:
+      // partials out first, the sample in, out again — lane_flush sees the pixel total reach 2^30 if it does.
       bool ordinary = true;
 #pragma unroll
       for (int k = 0; k < kAccValues; k++) ordinary = ordinary && (um::abs(vals[k]) < 1048576.0f);
       if (!ordinary) {
         bool finite = true;
 #pragma unroll
-        for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 1.0e9f);
+        for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 33554432.0f);   // 2^25: 32 lanes of them < 2^30
         if (finite) {
           lane_flush(tile, lane, acc_slot);
           counts = (uint32_t)depth + 1u;
@@ -226,8 +225,9 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       counts += 1u << 20;
     }
     tile.lane_counts[lane] = counts;
-    // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps
-    if (flush_now || (counts >> 20) >= 1024u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
+    // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps, and often enough (every
+    // 32 successes: a partial then stays below 2^25) for lane_flush's overflow window to be airtight
+    if (flush_now || (counts >> 20) >= 32u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
   };
 
   // One trip of the loop, for every lane of the warp:
@@ -282,11 +282,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       // that claims a tile reads the mapped flag, and tells the CTA's other warps to stop issuing samples)
       uint32_t t = 0;
       if (lane == 0) {
-#ifndef RTB_NO_CLAIM_CANCEL
         const bool cancelled = cancel_requested(a.cancel_flag, a.cancel_epoch);
-#else
-        const bool cancelled = false;
-#endif
         t = atomicAdd(a.tile_counter, 1u);
         if (cancelled) { *cta_cancelled = 1u; t = 0xffffffffu; }
       }
@@ -380,9 +376,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     // 122.7 / 123.7 / 132.3 ms, mesh world 70.2 -> 67.1 ms; on the linear list (converged walk: an idle lane is pure loss)
     // and on worlds of a dozen entities 1 is best — the plugin picks 8 for trees of >= 64 inner nodes.
     if (need && ((uint32_t)__popc(need) >= a.refill_min || need == 0xffffffffu)) {
-#ifndef RTB_NO_LOOP_CANCEL
       if (*cta_cancelled) next_item = total_items;      // cancelled: the tile's remaining samples are not started
-#endif
       const uint32_t my_item = next_item + __popc(need & lt_mask);
       if (!alive && my_item < total_items) {
         // item -> (pixel slot, sample) through the tile's prefix table

@@ -1075,12 +1075,15 @@ def test_cancellation_token_set_mid_flight(rtb):
 
 def test_accumulator_range_is_loud(rtb, oracle, ctx):
     """rtb.h "Accumulation range": the megakernel's per-pixel sums are 64-bit fixed point with 32 fraction bits.  Emitters far
-    brighter than any display range still add up like the reference's floats (2^20 <= sample < 1e9 takes the one-at-a-time
-    path); a pixel whose batch total reaches 2^31 is written as NaN — never a wrapped, sign-flipped value."""
+    brighter than any display range still add up like the reference's floats (2^20 <= sample < 2^25 takes the one-at-a-time
+    path); a pixel whose batch total reaches 2^30 is written as NaN — never a wrapped, sign-flipped value."""
     W, H, spp = 32, 18, 64
-    for emission, overflow in ((3.0e6, False), (9.0e7, True)):
+    for emission, overflow in ((3.0e6, False), (2.5e7, True)):
         scene = rtb.host.make_scene("three_spheres", max_bvh_depth=2)
         scene.materials = scene.materials.copy()
+        scene.materials["type"][:] = rtb.abi.MATERIAL_STANDARD     # black diffuse emitters: every sample that hits one is `emission`
+        scene.materials["glossiness"][:] = 0.0
+        scene.materials["metallic"][:] = 0.0
         scene.materials["albedo"][:] = 0.0
         scene.materials["emission"][:] = emission
         p = rtb.host.make_params(scene, W, H, spp, 8)
@@ -1088,7 +1091,7 @@ def test_accumulator_range_is_loud(rtb, oracle, ctx):
         oracle.sample_batch(scene, p, ref)
         got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
         assert np.array_equal(ref.out_color[:, 3], got.out_color[:, 3])
-        big = ref.out_color[:, 0] >= 2.0 ** 31
+        big = ref.out_color[:, 0] >= 2.0 ** 30
         assert big.any() == overflow
         assert np.isnan(got.out_color[big, :3]).all()
         ok = ~big
