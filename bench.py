@@ -8,9 +8,13 @@ defocus, 1920x1080, 256 spp, depth 50), one process per GPU.
     python bench.py --impl reference          # the reference's CPU algorithm on the host cores
 
 A "step" is one full sample batch of the frame (W*H*spp camera paths).  N > 1: the frame is
-sharded by row tiles (total work fixed -> "strong" scaling) and each step ends with the NCCL
-gather of the tiles to rank 0; time = max over ranks, CUDA events on the launching stream.
-Prints ONE JSON line (rank 0).
+sharded by balanced row tiles (total work fixed -> "strong" scaling); every rank's kernel writes its
+tile straight into rank 0's frame over NVLink (CUDA IPC mapping; --nccl-gather: the round-1 gather),
+and a step ends with a 4-byte all-reduce as the frame-complete signal; time = max over ranks, CUDA
+events on the launching stream.  `e2e`: the host-buffer C ABI call with a live cancellation token —
+rtb_sample_batch at N = 1, rtb_multi_sample_batch driving all N GPUs from rank 0's process at N > 1.
+`value_fast`: the same steps with the opt-in fast-arithmetic build.  The default run (config 3) also
+carries short lines for configs 2, 4 and 5 under `other_configs`.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import importlib
@@ -207,8 +211,228 @@ def run_reference(args):
     emit(line)
 
 
-def run_ours(args):
+def _pinned_host_buffers(rtb, abi, W, H):
+    """plugin.HostBuffers over pinned (page-locked) torch CPU tensors: the host's pooled NativeArrays (Raytracer.cs:279-303)."""
+    import torch
+    n = W * H
+    host = {}
+    for k, c in (("color", 4), ("weight", 1), ("normal", 3), ("albedo", 3)):
+        host["in_" + k] = torch.zeros(n, c, dtype=torch.float32).pin_memory()
+        host["out_" + k] = torch.zeros(n, c, dtype=torch.float32).pin_memory()
+    host["diag"] = torch.zeros(n, 4, dtype=torch.float32).pin_memory()
+    hb = rtb.plugin.HostBuffers(1, 1)
+    hb.width, hb.height = W, H
+    hb.in_color, hb.in_weight = host["in_color"].numpy(), host["in_weight"].numpy().reshape(-1)
+    hb.in_normal, hb.in_albedo = host["in_normal"].numpy(), host["in_albedo"].numpy()
+    hb.out_color, hb.out_weight = host["out_color"].numpy(), host["out_weight"].numpy().reshape(-1)
+    hb.out_normal, hb.out_albedo = host["out_normal"].numpy(), host["out_albedo"].numpy()
+    hb.diagnostics = host["diag"].numpy().view(abi.DIAGNOSTICS_DTYPE).reshape(-1)
+    return hb, host
+
+
+def measure_config(cfg, steps, warmup, rtb, renderer_mod, sharding, abi, dev, world, rank, local_rank, args, full):
+    """Times one BASELINE config at this world size.  `full`: the headline config — also the fast-arithmetic build, the
+    instrumented counters for the roofline, the end-to-end leg and the clocks; otherwise a short line (device-resident + e2e)."""
     import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    name, depth, W, H, spp, td, ap = CONFIGS[cfg]
+    scene = make_scene(rtb.host, cfg)
+    params = rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
+    fr = renderer_mod.FrameRenderer(scene, W, H, device_index=local_rank)
+    samples_per_step = W * H * spp
+    n = W * H
+    out = {"workload": WORKLOADS[cfg]}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    assembly = "single GPU"
+    if world > 1:
+        peer = (not args.nccl_gather) and fr.enable_peer_frame()
+        assembly = ("peer frame: every rank's kernel reads and writes its row tile in rank 0's HBM over NVLink (CUDA IPC mapping); "
+                    "one 4-byte all-reduce per frame as the frame-complete signal") if peer else \
+                   "one batched NCCL gather of all tile buffers to rank 0 per frame"
+
+    # ---- load-balanced row tiles (one process per GPU: the Python twin of the plugin's own balancer, rtb_balance_rows) ----
+    # (1) cost model from a cheap instrumented probe batch: per-row executed box tests, entity tests and rays (the
+    #     reference's FULL_DIAGNOSTICS counters, Raytracer.cs:56-60) weighted by their instruction cost;
+    # (2) feedback from measured per-rank kernel times during the warm-up steps.
+    tiles_kind = "equal"
+    row_cost = None
+    if world > 1 and not args.equal_tiles:
+        probe = rtb.host.make_params(scene, W, H, max(1, min(8, spp)), td, aperture=ap, seed=12345)
+        fr.ctx.set_option(abi.OPT_COUNTERS, 1)
+        fr.render_device(probe, gather=False)
+        fr.ctx.set_option(abi.OPT_COUNTERS, 0)
+        if fr.peer is None:
+            fr.gather(all_ranks=True)
+        else:
+            fr.frame_complete()
+        torch.cuda.synchronize()
+        cost_t = torch.zeros(H, dtype=torch.float64, device=dev)
+        if fr.peer is None or rank == 0:
+            d = fr.diag.view(H, W, 4).double()
+            cost_t = (450.0 * d[:, :, 0] + 35.0 * d[:, :, 1] + 40.0 * d[:, :, 2]).sum(dim=1)
+        if fr.peer is not None:
+            dist.broadcast(cost_t, src=0)
+        row_cost = cost_t.cpu().numpy()
+        bb = rtb.plugin.balance_rows(row_cost, 0, H, world)
+        fr.set_tiles(list(zip(bb[:-1], bb[1:])))
+        tiles_kind = "cost-model balanced + kernel-time feedback"
+
+    last_kernel_ms = [0.0]
+
+    def rebalance_from_times():
+        """Scale each tile's rows by measured time / modelled cost and re-partition (all ranks compute the same tiles)."""
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = last_kernel_ms[0]
+        dist.all_reduce(t)
+        times = t.cpu().numpy()
+        for g, (b, e) in enumerate(fr.tiles):
+            c = row_cost[b:e].sum()
+            if c > 0 and times[g] > 0:
+                row_cost[b:e] *= times[g] / c
+        bb = rtb.plugin.balance_rows(row_cost, 0, H, world)
+        fr.set_tiles(list(zip(bb[:-1], bb[1:])))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed_device_steps(k, w, rebalance):
+        """w warm-up + k timed device-resident steps; returns (total ms max over ranks, kernel ms of this rank, per rank)."""
+        wev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        for _ in range(w):
+            wev[0].record()
+            fr.render_device(params, gather=False)
+            wev[1].record()
+            fr.frame_complete()
+            torch.cuda.synchronize()
+            last_kernel_ms[0] = wev[0].elapsed_time(wev[1])
+            if rebalance and row_cost is not None:
+                rebalance_from_times()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        ev[0].record()
+        for i in range(k):
+            flush.zero_()                                   # evict L2 between timed iterations
+            kev[i][0].record()
+            fr.render_device(params, gather=False)
+            kev[i][1].record()
+            fr.frame_complete()                             # peer frame: 4-byte all-reduce; fallback: the NCCL gather
+        ev[1].record()
+        barrier()
+        total_ms = sharding.max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
+        kernel_ms = sum(x.elapsed_time(y) for x, y in kev) / k
+        per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+        per_rank[rank] = kernel_ms
+        if world > 1:
+            dist.all_reduce(per_rank)
+        return total_ms, kernel_ms, [round(float(x), 3) for x in per_rank.cpu()]
+
+    # ---- work counters of one step (instrumented kernel, untimed) for the roofline numerator ---
+    cnt = None
+    if full:
+        fr.ctx.set_option(abi.OPT_COUNTERS, 1)
+        fr.render_device(params, gather=False)
+        cnt = fr.ctx.counters()
+        fr.ctx.set_option(abi.OPT_COUNTERS, 0)
+        fr.frame_complete()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (the parity build: the headline) --------------------------------
+    sampler = ClockSampler(local_rank) if (rank == 0 and full) else None
+    t0 = time.perf_counter()
+    total_ms, kernel_ms, kernel_ms_per_rank = timed_device_steps(steps, warmup, True)
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    out.update(value=samples_per_step * steps / (total_ms * 1e-3) / 1e6, ms_per_step=total_ms / steps, kernel_ms=kernel_ms,
+               kernel_ms_max=max(kernel_ms_per_rank), kernel_ms_per_rank=kernel_ms_per_rank, clocks=clocks, counters=cnt,
+               row_tiles=[list(map(int, t)) for t in fr.tiles], tiles_kind=tiles_kind, assembly=assembly)
+    if rank == 0:
+        out["frame_checksum"] = float(fr.out["color"][:, :3].double().sum().item())
+
+    # ---- the opt-in fast-arithmetic build, same steps (RTB_OPT_MATH = 1; statistics: tools/fast_math_report.py) ----
+    if full:
+        fr.ctx.set_option(abi.OPT_MATH, abi.MATH_FAST)
+        f_total, f_kernel, _ = timed_device_steps(steps, 1, False)
+        fr.ctx.set_option(abi.OPT_MATH, abi.MATH_PARITY)
+        out["value_fast"] = samples_per_step * steps / (f_total * 1e-3) / 1e6
+        out["ms_per_step_fast"] = f_total / steps
+        if rank == 0:
+            fast = fr.out["color"].clone()
+            fr.render_device(params, gather=False)
+            fr.frame_complete()
+            torch.cuda.synchronize()
+            strict = fr.out["color"]
+            cs, cf = strict[:, 3:4].clamp(min=1), fast[:, 3:4].clamp(min=1)
+            d = (strict[:, :3] / cs - fast[:, :3] / cf).abs().max(dim=1).values
+            out["fast_vs_parity"] = {"mean_abs_rgb_diff": float(d.mean()), "rmse": float((d * d).mean().sqrt()),
+                                     "p999_abs_rgb_diff": float(torch.quantile(d[:: max(1, d.numel() // 1000000)].float(), 0.999)),
+                                     "pixels_over_1e-4": float((d > 1e-4).float().mean()),
+                                     "pixels_with_other_sample_count": float((strict[:, 3] != fast[:, 3]).float().mean()),
+                                     "image_mean_diff": float((strict[:, :3] / cs).mean() - (fast[:, :3] / cf).mean())}
+        else:
+            fr.render_device(params, gather=False)
+            fr.frame_complete()
+        barrier()
+
+    # ---- end to end through the host-buffer C ABI, with a LIVE cancellation token (the C# job always passes one) -------
+    # N = 1: rtb_sample_batch.  N > 1: ONE process (rank 0) drives all N GPUs through rtb_multi_sample_batch — the reference's
+    # single call site (Raytracer.cs:671-736) — on one set of pinned host arrays every device reads and writes in place; the
+    # other ranks only wait.  The timed region holds the host<->device traffic of every step (in place over PCIe).
+    cancel = np.zeros(1, np.uint8)
+    e2e = None
+    fr_flush = None
+    if rank == 0:
+        hb, host = _pinned_host_buffers(rtb, abi, W, H)
+        if world == 1:
+            ctx_e2e, api = fr.ctx, "rtb_sample_batch (C ABI, pinned host buffers read and written in place by the kernel over PCIe, live cancellation token)"
+
+            def e2e_step():
+                ctx_e2e.sample_batch(params, hb, cancel=cancel)
+        else:
+            multi = rtb.plugin.MultiContext(list(range(world)))
+            multi.upload(scene)
+            api = (f"rtb_multi_sample_batch (C ABI, ONE process drives {world} GPUs: row tiles balanced inside the plugin, every device reads and "
+                   "writes its tile of the pinned host frame in place over its own PCIe link, live cancellation token; no gather)")
+
+            def e2e_step():
+                multi.sample_batch(params, hb, cancel=cancel)
+        for _ in range(max(2, min(warmup, 3)) if full else 1):
+            e2e_step()
+        t = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        e2e_s = time.perf_counter() - t
+        # the same loop without a token: the token must cost nothing (VERDICT r1 item 2)
+        if full:
+            t = time.perf_counter()
+            for _ in range(steps):
+                (ctx_e2e.sample_batch(params, hb) if world == 1 else multi.sample_batch(params, hb))
+            e2e_s_no_token = time.perf_counter() - t
+        e2e = {"value": samples_per_step * steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": n * 44, "d2h_bytes_per_step": n * (48 + 16),
+               "api": api, "in_place": bool(fr.ctx.last_batch_in_place()) if world == 1 else True,
+               "out_color_checksum": float(host["out_color"][:, :3].double().sum().item())}
+        if full:
+            e2e["value_without_token"] = samples_per_step * steps / e2e_s_no_token / 1e6
+        if world > 1:
+            bounds, ms = multi.tiles()
+            e2e["row_bounds"], e2e["kernel_ms_per_device"] = bounds, [round(x, 3) for x in ms]
+            multi.close()
+        out["host_frame"] = (host["out_color"].numpy(), host["diag"].numpy()[:, 0])
+    barrier()
+    out["e2e"] = e2e
+    fr.close()
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
     import torch
     import torch.distributed as dist
 
@@ -227,206 +451,79 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    common = (rtb, renderer_mod, sharding, abi, dev, world, rank, local_rank, args)
+    m = measure_config(args.config, args.steps, args.warmup, *common, full=True)
+    cnt = m["counters"]
     name, depth, W, H, spp, td, ap = CONFIGS[args.config]
-    scene = make_scene(rtb.host, args.config)
-    params = rtb.host.make_params(scene, W, H, spp, td, aperture=ap)
-    fr = renderer_mod.FrameRenderer(scene, W, H, device_index=local_rank)
-    samples_per_step = W * H * spp
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- load-balanced row tiles ----------------------------------------------------------------
-    # (1) cost model from a cheap instrumented probe batch: per-row executed box tests, sphere tests and
-    #     rays (the reference's FULL_DIAGNOSTICS counters, Raytracer.cs:56-60) weighted by their
-    #     instruction cost; (2) feedback from measured per-rank kernel times during the warm-up steps.
-    tiles_kind = "equal"
-    row_cost = None
-    if world > 1 and not args.equal_tiles:
-        probe = rtb.host.make_params(scene, W, H, max(1, min(8, spp)), td, aperture=ap, seed=12345)
-        fr.ctx.set_option(abi.OPT_COUNTERS, 1)
-        fr.render_device(probe, all_ranks=True)          # every rank derives the same tiles from the same diagnostics
-        fr.ctx.set_option(abi.OPT_COUNTERS, 0)
-        torch.cuda.synchronize()
-        d = fr.diag.view(H, W, 4).double()
-        row_cost = (450.0 * d[:, :, 0] + 35.0 * d[:, :, 1] + 40.0 * d[:, :, 2]).sum(dim=1).cpu().numpy()
-        fr.set_tiles(sharding.balanced_row_tiles(row_cost, world))
-        tiles_kind = "cost-model balanced + kernel-time feedback"
-
-    def rebalance_from_times():
-        """Scale each tile's rows by measured time / modelled cost and re-partition (all ranks compute the same tiles)."""
-        t = torch.zeros(world, dtype=torch.float64, device=dev)
-        t[rank] = last_kernel_ms[0]
-        dist.all_reduce(t)
-        times = t.cpu().numpy()
-        cost = row_cost.copy()
-        for g, (b, e) in enumerate(fr.tiles):
-            c = cost[b:e].sum()
-            if c > 0 and times[g] > 0:
-                cost[b:e] *= times[g] / c
-        row_cost[:] = cost
-        fr.set_tiles(sharding.balanced_row_tiles(cost, world))
-
-    # ---- work counters of one step (instrumented kernel, untimed) for the roofline numerator ---
-    fr.ctx.set_option(abi.OPT_COUNTERS, 1)
-    fr.render_device(params, gather=False)
-    cnt = fr.ctx.counters()
-    fr.ctx.set_option(abi.OPT_COUNTERS, 0)
-    flops_rank = (cnt["sphere_tests"] * FLOP_SPHERE_TEST + cnt["node_tests"] * FLOP_NODE_TEST
-                  + cnt["shade_standard"] * FLOP_SHADE_STANDARD + cnt["shade_dielectric"] * FLOP_SHADE_DIELECTRIC
-                  + cnt["sky_hits"] * FLOP_SKY + cnt["samples"] * FLOP_CAMERA_RAY)
-    fp32_peak = fr.ctx.measure_fp32_peak(5)
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    # ---- device-resident throughput ---------------------------------------------------------
-    last_kernel_ms = [0.0]
-    wev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    for _ in range(args.warmup):
-        wev[0].record()
-        fr.render_device(params, gather=False)
-        wev[1].record()
-        fr.gather()
-        torch.cuda.synchronize()
-        last_kernel_ms[0] = wev[0].elapsed_time(wev[1])
-        if row_cost is not None:
-            rebalance_from_times()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.25 if sampler else 0)
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t0 = time.perf_counter()
-    ev[0].record()
-    for i in range(args.steps):
-        flush.zero_()                                   # evict L2 between timed iterations
-        kev[i][0].record()
-        fr.render_device(params, gather=False)
-        kev[i][1].record()
-        fr.gather()                                      # the one NCCL exchange per frame (no-op at N = 1)
-    ev[1].record()
-    barrier()
-    t1 = time.perf_counter()
-    total_ms = sharding.max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    kernel_ms_max = sharding.max_over_ranks(kernel_ms, dev)
-    per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
-    per_rank[rank] = kernel_ms
-    if world > 1:
-        dist.all_reduce(per_rank)
-    kernel_ms_per_rank = [round(float(x), 3) for x in per_rank.cpu()]
-    clocks = sampler.stop(t0, t1) if sampler else None
-    value = samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
-
-    # ---- end to end through the host-buffer API ------------------------------------------------
     n = W * H
-    host = {}
-    for k, c in (("color", 4), ("weight", 1), ("normal", 3), ("albedo", 3)):
-        host["in_" + k] = torch.zeros(n, c, dtype=torch.float32).pin_memory()
-        host["out_" + k] = torch.zeros(n, c, dtype=torch.float32).pin_memory()
-    host["diag"] = torch.zeros(n, 4, dtype=torch.float32).pin_memory()
-    if world == 1:
-        # the C-ABI call a host makes: rtb_sample_batch with HOST pointers (pinned)
-        hb = rtb.plugin.HostBuffers(W, H)
-        hb.in_color, hb.in_weight = host["in_color"].numpy(), host["in_weight"].numpy().reshape(-1)
-        hb.in_normal, hb.in_albedo = host["in_normal"].numpy(), host["in_albedo"].numpy()
-        hb.out_color, hb.out_weight = host["out_color"].numpy(), host["out_weight"].numpy().reshape(-1)
-        hb.out_normal, hb.out_albedo = host["out_normal"].numpy(), host["out_albedo"].numpy()
-        hb.diagnostics = host["diag"].numpy().view(abi.DIAGNOSTICS_DTYPE).reshape(-1)
 
-        def e2e_step():
-            fr.ctx.sample_batch(params, hb)
-            return n * 44, n * (48 + 16)
-    else:
-        # One host, N GPUs: the frame lives in ONE set of pinned host arrays (one /dev/shm mapping across the N rank
-        # processes, registered with each rank's context) and every rank's rtb_sample_batch renders its row tile
-        # straight into them — inputs and outputs cross each GPU's own PCIe link inside its kernel; no gather is
-        # needed on this path.  Falls back to H2D / kernel / NCCL gather / D2H when shared memory is not available.
-        shared = _shared_host_frame(W, H, rank, abi, rtb) if not args.no_shared_host else None
-        if shared is not None:
+    # ---- the other BASELINE configs, short runs (they are parity-test cases; their lines ride along) --------------
+    others = {}
+    if args.config == "c3" and not args.no_other_configs:
+        for cfg in ("c2", "c4", "c5"):
             try:
-                fr.ctx.register_host_buffers(shared)      # cudaHostRegister of the shared pages in this rank's context
-            except Exception as e:      # noqa: BLE001 — any failure here means "use the staged path"
-                sys.stderr.write(f"rank {rank}: cannot pin the shared frame: {e}\n")
-                shared = None
-        ok = torch.tensor([1.0 if shared is not None else 0.0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() > 0:
-            hb = shared
+                o = measure_config(cfg, 1 if cfg == "c5" else 2, 1, *common, full=False)
+                others[cfg] = {"workload": o["workload"], "value": o["value"], "unit": "Msamples/s", "ms_per_step": o["ms_per_step"],
+                               "kernel_ms_per_rank": o["kernel_ms_per_rank"], "e2e": ({k: v for k, v in o["e2e"].items() if k != "api"} if o["e2e"] else None),
+                               "frame_checksum": o.get("frame_checksum"), "steps": 1 if cfg == "c5" else 2, "warmup": 1}
+            except Exception as e:      # noqa: BLE001 — an extra line must not take the headline down
+                others[cfg] = {"error": str(e)[:300]}
 
-            def e2e_step():
-                return fr.render_host_in_place(params, hb)
-            e2e_api = ("FrameRenderer.render_host_in_place: rtb_sample_batch per rank on ONE pinned host frame shared by the ranks (/dev/shm mapping): each GPU's "
-                       "kernel reads and writes its row tile in place over its own PCIe link")
-            host["out_color"] = torch.from_numpy(hb.out_color)
-        else:
-            shared = None
-
-            def e2e_step():
-                return fr.render_host(params, host)
-            e2e_api = "FrameRenderer.render_host (H2D own rows, rtb_sample_batch_device, NCCL gather, D2H on rank 0)"
-
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        h2d, d2h = e2e_step()
-    barrier()
-    e2e_s = sharding.max_over_ranks(time.perf_counter() - t, dev)
-    in_place = world == 1 and fr.ctx.last_batch_in_place()
-    e2e_value = samples_per_step * args.steps / e2e_s / 1e6
-    if world > 1:
-        bt = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
-        dist.all_reduce(bt)
-        h2d, d2h = int(bt[0].item()), int(bt[1].item())
-    checksum = float(host["out_color"][:, :3].double().sum().item()) if rank == 0 else 0.0
-
-    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
-    cpu = None
+    # ---- CPU baseline + parity object (rank 0, N = 1 only) -------------------------------------------------------
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         vals, desc = cpu_reference(args.config, threads, target_seconds=12.0)
         cpu = {"value": vals[0], "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": desc,
                "reference_traversal_per_ray": getattr(cpu_reference, "work", None)}
         try:
-            parity = parity_sample(args.config, host["out_color"].numpy(), host["diag"].numpy()[:, 0], threads)
+            parity = parity_sample(args.config, *m["host_frame"], threads)
         except Exception as e:      # noqa: BLE001 — the checker must not take the measurement down
             parity = {"error": str(e)}
 
     if rank == 0:
-        traffic = None
+        fp32_peak = None
+        try:
+            ctx = rtb.plugin.Context(local_rank)
+            fp32_peak = ctx.measure_fp32_peak(5)
+            ctx.close()
+        except Exception:       # noqa: BLE001
+            pass
+        traffic, traffic_source = None, None
         summary = os.path.join(ROOT, "profiles", "ncu_summary_latest.json")
         if os.path.exists(summary):
             try:
-                traffic = json.load(open(summary)).get("dram_bytes_per_launch")
+                js = json.load(open(summary))
+                traffic = js.get("dram_bytes_per_launch")
+                traffic_source = f"profiles/ncu_summary_latest.json ({js.get('label', '')}; ncu --set full capture of {js.get('captured', 'this round')}, not of this run)"
             except (OSError, ValueError):
                 traffic = None
+        kernel_ms = m["kernel_ms"]
+        flops_rank = (cnt["sphere_tests"] * FLOP_SPHERE_TEST + cnt["node_tests"] * FLOP_NODE_TEST
+                      + cnt["shade_standard"] * FLOP_SHADE_STANDARD + cnt["shade_dielectric"] * FLOP_SHADE_DIELECTRIC
+                      + cnt["sky_hits"] * FLOP_SKY + cnt["samples"] * FLOP_CAMERA_RAY)
         achieved_tf = flops_rank / (kernel_ms * 1e-3) / 1e12
         line = {
-            "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": "Msamples/sec", "value": m["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": WORKLOADS[args.config], "seed": 1, "rng": "Philox4x32-10 keyed (pixel, sample, bounce)",
-                "parallelism": f"row tiles x{world} ({tiles_kind}) + one batched NCCL gather of all tile buffers to rank 0 per frame" if world > 1 else "single GPU",
+                "parallelism": f"row tiles x{world} ({m['tiles_kind']}); {m['assembly']}" if world > 1 else "single GPU",
                 "l2": "256 MB buffer written between timed iterations (inside the bracket, ~0.05 ms) and 191 MB of accumulators per step > 126 MB L2",
                 "outputs": "color + normal + albedo + sampleCountWeight + diagnostics (full job contract)",
+                "arithmetic": "parity build (strict IEEE, FMAs only where written; bit-checked against the CPU restatement); value_fast = the opt-in fast build",
             },
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": ("rtb_sample_batch (C ABI, pinned host buffers" + (", read and written in place by the kernel over PCIe)" if in_place else ", staged H2D/D2H copies)")) if world == 1 else e2e_api,
-                    "out_color_checksum": checksum},
+            "e2e": m["e2e"],
+            "value_fast": m.get("value_fast"), "ms_per_step_fast": m.get("ms_per_step_fast"), "fast_vs_parity": m.get("fast_vs_parity"),
             "gpu_launches": args.steps * world,
-            "kernel_ms_rank0": kernel_ms, "kernel_ms_max_rank": kernel_ms_max, "kernel_ms_per_rank": kernel_ms_per_rank,
-            "row_tiles": [list(map(int, t)) for t in fr.tiles],
-            "mrays_per_s": cnt["rays"] * (world if world > 1 else 1) / (kernel_ms_max * 1e-3) / 1e6 if world == 1 else None,
+            "kernel_ms_rank0": kernel_ms, "kernel_ms_max_rank": m["kernel_ms_max"], "kernel_ms_per_rank": m["kernel_ms_per_rank"],
+            "row_tiles": m["row_tiles"], "frame_checksum": m.get("frame_checksum"),
+            "mrays_per_s": cnt["rays"] / (kernel_ms * 1e-3) / 1e6 if world == 1 else None,
             "failed_sample_fraction": cnt["failed_samples"] / max(cnt["samples"], 1),
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_source,
                 "note": "path is FP32-ALU/latency bound (SURVEY §8d): executed algorithmic flops of rank 0's tile (kernel counters x per-unit constants) / rank 0 kernel time; peak = FP32 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32-pipe figure)",
                 "counters_rank0": cnt,
                 "executed_per_ray": {"box_tests": cnt["node_tests"] / max(cnt["rays"], 1), "sphere_tests": cnt["sphere_tests"] / max(cnt["rays"], 1)},
@@ -436,54 +533,16 @@ def run_ours(args):
                 "frac": BYTES_PER_PIXEL * n / world / (kernel_ms * 1e-3) / 1e9 / _hbm_peak(), "traffic": traffic,
                 "note": "92 B/pixel/batch algorithmic; HBM is not the bound of this path",
             },
-            "clocks": clocks,
+            "clocks": m["clocks"],
         }
+        if others:
+            line["other_configs"] = others
         if cpu:
             line["cpu_baseline"] = cpu
             line["parity"] = parity
         emit(line)
-    fr.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def _shared_host_frame(W, H, rank, abi, rtb):
-    """HostBuffers over files in /dev/shm mapped by every rank: rank 0 creates them, the others map the same pages."""
-    import numpy as np
-    import torch.distributed as dist
-    n = W * H
-    spec = [("in_color", (n, 4), np.float32), ("in_weight", (n,), np.float32), ("in_normal", (n, 3), np.float32),
-            ("in_albedo", (n, 3), np.float32), ("out_color", (n, 4), np.float32), ("out_weight", (n,), np.float32),
-            ("out_normal", (n, 3), np.float32), ("out_albedo", (n, 3), np.float32), ("diagnostics", (n,), abi.DIAGNOSTICS_DTYPE)]
-    stem = f"/dev/shm/rtb_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_"
-    hb, err = None, None
-    try:
-        if rank == 0:
-            for name, shape, dt in spec:
-                m = np.memmap(stem + name, dtype=dt, mode="w+", shape=shape)
-                m[...] = 0
-                m.flush()
-    except OSError as e:
-        err = e
-    dist.barrier()
-    try:
-        if err is None:
-            hb = rtb.plugin.HostBuffers(1, 1)
-            hb.width, hb.height = W, H
-            for name, shape, dt in spec:
-                setattr(hb, name, np.memmap(stem + name, dtype=dt, mode="r+", shape=shape))
-    except OSError as e:
-        hb, err = None, e
-    dist.barrier()
-    if rank == 0:       # every rank holds its mapping now: the names can go
-        for name, _, _ in spec:
-            try:
-                os.unlink(stem + name)
-            except OSError:
-                pass
-    if err is not None:
-        sys.stderr.write(f"shared host frame unavailable on rank {rank}: {err}\n")
-    return hb
 
 
 def _hbm_peak():
@@ -514,7 +573,8 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--equal-tiles", action="store_true", help="contiguous equal row tiles instead of ray-count balanced ones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-shared-host", action="store_true", help="N > 1: end-to-end through H2D / gather / D2H instead of one shared pinned host frame")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: assemble the frame with the NCCL gather instead of the peer-mapped frame on rank 0")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short c2 / c4 / c5 lines that ride along with the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
