@@ -250,6 +250,13 @@ def measure_config(cfg, steps, warmup, rtb, renderer_mod, sharding, abi, dev, wo
             dist.barrier()
         torch.cuda.synchronize()
 
+    def cpu_barrier():
+        """Host-side wait (gloo): an NCCL barrier would leave a spinning kernel on every other GPU, and a GPU time-slices
+        between processes — rank 0's end-to-end leg drives ALL the GPUs from its own process."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=args.cpu_group)
+
     assembly = "single GPU"
     if world > 1:
         peer = (not args.nccl_gather) and fr.enable_peer_frame()
@@ -354,6 +361,7 @@ def measure_config(cfg, steps, warmup, rtb, renderer_mod, sharding, abi, dev, wo
                row_tiles=[list(map(int, t)) for t in fr.tiles], tiles_kind=tiles_kind, assembly=assembly)
     if rank == 0:
         out["frame_checksum"] = float(fr.out["color"][:, :3].double().sum().item())
+    barrier()       # peer frame: the other ranks must not start the next image while rank 0 reads this one
 
     # ---- the opt-in fast-arithmetic build, same steps (RTB_OPT_MATH = 1; statistics: tools/fast_math_report.py) ----
     if full:
@@ -362,8 +370,9 @@ def measure_config(cfg, steps, warmup, rtb, renderer_mod, sharding, abi, dev, wo
         fr.ctx.set_option(abi.OPT_MATH, abi.MATH_PARITY)
         out["value_fast"] = samples_per_step * steps / (f_total * 1e-3) / 1e6
         out["ms_per_step_fast"] = f_total / steps
+        fast = fr.out["color"].clone() if rank == 0 else None
+        barrier()
         if rank == 0:
-            fast = fr.out["color"].clone()
             fr.render_device(params, gather=False)
             fr.frame_complete()
             torch.cuda.synchronize()
@@ -386,7 +395,7 @@ def measure_config(cfg, steps, warmup, rtb, renderer_mod, sharding, abi, dev, wo
     # other ranks only wait.  The timed region holds the host<->device traffic of every step (in place over PCIe).
     cancel = np.zeros(1, np.uint8)
     e2e = None
-    fr_flush = None
+    cpu_barrier()
     if rank == 0:
         hb, host = _pinned_host_buffers(rtb, abi, W, H)
         if world == 1:
@@ -424,7 +433,7 @@ def measure_config(cfg, steps, warmup, rtb, renderer_mod, sharding, abi, dev, wo
             e2e["row_bounds"], e2e["kernel_ms_per_device"] = bounds, [round(x, 3) for x in ms]
             multi.close()
         out["host_frame"] = (host["out_color"].numpy(), host["diag"].numpy()[:, 0])
-    barrier()
+    cpu_barrier()
     out["e2e"] = e2e
     fr.close()
     del flush
@@ -448,8 +457,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    args.cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        args.cpu_group = dist.new_group(backend="gloo")
 
     common = (rtb, renderer_mod, sharding, abi, dev, world, rank, local_rank, args)
     m = measure_config(args.config, args.steps, args.warmup, *common, full=True)
