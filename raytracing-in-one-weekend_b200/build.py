@@ -39,7 +39,7 @@ NVCC_FAST = ["-fmad=true"]
 NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static"]
 GXX_FLAGS = [
     "-std=c++17", "-O2", "-ffp-contract=off", "-march=x86-64-v3",
-    "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra",
+    "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra", "-pthread",
     "-I", INCLUDE,
 ]
 

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <set>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -215,6 +216,13 @@ Aabb sphere_world_bounds(const rtb_sphere& s) {
   return Aabb{mn, mx};
 }
 
+// Threads for the BVH build: RTB_BUILD_THREADS, else the hardware's (capped at 32).
+int build_threads() {
+  if (const char* e = getenv("RTB_BUILD_THREADS")) return std::max(1, atoi(e));
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::min(32u, std::max(1u, hw));
+}
+
 struct NodeData {  // BvhNodeData
   Aabb bounds{};
   int first_entity = -1, entity_count = 0, depth = 0;
@@ -246,10 +254,7 @@ struct Builder {
       // NativeSlice.Sort with comparer (int)sign(lhs.Min[axis] - rhs.Min[axis]) (:240-250).
       // Unity's sort is not stable; ties are measure-zero for these scenes and radiance does
       // not depend on tie order.  We use a stable sort so the flattened tree is reproducible.
-      const int ax = biggest;
-      std::stable_sort(ents, ents + count, [ax](const BuildEntity& a, const BuildEntity& b) {
-        return um::comp(a.bounds.mn, ax) < um::comp(b.bounds.mn, ax);
-      });
+      parallel_stable_sort(ents, count, biggest, threads_for(count));
     }
 
     if (depth == max_depth || count <= 1) {
@@ -276,16 +281,80 @@ struct Builder {
     }
     if (partition_length == count) partition_length--;
 
-    int l = (int)nodes.size();
-    nodes.emplace_back();
-    build(l, ents, partition_length, depth + 1, biggest);
-    int r = (int)nodes.size();
-    nodes.emplace_back();
-    build(r, ents + partition_length, count - partition_length, depth + 1, biggest);
+    int l, r;
+    if (count >= kParallelEntities && worker_budget > 1) {
+      // Large subtrees are built concurrently, each into its own builder, and spliced in the order the serial recursion
+      // creates them (left subtree's nodes and leaf entities first, then the right one's): same node array, same
+      // bvhEntities order, whatever the thread count.
+      Builder lb, rb;
+      lb.spheres = rb.spheres = spheres;
+      lb.max_depth = rb.max_depth = max_depth;
+      lb.worker_budget = worker_budget / 2;
+      rb.worker_budget = worker_budget - lb.worker_budget;
+      lb.nodes.emplace_back();
+      rb.nodes.emplace_back();
+      std::thread left_thread([&] { lb.build(0, ents, partition_length, depth + 1, biggest); });
+      rb.build(0, ents + partition_length, count - partition_length, depth + 1, biggest);
+      left_thread.join();
+      l = splice(lb);
+      r = splice(rb);
+    } else {
+      l = (int)nodes.size();
+      nodes.emplace_back();
+      build(l, ents, partition_length, depth + 1, biggest);
+      r = (int)nodes.size();
+      nodes.emplace_back();
+      build(r, ents + partition_length, count - partition_length, depth + 1, biggest);
+    }
     nd.left = l;
     nd.right = r;
     nd.bounds = enclose(nodes[l].bounds, nodes[r].bounds);
     nodes[self] = nd;
+  }
+
+  // ---- multithreaded build (the reference's BvhNodeData ctor is one serial job: 2.2 s for a million triangles) ----
+  static constexpr int kParallelEntities = 16384;
+  int worker_budget = 1;                // threads this subtree may use
+  int threads_for(int count) const { return count >= kParallelEntities ? worker_budget : 1; }
+
+  // appends another builder's subtree (root at its index 0): returns the index its root got
+  int splice(const Builder& b) {
+    const int node_base = (int)nodes.size(), entity_base = (int)bvh_entities.size();
+    for (NodeData n : b.nodes) {
+      if (n.left >= 0) n.left += node_base;
+      if (n.right >= 0) n.right += node_base;
+      if (n.first_entity >= 0) n.first_entity += entity_base;
+      nodes.push_back(n);
+    }
+    bvh_entities.insert(bvh_entities.end(), b.bvh_entities.begin(), b.bvh_entities.end());
+    return node_base;
+  }
+
+  // stable sort by bounds.min[axis]: chunks sorted concurrently, then merged pairwise (std::inplace_merge is stable)
+  static void parallel_stable_sort(BuildEntity* ents, int count, int ax, int threads) {
+    auto less = [ax](const BuildEntity& a, const BuildEntity& b) { return um::comp(a.bounds.mn, ax) < um::comp(b.bounds.mn, ax); };
+    if (threads <= 1 || count < kParallelEntities) {
+      std::stable_sort(ents, ents + count, less);
+      return;
+    }
+    int chunks = 1;
+    while (chunks * 2 <= threads && count / (chunks * 2) >= kParallelEntities / 4) chunks *= 2;
+    std::vector<int> cut(chunks + 1);
+    for (int i = 0; i <= chunks; i++) cut[i] = (int)((long long)count * i / chunks);
+    {
+      std::vector<std::thread> pool;
+      for (int i = 1; i < chunks; i++) pool.emplace_back([&, i] { std::stable_sort(ents + cut[i], ents + cut[i + 1], less); });
+      std::stable_sort(ents + cut[0], ents + cut[1], less);
+      for (auto& t : pool) t.join();
+    }
+    for (int width = 1; width < chunks; width *= 2) {
+      std::vector<std::thread> pool;
+      for (int i = 0; i + width < chunks; i += 2 * width) {
+        const int lo = cut[i], mid = cut[i + width], hi = cut[std::min(i + 2 * width, chunks)];
+        pool.emplace_back([=] { std::inplace_merge(ents + lo, ents + mid, ents + hi, less); });
+      }
+      for (auto& t : pool) t.join();
+    }
   }
 
   // BuildRuntimeBvhJob.WalkBvh (:18-33): post-order, written backwards, root lands on index 0.
@@ -449,6 +518,7 @@ int rtbh_build_bvh_from_bounds(const float* bounds, size_t entity_count, int max
   Builder b;
   b.spheres = nullptr;
   b.max_depth = max_depth;
+  b.worker_budget = build_threads();
   b.nodes.reserve(entity_count * 2 + 1);
   b.nodes.emplace_back();
   b.build(0, ents.data(), (int)entity_count, 0, -1);

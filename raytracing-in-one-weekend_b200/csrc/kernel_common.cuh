@@ -101,10 +101,12 @@ constexpr uint32_t kStatusHitListOverflow = 1u;   // sample_volumes: a ray met m
 
 // Bytes between inner-node records.  The walk reads a node as four LDS.128 at [ref + 16 k]; with 64-byte records the
 // k-th quad of EVERY node starts in one of two 16-byte bank groups (64 B = 16 banks), so divergent lanes pile up on
-// 8 of the 32 banks (ncu, round 1: 31 % of the shared wavefronts were conflict replays).  An odd multiple of 16 bytes
-// spreads the same quad of different nodes over all eight bank groups; refs are byte offsets, so the walk is unchanged.
+// 8 of the 32 banks (ncu: 31 % of the shared wavefronts are conflict replays).  An odd multiple of 16 bytes (80, 112)
+// spreads them over all eight bank groups — measured on config 3: no faster (80: 151.3 vs 151.4 ms, 129.9 vs 130.2;
+// 112: 155.2; the LSU pipe is at 20 % and the replays hide behind the ALU work), so the records stay packed.  Refs are
+// byte offsets, the walk does not depend on the stride.
 #ifndef RTB_NODE_STRIDE
-#define RTB_NODE_STRIDE 80
+#define RTB_NODE_STRIDE 64
 #endif
 constexpr uint32_t kNodeStride = RTB_NODE_STRIDE;
 static_assert(kNodeStride >= 64 && kNodeStride % 16 == 0, "node records are 4 x float4, 16-byte aligned");
@@ -560,7 +562,7 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 #define RTB_WALK_SYNC 1
 #endif
 __device__ __forceinline__ void walk_converge() {
-#if RTB_WALK_SYNC
+#if RTB_WALK_SYNC == 1
   __syncwarp(__activemask());
 #endif
 }
@@ -688,10 +690,19 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
         test_leaf(cur);
         need_pop = true;
       }
+#if RTB_WALK_SYNC == 2
+      // branch-free pop: the stack top is read every trip (the sentinel keeps the read valid) and taken when needed, so the
+      // loop has ONE latch whatever the compiler's mood
+      const int popped = top[-1];
+      top -= need_pop ? 1 : 0;
+      cur = need_pop ? popped : cur;
+      if (cur == kTraversalDone) break;
+#else
       if (need_pop) {
         cur = *--top;
         if (cur == kTraversalDone) break;
       }
+#endif
     }
   }
     return;

@@ -589,7 +589,7 @@ void choose_tiles(BatchArgs& a, uint32_t n_warps_full, uint32_t max_spp) {
   // tree), not when the world is a linear list every lane walks in step
   static const int refill_env = [] { const char* e = getenv("RTB_REFILL_MIN"); return e ? std::min(32, std::max(1, atoi(e))) : 0; }();
   a.refill_min = refill_env ? (uint32_t)refill_env : (a.scene.n_inner >= 64 ? 8u : 1u);
-  int tp = (int)std::min<uint32_t>(kTilePixelsMax, std::max<uint32_t>(1, (target + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
+  int tp = (int)std::min<uint32_t>(kHalfPixels, std::max<uint32_t>(1, (target + max_spp - 1) / std::max<uint32_t>(max_spp, 1)));
   while (tp > 1 && (a.n_active_pixels + tp - 1) / tp < 6 * n_warps_full && (uint64_t)(tp / 2) * max_spp >= 1024) tp /= 2;
   // guided self-scheduling: the last ~8 tiles per resident warp are a quarter of the size, the last ~8 after
   // those a sixteenth (never fewer than ~256 samples per tile: below that the per-tile drain costs more than the tail)

@@ -55,9 +55,14 @@ struct WarpTile {
   uint32_t sphere_tests[kTilePixelsMax];
   uint32_t non_finite[kTilePixelsMax];
   float fallback[kTilePixelsMax][6];     // first sample's normal/albedo (SampleBatchJob.cs:152-156)
-  uint32_t prefix[kTilePixelsMax + 1];   // exclusive prefix of per-pixel sample counts
-  uint32_t pix_xy[kTilePixelsMax];       // image coordinates of the tile's pixels: x | y << 16
+  // Two tiles are in flight per warp: the one whose samples are being issued and the previous one, whose last paths are
+  // still running (its lanes are refilled from the NEXT tile meanwhile, so no lane idles through a tile's drain).  A tile
+  // occupies one half of the pixel slots: slots [0, kHalfPixels) or [kHalfPixels, kTilePixelsMax).
+  uint32_t prefix[2][kTilePixelsMax / 2 + 1];   // per half: exclusive prefix of per-pixel sample counts
+  uint32_t pix_xy[kTilePixelsMax];       // image coordinates of the slot's pixel: x | y << 16
+  uint32_t half_base[2];                 // per half: first active-pixel index of its tile
 };
+constexpr int kHalfPixels = kTilePixelsMax / 2;
 
 // lane-private += x (exact: x * 2^32 is an integer for |x| >= 2^-9, rounded to 2^-32 below that)
 __device__ __forceinline__ void lane_add(WarpTile& t, int lane, int v, float x) {
@@ -75,7 +80,7 @@ __device__ __forceinline__ void lane_add(WarpTile& t, int lane, int v, float x) 
 // this lane's own adds, so the lane whose add carries a total across 2^30 sees it there (the concurrent flushes of the 31
 // other lanes move it by < 31 * 2^25 < 2^30 meanwhile).  The hi-word add itself stays a fire-and-forget shared atomic: waiting for its result
 // (ten dependent round trips per flush) cost the 64-spp configs up to 10 % (measured on the Cornell world).
-__device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
+__device__ __forceinline__ void lane_flush_inline(WarpTile& t, int lane, int slot) {
 #pragma unroll
   for (int v = 0; v < kAccValues; v++) {
     const uint2 cur = t.lane_acc[v][lane];
@@ -100,6 +105,15 @@ __device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
     t.lane_counts[lane] = 0;
   }
 }
+// The lean sphere builds call it out of line (their hot loop is instruction-fetch sensitive: three inlined copies raised
+// ncu's no-instruction stalls from 0.35 to 0.98 per issue on config 3); the general and placed builds, which run 64-spp
+// worlds with a flush every other path and have registers to spare, inline it (Cornell world: 179 -> 161 ms).
+__device__ __noinline__ void lane_flush_call(WarpTile& t, int lane, int slot) { lane_flush_inline(t, lane, slot); }
+template <int FLAVOR>
+__device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
+  if (FLAVOR >= kFlavorGeneral) lane_flush_inline(t, lane, slot);
+  else lane_flush_call(t, lane, slot);
+}
 __device__ __forceinline__ float fixed_read(const WarpTile& t, int slot, int v) {
   long long q = (long long)(((unsigned long long)t.acc_hi[slot][v] << 32) | t.acc_lo[slot][v]);
   return __ll2float_rn(q) * kFixedInvScale;
@@ -119,6 +133,102 @@ __device__ __forceinline__ void active_pixel(const BatchArgs& a, uint32_t k, int
   *cy = a.first_row + (int)j * a.row_step;
   *index = (uint32_t)*cy * (uint32_t)a.width + (uint32_t)*cx;
 }
+
+// Writes the finished tile of `half` (n pixels) to the output buffers: lanes 0..n-1, one pixel each, float4 colour store.
+// Out of line, like claim_tile: once per tile, and the hot loop stays short.
+__device__ __noinline__ void retire_tile(WarpTile& tile, const BatchArgs& a, int lane, int half, int n) {
+  if (lane < n) {
+    const int s = half * kHalfPixels + lane;
+    int cx, cy;
+    uint32_t index;
+    active_pixel(a, tile.half_base[half] + (uint32_t)lane, &cx, &cy, &index);
+    const float4 in_color = reinterpret_cast<const float4*>(a.b.in_color)[index];
+    const float in_weight = a.b.in_sample_count_weight[index];
+    const int succ = (int)tile.successes[s];
+    const int sample_count = (int)in_color.w + succ;
+    const bool bad = tile.non_finite[s] != 0;
+    const float nan = um::asfloat(0x7fc00000u);
+    float v[kAccValues];
+#pragma unroll
+    for (int k = 0; k < kAccValues; k++) v[k] = bad ? nan : fixed_read(tile, s, k);
+    float4 oc = make_float4(in_color.x + v[0], in_color.y + v[1], in_color.z + v[2], (float)sample_count);
+    reinterpret_cast<float4*>(a.b.out_color)[index] = oc;
+    const float* in_n = a.b.in_normal + 3 * (size_t)index;
+    const float* in_a = a.b.in_albedo + 3 * (size_t)index;
+    float* on = a.b.out_normal + 3 * (size_t)index;
+    float* oa = a.b.out_albedo + 3 * (size_t)index;
+    if (sample_count == 0) {
+      on[0] = tile.fallback[s][0]; on[1] = tile.fallback[s][1]; on[2] = tile.fallback[s][2];
+      oa[0] = tile.fallback[s][3]; oa[1] = tile.fallback[s][4]; oa[2] = tile.fallback[s][5];
+    } else {
+      on[0] = in_n[0] + v[3]; on[1] = in_n[1] + v[4]; on[2] = in_n[2] + v[5];
+      oa[0] = in_a[0] + v[6]; oa[1] = in_a[1] + v[7]; oa[2] = in_a[2] + v[8];
+    }
+    a.b.out_sample_count_weight[index] = in_weight + v[9];
+    if (a.b.out_diagnostics) {
+      rtb_diagnostics dg;
+      dg.ray_count = (float)tile.rays[s];
+      dg.bounds_hit_count = (float)tile.node_tests[s];
+      dg.candidate_count = (float)tile.sphere_tests[s];
+      dg.sample_count_weight = um::div(in_weight, (float)(int)in_color.w);
+      a.b.out_diagnostics[index] = dg;
+    }
+  }
+}
+// Claims the launch's next tile into `half`: its pixels' slots are cleared and the (pixel slot, sample) stream is set up.
+// Returns the tile's pixel count and its total sample count, or pixel count -1 when there is none (or the host's
+// CancellationToken was set: SampleBatchJob.cs:61 polls it per pixel; here the warp that claims a tile reads the flag, and
+// tells the CTA's other warps to stop issuing samples).
+struct ClaimedTile { int n; uint32_t items; };
+__device__ __noinline__ ClaimedTile claim_tile(WarpTile& tile, const BatchArgs& a, int lane, int half, volatile uint32_t* cta_cancelled) {
+  const rtb_batch_params& p = a.p;
+  int tile_n = 0;
+  uint32_t total_items = 0;
+  uint32_t t = 0;
+  if (lane == 0) {
+    const bool cancelled = cancel_requested(a.cancel_flag, a.cancel_epoch);
+    t = atomicAdd(a.tile_counter, 1u);
+    if (cancelled) { *cta_cancelled = 1u; t = 0xffffffffu; }
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t >= a.n_tiles) return ClaimedTile{-1, 0u};
+  uint32_t base;
+  tile_range(a, t, &base, &tile_n);
+  uint32_t n_samples = 0;
+  if (lane < tile_n) {
+    const int s = half * kHalfPixels + lane;
+    int cx, cy;
+    uint32_t index;
+    active_pixel(a, base + (uint32_t)lane, &cx, &cy, &index);
+    tile.pix_xy[s] = (uint32_t)cx | ((uint32_t)cy << 16);
+    const float in_w = a.b.in_color[4 * (size_t)index + 3];
+    const float in_weight = a.b.in_sample_count_weight[index];
+    float scw;
+    n_samples = samples_to_accumulate(p, in_w, in_weight, &scw);
+#pragma unroll
+    for (int k = 0; k < kAccValues; k++) { tile.acc_lo[s][k] = 0; tile.acc_hi[s][k] = 0; }
+    tile.successes[s] = 0;
+    tile.rays[s] = 0;
+    tile.node_tests[s] = 0;
+    tile.sphere_tests[s] = 0;
+    tile.non_finite[s] = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) tile.fallback[s][k] = 0;
+  }
+  // exclusive prefix over the tile's pixels
+  uint32_t incl = n_samples;
+#pragma unroll
+  for (int o = 1; o < kHalfPixels; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane < tile_n) tile.prefix[half][lane] = incl - n_samples;
+  total_items = __shfl_sync(0xffffffffu, incl, kHalfPixels - 1);
+  if (lane == 0) { tile.prefix[half][tile_n] = total_items; tile.half_base[half] = base; }
+  __syncwarp();
+  return ClaimedTile{tile_n, total_items};
+}
+
 
 template <bool SMEM, bool COUNTERS, int FLAVOR>
 __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
@@ -173,15 +283,17 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
   tile.lane_counts[lane] = 0;
 
   // ---- warp-uniform tile state ----
-  uint32_t tile_base = 0, next_item = 0, total_items = 0;
-  int tile_n = 0;
+  uint32_t next_item = 0, total_items = 0;   // work stream of the tile being issued
+  int tile_n = 0;             // its pixel count (0: none)
+  int drain_n = 0;            // pixel count of the previous tile while its last paths run (0: none)
+  uint32_t tile_flags = 0;    // bit 0: half of the tile being issued; bit 1: the launch has no tiles left
 
   // A finished path (sky reached: success; TraceDepth exhausted: failed, SampleBatchJob.cs:379-381) is added to the
   // lane's private partial sums for its pixel; the lane is then free for the tile's next pixel-sample.
   auto finish_path = [&](bool success) {
     alive = false;
     if (acc_slot != slot) {
-      if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
+      if (acc_slot >= 0) lane_flush<FLAVOR>(tile, lane, acc_slot);
       acc_slot = slot;
     }
     if (COUNTERS) {
@@ -210,7 +322,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
 #pragma unroll
         for (int k = 0; k < kAccValues; k++) finite = finite && (um::abs(vals[k]) < 33554432.0f);   // 2^25: 32 lanes of them < 2^30
         if (finite) {
-          lane_flush(tile, lane, acc_slot);
+          lane_flush<FLAVOR>(tile, lane, acc_slot);
           counts = (uint32_t)depth + 1u;
           flush_now = true;
         } else {
@@ -227,7 +339,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     tile.lane_counts[lane] = counts;
     // the packed counters hold 2^12 - 1 successes / 2^20 - 1 rays: flush well before either wraps, and often enough (every
     // 32 successes: a partial then stays below 2^25) for lane_flush's overflow window to be airtight
-    if (flush_now || (counts >> 20) >= 32u || (counts & 0xfffffu) >= 0x80000u) lane_flush(tile, lane, acc_slot);
+    if (flush_now || (counts >> 20) >= 32u || (counts & 0xfffffu) >= 0x80000u) lane_flush<FLAVOR>(tile, lane, acc_slot);
   };
 
   // One trip of the loop, for every lane of the warp:
@@ -237,90 +349,30 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
   //               camera ray (refilled lanes), and the sincos both need
   //   (4) shade   hit lanes finish Material.Scatter and form the next ray; refilled lanes form their camera ray
   for (;;) {
-    // nothing in flight and nothing left in the tile: retire it, claim the next one
-    if (__ballot_sync(0xffffffffu, alive) == 0 && next_item >= total_items) {
-      if (acc_slot >= 0) lane_flush(tile, lane, acc_slot);
-      acc_slot = -1;
-      __syncwarp();
-      if (tile_n > 0 && lane < tile_n) {
-        int cx, cy;
-        uint32_t index;
-        active_pixel(a, tile_base + (uint32_t)lane, &cx, &cy, &index);
-        const float4 in_color = reinterpret_cast<const float4*>(a.b.in_color)[index];
-        const float in_weight = a.b.in_sample_count_weight[index];
-        const int succ = (int)tile.successes[lane];
-        const int sample_count = (int)in_color.w + succ;
-        const bool bad = tile.non_finite[lane] != 0;
-        const float nan = um::asfloat(0x7fc00000u);
-        float v[kAccValues];
-#pragma unroll
-        for (int k = 0; k < kAccValues; k++) v[k] = bad ? nan : fixed_read(tile, lane, k);
-        float4 oc = make_float4(in_color.x + v[0], in_color.y + v[1], in_color.z + v[2], (float)sample_count);
-        reinterpret_cast<float4*>(a.b.out_color)[index] = oc;
-        const float* in_n = a.b.in_normal + 3 * (size_t)index;
-        const float* in_a = a.b.in_albedo + 3 * (size_t)index;
-        float* on = a.b.out_normal + 3 * (size_t)index;
-        float* oa = a.b.out_albedo + 3 * (size_t)index;
-        if (sample_count == 0) {
-          on[0] = tile.fallback[lane][0]; on[1] = tile.fallback[lane][1]; on[2] = tile.fallback[lane][2];
-          oa[0] = tile.fallback[lane][3]; oa[1] = tile.fallback[lane][4]; oa[2] = tile.fallback[lane][5];
-        } else {
-          on[0] = in_n[0] + v[3]; on[1] = in_n[1] + v[4]; on[2] = in_n[2] + v[5];
-          oa[0] = in_a[0] + v[6]; oa[1] = in_a[1] + v[7]; oa[2] = in_a[2] + v[8];
-        }
-        a.b.out_sample_count_weight[index] = in_weight + v[9];
-        if (a.b.out_diagnostics) {
-          rtb_diagnostics dg;
-          dg.ray_count = (float)tile.rays[lane];
-          dg.bounds_hit_count = (float)tile.node_tests[lane];
-          dg.candidate_count = (float)tile.sphere_tests[lane];
-          dg.sample_count_weight = um::div(in_weight, (float)(int)in_color.w);
-          a.b.out_diagnostics[index] = dg;
-        }
+    const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+    // the previous tile retires as soon as its last path has finished
+    if (drain_n > 0) {
+      const int dh = (int)(tile_flags & 1u) ^ 1;
+      if (__ballot_sync(0xffffffffu, alive && (slot >= kHalfPixels ? 1 : 0) == dh) == 0) {
+        if (acc_slot >= 0 && (acc_slot >= kHalfPixels ? 1 : 0) == dh) { lane_flush<FLAVOR>(tile, lane, acc_slot); acc_slot = -1; }
+        __syncwarp();
+        retire_tile(tile, a, lane, dh, drain_n);
+        drain_n = 0;
       }
-      // next tile — unless the host's CancellationToken was set (SampleBatchJob.cs:61 polls it per pixel; here the warp
-      // that claims a tile reads the mapped flag, and tells the CTA's other warps to stop issuing samples)
-      uint32_t t = 0;
-      if (lane == 0) {
-        const bool cancelled = cancel_requested(a.cancel_flag, a.cancel_epoch);
-        t = atomicAdd(a.tile_counter, 1u);
-        if (cancelled) { *cta_cancelled = 1u; t = 0xffffffffu; }
+    }
+    // the tile being issued has no samples left: it becomes the draining one, the next tile goes to the other half
+    // (if the previous tile is STILL draining — a path of it outlived a whole tile — the free lanes wait for it)
+    if (next_item >= total_items && drain_n == 0) {
+      if (!(tile_flags & 2u)) {
+        drain_n = tile_n;
+        tile_flags ^= 1u;
+        const ClaimedTile c = claim_tile(tile, a, lane, (int)(tile_flags & 1u), cta_cancelled);
+        next_item = 0;
+        if (c.n < 0) { tile_flags |= 2u; tile_n = 0; total_items = 0; }
+        else { tile_n = c.n; total_items = c.items; }
+      } else if (alive_mask == 0) {
+        break;                // no tile left, nothing draining, nothing in flight
       }
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= a.n_tiles) break;
-      tile_range(a, t, &tile_base, &tile_n);
-      uint32_t n_samples = 0;
-      if (lane < tile_n) {
-        int cx, cy;
-        uint32_t index;
-        active_pixel(a, tile_base + (uint32_t)lane, &cx, &cy, &index);
-        tile.pix_xy[lane] = (uint32_t)cx | ((uint32_t)cy << 16);
-        const float in_w = a.b.in_color[4 * (size_t)index + 3];
-        const float in_weight = a.b.in_sample_count_weight[index];
-        float scw;
-        n_samples = samples_to_accumulate(p, in_w, in_weight, &scw);
-#pragma unroll
-        for (int k = 0; k < kAccValues; k++) { tile.acc_lo[lane][k] = 0; tile.acc_hi[lane][k] = 0; }
-        tile.successes[lane] = 0;
-        tile.rays[lane] = 0;
-        tile.node_tests[lane] = 0;
-        tile.sphere_tests[lane] = 0;
-        tile.non_finite[lane] = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) tile.fallback[lane][k] = 0;
-      }
-      // exclusive prefix over the tile's pixels
-      uint32_t incl = n_samples;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      if (lane < tile_n) tile.prefix[lane] = incl - n_samples;
-      total_items = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 0) tile.prefix[tile_n] = total_items;
-      next_item = 0;
-      __syncwarp();
     }
 
     // (1) one walk for every live lane (SampleBatchJob.cs:184-206, 341-374)
@@ -380,14 +432,15 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       const uint32_t my_item = next_item + __popc(need & lt_mask);
       if (!alive && my_item < total_items) {
         // item -> (pixel slot, sample) through the tile's prefix table
-        int lo = 0, hi = tile_n;   // find the last slot with prefix[slot] <= my_item
+        const uint32_t* prefix = tile.prefix[tile_flags & 1u];
+        int lo = 0, hi = tile_n;   // find the last pixel with prefix[pixel] <= my_item
         while (hi - lo > 1) {
           int mid = (lo + hi) >> 1;
-          if (tile.prefix[mid] <= my_item) lo = mid; else hi = mid;
+          if (prefix[mid] <= my_item) lo = mid; else hi = mid;
         }
-        slot = lo;
-        sample = my_item - tile.prefix[lo];
-        const uint32_t xy = tile.pix_xy[lo];
+        sample = my_item - prefix[lo];
+        slot = (int)(tile_flags & 1u) * kHalfPixels + lo;
+        const uint32_t xy = tile.pix_xy[slot];
         cx = (int)(xy & 0xffffu);
         cy = (int)(xy >> 16);
         pixel = (uint32_t)cy * (uint32_t)a.width + (uint32_t)cx;

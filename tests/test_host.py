@@ -141,3 +141,29 @@ def test_plugin_row_balancer_matches_the_python_partition(rtb):
     assert rtb.plugin.balance_rows(np.ones(100), 40, 60, 4) == [40, 45, 50, 55, 60]
     b = rtb.plugin.balance_rows(None, 0, 2, 4)
     assert b[0] == 0 and b[-1] == 2 and all(b[g + 1] >= b[g] for g in range(4)) and sum(b[g + 1] - b[g] for g in range(4)) == 2
+
+
+def test_threaded_bvh_build_is_identical_to_the_serial_one(rtb, monkeypatch):
+    """rtbh_build_bvh_from_bounds builds large subtrees concurrently and splices them in the serial recursion's order: the
+    node array and the BVH-ordered entity list do not depend on the thread count (BvhNodeData.cs:122-213 is one serial job)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(3)
+    n = 60000
+    c = rng.normal(size=(n, 3)).astype(np.float32) * 5
+    e = (np.abs(rng.normal(size=(n, 3))) * 0.05 + 1e-3).astype(np.float32)
+    bounds = np.ascontiguousarray(np.hstack([c - e, c + e]), dtype=np.float32)
+
+    def build():
+        order = np.zeros(n, np.uint32)
+        nodes = np.zeros(2 * n + 1, dtype=rtb.abi.BVH_NODE_DTYPE)
+        count = C.c_size_t(0)
+        assert rtb.host.lib().rtbh_build_bvh_from_bounds(bounds.ctypes.data, n, 32, order.ctypes.data, n, nodes.ctypes.data, len(nodes), C.byref(count)) == 0
+        return order, nodes[: count.value].copy()
+
+    monkeypatch.setenv("RTB_BUILD_THREADS", "1")
+    o1, n1 = build()
+    monkeypatch.setenv("RTB_BUILD_THREADS", "8")
+    o8, n8 = build()
+    assert np.array_equal(o1, o8) and n1.tobytes() == n8.tobytes()
+    assert sorted(o1.tolist()) == list(range(n))

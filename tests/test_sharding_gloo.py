@@ -81,6 +81,30 @@ def test_row_tile_shard_and_gather_world2(tmp_path, oracle, rtb, mode):
     assert np.array_equal(np.load(tmp_path / f"rootn_{mode}_0.npy"), full.out_normal.reshape(H, W, 3))
 
 
+def _shared_frame(W, H, rank, abi, rtb, stem):
+    """HostBuffers over files in /dev/shm mapped by every rank: rank 0 creates them, the others map the same pages — the CPU
+    stand-in for the frame that lives in rank 0's HBM and is mapped by the other ranks (renderer.FrameRenderer.enable_peer_frame)."""
+    n = W * H
+    spec = [("in_color", (n, 4), np.float32), ("in_weight", (n,), np.float32), ("in_normal", (n, 3), np.float32),
+            ("in_albedo", (n, 3), np.float32), ("out_color", (n, 4), np.float32), ("out_weight", (n,), np.float32),
+            ("out_normal", (n, 3), np.float32), ("out_albedo", (n, 3), np.float32), ("diagnostics", (n,), abi.DIAGNOSTICS_DTYPE)]
+    if rank == 0:
+        for name, shape, dt in spec:
+            m = np.memmap(stem + name, dtype=dt, mode="w+", shape=shape)
+            m[...] = 0
+            m.flush()
+    dist.barrier()
+    hb = rtb.plugin.HostBuffers(1, 1)
+    hb.width, hb.height = W, H
+    for name, shape, dt in spec:
+        setattr(hb, name, np.memmap(stem + name, dtype=dt, mode="r+", shape=shape))
+    dist.barrier()
+    if rank == 0:       # every rank holds its mapping now: the names can go
+        for name, _, _ in spec:
+            os.unlink(stem + name)
+    return hb
+
+
 def _shared_frame_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -88,29 +112,35 @@ def _shared_frame_worker(rank, world, port, out_dir):
 
     import oracle_lib as O
 
-    bench = importlib.import_module("bench")
-    sh = importlib.import_module("raytracing-in-one-weekend_b200.sharding")
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         W, H, spp = 40, 22, 4
-        hb = bench._shared_host_frame(W, H, rank, O.abi, O.rtb)       # ONE frame mapped by both rank processes
-        assert hb is not None and hb.out_color.shape == (W * H, 4) and hb.diagnostics.shape == (W * H,)
+        hb = _shared_frame(W, H, rank, O.abi, O.rtb, f"/dev/shm/rtb_test_{port}_")     # ONE frame mapped by both rank processes
+        assert hb.out_color.shape == (W * H, 4) and hb.diagnostics.shape == (W * H,)
         scene = O.rtb.host.make_scene("three_spheres")
-        b, e = sh.row_tiles(H, world)[rank]
+        # rank 0's cost model -> every rank (bench.py broadcasts the probe's row costs the same way), tiles from the
+        # plugin's own balancer (rtb_balance_rows)
+        cost = torch.from_numpy(np.linspace(1.0, 5.0, H)) if rank == 0 else torch.zeros(H, dtype=torch.float64)
+        dist.broadcast(cost, src=0)
+        bounds = O.rtb.plugin.balance_rows(cost.numpy(), 0, H, world)
+        b, e = bounds[rank], bounds[rank + 1]
         p = O.rtb.host.make_params(scene, W, H, spp, 8, row_begin=b, row_end=e)
         O.sample_batch(scene, p, hb, threads=2)                        # each rank writes its own rows, in place
-        dist.barrier()
+        done = torch.zeros(1)
+        dist.all_reduce(done)                                          # the frame-complete signal (4 bytes on the GPU path)
         if rank == 0:                                                  # ... and rank 0 sees the whole frame without a gather
             np.save(os.path.join(out_dir, "shared_color.npy"), np.array(hb.out_color))
             np.save(os.path.join(out_dir, "shared_rays.npy"), np.array(hb.diagnostics["ray_count"]))
+            np.save(os.path.join(out_dir, "bounds.npy"), np.array(bounds))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def test_one_host_frame_shared_by_the_ranks_world2(tmp_path, oracle, rtb):
-    """bench.py's N > 1 end-to-end path: the ranks map ONE set of host arrays (/dev/shm) and each renders its row tile into
-    them in place; the frame is complete on the host without any exchange."""
+def test_one_frame_written_in_place_by_the_ranks_world2(tmp_path, oracle, rtb):
+    """bench.py's N > 1 protocol on CPU: ONE frame every rank maps (rank 0's HBM over CUDA IPC on the GPU box, /dev/shm here),
+    row tiles from the plugin's balancer on a cost model rank 0 broadcasts, each rank renders its tile into the frame in place,
+    one tiny all-reduce marks the frame complete — no gather — and rank 0 holds the same bits as a single-process render."""
     world = 2
     mp.spawn(_shared_frame_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     W, H, spp = 40, 22, 4
@@ -119,4 +149,6 @@ def test_one_host_frame_shared_by_the_ranks_world2(tmp_path, oracle, rtb):
     oracle.sample_batch(scene, rtb.host.make_params(scene, W, H, spp, 8), full)
     assert np.array_equal(np.load(tmp_path / "shared_color.npy"), full.out_color)
     assert np.array_equal(np.load(tmp_path / "shared_rays.npy"), full.diagnostics["ray_count"])
-    assert not [f for f in os.listdir("/dev/shm") if f.startswith("rtb_bench_")]      # the names are unlinked once mapped
+    bounds = np.load(tmp_path / "bounds.npy")
+    assert bounds[0] == 0 and bounds[-1] == H and bounds[1] > H // 2          # the cheap rows make the first tile the longer one
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("rtb_test_")]      # the names are unlinked once mapped
