@@ -557,7 +557,10 @@ __device__ __forceinline__ f3 hit_normal(const SceneView<SMEM>& sv, float4 prim,
 // structure — the same source has compiled into one loop (box visit executed with 20.3 of 32 lanes on config 3) and into a
 // loop nest in which lanes iterate "visits that need no pop" on their own (13.8 lanes, +17 % kernel time), flipped by
 // unrelated edits elsewhere in the kernel (profiles/README.md, round 2).  A convergent operation at the loop top pins the
-// one-loop form: 4 instructions per trip (VOTE, R2UR, BRA.DIV, NOP).
+// one-loop form: 4 instructions per trip (VOTE, R2UR, BRA.DIV, NOP).  Measured alternatives: the same operation at the
+// loop's latch (132.8 vs 127.2 ms: the pop predicate then lives in a register across it), an uniform-exit loop on
+// __any_sync (137.4), a branch-free pop that leaves the loop a single latch (139.8), empty inline asm / __activemask()
+// alone (the nest comes back: 159.8).
 #ifndef RTB_WALK_SYNC
 #define RTB_WALK_SYNC 1
 #endif
@@ -690,19 +693,10 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
         test_leaf(cur);
         need_pop = true;
       }
-#if RTB_WALK_SYNC == 2
-      // branch-free pop: the stack top is read every trip (the sentinel keeps the read valid) and taken when needed, so the
-      // loop has ONE latch whatever the compiler's mood
-      const int popped = top[-1];
-      top -= need_pop ? 1 : 0;
-      cur = need_pop ? popped : cur;
-      if (cur == kTraversalDone) break;
-#else
       if (need_pop) {
         cur = *--top;
         if (cur == kTraversalDone) break;
       }
-#endif
     }
   }
     return;

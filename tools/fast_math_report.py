@@ -47,8 +47,10 @@ lines = [f"# Fast-arithmetic build vs parity build — {bench.WORKLOADS[args.con
 for r in rows:
     lines.append(f"| {r[0]} | {r[1]:.1f} | {r[2]:.1f} | {r[1] / r[2]:.3f}x | {r[3]:.2e} | {r[4]:.2e} | {r[5]:.2e} | {100 * r[6]:.2f} % | {100 * r[7]:.3f} % | {r[8]:.6f} / {r[9]:.6f} |")
 lines += ["", "A differing pixel is one in which at least one of its paths took another discrete decision (hit / miss at a grazing angle,",
-          "reflect / refract at the Schlick threshold): one flipped decision moves a pixel by up to 1 / spp of a path's radiance, which is",
-          "why the fraction over 1e-4 shrinks with the sample count while the image means agree to 1e-6."]
+          "reflect / refract at the Schlick threshold; about one path in 40 000).  One flipped decision moves a pixel by up to 1 / spp of a",
+          "path's radiance: with more samples per pixel MORE pixels contain a flipped path (the fraction over 1e-4 grows) while each",
+          "difference gets smaller (mean, RMSE and p99.9 shrink), and the image means agree to 1e-6 at every sample count: the fast",
+          "build is the same estimator with the same random numbers, not a biased one."]
 text = "\n".join(lines) + "\n"
 print(text)
 if args.out:
