@@ -25,7 +25,7 @@ namespace rtbk {
 #define RTB_MEGA_BLOCK_GENERAL 896    // the general flavour (triangles) needs 72 registers to stay out of local memory
 #endif
 #ifndef RTB_MEGA_BLOCK_PLACED
-#define RTB_MEGA_BLOCK_PLACED 640     // the placed-entity flavour (transforms, Rect, Box): 96 registers (measured: 512 / 640 / 768 / 896 threads = 131 / 120 / 141 / 148 ms on the Cornell world)
+#define RTB_MEGA_BLOCK_PLACED 768     // the placed-entity flavour (transforms, Rect, Box): 80 registers.  The flavour is instruction-fetch bound (ncu: 5.8 no-instruction stalls per issue at 640 threads): more warps hide it — round 2, Cornell world: 384 / 512 / 640 / 704 / 768 / 832 / 896 / 1024 threads = 213 / 188 / 168 / 147 / 133 / 144 / 140 / 144 ms
 #endif
 // Threads per CTA by kernel flavour (measured on B200, profiles/README.md): 1024 x 64 registers for the lean sphere
 // builds, 896 x 72 registers for the general build.
@@ -111,8 +111,12 @@ __device__ __forceinline__ void lane_flush_inline(WarpTile& t, int lane, int slo
 __device__ __noinline__ void lane_flush_call(WarpTile& t, int lane, int slot) { lane_flush_inline(t, lane, slot); }
 template <int FLAVOR>
 __device__ __forceinline__ void lane_flush(WarpTile& t, int lane, int slot) {
+#ifdef RTB_FLUSH_CALL_ALWAYS
+  lane_flush_call(t, lane, slot);
+#else
   if (FLAVOR >= kFlavorGeneral) lane_flush_inline(t, lane, slot);
   else lane_flush_call(t, lane, slot);
+#endif
 }
 __device__ __forceinline__ float fixed_read(const WarpTile& t, int slot, int v) {
   long long q = (long long)(((unsigned long long)t.acc_hi[slot][v] << 32) | t.acc_lo[slot][v]);

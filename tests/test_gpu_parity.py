@@ -823,6 +823,28 @@ def test_finalize_device_matches_the_restated_job_and_runs_at_hbm_rate(rtb, orac
     assert gbs > 2000
 
 
+def test_full_size_config2_rows_match_the_oracle(rtb, oracle, ctx):
+    """BASELINE config 2 at full size (book-1 final scene as ONE leaf of 482 spheres — the linear hit list —, 1280x720, 64 spp,
+    depth 50): every sample accounted for, and three whole rows (ground, sphere band, sky) equal the oracle's decisions exactly,
+    RGB within tolerance.  This is the build with the deferred division in the big leaf (kFlavorChains)."""
+    W, H, spp = 1280, 720, 64
+    scene = rtb.host.make_scene("final", max_bvh_depth=0)
+    p = rtb.host.make_params(scene, W, H, spp, 50)
+    a = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    cnt = a.out_color[:, 3]
+    assert cnt.max() == spp and (W * H * spp - cnt.astype(np.int64).sum()) < 1e-3 * W * H * spp
+    assert np.isfinite(a.out_color).all()
+    rgb = a.rgb()
+    for row in (60, 300, 650):
+        pr = rtb.host.make_params(scene, W, H, spp, 50, row_begin=row, row_end=row + 1)
+        ref = oracle.Buffers(W, H)
+        oracle.sample_batch(scene, pr, ref)
+        rs = slice(row * W, (row + 1) * W)
+        assert np.array_equal(ref.out_color[rs, 3], a.out_color[rs, 3])
+        assert np.array_equal(ref.diagnostics["ray_count"][rs], a.diagnostics["ray_count"][rs])
+        assert np.abs(ref.rgb()[row] - rgb[row]).max() <= RGB_TOL
+
+
 def test_full_size_properties_config4(rtb, oracle, ctx):
     """BASELINE config 4 at full size on one GPU (3840x2160, 1024 spp, depth 50: 8.5 G camera paths): every sample
     accounted for, finite, radiance bounded by the sky, and one row checked against the oracle exactly."""
