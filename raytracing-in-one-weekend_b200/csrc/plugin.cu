@@ -923,7 +923,7 @@ int host_batch_end(rtb_ctx* ctx, HostBatch* st, const volatile uint8_t* cancel) 
   if (ctx->cancel_sent || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
   if (st->status & kStatusHitListOverflow) {
     cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
-    return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met more than %d entities in a world with participating media (the reference's hit list grows, "
+    return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met %d or more entities in a world with participating media (the reference's hit list grows, "
                 "HybridCollections.cs:65-71; this kernel's does not): outputs are not the reference's", kMaxRayHits);
   }
   return RTB_OK;

@@ -14,7 +14,7 @@ namespace rtbk {
 
 constexpr uint32_t kLaneSamples = 8;  // samples a lane traces back to back before the warp accumulates (Philox mode)
 constexpr int kMaxRayHits = 48;     // hit records kept per ray (the reference's list starts at 32 and grows, SampleBatchJob.cs:21;
-                                    // HybridCollections.cs:65-71).  A ray that meets more raises kStatusHitListOverflow and the
+                                    // HybridCollections.cs:65-71).  A ray that fills the list raises kStatusHitListOverflow and the
                                     // batch fails with RTB_ERR_UNSUPPORTED: never a silently different image
 
 struct RayHits {                    // FindHits' sorted hitBuffer
@@ -91,7 +91,6 @@ __device__ __noinline__ bool collect_hits(const int MODE, const SceneView<false>
   auto insert = [&](float t, int slot, f3 n) {
     int pos = 0;
     while (pos < hits->count && hits->t[pos] < t) pos++;       // before the first record that is not nearer
-    if (hits->count >= kMaxRayHits && sd.status) atomicOr(sd.status, kStatusHitListOverflow);   // a record is about to be lost
     if (pos >= kMaxRayHits) return;
     const int last = hits->count < kMaxRayHits ? hits->count : kMaxRayHits - 1;
     for (int k = last; k > pos; k--) { hits->t[k] = hits->t[k - 1]; hits->slot[k] = hits->slot[k - 1]; hits->n[k] = hits->n[k - 1]; }
@@ -167,6 +166,9 @@ __device__ __noinline__ VolumeSample trace_volume_sample(const BatchArgs& a, con
     uint32_t volume_draws = 0;
     float events = 0;                               // rng.RandomEvents of this iteration
     collect_hits<COUNTERS>(0, sv, sd, ray.o, ray.d, clk, &hits, wc);
+    // a FULL list may have lost records (checked here, once per ray: anything in the insert path itself — an atomic, even a
+    // flag store — cost this kernel 20-100 %): the batch then fails with RTB_ERR_UNSUPPORTED
+    if (hits.count >= kMaxRayHits && sd.status) atomicOr(sd.status, kStatusHitListOverflow);
     if (current_volume < 0) {                       // DetermineVolumeContainment (:477-506)
       for (int i = 0; i < hits.count; i++) {
         const uint32_t hm = sv.material_of(hits.slot[i]);
@@ -323,7 +325,10 @@ __device__ __noinline__ VolumeSample trace_volume_sample(const BatchArgs& a, con
 // same, paths of neighbouring pixels do not), then the warp adds the 32 results in sample order, every lane the same sums, so
 // the accumulation order is the reference's.  White-noise mode (one sequential stream per pixel): one THREAD per pixel.
 template <bool COUNTERS, bool WHITE>
-__global__ void __launch_bounds__(128) sample_volumes(const __grid_constant__ BatchArgs a) {
+#ifndef RTB_VOLUME_MIN_BLOCKS
+#define RTB_VOLUME_MIN_BLOCKS 4   // <= 128 registers: the kernel is instruction-fetch bound, occupancy hides it (1462 -> 1249 ms on the fog Cornell box)
+#endif
+__global__ void __launch_bounds__(128, RTB_VOLUME_MIN_BLOCKS) sample_volumes(const __grid_constant__ BatchArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t k = WHITE ? blockIdx.x * blockDim.x + threadIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= a.n_active_pixels) return;
