@@ -90,7 +90,8 @@ struct SceneDesc {
   const float2* tri_uv;              // 3 per triangle (Triangle.TextureCoordinates columns) or nullptr
   const uint16_t* sky_faces;    // Environment.SkyCubemap texels (6 faces of RGBA halves) or nullptr
   int sky_w, sky_h;
-  uint32_t has_volumes;         // some material is a ProbabilisticVolume: batches run sample_volumes (volume_kernel.cuh)
+  uint32_t has_volumes;         // some entity wears a ProbabilisticVolume: batches run the megakernel's media flavour (media.cuh) or, as the
+                                // bit-exact validator / for the white-noise stream / with image textures, sample_volumes (volume_kernel.cuh)
   uint32_t has_big_leaves;      // some leaf holds 16 or more entities (count code 15: the count is in leaf_count)
   uint32_t has_chains;          // 1: some leaf is a collapsed subtree, accepted hits go through chain_guard; 2: always walk the chain (test knob)
   const uint32_t* chain_ref;    // per sphere: first chain box | box count << 24
@@ -296,7 +297,9 @@ constexpr int kFlavorGeneral = 2;        // + EntityType.Triangle entities
 constexpr int kFlavorPlaced = 3;         // + placed entities: rotation, motion (Ray.Time), EntityType.Rect, EntityType.Box
 constexpr int kFlavorPlacedTextured = 4; // the same with image textures (the general flavour always has them; here the
                                          // texture code costs the untextured walk 14 %, so it is its own instantiation)
-__host__ __device__ constexpr bool flavor_has_textures(int flavor) { return flavor == kFlavorGeneral || flavor >= kFlavorPlacedTextured; }
+constexpr int kFlavorMedia = 5;          // every entity kind (no image textures) + MaterialType.ProbabilisticVolume: the walk is replaced
+                                         // by the media hit search of media.cuh (pruned_hits + the reference's volume bookkeeping)
+__host__ __device__ constexpr bool flavor_has_textures(int flavor) { return flavor == kFlavorGeneral || flavor == kFlavorPlacedTextured; }
 
 // Ray.Time (View.cs:47; kept by every scattered ray, Material.cs:95-159): one draw per camera path, slot 4 of the
 // camera ray's draws = word 0 of Philox block 1.  Only moving entities read it, so the megakernel re-derives it from
@@ -441,9 +444,12 @@ __device__ __forceinline__ float sign_of(float x) { return (x > 0 ? 1.0f : 0.0f)
 // SampleBatchJob.cs:457): the transform at the ray's time, the ray in entity space, then the Sphere / Rect / Box test
 // (HitTests.cs:23-111) in the reference's operation order.  Returns the distance and the entity-space normal rotated
 // back by the transform (not yet normalised).
-template <bool SMEM>
-__device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pidx, f3 o, f3 d, const RayClock& clk,
-                                         float* t_out, f3* n_out, float tmin = 0.0f) {
+// WITH_EXIT (media.cuh): also the hit FindHits injects behind a convex medium's entry (SampleBatchJob.cs:462-469) — Entity.Hit
+// again with tMin = distance + 0.001 — from the same transform: for a sphere the same two roots decide it, a Box repeats its
+// test from the offset origin (HitTests.cs:84), a Rect has none (not a convex hull).  *t_exit < 0: no such hit.
+template <bool SMEM, bool WITH_EXIT>
+__device__ __forceinline__ bool placed_test_core(const SceneView<SMEM>& sv, uint32_t pidx, f3 o, f3 d, const RayClock& clk,
+                                                 float* t_out, f3* n_out, float tmin, float* t_exit, f3* n_exit) {
   const float4 p0 = sv.placed(pidx, 0), p1 = sv.placed(pidx, 1);
   const uint32_t flags = __float_as_uint(p1.w);
   um::quat rot;
@@ -468,6 +474,7 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
   const uint32_t type = flags & 0xffu;
   float t;
   f3 n;
+  if (WITH_EXIT) *t_exit = -1.0f;
   if (type == RTB_ENTITY_SPHERE) {              // HitTests.cs:23-60
     const float radius = p5.y;
     const float a = um::dot(ed, ed), b = um::dot(eo, ed), c = um::dot(eo, eo) - radius * radius;
@@ -475,11 +482,21 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
     if (!(disc > 0)) return false;
     const float sq = um::sqrt(disc);
     t = um::div(-b - sq, a);
+    bool first_root = true;
     if (!(t < um::INF && t > tmin)) {
       t = um::div(-b + sq, a);
+      first_root = false;
       if (!(t < um::INF && t > tmin)) return false;
     }
     n = um::mad(ed, t, eo) / radius;
+    if (WITH_EXIT && first_root) {
+      // the second call finds the first root again (not beyond t + 0.001), then the second one
+      const float t2 = um::div(-b + sq, a);
+      if (t2 < um::INF && t2 > t + 0.001f) {
+        *t_exit = t2;
+        *n_exit = um::rotate(rot, um::mad(ed, t2, eo) / radius);
+      }
+    }
   } else if (type == RTB_ENTITY_RECT) {         // HitTests.cs:62-78
     if (ed.z >= 0) return false;
     t = um::div(-eo.z, ed.z);
@@ -491,25 +508,43 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
   } else {                                      // Box, HitTests.cs:80-111
     const float4 p6 = sv.placed(pidx, 6);
     const f3 ext = um::mk(p5.y, p5.z, p5.w), inv_ext = um::mk(p6.x, p6.y, p6.z);
-    const f3 bo = eo + ed * tmin;               // "offset origin by tMin"
-    const f3 ao = um::mk(um::abs(bo.x), um::abs(bo.y), um::abs(bo.z)) * inv_ext;
-    const float winding = um::cmax(ao) < 1 ? -1.0f : 1.0f;
     const f3 sgn = um::mk(-sign_of(ed.x), -sign_of(ed.y), -sign_of(ed.z));
-    const f3 num = ext * winding * sgn - bo;
-    const f3 dp = um::mk(um::div(num.x, ed.x), um::div(num.y, ed.y), um::div(num.z, ed.z));
-    const bool tx = dp.x >= 0 && um::abs(bo.y + ed.y * dp.x) < ext.y && um::abs(bo.z + ed.z * dp.x) < ext.z;
-    const bool ty = dp.y >= 0 && um::abs(bo.z + ed.z * dp.y) < ext.z && um::abs(bo.x + ed.x * dp.y) < ext.x;
-    const bool tz = dp.z >= 0 && um::abs(bo.x + ed.x * dp.z) < ext.x && um::abs(bo.y + ed.y * dp.z) < ext.y;
-    n = tx ? um::mk(sgn.x, 0.0f, 0.0f) : ty ? um::mk(0.0f, sgn.y, 0.0f) : um::mk(0.0f, 0.0f, tz ? sgn.z : 0.0f);
-    const bool nzx = n.x != 0, nzy = n.y != 0, nzz = n.z != 0;
-    if (!(nzx || nzy || nzz)) return false;
-    t = nzx ? dp.x : nzy ? dp.y : dp.z;
-    t += tmin;
-    if (t > um::INF) return false;
+    float from = tmin;
+#pragma unroll 1
+    for (int pass = 0; pass < (WITH_EXIT ? 2 : 1); pass++) {
+      const f3 bo = eo + ed * from;             // "offset origin by tMin"
+      const f3 ao = um::mk(um::abs(bo.x), um::abs(bo.y), um::abs(bo.z)) * inv_ext;
+      const float winding = um::cmax(ao) < 1 ? -1.0f : 1.0f;
+      const f3 num = ext * winding * sgn - bo;
+      const f3 dp = um::mk(um::div(num.x, ed.x), um::div(num.y, ed.y), um::div(num.z, ed.z));
+      const bool tx = dp.x >= 0 && um::abs(bo.y + ed.y * dp.x) < ext.y && um::abs(bo.z + ed.z * dp.x) < ext.z;
+      const bool ty = dp.y >= 0 && um::abs(bo.z + ed.z * dp.y) < ext.z && um::abs(bo.x + ed.x * dp.y) < ext.x;
+      const bool tz = dp.z >= 0 && um::abs(bo.x + ed.x * dp.z) < ext.x && um::abs(bo.y + ed.y * dp.z) < ext.y;
+      const f3 bn = tx ? um::mk(sgn.x, 0.0f, 0.0f) : ty ? um::mk(0.0f, sgn.y, 0.0f) : um::mk(0.0f, 0.0f, tz ? sgn.z : 0.0f);
+      const bool nzx = bn.x != 0, nzy = bn.y != 0, nzz = bn.z != 0;
+      bool ok = nzx || nzy || nzz;
+      float bt = nzx ? dp.x : nzy ? dp.y : dp.z;
+      bt += from;
+      if (bt > um::INF) ok = false;
+      if (pass == 0) {
+        if (!ok) return false;
+        t = bt;
+        n = bn;
+        from = bt + 0.001f;
+      } else if (ok) {
+        *t_exit = bt;
+        *n_exit = um::rotate(rot, bn);
+      }
+    }
   }
   *t_out = t;
   *n_out = um::rotate(rot, n);
   return true;
+}
+template <bool SMEM>
+__device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pidx, f3 o, f3 d, const RayClock& clk,
+                                         float* t_out, f3* n_out, float tmin = 0.0f) {
+  return placed_test_core<SMEM, false>(sv, pidx, o, d, clk, t_out, n_out, tmin, nullptr, nullptr);
 }
 template <bool SMEM>
 __device__ __forceinline__ void placed_hit(const SceneView<SMEM>& sv, uint32_t pidx, int idx, f3 o, f3 d, const RayClock& clk,

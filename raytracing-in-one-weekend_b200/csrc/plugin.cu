@@ -93,7 +93,7 @@ struct rtb_ctx {
   int64_t opt_counters = 0, opt_kernel = 0, opt_collapse = kDefaultCollapse, opt_walk_chains = 0, opt_host_access = 1, opt_noise = 0, opt_math = 0;
   bool last_in_place = false;
   float last_ms = 0.0f;
-  bool smem_attr_set[2][10] = {};
+  bool smem_attr_set[2][12] = {};
 
   DeviceBuffers buf;
   MetricsAcc* d_metrics_partial = nullptr;
@@ -156,6 +156,8 @@ struct Flattener {
   bool not_plain_sphere(size_t e) const { return is_triangle(e) || is_placed(e); }
   const rtb_sphere& sphere_of(size_t e) const { return spheres[entities ? entities[e].index : e]; }
   std::vector<uint8_t> visited;
+  std::vector<uint8_t> entity_is_medium;   // per leaf-list entity: it wears a ProbabilisticVolume (empty: the world has no media)
+  std::vector<uint8_t> subtree_media;      // per reference node: some entity below it wears a medium
   std::vector<uint32_t> subtree_spheres;   // per reference node
   std::vector<float> inner;                // 16 floats per device inner node
   std::vector<uint32_t> order;             // device sphere -> host sphere
@@ -183,9 +185,12 @@ struct Flattener {
         return 0;
       }
       c = (uint32_t)nd.entity_count;
+      if (!entity_is_medium.empty())
+        for (int i = 0; i < nd.entity_count; i++) subtree_media[n] |= entity_is_medium[(size_t)nd.first_entity + i];
     } else {
       if (nd.left < 0 || nd.right < 0) { error = "BVH inner node without two children"; return 0; }
       c = count_pass(nd.left, depth + 1) + count_pass(nd.right, depth + 1);
+      if (!error) subtree_media[n] = subtree_media[nd.left] | subtree_media[nd.right];
     }
     subtree_spheres[n] = c;
     return c;
@@ -296,6 +301,9 @@ struct Flattener {
     q[8] = r.bounds_min[2]; q[9] = r.bounds_max[0]; q[10] = r.bounds_max[1]; q[11] = r.bounds_max[2];
     memcpy(&q[12], &lref, 4);
     memcpy(&q[13], &rref, 4);
+    // word 14: which child subtrees hold an entity that wears a medium (media.cuh: the media walks skip the others)
+    const uint32_t media = (subtree_media[nd.left] ? 1u : 0u) | (subtree_media[nd.right] ? 2u : 0u);
+    memcpy(&q[14], &media, 4);
     return self * (int32_t)kNodeStride; // inner refs are BYTE offsets of the node record in the blob (inner_off == 0)
   }
   // a chain holds at most 255 boxes
@@ -371,6 +379,18 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   f.collapse_k = std::max<uint32_t>(1, std::min<uint32_t>(collapse_k, 15));
   f.visited.assign(node_count, 0);
   f.subtree_spheres.assign(node_count, 0);
+  f.subtree_media.assign(node_count, 0);
+  if (has_volumes) {
+    f.entity_is_medium.assign(leaf_list_count, 0);
+    for (size_t i = 0; i < leaf_list_count; i++) {
+      uint32_t m;
+      if (!entities) m = spheres[i].material;
+      else if (Flattener::is_placed_type(entities[i].type)) m = placed[entities[i].index].material;
+      else if ((entities[i].type & ~(uint32_t)RTB_ENTITY_PLACED) == RTB_ENTITY_TRIANGLE) m = triangles[entities[i].index].material;
+      else m = spheres[entities[i].index].material;
+      f.entity_is_medium[i] = wears_volume(m) ? 1 : 0;
+    }
+  }
   SceneDesc& d = out->desc;
   d = SceneDesc{};
   if (node_count > 0) {
@@ -666,9 +686,19 @@ int launch_batch(rtb_ctx* ctx, const rtb_batch_params& p, const rtb_batch_buffer
 
   int kernel_kind = (int)ctx->opt_kernel;
   if (kernel_kind == 0) kernel_kind = ctx->default_kernel;
+  // Worlds with ProbabilisticVolume materials (media.cuh).  The product path is the megakernel's media flavour; the collect-all
+  // kernel sample_volumes (bit-identical to the CPU oracle: the reference's list, the reference's accumulation order) runs as
+  // the validator (RTB_OPT_KERNEL = 1), for the reference's sequential white-noise stream, and for media worlds with image
+  // textures (the media flavour has no texture code).
+  const bool media_mega = ctx->scene.has_volumes && kernel_kind != 1 && !ctx->opt_noise && !ctx->d_mat_textures;
+  if (media_mega) {
+    const bool fits = mega_smem_bytes(ctx->scene.blob_bytes, true, kFlavorMedia) <= (size_t)ctx->max_smem_optin && ctx->scene.blob_bytes < (1u << 20);
+    int rc;
+    if (fits) rc = counters ? launch_mega_t<true, true, kFlavorMedia>(ctx, a, stream, max_spp) : launch_mega_t<true, false, kFlavorMedia>(ctx, a, stream, max_spp);
+    else rc = counters ? launch_mega_t<false, true, kFlavorMedia>(ctx, a, stream, max_spp) : launch_mega_t<false, false, kFlavorMedia>(ctx, a, stream, max_spp);
+    if (rc != RTB_OK) return rc;
+  } else
   if (ctx->scene.has_volumes) {
-    // worlds with ProbabilisticVolume materials need every hit along a ray, sorted (volume_kernel.cuh): one kernel for them,
-    // whatever RTB_OPT_KERNEL says
     if (ctx->opt_noise) {                       // one thread per pixel (a sequential stream per pixel)
       const uint32_t grid = (a.n_active_pixels + 127) / 128;
       if (counters) sample_volumes<true, true><<<grid, 128, 0, stream>>>(a);

@@ -12,6 +12,7 @@
 #pragma once
 
 #include "kernel_common.cuh"
+#include "media.cuh"
 
 namespace rtbk {
 
@@ -27,10 +28,13 @@ namespace rtbk {
 #ifndef RTB_MEGA_BLOCK_PLACED
 #define RTB_MEGA_BLOCK_PLACED 768     // the placed-entity flavour (transforms, Rect, Box): 80 registers.  The flavour is instruction-fetch bound (ncu: 5.8 no-instruction stalls per issue at 640 threads): more warps hide it — round 2, Cornell world: 384 / 512 / 640 / 704 / 768 / 832 / 896 / 1024 threads = 213 / 188 / 168 / 147 / 133 / 144 / 140 / 144 ms
 #endif
+#ifndef RTB_MEGA_BLOCK_MEDIA
+#define RTB_MEGA_BLOCK_MEDIA 768      // the media flavour: the placed flavour's walk + the hit lists of media.cuh (local memory)
+#endif
 // Threads per CTA by kernel flavour (measured on B200, profiles/README.md): 1024 x 64 registers for the lean sphere
 // builds, 896 x 72 registers for the general build.
 __host__ __device__ constexpr int mega_block(int flavor) {
-  return flavor >= kFlavorPlaced ? RTB_MEGA_BLOCK_PLACED : flavor >= kFlavorGeneral ? RTB_MEGA_BLOCK_GENERAL : RTB_MEGA_BLOCK;
+  return flavor == kFlavorMedia ? RTB_MEGA_BLOCK_MEDIA : flavor >= kFlavorPlaced ? RTB_MEGA_BLOCK_PLACED : flavor >= kFlavorGeneral ? RTB_MEGA_BLOCK_GENERAL : RTB_MEGA_BLOCK;
 }
 constexpr float kFixedScale = 4294967296.0f;            // 2^32
 constexpr float kFixedInvScale = 2.3283064365386963e-10f;  // 2^-32
@@ -234,6 +238,16 @@ __device__ __noinline__ ClaimedTile claim_tile(WarpTile& tile, const BatchArgs& 
 }
 
 
+// The media flavour's step (1): one bounce-loop iteration's hit search with the volume bookkeeping (media.cuh), out of line —
+// its hit list lives in this call's frame, not in the kernel's.
+template <bool SMEM, bool COUNTERS>
+__device__ __noinline__ void media_step_call(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d, const RayClock& clk, int current_volume,
+                                             uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t seed, WorkCounters& wc, MediaStep* out) {
+  RayHits hits;
+  WhiteNoise unused{};
+  *out = media_step<SMEM, COUNTERS, true, false>(sv, sd, o, d, clk, current_volume, pixel, sample, depth, seed, unused, wc, hits);
+}
+
 template <bool SMEM, bool COUNTERS, int FLAVOR>
 __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sample_megakernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -278,6 +292,10 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
   PathRay ray{um::mk(0.0f), um::mk(0.0f)};
   f3 throughput = um::mk(1.0f), radiance = um::mk(0.0f);
   float events_acc = 0;
+  // media flavour only: currentProbabilisticVolumeMaterial (material index, -1 = null; SampleBatchJob.cs:181) and "the ray's Time
+  // is 0" (a ray scattered inside a medium is a new Ray(point, direction): Material.cs:163-168)
+  int current_volume = -1;
+  bool time_zero = false;
   auto set_normal = [&](f3 n) { tile.aov[0][lane] = n.x; tile.aov[1][lane] = n.y; tile.aov[2][lane] = n.z; };
   auto set_albedo = [&](f3 c) { tile.aov[3][lane] = c.x; tile.aov[4][lane] = c.y; tile.aov[5][lane] = c.z; };
   int acc_slot = -1;          // pixel slot this lane's private partial sums belong to
@@ -384,13 +402,33 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     float t_hit = 0;
     float4 m0 = make_float4(0, 0, 0, 0), m1 = m0, m2 = m0, m3 = m0;
     f3 N = um::mk(0.0f), P = um::mk(0.0f);
+    float events0 = 0;          // media flavour: RandomEvents of this iteration's Material.ProbabilisticHit draws
     if (alive) {
       int hit_idx = -1;
-      const RayClock clk{pixel, sample, p.seed, 0.0f, false};
+      const RayClock clk{pixel, sample, p.seed, 0.0f, FLAVOR == kFlavorMedia && time_zero};
       const bool exhausted = depth == p.trace_depth;      // a failed sample (SampleBatchJob.cs:379-381), found at the end of the last trip
-      if (!exhausted) closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
+      if (FLAVOR == kFlavorMedia) {
+        if (!exhausted) {
+          // the iteration's hit search + the reference's volume bookkeeping (SampleBatchJob.cs:184-303; media.cuh)
+          MediaStep st;
+          media_step_call<SMEM, COUNTERS>(sv, a.scene, ray.o, ray.d, clk, current_volume, pixel, sample, (uint32_t)depth, p.seed, wc, &st);
+          current_volume = st.current_volume;
+          events0 = st.events;
+          if (st.hit) {
+            hit_idx = 0;
+            t_hit = st.t;
+            const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + st.material);
+            m0 = __ldg(mp); m1 = __ldg(mp + 1); m2 = __ldg(mp + 2); m3 = __ldg(mp + 3);
+            N = st.n;                                     // the record's normal (-direction for a hit inside a medium)
+            P = um::mad(ray.d, t_hit, ray.o);
+          }
+        }
+      } else if (!exhausted) {
+        closest_hit<SMEM, COUNTERS, FLAVOR>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
+      }
       if (hit_idx >= 0) {
         hit = true;
+        if (FLAVOR != kFlavorMedia) {
         const float4 s = sv.sphere(hit_idx);
         const uint32_t mi = sv.material_of(hit_idx);
         const float4* mp = reinterpret_cast<const float4*>(a.scene.materials + mi);
@@ -404,10 +442,12 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         // HitRecord (Entity.cs:57-72, HitTests.cs:41-45)
         N = hit_normal<SMEM, FLAVOR>(sv, s, ray.o, ray.d, t_hit, clk);
         P = um::mad(ray.d, t_hit, ray.o);
+        }
       } else {
         if (!exhausted) {
           const f3 sky = sky_color(p.environment, a.scene, ray.d);
           radiance = um::mad(throughput, sky, radiance);
+          if (FLAVOR == kFlavorMedia) events_acc += events0 * pow2_neg((uint32_t)depth);   // draws of media the ray passed through
           if (!first_non_specular) {
             const f3 s_normal = -ray.d;
             set_albedo(sky);
@@ -456,6 +496,8 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         set_normal(um::mk(0.0f));
         set_albedo(um::mk(0.0f));
         events_acc = 0;
+        current_volume = -1;
+        time_zero = false;
       }
       next_item = min(next_item + (uint32_t)__popc(need), total_items);
     }
@@ -464,8 +506,10 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     ScatterPlan pl{};
     bool want_rng = false, want_angle = false;
     uint32_t c2 = kBounceCamera, c3 = 0;
+    const bool isotropic = FLAVOR == kFlavorMedia && hit && __float_as_uint(m0.w) == RTB_MATERIAL_PROBABILISTIC_VOLUME;
     if (hit) {
       pl = scatter_plan(m0, m1, m2);
+      if (isotropic) { pl.block = 0u; pl.need_angle = true; }   // Material.cs:163-168: RandomSource.NextFloat3Direction, block 0's u, v
       c2 = (uint32_t)depth;
       c3 = pl.block;
       want_rng = true;
@@ -483,8 +527,16 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
 
     // (4) shade / camera ray
     if (hit) {
-      const ScatterResult sc = scatter_finish(m0, m1, m2, m3, ray.d, N, pl, r, sn, cs, pixel, sample, (uint32_t)depth, p.seed);
-      if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+      ScatterResult sc;
+      if (isotropic) {
+        sc.dir = random_direction(u2f(r.x), sn, cs);
+        sc.reflectance = um::mk(m0.x, m0.y, m0.z);
+        sc.random_events = events0 + 2.0f;
+        time_zero = true;
+      } else {
+        sc = scatter_finish(m0, m1, m2, m3, ray.d, N, pl, r, sn, cs, pixel, sample, (uint32_t)depth, p.seed, FLAVOR == kFlavorMedia ? events0 : 0.0f);
+        if (COUNTERS) { if (__float_as_uint(m0.w) == RTB_MATERIAL_DIELECTRIC) wc.shade_dielectric++; else wc.shade_standard++; }
+      }
       const f3 emission = um::mk(m1.x, m1.y, m1.z);
       if (depth == 0) {
         set_normal(N);

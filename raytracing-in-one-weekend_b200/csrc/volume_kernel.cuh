@@ -9,134 +9,11 @@
 #pragma once
 
 #include "sample_kernels.cuh"
+#include "media.cuh"
 
 namespace rtbk {
 
 constexpr uint32_t kLaneSamples = 8;  // samples a lane traces back to back before the warp accumulates (Philox mode)
-constexpr int kMaxRayHits = 48;     // hit records kept per ray (the reference's list starts at 32 and grows, SampleBatchJob.cs:21;
-                                    // HybridCollections.cs:65-71).  A ray that fills the list raises kStatusHitListOverflow and the
-                                    // batch fails with RTB_ERR_UNSUPPORTED: never a silently different image
-
-struct RayHits {                    // FindHits' sorted hitBuffer
-  float t[kMaxRayHits];
-  int slot[kMaxRayHits];
-  f3 n[kMaxRayHits];
-  int count;
-};
-
-// Entity.Hit (Entity.cs:57-72) of the entity in `slot` for t in (tmin, +inf): distance and world normal.
-template <bool SMEM>
-__device__ __noinline__ bool entity_hit(const SceneView<SMEM>& sv, int slot, f3 o, f3 d, float tmin, const RayClock& clk, float* t_out,
-                                        f3* n_out) {
-  const float4 prim = sv.sphere(slot);
-  if (prim.w != prim.w) {
-    if (__float_as_uint(prim.y) != 0u) {
-      f3 n;
-      if (!placed_test(sv, __float_as_uint(prim.x), o, d, clk, t_out, &n, tmin)) return false;
-      *n_out = um::normalize(n);
-      return true;
-    }
-    float u, v, t;
-    if (!triangle_uvt(sv, __float_as_uint(prim.x), o, d, &u, &v, &t)) return false;
-    if (t < tmin) return false;                       // HitTests.cs:141 (tMax = +inf)
-    *t_out = t;
-    *n_out = hit_normal<SMEM, kFlavorGeneral>(sv, prim, o, d, t, clk);
-    return true;
-  }
-  // HitTests.Hit(this Sphere) (HitTests.cs:23-60) behind the identity-rotation transform
-  const f3 oc = o + um::mk(-prim.x, -prim.y, -prim.z);
-  const float a = um::dot(d, d), b = um::dot(oc, d), c = um::dot(oc, oc) - prim.w * prim.w;
-  const float disc = um::fma(b, b, -(a * c));
-  if (!(disc > 0.0f)) return false;
-  const float sq = um::sqrt(disc);
-  float t = um::div(-b - sq, a);
-  if (!(t < um::INF && t > tmin)) {
-    t = um::div(-b + sq, a);
-    if (!(t < um::INF && t > tmin)) return false;
-  }
-  *t_out = t;
-  *n_out = um::normalize(um::mad(d, t, oc) / prim.w);
-  return true;
-}
-
-__device__ __forceinline__ bool is_volume(const SceneDesc& sd, uint32_t material) {
-  return __ldg(reinterpret_cast<const uint32_t*>(sd.materials + material) + 3) == RTB_MATERIAL_PROBABILISTIC_VOLUME;
-}
-// EntityType.IsConvexHull (Entity.cs:22-25): Sphere or Box
-__device__ __forceinline__ bool is_convex_hull(const SceneView<false>& sv, float4 prim) {
-  if (prim.w == prim.w) return true;
-  if (__float_as_uint(prim.y) == 0u) return false;    // triangle
-  const uint32_t type = __float_as_uint(sv.placed(__float_as_uint(prim.x), 1).w) & 0xffu;
-  return type == RTB_ENTITY_SPHERE || type == RTB_ENTITY_BOX;
-}
-
-// FindHitCandidates + FindHits (SampleBatchJob.cs:403-475) without pruning: every entity of every leaf whose box chain
-// the ray hits, in the reference's visit order (children pushed Left then Right, Right popped first).  The reference
-// pops candidates from the END of that list and then sorts by distance; with a stable order among equal distances that
-// is: a later candidate goes BEFORE an earlier one at the same distance — the insertion rule used here.
-// MODE 0: fill `hits`.  MODE 1 (AnyBackwardsVolumeEntryHit, :508-524): is there a volume entity the ray enters?
-template <bool COUNTERS>
-__device__ __noinline__ bool collect_hits(const int MODE, const SceneView<false>& sv, const SceneDesc& sd, f3 o, f3 d, const RayClock& clk,
-                                          RayHits* hits, WorkCounters& wc) {
-  if (MODE == 0) hits->count = 0;
-  if (!sd.has_root) return false;
-  f3 inv = um::rcp(d);
-  inv = um::mk(um::isnan(inv.x) ? um::INF : inv.x, um::isnan(inv.y) ? um::INF : inv.y, um::isnan(inv.z) ? um::INF : inv.z);
-  float t_enter;
-  if (COUNTERS) wc.node_tests++;
-  if (!aabb_hit(v3(sd.root_min), v3(sd.root_max), o, inv, &t_enter)) return false;
-  int stack[kStackMax + 2];
-  int sp = 0;
-  stack[sp++] = sd.root_ref;
-  auto insert = [&](float t, int slot, f3 n) {
-    int pos = 0;
-    while (pos < hits->count && hits->t[pos] < t) pos++;       // before the first record that is not nearer
-    if (pos >= kMaxRayHits) return;
-    const int last = hits->count < kMaxRayHits ? hits->count : kMaxRayHits - 1;
-    for (int k = last; k > pos; k--) { hits->t[k] = hits->t[k - 1]; hits->slot[k] = hits->slot[k - 1]; hits->n[k] = hits->n[k - 1]; }
-    hits->t[pos] = t; hits->slot[pos] = slot; hits->n[pos] = n;
-    if (hits->count < kMaxRayHits) hits->count++;
-  };
-  while (sp > 0) {
-    const int cur = stack[--sp];
-    if (cur >= 0) {
-      const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
-      float tl, tr;
-      const bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
-      const bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
-      if (COUNTERS) wc.node_tests += 2;
-      if (hl) stack[sp++] = __float_as_int(q3.x);
-      if (hr) stack[sp++] = __float_as_int(q3.y);
-      continue;
-    }
-    const uint32_t code = (uint32_t)~cur;
-    const int first = (int)(code & ~15u);
-    int count = (int)(code & 15u) + 1;
-    if (count == 16) count = (int)sv.leaf_count(first);
-    if (COUNTERS) wc.sphere_tests += count;
-    for (int i = 0; i < count; i++) {
-      const int slot = first + 16 * i;
-      const uint32_t material = sv.material_of(slot);
-      if (MODE == 1 && !is_volume(sd, material)) continue;
-      float t;
-      f3 n;
-      if (!entity_hit(sv, slot, o, d, 0.0f, clk, &t, &n)) continue;
-      if (MODE == 1) {
-        if (um::dot(n, d) > 0) return true;           // (the caller passes the backwards ray)
-        continue;
-      }
-      // Inject exit hits for probabilistic convex hulls (:462-469); the pair is pushed entry first, so at equal
-      // distances the exit must end up behind the entry: insert it first
-      if (is_volume(sd, material) && is_convex_hull(sv, sv.sphere(slot))) {
-        float t2;
-        f3 n2;
-        if (entity_hit(sv, slot, o, d, t + 0.001f, clk, &t2, &n2)) insert(t2, slot, n2);
-      }
-      insert(t, slot, n);
-    }
-  }
-  return false;
-}
 
 struct VolumeSample {            // what one camera path hands to the pixel's accumulators (SampleBatchJob.cs:136-157)
   bool ok;                       // Sample() returned true (the path reached the sky within TraceDepth)
@@ -163,95 +40,20 @@ __device__ __noinline__ VolumeSample trace_volume_sample(const BatchArgs& a, con
   int depth = 0, entries = 0;
   int current_volume = -1;                          // currentProbabilisticVolumeMaterial (material index, -1 = null)
   for (; depth < p.trace_depth; depth++) {
-    uint32_t volume_draws = 0;
-    float events = 0;                               // rng.RandomEvents of this iteration
-    collect_hits<COUNTERS>(0, sv, sd, ray.o, ray.d, clk, &hits, wc);
-    // a FULL list may have lost records (checked here, once per ray: anything in the insert path itself — an atomic, even a
-    // flag store — cost this kernel 20-100 %): the batch then fails with RTB_ERR_UNSUPPORTED
-    if (hits.count >= kMaxRayHits && sd.status) atomicOr(sd.status, kStatusHitListOverflow);
-    if (current_volume < 0) {                       // DetermineVolumeContainment (:477-506)
-      for (int i = 0; i < hits.count; i++) {
-        const uint32_t hm = sv.material_of(hits.slot[i]);
-        if (!is_volume(sd, hm)) continue;
-        if (um::dot(hits.n[i], ray.d) < 0) break;   // entry hit: not inside
-        if (collect_hits<COUNTERS>(1, sv, sd, ray.o, -ray.d, clk, &hits, wc)) { current_volume = (int)hm; break; }
-      }
-    }
+    // the iteration's hit search + volume bookkeeping (media.cuh), on the reference's own list: every hit, sorted
+    const MediaStep st = media_step<false, COUNTERS, false, WHITE>(sv, sd, ray.o, ray.d, clk, current_volume, index, s, (uint32_t)depth,
+                                                                    p.seed, white, wc, hits);
+    current_volume = st.current_volume;
+    float events = st.events;                       // rng.RandomEvents of this iteration
     out.rays++;
 
     bool scattered = false;
-    int hit_index = 0;
-    while (hit_index < hits.count) {
-      float rec_t = hits.t[hit_index];
-      f3 rec_n = hits.n[hit_index];
-      int rec_slot = hits.slot[hit_index];
-      uint32_t mi = sv.material_of(rec_slot);
-      bool medium_hit = false;
-
-      if (current_volume >= 0 || is_volume(sd, mi)) {
-        const bool is_entry_hit = current_volume < 0;
-        if (current_volume < 0) current_volume = (int)mi;
-        int exit_index = hit_index, last_exit = -1, same_entries = 0;
-        while (exit_index < hits.count) {
-          if ((int)sv.material_of(hits.slot[exit_index]) == current_volume) {
-            if (um::dot(hits.n[exit_index], ray.d) < 0) {
-              same_entries++;
-            } else {
-              same_entries--;
-              last_exit = exit_index;
-            }
-            if (same_entries <= 0) break;
-          } else {
-            break;
-          }
-          exit_index++;
-        }
-        if (same_entries > 0 && last_exit != -1) exit_index = last_exit;
-
-        if (exit_index < hits.count) {
-          float distance_in_volume = hits.t[exit_index];
-          float entry_distance = 0;
-          if (is_entry_hit) {
-            entry_distance = rec_t;
-            distance_in_volume -= rec_t;
-          }
-          // Material.ProbabilisticHit (Material.cs:48-65); Density = the material's parameter
-          const float density = __ldg(reinterpret_cast<const float*>(sd.materials + current_volume) + 9);
-          events += 1.0f;
-          float u;
-          if (WHITE) {
-            u = white.next_float();
-          } else {
-            const uint4 r = philox4x32_10(index, s, (uint32_t)depth, 2u + (volume_draws >> 2), p.seed, kPhiloxKey1);
-            const uint32_t w = volume_draws & 3u;
-            u = u2f(w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w);
-            volume_draws++;
-          }
-          const float volume_hit_distance = -um::div(1.0f, um::max(density, 1.1920928955078125e-7f)) * um::log_unit(u);
-          if (volume_hit_distance < distance_in_volume) {
-            // we hit inside the volume: the record becomes (distance, point, -direction), the material the medium's
-            rec_t = entry_distance + volume_hit_distance;
-            rec_n = -ray.d;
-            mi = (uint32_t)current_volume;
-            medium_hit = true;
-          } else {
-            const uint32_t exit_material = sv.material_of(hits.slot[exit_index]);
-            current_volume = -1;
-            if (is_volume(sd, exit_material) && um::dot(hits.n[exit_index], ray.d) > 0) {
-              hit_index = exit_index + 1;           // volume exit: move to the next hit
-              continue;
-            }
-            rec_t = hits.t[exit_index];             // obstacle: scatter on the exit hit
-            rec_n = hits.n[exit_index];
-            rec_slot = hits.slot[exit_index];
-            mi = exit_material;
-          }
-        } else {
-          hits.count = 0;                           // no more surfaces to hit (the volume has holes)
-          break;
-        }
-      }
-
+    if (st.hit) {
+      const float rec_t = st.t;
+      const f3 rec_n = st.n;
+      const int rec_slot = st.slot;
+      const uint32_t mi = st.material;
+      const bool medium_hit = st.medium_hit;
       const float4* mp = reinterpret_cast<const float4*>(sd.materials + mi);
       float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
       if (__float_as_uint(m3.w) != 0u) {
@@ -295,7 +97,6 @@ __device__ __noinline__ VolumeSample trace_volume_sample(const BatchArgs& a, con
       ray.o = um::mad(off_n, 0.001f, P);
       ray.d = sc.dir;
       scattered = true;
-      break;
     }
 
     if (!scattered) {                               // no hit (or every hit passed through / dropped): the sky ends the path

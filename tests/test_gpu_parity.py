@@ -971,8 +971,9 @@ def test_random_worlds_of_every_entity_kind(rtb, oracle, ctx):
 def test_fog_cornell_world_matches_the_oracle(rtb, oracle, ctx, depth, moving, aperture):
     """MaterialType.ProbabilisticVolume (SampleBatchJob.cs:194-303, 450-524; Material.cs:48-65,163-168): balls of fog and
     smoke (one of them moving), a medium inside the glass ball, an inert Box medium — entry / exit bookkeeping over the sorted
-    list of all hits, injected exit hits, backwards containment rays.  The volume kernel is bit-identical to the oracle
-    whatever RTB_OPT_KERNEL asks for."""
+    list of all hits, injected exit hits, backwards containment rays.  The collect-all kernel (RTB_OPT_KERNEL = 1) is bit-identical
+    to the oracle; the megakernel's media flavour (two pruned walks instead of the list of every hit, media.cuh) takes the same
+    decisions — equal sample counts and ray counts in every pixel, sums equal up to the accumulation order."""
     W, H, spp = 96, 54, 16
     scene = rtb.host.make_cornell_scene(max_bvh_depth=depth, moving=moving, fog=True)
     p = rtb.host.make_params(scene, W, H, spp, 50, aperture=aperture)
@@ -981,9 +982,27 @@ def test_fog_cornell_world_matches_the_oracle(rtb, oracle, ctx, depth, moving, a
     plain = oracle.Buffers(W, H)
     oracle.sample_batch(rtb.host.make_cornell_scene(max_bvh_depth=depth, moving=moving), p, plain)
     assert np.abs(ref.rgb() - plain.rgb()).max() > 0.5                       # the media are visible
-    for kernel in (rtb.abi.KERNEL_SIMPLE, rtb.abi.KERNEL_MEGA):
+    for kernel, exact in ((rtb.abi.KERNEL_SIMPLE, True), (rtb.abi.KERNEL_MEGA, False)):
         got = render_gpu(rtb, ctx, scene, p, W, H, kernel)
-        assert_parity(ref, got, exact=True)
+        assert_parity(ref, got, exact=exact)
+
+
+def test_media_flavour_takes_the_collect_all_kernels_decisions(rtb, ctx):
+    """The megakernel's media flavour against the collect-all validator kernel on larger frames than the oracle affords (GPU
+    against GPU): the fog Cornell box, the same with the camera inside a ball of fog (every camera ray starts with the containment
+    test and its backwards ray), and a linear list (one leaf holding every entity: the candidate order inside a leaf)."""
+    W, H, spp = 320, 180, 32
+    for depth, inside in ((16, False), (16, True), (0, False)):
+        scene = rtb.host.make_cornell_scene(max_bvh_depth=depth, moving=True, fog=True)
+        if inside:
+            scene.spheres["center"][2] = (2.775, 2.775, -8.0)
+            scene.spheres["radius"][2] = 1.5
+            scene = rtb.host.build_world(scene.spheres, [], scene.materials, depth, scene.camera, scene.environment, scene.focus_distance,
+                                         placed=scene.placed)
+        p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.05)
+        ref = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE)
+        got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+        assert_parity(ref, got, exact=False)
 
 
 def test_fog_world_white_noise_stream_and_camera_inside_a_medium(rtb, oracle, ctx):
