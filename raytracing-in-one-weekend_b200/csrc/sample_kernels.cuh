@@ -29,7 +29,8 @@ namespace rtbk {
 #define RTB_MEGA_BLOCK_PLACED 768     // the placed-entity flavour (transforms, Rect, Box): 80 registers.  The flavour is instruction-fetch bound (ncu: 5.8 no-instruction stalls per issue at 640 threads): more warps hide it — round 2, Cornell world: 384 / 512 / 640 / 704 / 768 / 832 / 896 / 1024 threads = 213 / 188 / 168 / 147 / 133 / 144 / 140 / 144 ms
 #endif
 #ifndef RTB_MEGA_BLOCK_MEDIA
-#define RTB_MEGA_BLOCK_MEDIA 768      // the media flavour: the placed flavour's walk + the hit lists of media.cuh (local memory)
+#define RTB_MEGA_BLOCK_MEDIA 896      // the media flavour (media.cuh; hit lists in local memory).  Instruction-fetch bound like the placed flavour and
+                                      // insensitive to the CTA size: fog Cornell box, 384 / 512 / 640 / 768 / 896 / 1024 threads = 708 / 638 / 633 / 643 / 619 / 624 ms
 #endif
 // Threads per CTA by kernel flavour (measured on B200, profiles/README.md): 1024 x 64 registers for the lean sphere
 // builds, 896 x 72 registers for the general build.
