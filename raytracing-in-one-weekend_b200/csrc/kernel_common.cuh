@@ -736,7 +736,10 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   }
     return;
   }
-  // The general and placed flavours: one node (inner OR leaf) per trip (measured faster for them: 72.8 vs 78.8 ms on the mesh world).
+  // The general and placed flavours: one node (inner OR leaf) per trip (measured faster for them than the lean builds' fused
+  // trips: 72.8 vs 78.8 ms on the mesh world).  Walking in rounds (collect 2 / 4 / 8 candidate entities, then intersect them with
+  // the warp converged — what media.cuh's gather_hits does, where it pays) was measured here too: Cornell box 132.8 -> 139.4 /
+  // 136.0 / 136.3 ms, as a linear list 99.3 -> 115.4 / 114.1 / 118.4, mesh world 69.4 -> 68.0 / 66.2 / 67.4 — not kept.
   int* top = stack + 1;
   for (;;) {
     walk_converge();

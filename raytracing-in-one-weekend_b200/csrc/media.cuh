@@ -69,8 +69,14 @@ __device__ __noinline__ bool entity_hit(const SceneView<SMEM>& sv, int slot, f3 
   return true;
 }
 
-__device__ __forceinline__ bool is_volume(const SceneDesc& sd, uint32_t material) {
-  return __ldg(reinterpret_cast<const uint32_t*>(sd.materials + material) + 3) == RTB_MATERIAL_PROBABILISTIC_VOLUME;
+// In worlds with media, upload marks the material word of every entity that wears one (bit 31: plugin.cu, build_blob), so
+// "is this entity's material a ProbabilisticVolume" costs no second, dependent load from the material table.
+constexpr uint32_t kMediumBit = 0x80000000u;
+template <bool SMEM>
+__device__ __forceinline__ uint32_t slot_material(const SceneView<SMEM>& sv, int slot, bool* medium) {
+  const uint32_t raw = sv.material_of(slot);
+  *medium = (raw & kMediumBit) != 0u;
+  return raw & ~kMediumBit;
 }
 // EntityType.IsConvexHull (Entity.cs:22-25): Sphere or Box
 template <bool SMEM>
@@ -102,6 +108,10 @@ __device__ __forceinline__ void hits_insert(RayHits* hits, float t, int slot, in
   hits->t[pos] = t; hits->slot[pos] = slot; hits->first[pos] = first; hits->n[pos] = n;
   if (hits->count < kMaxRayHits) hits->count++;
 }
+
+template <bool SMEM>
+__device__ __noinline__ bool entity_records(const SceneView<SMEM>& sv, int slot, bool with_exit, f3 o, f3 d, const RayClock& clk,
+                                            float* t_out, f3* n_out, float* t2_out, f3* n2_out);
 
 // FindHitCandidates + FindHits (SampleBatchJob.cs:403-475) without pruning: every entity of every leaf whose box chain
 // the ray hits, in the reference's visit order.  With a stable order among equal distances the reference's pop + sort is:
@@ -146,12 +156,18 @@ __device__ __noinline__ bool collect_hits(const int MODE, const SceneView<SMEM>&
     if (COUNTERS) wc.sphere_tests += count;
     for (int i = 0; i < count; i++) {
       const int slot = first + 16 * i;
-      const uint32_t material = sv.material_of(slot);
-      const bool medium = is_volume(sd, material);
+      bool medium;
+      slot_material(sv, slot, &medium);
       if ((MODE == 1 || MEDIA_ONLY) && !medium) continue;
       float t;
       f3 n;
-      if (!entity_hit(sv, slot, o, d, 0.0f, clk, &t, &n)) continue;
+      if (MEDIA_ONLY) {                               // (the media flavour's one copy of the entity tests: same arithmetic)
+        float t2;
+        f3 n2;
+        if (!entity_records(sv, slot, false, o, d, clk, &t, &n, &t2, &n2)) continue;
+      } else if (!entity_hit(sv, slot, o, d, 0.0f, clk, &t, &n)) {
+        continue;
+      }
       if (MODE == 1) {
         if (um::dot(n, d) > 0) return true;           // (the caller passes the backwards ray)
         continue;
@@ -308,7 +324,8 @@ __device__ __forceinline__ void gather_hits(const SceneView<SMEM>& sv, const Sce
     if (nc == 0) break;
     for (int k = 0; k < nc; k++) {
       const int slot = cand[k], first = cand_first[k];
-      const bool medium = is_volume(sd, sv.material_of(slot));
+      bool medium;
+      slot_material(sv, slot, &medium);
       float t, t2;
       f3 n, n2;
       if (!entity_records(sv, slot, medium, o, d, clk, &t, &n, &t2, &n2)) continue;
@@ -362,8 +379,9 @@ __device__ __forceinline__ MediaStep media_step(const SceneView<SMEM>& sv, const
   if (hits.count >= kMaxRayHits && sd.status) atomicOr(sd.status, kStatusHitListOverflow);
   if (current_volume < 0) {                       // DetermineVolumeContainment (:477-506)
     for (int i = 0; i < hits.count; i++) {
-      const uint32_t hm = sv.material_of(hits.slot[i]);
-      if (!is_volume(sd, hm)) continue;
+      bool medium;
+      const uint32_t hm = slot_material(sv, hits.slot[i], &medium);
+      if (!medium) continue;
       if (um::dot(hits.n[i], rd) < 0) break;      // entry hit: not inside
       // (the backwards ray does not depend on i, and neither does its answer)
       if (collect_hits<SMEM, COUNTERS, PRUNED>(1, sv, sd, ro, -rd, clk, &hits, wc)) current_volume = (int)hm;
@@ -376,15 +394,16 @@ __device__ __forceinline__ MediaStep media_step(const SceneView<SMEM>& sv, const
     float rec_t = hits.t[hit_index];
     f3 rec_n = hits.n[hit_index];
     int rec_slot = hits.slot[hit_index];
-    uint32_t mi = sv.material_of(rec_slot);
+    bool rec_medium;
+    uint32_t mi = slot_material(sv, rec_slot, &rec_medium);
     bool medium_hit = false;
 
-    if (current_volume >= 0 || is_volume(sd, mi)) {
+    if (current_volume >= 0 || rec_medium) {
       const bool is_entry_hit = current_volume < 0;
       if (current_volume < 0) current_volume = (int)mi;
       int exit_index = hit_index, last_exit = -1, same_entries = 0;
       while (exit_index < hits.count) {
-        if ((int)sv.material_of(hits.slot[exit_index]) == current_volume) {
+        if ((int)(sv.material_of(hits.slot[exit_index]) & ~kMediumBit) == current_volume) {
           if (um::dot(hits.n[exit_index], rd) < 0) {
             same_entries++;
           } else {
@@ -426,9 +445,10 @@ __device__ __forceinline__ MediaStep media_step(const SceneView<SMEM>& sv, const
           mi = (uint32_t)current_volume;
           medium_hit = true;
         } else {
-          const uint32_t exit_material = sv.material_of(hits.slot[exit_index]);
+          bool exit_medium;
+          const uint32_t exit_material = slot_material(sv, hits.slot[exit_index], &exit_medium);
           current_volume = -1;
-          if (is_volume(sd, exit_material) && um::dot(hits.n[exit_index], rd) > 0) {
+          if (exit_medium && um::dot(hits.n[exit_index], rd) > 0) {
             hit_index = exit_index + 1;           // volume exit: move to the next hit
             continue;
           }

@@ -471,6 +471,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
     }
     memcpy(b + d.sphere_off + i * 16, s, 16);
     memcpy(b + d.leaf_count_off + i * 4, &f.leaf_count[i], 4);
+    if (has_volumes && wears_volume(mat)) mat |= 0x80000000u;   // media.cuh: kMediumBit (only worlds with media carry it, and only media.cuh reads those)
     memcpy(b + d.mat_index_off + i * 4, &mat, 4);
   }
   for (size_t i = 0; i < triangle_count; i++) {
