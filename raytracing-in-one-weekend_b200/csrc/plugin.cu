@@ -1482,9 +1482,23 @@ int rtb_finalize_device(rtb_ctx* ctx, int width, int height, const float* color3
     return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_finalize_device: missing input");
   DeviceGuard g(ctx->device);
   const int n = width * height;
-  const int grid = std::max(1, std::min((n + 255) / 256, ctx->sm_count * 16));
-  finalize_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(n, color3, normal3, albedo3, out_color_rgba, out_normal_rgba, out_albedo_rgba);
-  RTB_CUDA(ctx, cudaGetLastError());
+  // four pixels per thread (float4 loads, uint4 stores) when every array is 16-byte aligned; the ragged end, or everything, per pixel
+  auto aligned = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+  const bool x4 = aligned(color3) && aligned(normal3) && aligned(albedo3) && aligned(out_color_rgba) && aligned(out_normal_rgba) && aligned(out_albedo_rgba);
+  const int n_quads = x4 ? n / 4 : 0;
+  if (n_quads > 0) {
+    const int grid = std::max(1, std::min((n_quads + 255) / 256, ctx->sm_count * 16));
+    finalize_kernel_x4<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(n_quads, reinterpret_cast<const float4*>(color3), reinterpret_cast<const float4*>(normal3),
+                                                                   reinterpret_cast<const float4*>(albedo3), reinterpret_cast<uint4*>(out_color_rgba),
+                                                                   reinterpret_cast<uint4*>(out_normal_rgba), reinterpret_cast<uint4*>(out_albedo_rgba));
+    RTB_CUDA(ctx, cudaGetLastError());
+  }
+  if (4 * n_quads < n) {
+    const int rest = n - 4 * n_quads;
+    const int grid = std::max(1, std::min((rest + 255) / 256, ctx->sm_count * 16));
+    finalize_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(n, color3, normal3, albedo3, out_color_rgba, out_normal_rgba, out_albedo_rgba, 4 * n_quads);
+    RTB_CUDA(ctx, cudaGetLastError());
+  }
   return RTB_OK;
 }
 

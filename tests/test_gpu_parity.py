@@ -820,7 +820,37 @@ def test_finalize_device_matches_the_restated_job_and_runs_at_hbm_rate(rtb, orac
     torch.cuda.synchronize()
     gbs = 20 * n * 48 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
     print(f"finalize_kernel: {gbs:.0f} GB/s algorithmic")
-    assert gbs > 2000
+    assert gbs > 4000
+
+
+def test_finalize_fast_path_equals_the_exact_pow_on_a_dense_sweep(rtb, oracle, ctx):
+    """The finalize kernel takes a MUFU estimate of pow wherever it lies further from a byte boundary than it can be wrong, and
+    the polynomial pow of the job's restatement elsewhere (aux_kernels.cuh: gamma_byte).  Every float k / 2^24 of [0, 1] — steps
+    far finer than the guard, on both sides of all 255 boundaries — and a log sweep of [1e-7, 40] must give the restated job's
+    byte; the ragged size also takes the kernel's per-pixel tail."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    dense = (np.arange(3 * 5592406, dtype=np.float64) / 2.0**24).astype(np.float32)
+    logs = np.exp(np.linspace(np.log(1e-7), np.log(40.0), 3 * 700001)).astype(np.float32)
+    for vals in (dense, logs):
+        n = len(vals) // 3
+        x = torch.from_numpy(vals.reshape(n, 3).copy()).to(dev)
+        out = torch.zeros(n, dtype=torch.int32, device=dev)
+        ctx.finalize_device(1, n, x, None, None, out, None, None, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint32)
+        p = np.zeros_like(vals)
+        pos = vals > 0
+        src = np.ascontiguousarray(vals[pos])
+        dst = np.zeros_like(src)
+        oracle.lib().oracle_umath_pow(src.ctypes.data, np.float32(0.416666667), dst.ctypes.data, len(src))
+        p[pos] = dst
+        g = np.maximum(np.float32(1.055) * p - np.float32(0.055), np.float32(0))
+        b = (np.clip(g, 0, 1).astype(np.float32) * np.float32(255)).astype(np.uint32).reshape(n, 3)
+        want = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16) | np.uint32(0xff000000)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (len(bad), vals.reshape(n, 3)[bad[:5]], got[bad[:5]], want[bad[:5]])
 
 
 def test_full_size_config2_rows_match_the_oracle(rtb, oracle, ctx):
