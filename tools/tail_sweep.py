@@ -13,7 +13,7 @@ scene = rtb.host.make_scene("final", max_bvh_depth=16)
 ctx = rtb.plugin.Context(0); ctx.upload(scene)
 b = rtb.plugin.HostBuffers(W, H); ctx.register_host_buffers(b)
 def ms(r0, r1, reps=2):
-    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1, row_begin=r0, row_end=r1)
+    p = rtb.host.make_params(scene, W, H, spp, int(os.environ.get("SWEEP_TRACE_DEPTH", "50")), aperture=0.1, row_begin=r0, row_end=r1)
     best = 1e9
     for _ in range(reps):
         ctx.sample_batch(p, b); best = min(best, ctx.last_kernel_ms())
