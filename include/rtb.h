@@ -116,7 +116,9 @@ typedef enum rtb_material_type {     /* Material.cs:9-14 */
   RTB_MATERIAL_STANDARD = 0,
   RTB_MATERIAL_DIELECTRIC = 1,
   RTB_MATERIAL_PROBABILISTIC_VOLUME = 2   /* participating medium (Material.cs:48-65,163-168): albedo = Albedo.MainColor, density in
-                                           * index_of_refraction (Material.parameter); worlds with one run the collect-all kernel */
+                                           * index_of_refraction (Material.parameter); worlds in which an entity wears one run the
+                                           * megakernel's media flavour (RTB_OPT_KERNEL = 1, RTB_OPT_NOISE = 1 or image textures: the
+                                           * collect-all kernel, bit-identical to the CPU restatement) */
 } rtb_material_type;
 
 /* Material with constant textures only (Material.cs:16-26, Texture.cs:50-59,101-108:
@@ -322,7 +324,7 @@ RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
  * token: the kernel polls a word in device memory owned by the context (a volatile load whenever a warp claims a
  * work tile; a CTA that saw it stops issuing samples), and the blocking call watches *cancel while it waits and
  * writes that word from a second stream when the token is set.  Once set, the call returns RTB_ERR_CANCELLED within a fraction of a millisecond
- * (worlds with participating media: within one pixel's samples); outputs are then unspecified, as in the
+ * (the collect-all kernel of worlds with participating media: within one pixel's samples); outputs are then unspecified, as in the
  * reference (the host discards them).
  *
  * Accumulation range.  Per pixel and batch the sums of colour, normal, albedo and sampleCountWeight are kept in
