@@ -14,6 +14,7 @@ cases = [(rtb.host.make_scene("final", max_bvh_depth=16), 0.1, 1), (rtb.host.mak
 wide = os.environ.get("SANITIZE_WIDE", "0") == "1"     # the worlds beyond the BASELINE configs instead
 if wide:
     cases = [(rtb.host.make_cornell_scene(max_bvh_depth=16), 0.0, 1), (rtb.host.make_cornell_scene(max_bvh_depth=2, fog=True), 0.1, 1),
+             (rtb.host.make_cornell_scene(max_bvh_depth=16, fog=True), 0.0, 1),
              (rtb.host.make_mesh_scene(max_bvh_depth=16, textured=True), 0.0, 1), (rtb.host.make_random_placed_scene(3, count=24), 0.1, 1)]
 W, H, spp = 64, 36, 8
 for scene, ap, k in cases:
