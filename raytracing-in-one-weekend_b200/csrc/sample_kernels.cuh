@@ -29,8 +29,9 @@ namespace rtbk {
 #define RTB_MEGA_BLOCK_PLACED 768     // the placed-entity flavour (transforms, Rect, Box): 80 registers.  The flavour is instruction-fetch bound (ncu: 5.8 no-instruction stalls per issue at 640 threads): more warps hide it — round 2, Cornell world: 384 / 512 / 640 / 704 / 768 / 832 / 896 / 1024 threads = 213 / 188 / 168 / 147 / 133 / 144 / 140 / 144 ms
 #endif
 #ifndef RTB_MEGA_BLOCK_MEDIA
-#define RTB_MEGA_BLOCK_MEDIA 896      // the media flavour (media.cuh; hit lists in local memory).  Instruction-fetch bound like the placed flavour and
-                                      // insensitive to the CTA size: fog Cornell box, 384 / 512 / 640 / 768 / 896 / 1024 threads = 708 / 638 / 633 / 643 / 619 / 624 ms
+#define RTB_MEGA_BLOCK_MEDIA 512      // the media flavour (media.cuh; hit lists in local memory): 128 registers.  With the CTA's warps running in step
+                                      // (kPhased): 256 / 384 / 448 / 512 / 576 / 640 / 768 / 896 / 1024 threads = 523 / 410 / 387 / 356 / 392 / 372 / 397 /
+                                      // 392 / 427 ms on the fog Cornell box (free-running warps: 708 ... 619 ms for 384 ... 1024 threads)
 #endif
 // Threads per CTA by kernel flavour (measured on B200, profiles/README.md): 1024 x 64 registers for the lean sphere
 // builds, 896 x 72 registers for the general build.
@@ -371,7 +372,20 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
   //   (3) draw    ONE converged step serves both kinds of lanes: the Philox block of the bounce (hit lanes) or of the
   //               camera ray (refilled lanes), and the sincos both need
   //   (4) shade   hit lanes finish Material.Scatter and form the next ray; refilled lanes form their camera ray
+  // The placed and media flavours run the trip's two halves IN STEP across the CTA's warps: a barrier at the top of the trip
+  // and one between step (1) — the walk with its entity tests, the media bookkeeping, the accumulation of finished paths —
+  // and steps (2)-(4) — refill, draw, shade.  These flavours are bound by instruction fetch (ncu: 5.8 and 17 no-instruction
+  // stalls per issue; 5 k and 6.6 k instructions of divergent code against a 32 KB L1.5 instruction cache, insensitive to the
+  // CTA size): with every warp of the SM inside the same half, the code in flight fits.  Measured (bit-identical images):
+  // Cornell box 132.8 -> 114.9 ms, as a linear list 99.3 -> 86.0, with media 593 -> 393; barrier only at the top 123.7 /
+  // 513; a third one before the shade 115.7 / 393; barriers inside the media hit search (walk | tests) 500.  The general
+  // flavour (mesh world 69 -> 135 ms: long walks of uneven length wait for each other) and the lean sphere builds (config 3
+  // 128.5 -> 163) are not fetch-bound and keep free-running warps.
+  constexpr bool kPhased = FLAVOR >= kFlavorPlaced;
+  bool warp_done = false;     // kPhased: this warp has nothing left, but keeps meeting the CTA's barriers until every warp says so
   for (;;) {
+    if (kPhased) { if (__syncthreads_and(warp_done ? 1 : 0)) break; }
+    if (!(kPhased && warp_done)) {
     const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
     // the previous tile retires as soon as its last path has finished
     if (drain_n > 0) {
@@ -394,8 +408,10 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
         if (c.n < 0) { tile_flags |= 2u; tile_n = 0; total_items = 0; }
         else { tile_n = c.n; total_items = c.items; }
       } else if (alive_mask == 0) {
+        if (kPhased) warp_done = true; else
         break;                // no tile left, nothing draining, nothing in flight
       }
+    }
     }
 
     // (1) one walk for every live lane (SampleBatchJob.cs:184-206, 341-374)
@@ -463,6 +479,7 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
       }
     }
 
+    if (kPhased) __syncthreads();
     // (2) refill dead lanes from the tile's work stream
     bool fresh = false;
     int cx = 0, cy = 0;
