@@ -80,7 +80,13 @@ struct rtb_ctx {
   // CancellationToken relay (BatchArgs::cancel_flag / cancel_epoch): the kernels poll a device word; the blocking call
   // watches the caller's token while it waits and, when it is set, copies the batch's epoch into that word on cancel_stream.
   uint32_t* d_cancel = nullptr;       // device word
-  uint32_t* h_epoch = nullptr;        // pinned source of the cancel copy
+  uint32_t* h_epoch = nullptr;        // pinned source of the cancel copy (first word of a 256-byte pinned block)
+  // Pinned landing places of the per-batch read-backs.  They must NOT be pageable: an "asynchronous" device-to-host copy into
+  // pageable memory blocks the calling thread until the stream reaches it — i.e. until the kernel has finished —, and the
+  // thread that is to relay the CancellationToken (wait_for_streams) would only start watching it afterwards (found in
+  // round 2: batches of worlds with media could not be cancelled in flight).
+  uint32_t* h_status = nullptr;       // h_epoch + 4
+  rtb_counters* h_counters = nullptr; // (char*)h_epoch + 64
   uint32_t cancel_epoch = 0;          // epoch of the batch in flight (never 0: the word starts as 0)
   bool cancel_sent = false;           // this batch's cancel copy was issued
   cudaStream_t cancel_stream = nullptr;
@@ -942,8 +948,8 @@ int host_batch_drain(rtb_ctx* ctx, HostBatch* st) {
       RTB_CUDA(ctx, copy_rows(host->out_diagnostics, d.diagnostics, sizeof(rtb_diagnostics), st->width, st->all, cudaMemcpyDeviceToHost, s));
   }
   if (ctx->opt_counters)
-    RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
-  if (ctx->scene.has_volumes) RTB_CUDA(ctx, cudaMemcpyAsync(&st->status, ctx->d_status, sizeof st->status, cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, s));
+  if (ctx->scene.has_volumes) RTB_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   return RTB_OK;
 }
 
@@ -952,6 +958,8 @@ int host_batch_end(rtb_ctx* ctx, HostBatch* st, const volatile uint8_t* cancel) 
   RTB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_start, ctx->ev_stop));
   if (ctx->cancel_sent) cudaStreamSynchronize(ctx->cancel_stream);   // the pinned source is reused by the next batch
   if (ctx->cancel_sent || (cancel && *cancel)) return fail(ctx, RTB_ERR_CANCELLED, "cancelled");
+  if (ctx->opt_counters) ctx->counters = *ctx->h_counters;
+  if (ctx->scene.has_volumes) st->status = *ctx->h_status;
   if (st->status & kStatusHitListOverflow) {
     cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
     return fail(ctx, RTB_ERR_UNSUPPORTED, "a ray met %d or more entities in a world with participating media (the reference's hit list grows, "
@@ -1196,7 +1204,11 @@ int rtb_create(int device, rtb_ctx** out_ctx) {
   if ((e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
   if ((e = cudaMalloc(&ctx->d_cancel, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
   if ((e = cudaMemset(ctx->d_cancel, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
-  if ((e = cudaHostAlloc((void**)&ctx->h_epoch, 64, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+  if ((e = cudaHostAlloc((void**)&ctx->h_epoch, 256, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+  memset(ctx->h_epoch, 0, 256);
+  ctx->h_status = ctx->h_epoch + 4;
+  ctx->h_counters = reinterpret_cast<rtb_counters*>(reinterpret_cast<char*>(ctx->h_epoch) + 64);
+  static_assert(sizeof(rtb_counters) <= 192, "pinned block");
   if ((e = cudaStreamCreateWithFlags(&ctx->cancel_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   if ((e = cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
   if ((e = cudaMalloc(&ctx->d_metrics_partial, 1024 * sizeof(MetricsAcc))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -1431,9 +1443,14 @@ int rtb_sample_batch(rtb_ctx* ctx, const rtb_batch_params* params, const rtb_bat
   HostBatch st;
   int rc = host_batch_begin(ctx, params, host, &st);
   if (rc != RTB_OK || st.empty) return rc;
-  if ((rc = host_batch_drain(ctx, &st)) != RTB_OK) return rc;
+  // the kernel first, with the token relayed while it runs; only then the read-backs (a device-to-host copy into pageable
+  // memory blocks the caller until the stream reaches it: queued before the wait, it would keep this thread from watching the token)
   rtb_ctx* one[1] = {ctx};
   RTB_CUDA(ctx, wait_for_streams(one, 1, cancel));
+  if (!ctx->cancel_sent && !(cancel && *cancel)) {
+    if ((rc = host_batch_drain(ctx, &st)) != RTB_OK) return rc;
+    RTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return host_batch_end(ctx, &st, cancel);
 }
 
@@ -1542,8 +1559,9 @@ int rtb_get_counters(rtb_ctx* ctx, rtb_counters* out) {
   DeviceGuard g(ctx->device);
   // device-buffer batches do not synchronise: fetch the counters behind the last instrumented launch, on ITS stream
   // (not a device-wide synchronisation: other streams of the process keep running)
-  RTB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, ctx->counters_stream));
+  RTB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(rtb_counters), cudaMemcpyDeviceToHost, ctx->counters_stream));
   RTB_CUDA(ctx, cudaStreamSynchronize(ctx->counters_stream));
+  ctx->counters = *ctx->h_counters;
   *out = ctx->counters;
   return RTB_OK;
 }
@@ -1751,11 +1769,16 @@ int rtb_multi_sample_batch(rtb_multi* m, const rtb_batch_params* params, const r
   }
   if (first_rc != RTB_OK)                            // stop what was started
     for (rtb_ctx* c : busy) send_cancel(c);
-  for (int g = 0; g < n && first_rc == RTB_OK; g++)
-    if (!st[g].empty && (rc = host_batch_drain(m->ctx[g], &st[g])) != RTB_OK) first_rc = mforward(m, g, rc);
-  if (!busy.empty()) {
+  if (!busy.empty()) {                               // the kernels first, with the token relayed while they run (see rtb_sample_batch)
     const cudaError_t e = wait_for_streams(busy.data(), (int)busy.size(), cancel);
     if (e != cudaSuccess && first_rc == RTB_OK) first_rc = mfail(m, RTB_ERR_CUDA + (int)e, "waiting for the devices: %s", cudaGetErrorString(e));
+  }
+  const bool cancelled = cancel && *cancel;
+  for (int g = 0; g < n && first_rc == RTB_OK && !cancelled; g++)
+    if (!st[g].empty && (rc = host_batch_drain(m->ctx[g], &st[g])) != RTB_OK) first_rc = mforward(m, g, rc);
+  if (!busy.empty() && first_rc == RTB_OK && !cancelled) {
+    const cudaError_t e = wait_for_streams(busy.data(), (int)busy.size(), nullptr);
+    if (e != cudaSuccess) first_rc = mfail(m, RTB_ERR_CUDA + (int)e, "waiting for the devices: %s", cudaGetErrorString(e));
   }
   if (first_rc != RTB_OK) return first_rc;
   for (int g = 0; g < n; g++) {

@@ -1144,6 +1144,54 @@ def test_cancellation_token_set_mid_flight(rtb):
         c.close()
 
 
+def test_cancellation_stops_the_kernels_whose_warps_run_in_step(rtb):
+    """The placed-entity and media flavours synchronise their CTA's warps twice per trip and leave the loop by consensus
+    (sample_kernels.cuh: kPhased): a token set mid-flight must still end the batch at once — no warp may wait at a barrier
+    for one that has left —, and the context must render the full frame afterwards.  The media world also reads a status word
+    back after every batch, and the placed world is rendered through PAGEABLE host arrays here (staged copies): neither
+    read-back may keep the calling thread from watching the token while the kernel runs."""
+    import threading
+    import time
+
+    abi = rtb.abi
+    W, H, spp = 1920, 1080, 64
+    for fog in (False, True):
+        scene = rtb.host.make_cornell_scene(max_bvh_depth=16, fog=fog)
+        p = rtb.host.make_params(scene, W, H, spp, 50)
+        c = rtb.plugin.Context(0)
+        try:
+            c.upload(scene)
+            b = rtb.plugin.HostBuffers(W, H, diagnostics=False)
+            if fog:
+                c.register_host_buffers(b)
+            c.sample_batch(p, b)
+            t = time.perf_counter()
+            c.sample_batch(p, b)
+            full = time.perf_counter() - t
+            want = b.out_color.copy()
+            cancel = np.zeros(1, np.uint8)
+            set_at = [0.0]
+
+            def fire():
+                time.sleep(0.25 * full)
+                set_at[0] = time.perf_counter()
+                cancel[0] = 1
+
+            th = threading.Thread(target=fire)
+            th.start()
+            with pytest.raises(rtb.plugin.RtbError) as e:
+                c.sample_batch(p, b, cancel=cancel)
+            returned = time.perf_counter()
+            th.join()
+            assert e.value.code == abi.RTB_ERR_CANCELLED
+            assert returned - set_at[0] < 0.02, f"cancel took {1e3 * (returned - set_at[0]):.2f} ms"
+            cancel[0] = 0
+            c.sample_batch(p, b, cancel=cancel)
+            assert np.array_equal(b.out_color, want)               # same bits as the undisturbed batch
+        finally:
+            c.close()
+
+
 def test_accumulator_range_is_loud(rtb, oracle, ctx):
     """rtb.h "Accumulation range": the megakernel's per-pixel sums are 64-bit fixed point with 32 fraction bits.  Emitters far
     brighter than any display range still add up like the reference's floats (2^20 <= sample < 2^25 takes the one-at-a-time
