@@ -515,9 +515,11 @@ def make_cornell_scene(max_bvh_depth=16, moving=True, fog=False):
                        placed=np.array(placed, dtype=abi.PLACED_DTYPE))
 
 
-def make_random_placed_scene(seed, count=24, max_bvh_depth=8):
+def make_random_placed_scene(seed, count=24, max_bvh_depth=8, media=0):
     """A random world of every entity kind (plain spheres, rotated / moving spheres, Rects, Boxes, a few triangles) with
-    random Standard / Dielectric / emissive materials, inside a gradient sky: the fuzz input of the parity tests."""
+    random Standard / Dielectric / emissive materials, inside a gradient sky: the fuzz input of the parity tests.
+    media = k turns k of the eight materials into ProbabilisticVolume media of random density (whatever entities wear
+    them: overlapping, nested, moving, non-convex ones too), without changing anything else of the world."""
     rng = np.random.default_rng(seed)
     mats = []
     for _ in range(8):
@@ -529,6 +531,10 @@ def make_random_placed_scene(seed, count=24, max_bvh_depth=8):
             mats.append(_material(abi.MATERIAL_DIELECTRIC, (1, 1, 1), gloss=float(rng.choice([1.0, 0.8])), ior=1.5))
         else:
             mats.append(_material(abi.MATERIAL_STANDARD, rng.random(3) * 0.5, emission=rng.random(3) * 4))
+    if media:
+        mrng = np.random.default_rng(seed + 7919)
+        for k in mrng.choice(len(mats), size=media, replace=False):
+            mats[int(k)] = _material(abi.MATERIAL_PROBABILISTIC_VOLUME, mrng.random(3), ior=float(0.1 + 3.0 * mrng.random()))
     materials = np.array(mats, dtype=abi.MATERIAL_DTYPE)
 
     def rand_quat():

@@ -1035,6 +1035,35 @@ def test_media_flavour_takes_the_collect_all_kernels_decisions(rtb, ctx):
         assert_parity(ref, got, exact=False)
 
 
+def test_random_worlds_with_media(rtb, oracle, ctx):
+    """Fuzz over random worlds of every entity kind in which two or three of the eight materials are participating media —
+    overlapping, nested, moving and non-convex media (Rects, triangles: no injected exit), media worn by several entities,
+    multi-entity leaves (shallow trees) and linear lists: the collect-all kernel is bit-identical to the oracle, the
+    megakernel's media flavour takes the same decisions; on larger frames the two kernels are compared with each other."""
+    for seed in range(16):
+        scene = rtb.host.make_random_placed_scene(seed, count=10 + 3 * (seed % 5), max_bvh_depth=[0, 2, 8, 16][seed % 4], media=2 + seed % 2)
+        W, H, spp = 48, 27, 6
+        p = rtb.host.make_params(scene, W, H, spp, 12 if seed % 3 else 50, seed=seed + 1, aperture=0.15 if seed % 2 else 0.0)
+        ref = oracle.Buffers(W, H)
+        oracle.sample_batch(scene, p, ref)
+        for kernel, exact in ((rtb.abi.KERNEL_SIMPLE, True), (rtb.abi.KERNEL_MEGA, False)):
+            got = render_gpu(rtb, ctx, scene, p, W, H, kernel)
+            try:
+                assert_parity(ref, got, exact=exact)
+            except AssertionError as e:
+                raise AssertionError(f"random media world {seed}, kernel {kernel}: {e}")
+    for seed in (3, 6, 9):
+        scene = rtb.host.make_random_placed_scene(seed, count=20, max_bvh_depth=[2, 16, 0][seed % 3], media=3)
+        W, H, spp = 256, 144, 24
+        p = rtb.host.make_params(scene, W, H, spp, 50, seed=seed, aperture=0.1)
+        ref = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE)
+        got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+        try:
+            assert_parity(ref, got, exact=False)
+        except AssertionError as e:
+            raise AssertionError(f"random media world {seed} at {W}x{H}x{spp}: {e}")
+
+
 def test_fog_world_white_noise_stream_and_camera_inside_a_medium(rtb, oracle, ctx):
     """The reference's xorshift32 stream through the media (ProbabilisticHit's draw and the isotropic direction are taken in
     stream order), with the camera INSIDE a ball of fog so that every camera ray starts with the containment test."""
