@@ -349,6 +349,59 @@ __device__ __forceinline__ void aabb_range(f3 mn, f3 mx, f3 o, f3 inv, float* t_
   *t_exit = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
 }
 
+// Inner-node records (64 bytes; plugin.cu: Flattener::ref_of) keep the two child boxes so that x and y of every corner form
+// an aligned pair and the four z's two pairs:
+//   q0 = (L.min.x, L.min.y, L.max.x, L.max.y)   q1 = (R.min.x, R.min.y, R.max.x, R.max.y)
+//   q2 = (L.min.z, L.max.z, R.min.z, R.max.z)   q3 = (left ref, right ref, media flags, -)
+__device__ __forceinline__ f3 node_lmin(float4 q0, float4 q1, float4 q2) { return um::mk(q0.x, q0.y, q2.x); }
+__device__ __forceinline__ f3 node_lmax(float4 q0, float4 q1, float4 q2) { return um::mk(q0.z, q0.w, q2.y); }
+__device__ __forceinline__ f3 node_rmin(float4 q0, float4 q1, float4 q2) { return um::mk(q1.x, q1.y, q2.z); }
+__device__ __forceinline__ f3 node_rmax(float4 q0, float4 q1, float4 q2) { return um::mk(q1.z, q1.w, q2.w); }
+
+// Blackwell's packed FP32 instructions (add / mul / fma .f32x2: SASS FADD2 / FMUL2 / FFMA2) do two IEEE round-to-nearest
+// operations on a 64-bit register pair in ONE issue slot — and issue slots, not the FMA pipe, are what the walk runs out
+// of (ncu: 87 % issue, FMA pipe 31 %).  Each half is the scalar instruction's result bit for bit, so the slab test of a
+// visit — 12 subtractions and 12 products — is 6 + 6 packed instructions with the same 24 roundings.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+struct RayPairs { f32x2 oxy, ozz, ixy, izz; };     // (o.x, o.y), (o.z, o.z), (inv.x, inv.y), (inv.z, inv.z)
+// aabb_range of both child boxes of a node record: the same (mn - o) * inv, (mx - o) * inv and min / max as two calls of it
+__device__ __forceinline__ void aabb_range_pair(float4 q0, float4 q1, float4 q2, const RayPairs& rp,
+                                                float* tl, float* xl, float* tr, float* xr) {
+  float l0x, l0y, l1x, l1y, r0x, r0y, r1x, r1y, l0z, l1z, r0z, r1z;
+  unpack2(mul2(sub2(pack2(q0.x, q0.y), rp.oxy), rp.ixy), l0x, l0y);
+  unpack2(mul2(sub2(pack2(q0.z, q0.w), rp.oxy), rp.ixy), l1x, l1y);
+  unpack2(mul2(sub2(pack2(q1.x, q1.y), rp.oxy), rp.ixy), r0x, r0y);
+  unpack2(mul2(sub2(pack2(q1.z, q1.w), rp.oxy), rp.ixy), r1x, r1y);
+  unpack2(mul2(sub2(pack2(q2.x, q2.y), rp.ozz), rp.izz), l0z, l1z);
+  unpack2(mul2(sub2(pack2(q2.z, q2.w), rp.ozz), rp.izz), r0z, r1z);
+  *tl = fmaxf(0.0f, fmaxf(fmaxf(fminf(l0x, l1x), fminf(l0y, l1y)), fminf(l0z, l1z)));
+  *xl = fminf(fminf(fmaxf(l0x, l1x), fmaxf(l0y, l1y)), fmaxf(l0z, l1z));
+  *tr = fmaxf(0.0f, fmaxf(fmaxf(fminf(r0x, r1x), fminf(r0y, r1y)), fminf(r0z, r1z)));
+  *xr = fminf(fminf(fmaxf(r0x, r1x), fmaxf(r0y, r1y)), fmaxf(r0z, r1z));
+}
+
+// The fast build's version (see aabb_range_fast): t = mn * inv + (-(o * inv)), one packed FMA per pair of planes; rp.oxy / rp.ozz
+// hold -(o * inv).
+__device__ __forceinline__ void aabb_range_pair_fast(float4 q0, float4 q1, float4 q2, const RayPairs& rp,
+                                                     float* tl, float* xl, float* tr, float* xr) {
+  float l0x, l0y, l1x, l1y, r0x, r0y, r1x, r1y, l0z, l1z, r0z, r1z;
+  unpack2(fma2(pack2(q0.x, q0.y), rp.ixy, rp.oxy), l0x, l0y);
+  unpack2(fma2(pack2(q0.z, q0.w), rp.ixy, rp.oxy), l1x, l1y);
+  unpack2(fma2(pack2(q1.x, q1.y), rp.ixy, rp.oxy), r0x, r0y);
+  unpack2(fma2(pack2(q1.z, q1.w), rp.ixy, rp.oxy), r1x, r1y);
+  unpack2(fma2(pack2(q2.x, q2.y), rp.izz, rp.ozz), l0z, l1z);
+  unpack2(fma2(pack2(q2.z, q2.w), rp.izz, rp.ozz), r0z, r1z);
+  *tl = fmaxf(0.0f, fmaxf(fmaxf(fminf(l0x, l1x), fminf(l0y, l1y)), fminf(l0z, l1z)));
+  *xl = fminf(fminf(fmaxf(l0x, l1x), fmaxf(l0y, l1y)), fmaxf(l0z, l1z));
+  *tr = fmaxf(0.0f, fmaxf(fmaxf(fminf(r0x, r1x), fminf(r0y, r1y)), fminf(r0z, r1z)));
+  *xr = fminf(fminf(fmaxf(r0x, r1x), fmaxf(r0y, r1y)), fmaxf(r0z, r1z));
+}
+
 #ifdef RTB_FAST_MATH
 // The fast build's slab test: t = mn * inv - o * inv with o * inv hoisted out of the walk — one FMA per plane instead of a
 // subtraction and a product (12 instead of 24 FP32 instructions per two-box visit).  Not the parity build's roundings.
@@ -605,6 +658,9 @@ __device__ __forceinline__ void walk_converge() {
 #endif
 }
 
+#ifndef RTB_PACKED_SLABS
+#define RTB_PACKED_SLABS 1
+#endif
 constexpr float kPruneMargin = 1.0005f;
 constexpr int kTraversalDone = (int)0x80000000;   // stack sentinel: neither an inner index (>= 0) nor ~first
 
@@ -691,10 +747,14 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   // once per trip (measured 131.4 -> 129.1 ms on config 3; the general flavour is faster with the split trips below).
   {
     int* top = stack + 1;
+#if RTB_PACKED_SLABS && !defined(RTB_FAST_MATH)
+    const RayPairs rp{pack2(o.x, o.y), pack2(o.z, o.z), pack2(inv.x, inv.y), pack2(inv.z, inv.z)};
+#endif
 #ifdef RTB_FAST_MATH
     // -(o * inv).  A direction component of exactly 0 gives inv = inf and inf - inf = NaN planes, which fminf / fmaxf drop:
     // that axis then constrains nothing (the box test errs on the side of visiting), the entity tests decide
     const f3 noi = um::mk(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+    const RayPairs rpf{pack2(noi.x, noi.y), pack2(noi.z, noi.z), pack2(inv.x, inv.y), pack2(inv.z, inv.z)};
 #endif
     for (;;) {
       walk_converge();
@@ -703,11 +763,12 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
         const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
         float tl, tr, xl, xr;
 #ifdef RTB_FAST_MATH
-        aabb_range_fast(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), inv, noi, &tl, &xl);
-        aabb_range_fast(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), inv, noi, &tr, &xr);
+        aabb_range_pair_fast(q0, q1, q2, rpf, &tl, &xl, &tr, &xr);
+#elif RTB_PACKED_SLABS
+        aabb_range_pair(q0, q1, q2, rp, &tl, &xl, &tr, &xr);
 #else
-        aabb_range(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl, &xl);
-        aabb_range(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr, &xr);
+        aabb_range(node_lmin(q0, q1, q2), node_lmax(q0, q1, q2), o, inv, &tl, &xl);
+        aabb_range(node_rmin(q0, q1, q2), node_rmax(q0, q1, q2), o, inv, &tr, &xr);
 #endif
         const float limit = best_t * kPruneMargin;
         const bool hl = tl < fminf(xl, limit);
@@ -741,6 +802,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   // the warp converged — what media.cuh's gather_hits does, where it pays) was measured here too: Cornell box 132.8 -> 139.4 /
   // 136.0 / 136.3 ms, as a linear list 99.3 -> 115.4 / 114.1 / 118.4, mesh world 69.4 -> 68.0 / 66.2 / 67.4 — not kept.
   int* top = stack + 1;
+  const RayPairs rp{pack2(o.x, o.y), pack2(o.z, o.z), pack2(inv.x, inv.y), pack2(inv.z, inv.z)};
   for (;;) {
     walk_converge();
     if (cur >= 0) {
@@ -748,8 +810,12 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       // "box hit (t_enter < t_exit) and not beyond the best hit (t_enter < limit)" as ONE comparison per child
       // against min(t_exit, limit) (t_exit is never NaN: fminf/fmaxf drop NaN operands)
       float tl, tr, xl, xr;
-      aabb_range(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl, &xl);
-      aabb_range(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr, &xr);
+      if (FLAVOR == kFlavorGeneral) {     // packed slabs: mesh world 69.7 -> 68.9 ms; the placed flavours lose with them (Cornell box 114.5 -> 116.1)
+        aabb_range_pair(q0, q1, q2, rp, &tl, &xl, &tr, &xr);
+      } else {
+        aabb_range(node_lmin(q0, q1, q2), node_lmax(q0, q1, q2), o, inv, &tl, &xl);
+        aabb_range(node_rmin(q0, q1, q2), node_rmax(q0, q1, q2), o, inv, &tr, &xr);
+      }
       const float limit = best_t * kPruneMargin;
       const bool hl = tl < fminf(xl, limit);
       const bool hr = tr < fminf(xr, limit);

@@ -137,8 +137,8 @@ __device__ __noinline__ bool collect_hits(const int MODE, const SceneView<SMEM>&
     if (cur >= 0) {
       const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
       float tl, tr;
-      bool hl = aabb_hit(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl);
-      bool hr = aabb_hit(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr);
+      bool hl = aabb_hit(node_lmin(q0, q1, q2), node_lmax(q0, q1, q2), o, inv, &tl);
+      bool hr = aabb_hit(node_rmin(q0, q1, q2), node_rmax(q0, q1, q2), o, inv, &tr);
       if (COUNTERS) wc.node_tests += 2;
       if (MEDIA_ONLY) {
         const uint32_t media = __float_as_uint(q3.z);
@@ -277,6 +277,7 @@ __device__ __forceinline__ void gather_hits(const SceneView<SMEM>& sv, const Sce
   int cur = sd.root_ref;
   bool have_cur = true;
   int leaf_first = 0, leaf_i = 0, leaf_n = 0;       // the leaf being unpacked into candidates
+  const RayPairs rp{pack2(o.x, o.y), pack2(o.z, o.z), pack2(inv.x, inv.y), pack2(inv.z, inv.z)};
   for (;;) {
     int nc = 0;
     while (nc < kCandBatch) {
@@ -295,8 +296,7 @@ __device__ __forceinline__ void gather_hits(const SceneView<SMEM>& sv, const Sce
       if (cur >= 0) {
         const float4 q0 = sv.node(cur, 0), q1 = sv.node(cur, 1), q2 = sv.node(cur, 2), q3 = sv.node(cur, 3);
         float tl, tr, xl, xr;
-        aabb_range(um::mk(q0.x, q0.y, q0.z), um::mk(q0.w, q1.x, q1.y), o, inv, &tl, &xl);
-        aabb_range(um::mk(q1.z, q1.w, q2.x), um::mk(q2.y, q2.z, q2.w), o, inv, &tr, &xr);
+        aabb_range_pair(q0, q1, q2, rp, &tl, &xl, &tr, &xr);
         const float limit = best_t * kPruneMargin;
         const uint32_t media = __float_as_uint(q3.z);
         const bool hl = tl < xl && (tl < limit || (media & 1u));

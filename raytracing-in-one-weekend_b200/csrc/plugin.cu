@@ -302,9 +302,10 @@ struct Flattener {
     const int32_t rref = ref_of(nd.right, depth + 1);
     if (error) return 0;
     float* q = &inner[(size_t)self * 16];
-    q[0] = l.bounds_min[0]; q[1] = l.bounds_min[1]; q[2] = l.bounds_min[2]; q[3] = l.bounds_max[0];
-    q[4] = l.bounds_max[1]; q[5] = l.bounds_max[2]; q[6] = r.bounds_min[0]; q[7] = r.bounds_min[1];
-    q[8] = r.bounds_min[2]; q[9] = r.bounds_max[0]; q[10] = r.bounds_max[1]; q[11] = r.bounds_max[2];
+    // x and y of every corner as an aligned pair, the four z's as two pairs (kernel_common.cuh: node_lmin ..., aabb_range_pair)
+    q[0] = l.bounds_min[0]; q[1] = l.bounds_min[1]; q[2] = l.bounds_max[0]; q[3] = l.bounds_max[1];
+    q[4] = r.bounds_min[0]; q[5] = r.bounds_min[1]; q[6] = r.bounds_max[0]; q[7] = r.bounds_max[1];
+    q[8] = l.bounds_min[2]; q[9] = l.bounds_max[2]; q[10] = r.bounds_min[2]; q[11] = r.bounds_max[2];
     memcpy(&q[12], &lref, 4);
     memcpy(&q[13], &rref, 4);
     // word 14: which child subtrees hold an entity that wears a medium (media.cuh: the media walks skip the others)
