@@ -314,6 +314,16 @@ RTB_API int rtb_describe_scene(const rtb_sphere* spheres, size_t sphere_count,
                                const rtb_bvh_node* nodes, size_t node_count,
                                int leaf_spheres, rtb_scene_layout* out);
 
+/* The tree the device walks under RTB_OPT_RETREE (no device needed; for tests and hosts that want to see it): a
+ * surface-area-heuristic topology over the NON-EMPTY LEAVES of `nodes` — every leaf record (bounds, first_entity,
+ * entity_count) is copied unchanged, inner bounds are unions of what lies below them, the root is node 0, nodes are in
+ * depth-first order, no leaf lies deeper than 62 inner nodes.  Writes at most `capacity` nodes (2 * leaves - 1 <=
+ * node_count are needed) and their count.  Returns RTB_OK with *out_count = 0 when the world does not qualify (a leaf box that is
+ * flat, inverted or not finite, an inner box of `nodes` that does not contain its children's, a malformed tree, fewer than
+ * two non-empty leaves): the host's topology is walked then.  Why the image cannot depend on the topology: csrc/retree.hpp. */
+RTB_API int rtb_retree_bvh(const rtb_bvh_node* nodes, size_t node_count,
+                           rtb_bvh_node* out_nodes, size_t capacity, size_t* out_count);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* Replaces `sampleBatchJob.Schedule(W*H, 1, dep).Complete()` (Raytracer.cs:730-736) with HOST
  * buffers: returns when the out_* arrays are fully written.  Pinned arrays (rtb_register_host_buffer /
@@ -488,6 +498,20 @@ typedef enum rtb_option {
                                  * parity build by a few flipped decisions per million paths (tools/fast_math_report.py).  Worlds
                                  * with triangles, placed entities, textures or media, and instrumented batches, keep the parity
                                  * kernels whatever this says. */
+  RTB_OPT_RETREE = 10,          /* 1 (default): worlds of plain spheres without media are walked through a surface-area-heuristic tree
+                                 * built over the LEAVES of the host's BVH (same leaf boxes, same entity ranges; rtb_retree_bvh) instead
+                                 * of the host's topology, when every leaf box has min < max on every axis and every inner box of
+                                 * the host's tree contains its children's.  An
+                                 * inner box of the reference's tree is the exact union of its children's (BvhNodeData.cs:205-212)
+                                 * and the slab test is monotonic in the box, so a ray that passes a leaf's box passes its whole
+                                 * chain: the reference's candidates are the entities of the leaves whose own box is hit, whatever
+                                 * lies above them (csrc/retree.hpp) — same image bit for bit (config 3: 125.0 ->
+                                 * 115.0 ms), fewer boxes per ray.  2: also worlds with triangles and placed entities (mesh world
+                                 * 69.0 -> 63.8 ms, Cornell box 114.5 -> 108.7): their entity tests run in entity space / on edge
+                                 * vectors, a hit a few 1e-5 in FRONT of its own box can be pruned or not depending on what the walk
+                                 * found first, and 1 path in 1.3e8 came out differently — hence opt-in.  Media worlds always keep the
+                                 * host's topology.  0: walk the host's topology.  Takes effect at the next upload; the traversal
+                                 * counters of instrumented batches count the walk that ran */
   RTB_OPT_BALANCE_TILES = 8,    /* rtb_multi only. 1 (default): cost-model + kernel-time balanced row tiles; 0: equal row counts */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
                                  * instead of only when the hit geometry does not already prove them (same results, slower) */

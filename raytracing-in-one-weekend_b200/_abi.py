@@ -79,7 +79,7 @@ RTB_ERR_UNSUPPORTED = 4
 RTB_ERR_OUT_OF_MEMORY = 5
 RTB_ERR_CUDA = 100
 
-OPT_COUNTERS, OPT_KERNEL, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS, OPT_HOST_ACCESS, OPT_NOISE, OPT_BALANCE_TILES, OPT_MATH = 1, 2, 4, 5, 6, 7, 8, 9
+OPT_COUNTERS, OPT_KERNEL, OPT_LEAF_SPHERES, OPT_ALWAYS_WALK_CHAINS, OPT_HOST_ACCESS, OPT_NOISE, OPT_BALANCE_TILES, OPT_MATH, OPT_RETREE = 1, 2, 4, 5, 6, 7, 8, 9, 10
 MATH_PARITY, MATH_FAST = 0, 1
 NOISE_PHILOX, NOISE_WHITE = 0, 1
 KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_MEGA = 0, 1, 2

@@ -113,7 +113,7 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern RtbStatus rtb_multi_unregister_host_buffer(IntPtr multi, void* ptr);
 		[DllImport(Lib)] public static extern RtbStatus rtb_multi_sample_batch(IntPtr multi, RtbBatchParams* p, RtbBatchBuffers* hostBuffers, bool* cancel);
 		[DllImport(Lib)] public static extern RtbStatus rtb_multi_get_tiles(IntPtr multi, int* outBounds, float* outKernelMs);
-		// rtb_option (include/rtb.h): Counters = 1, Kernel = 2, LeafSpheres = 4, AlwaysWalkChains = 5, HostAccess = 6, Noise = 7, BalanceTiles = 8, Math = 9
+		// rtb_option (include/rtb.h): Counters = 1, Kernel = 2, LeafSpheres = 4, AlwaysWalkChains = 5, HostAccess = 6, Noise = 7, BalanceTiles = 8, Math = 9, Retree = 10
 		[DllImport(Lib)] public static extern RtbStatus rtb_set_option(IntPtr ctx, int option, long value);
 		[DllImport(Lib)] public static extern RtbStatus rtb_last_kernel_ms(IntPtr ctx, out float ms);
 		[DllImport(Lib)] public static extern RtbStatus rtb_last_batch_in_place(IntPtr ctx, out int inPlace);

@@ -22,7 +22,7 @@ CUDA_SOURCES = [os.path.join(CSRC, "plugin.cu")]
 FAST_SOURCES = [os.path.join(CSRC, "fast_kernels.cu")]       # the opt-in fast-arithmetic build of the sphere megakernel
 CUDA_DEPS = [
     os.path.join(CSRC, f)
-    for f in ("kernel_common.cuh", "media.cuh", "sample_kernels.cuh", "volume_kernel.cuh", "aux_kernels.cuh")
+    for f in ("kernel_common.cuh", "media.cuh", "sample_kernels.cuh", "volume_kernel.cuh", "aux_kernels.cuh", "retree.hpp")
 ] + [os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
 HOST_DEPS = [os.path.join(INCLUDE, "rtb_host.h"), os.path.join(INCLUDE, "rtb.h"), os.path.join(INCLUDE, "rtb", "umath.h")]
 

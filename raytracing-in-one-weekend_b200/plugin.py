@@ -15,7 +15,7 @@ from . import build as _build
 
 EXPORTS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_log_callback",
-    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_placed_world", "rtb_upload_textures", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_sample_batch", "rtb_sample_batch_device",
+    "rtb_upload_scene", "rtb_upload_world", "rtb_upload_placed_world", "rtb_upload_textures", "rtb_upload_sky_cubemap", "rtb_describe_scene", "rtb_retree_bvh", "rtb_sample_batch", "rtb_sample_batch_device",
     "rtb_register_host_buffer", "rtb_unregister_host_buffer",
     "rtb_combine_device", "rtb_finalize_device", "rtb_reduce_metrics_device",
     "rtb_get_counters", "rtb_set_option", "rtb_last_kernel_ms", "rtb_last_batch_in_place", "rtb_measure_fp32_peak",
@@ -60,6 +60,7 @@ def lib():
         L.rtb_upload_textures.argtypes = [vp, vp, sz, vp, sz, vp, sz]
         L.rtb_upload_sky_cubemap.argtypes = [vp, vp, C.c_int, C.c_int]
         L.rtb_describe_scene.argtypes = [vp, sz, vp, sz, vp, sz, C.c_int, C.POINTER(abi.SceneLayout)]
+        L.rtb_retree_bvh.argtypes = [vp, sz, vp, sz, C.POINTER(C.c_size_t)]
         L.rtb_sample_batch.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
         L.rtb_sample_batch_device.argtypes = [vp, C.POINTER(abi.BatchParams), C.POINTER(abi.BatchBuffers), vp]
         L.rtb_register_host_buffer.argtypes = [vp, vp, sz]
@@ -196,6 +197,19 @@ def describe_scene(scene, leaf_spheres=1):
     if rc != 0:
         raise RtbError(rc, (L.rtb_last_error(None) or b"").decode())
     return {name: getattr(out, name) for name, _ in abi.SceneLayout._fields_}
+
+
+def retree_bvh(nodes):
+    """rtb_retree_bvh: the topology the device walks under RTB_OPT_RETREE (host-side only, no GPU needed).
+    -> BVH_NODE_DTYPE array (root = 0), or None when the world does not qualify."""
+    nodes = np.ascontiguousarray(nodes, dtype=abi.BVH_NODE_DTYPE)
+    out = np.zeros(max(len(nodes), 1), dtype=abi.BVH_NODE_DTYPE)
+    count = C.c_size_t(0)
+    L = lib()
+    rc = L.rtb_retree_bvh(nodes.ctypes.data if len(nodes) else None, len(nodes), out.ctypes.data, len(out), C.byref(count))
+    if rc != 0:
+        raise RtbError(rc, (L.rtb_last_error(None) or b"").decode())
+    return out[: count.value].copy() if count.value else None
 
 
 class Context:

@@ -1446,3 +1446,68 @@ def test_fast_math_build_agrees_statistically(rtb, ctx):
     assert (d > 1e-4).mean() < 0.10
     assert abs(float(strict.rgb().mean()) - float(fast.rgb().mean())) < 1e-4
     assert (strict.out_color[:, 3] != fast.out_color[:, 3]).mean() < 0.01
+
+
+# ---- RTB_OPT_RETREE: another topology over the host tree's leaves (csrc/retree.hpp; CPU side: tests/test_retree.py) ----------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["simple", "mega"])
+@pytest.mark.parametrize("case", [("final", 16, 0, 256, 144, 32, 0.1), ("final", 3, 0, 96, 54, 16, 0.1), ("stress", 16, 3000, 160, 90, 16, 0.1)],
+                         ids=lambda c: f"{c[0]}-bvh{c[1]}-{c[3]}x{c[4]}x{c[5]}")
+def test_retree_does_not_change_a_bit_on_sphere_worlds(rtb, ctx, case, kernel):
+    """Every output word of a batch — colour sums, AOVs, sample counts, ray counts — is the same whether the device walks the
+    host's topology (RTB_OPT_RETREE = 0) or the re-built one (1, the default): the reference's candidates are the leaves whose
+    own box is hit, whatever lies above them."""
+    name, depth, target, W, H, spp, ap = case
+    scene = rtb.host.make_scene(name, max_bvh_depth=depth, target_count=target)
+    assert rtb.plugin.retree_bvh(scene.nodes) is not None
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=ap)
+    k = {"simple": rtb.abi.KERNEL_SIMPLE, "mega": rtb.abi.KERNEL_MEGA}[kernel]
+    out = []
+    try:
+        for mode in (0, 1):
+            ctx.set_option(rtb.abi.OPT_RETREE, mode)
+            out.append(render_gpu(rtb, ctx, scene, p, W, H, k))
+    finally:
+        ctx.set_option(rtb.abi.OPT_RETREE, 1)
+    a, b = out
+    assert np.array_equal(a.out_color, b.out_color) and np.array_equal(a.out_normal, b.out_normal)
+    assert np.array_equal(a.out_albedo, b.out_albedo) and np.array_equal(a.out_weight, b.out_weight)
+    assert np.array_equal(a.diagnostics["ray_count"], b.diagnostics["ray_count"])
+    assert a.out_color[:, 3].sum() > 0
+
+
+@pytest.mark.gpu
+def test_retree_walks_fewer_boxes(rtb, ctx):
+    """The point of it: the instrumented build counts the walk that ran — fewer box tests per ray through the re-built tree."""
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, 160, 90, 16, 50, aperture=0.1)
+    per_ray = []
+    ctx.set_option(rtb.abi.OPT_COUNTERS, 1)
+    try:
+        for mode in (0, 1):
+            ctx.set_option(rtb.abi.OPT_RETREE, mode)
+            render_gpu(rtb, ctx, scene, p, 160, 90, rtb.abi.KERNEL_MEGA)
+            cnt = ctx.counters()
+            per_ray.append(cnt["node_tests"] / cnt["rays"])
+    finally:
+        ctx.set_option(rtb.abi.OPT_RETREE, 1)
+        ctx.set_option(rtb.abi.OPT_COUNTERS, 0)
+    assert per_ray[1] < 0.95 * per_ray[0], per_ray
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", ["mesh", "cornell"])
+def test_retree_opt_in_for_the_wider_worlds_keeps_oracle_parity(rtb, oracle, ctx, world):
+    """RTB_OPT_RETREE = 2 (triangles, placed entities): the decisions and the image still match the oracle on the test sizes;
+    the default (1) leaves these worlds on the host's topology."""
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=16, subdivisions=2) if world == "mesh" else rtb.host.make_cornell_scene(max_bvh_depth=16)
+    W, H, spp = 96, 54, 8
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.0)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    try:
+        ctx.set_option(rtb.abi.OPT_RETREE, 2)
+        got = render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA)
+    finally:
+        ctx.set_option(rtb.abi.OPT_RETREE, 1)
+    assert_parity(ref, got, exact=False)
