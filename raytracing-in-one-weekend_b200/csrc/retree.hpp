@@ -190,9 +190,144 @@ class Builder {
   std::vector<double> right_area_;
 };
 
+// Insertion-based optimisation of the built tree (Bittner, Hapala, Havran 2013): a subtree is taken out together with its
+// parent and put back where it adds the least surface area to the tree (branch-and-bound search from the root over
+// "area its ancestors would grow by + area of the new parent"), largest boxes first, for a few passes.  The sum of the inner
+// boxes' areas — the expected number of visits of a ray — only goes down; the leaves are untouched.
+class Optimizer {
+ public:
+  explicit Optimizer(const std::vector<rtb_bvh_node>& in) : n_(in.size()), box_(in.size()), parent_(in.size(), -1), left_(in.size(), -1), right_(in.size(), -1), leaf_(in.size()) {
+    for (size_t i = 0; i < n_; i++) {
+      for (int k = 0; k < 3; k++) { box_[i].mn[k] = in[i].bounds_min[k]; box_[i].mx[k] = in[i].bounds_max[k]; }
+      leaf_[i] = in[i];
+      if (in[i].first_entity < 0) {
+        left_[i] = in[i].left; right_[i] = in[i].right;
+        parent_[in[i].left] = (int32_t)i; parent_[in[i].right] = (int32_t)i;
+      }
+    }
+  }
+  double inner_area() const {
+    double a = 0;
+    for (size_t i = 0; i < n_; i++) if (left_[i] >= 0) a += box_[i].area();
+    return a;
+  }
+  void run(int passes) {
+    std::vector<int32_t> order;
+    for (int pass = 0; pass < passes; pass++) {
+      order.clear();
+      for (size_t i = 0; i < n_; i++) if ((int32_t)i != root_ && parent_[i] != root_) order.push_back((int32_t)i);
+      std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        const double x = box_[a].area(), y = box_[b].area();
+        return x != y ? x > y : a < b;
+      });
+      const double before = inner_area();
+      for (int32_t n : order) {
+        if (n == root_ || parent_[n] < 0 || parent_[n] == root_) continue;
+        reinsert(n);
+      }
+      if (!(inner_area() < before * (1.0 - 1e-4))) break;
+    }
+  }
+  int depth() const {
+    int deepest = 0;
+    std::vector<std::pair<int32_t, int>> st{{root_, 0}};
+    while (!st.empty()) {
+      auto [i, d] = st.back();
+      st.pop_back();
+      deepest = std::max(deepest, d);
+      if (left_[i] >= 0) { st.push_back({left_[i], d + 1}); st.push_back({right_[i], d + 1}); }
+    }
+    return deepest;
+  }
+  // depth-first order, root at 0; of two children the one with the larger box first (it is the likelier first visit)
+  void emit(std::vector<rtb_bvh_node>& out) const {
+    out.clear();
+    out.reserve(n_);
+    emit_node(root_, out);
+  }
+
+ private:
+  int32_t emit_node(int32_t i, std::vector<rtb_bvh_node>& out) const {
+    const int32_t self = (int32_t)out.size();
+    out.emplace_back();
+    if (left_[i] < 0) {
+      out[self] = leaf_[i];
+      out[self].left = out[self].right = -1;
+      return self;
+    }
+    const int32_t l = emit_node(left_[i], out);
+    const int32_t r = emit_node(right_[i], out);
+    rtb_bvh_node nd;
+    for (int k = 0; k < 3; k++) { nd.bounds_min[k] = box_[i].mn[k]; nd.bounds_max[k] = box_[i].mx[k]; }
+    nd.left = l; nd.right = r; nd.first_entity = -1; nd.entity_count = 0;
+    out[self] = nd;
+    return self;
+  }
+  void refit_up(int32_t i) {
+    for (; i >= 0; i = parent_[i]) {
+      Box b = box_[left_[i]];
+      b.grow(box_[right_[i]]);
+      box_[i] = b;
+    }
+  }
+  void reinsert(int32_t n) {
+    const int32_t p = parent_[n], g = parent_[p];
+    const int32_t s = left_[p] == n ? right_[p] : left_[p];
+    // take n and its parent out: the sibling moves up
+    (left_[g] == p ? left_[g] : right_[g]) = s;
+    parent_[s] = g;
+    refit_up(g);
+    // the position that adds the least area
+    const double an = box_[n].area();
+    double best = std::numeric_limits<double>::infinity();
+    int32_t best_x = s;
+    heap_.clear();
+    heap_.push_back({0.0, root_});
+    while (!heap_.empty()) {
+      std::pop_heap(heap_.begin(), heap_.end(), cmp_);
+      const Item it = heap_.back();
+      heap_.pop_back();
+      if (it.induced + an >= best) break;
+      Box u = box_[it.node];
+      u.grow(box_[n]);
+      const double total = it.induced + u.area();
+      if (total < best) { best = total; best_x = it.node; }
+      if (left_[it.node] >= 0) {
+        const double child = total - box_[it.node].area();
+        if (child + an < best) {
+          heap_.push_back({child, left_[it.node]});
+          std::push_heap(heap_.begin(), heap_.end(), cmp_);
+          heap_.push_back({child, right_[it.node]});
+          std::push_heap(heap_.begin(), heap_.end(), cmp_);
+        }
+      }
+    }
+    // p becomes the parent of (best_x, n) where best_x was
+    const int32_t x = best_x, gx = parent_[x];
+    if (gx < 0) root_ = p; else (left_[gx] == x ? left_[gx] : right_[gx]) = p;
+    parent_[p] = gx;
+    left_[p] = x; right_[p] = n;
+    parent_[x] = p; parent_[n] = p;
+    refit_up(p);
+  }
+  struct Item { double induced; int32_t node; };
+  static bool cmp_(const Item& a, const Item& b) { return a.induced != b.induced ? a.induced > b.induced : a.node > b.node; }
+  size_t n_;
+  std::vector<Box> box_;
+  std::vector<int32_t> parent_, left_, right_;
+  std::vector<rtb_bvh_node> leaf_;
+  std::vector<Item> heap_;
+  int32_t root_ = 0;
+};
+
+constexpr size_t kOptimizeMaxLeaves = 1u << 16;   // above this the sweep / binned tree is used as built (upload time)
+#ifndef RTB_RETREE_PASSES
+#define RTB_RETREE_PASSES 8
+#endif
+
 // -> true and `out` (root at 0, depth-first order, leaves = the reference's non-empty leaves) when the world qualifies.
 // depth_limit: the deepest leaf the device walk's stack allows.
-inline bool retree(const rtb_bvh_node* ref, size_t node_count, int depth_limit, std::vector<rtb_bvh_node>& out) {
+inline bool retree(const rtb_bvh_node* ref, size_t node_count, int depth_limit, std::vector<rtb_bvh_node>& out, int passes = RTB_RETREE_PASSES) {
   out.clear();
   if (!ref || node_count < 3) return false;
   std::vector<uint8_t> seen(node_count, 0);
@@ -232,6 +367,11 @@ inline bool retree(const rtb_bvh_node* ref, size_t node_count, int depth_limit, 
   out.reserve(2 * leaves.size());
   Builder b(ref, leaves, depth_limit, out);
   b.build(0, leaves.size(), 0);
+  if (passes > 0 && leaves.size() >= 4 && leaves.size() <= kOptimizeMaxLeaves) {
+    Optimizer opt(out);
+    opt.run(passes);
+    if (opt.depth() <= depth_limit) opt.emit(out);     // a tree the walk's stack cannot hold: keep the one as built
+  }
   return true;
 }
 

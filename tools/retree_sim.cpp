@@ -98,7 +98,14 @@ int main(int argc, char** argv) {
   rtbh_build_bvh(spheres.data(), spheres.size(), 16, ordered.data(), ordered.size(), ref.data(), ref.size(), &nn);
   ref.resize(nn);
   std::vector<rtb_bvh_node> sah;
-  const bool ok = rtb_retree::retree(ref.data(), ref.size(), 60, sah);
+  const int passes = argc > 4 ? atoi(argv[4]) : RTB_RETREE_PASSES;
+  const bool ok = rtb_retree::retree(ref.data(), ref.size(), 60, sah, passes);
+  auto inner_area = [](const std::vector<rtb_bvh_node>& t) {
+    double a = 0;
+    for (const auto& n : t) if (n.first_entity < 0) a += ((double)n.bounds_max[0] - n.bounds_min[0]) * ((double)n.bounds_max[1] - n.bounds_min[1]) + ((double)n.bounds_max[1] - n.bounds_min[1]) * ((double)n.bounds_max[2] - n.bounds_min[2]) + ((double)n.bounds_max[2] - n.bounds_min[2]) * ((double)n.bounds_max[0] - n.bounds_min[0]);
+    return a;
+  };
+  printf("sum of inner areas: reference %.4g, re-built %.4g (passes %d)\n", inner_area(ref), inner_area(sah), passes);
   printf("spheres %zu, reference nodes %zu, retree %s, nodes %zu\n", spheres.size(), ref.size(), ok ? "applied" : "NOT applied", sah.size());
   if (!ok) return 1;
   rtb_view view;
