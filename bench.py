@@ -524,6 +524,7 @@ def run_ours(args):
                 "l2": "256 MB buffer written between timed iterations (inside the bracket, ~0.05 ms) and 191 MB of accumulators per step > 126 MB L2",
                 "outputs": "color + normal + albedo + sampleCountWeight + diagnostics (full job contract)",
                 "arithmetic": "parity build (strict IEEE, FMAs only where written; bit-checked against the CPU restatement); value_fast = the opt-in fast build",
+                "tree": "RTB_OPT_RETREE = 1 (plugin default): the walk's topology is a surface-area-heuristic tree over the host BVH's leaves — same leaf boxes, same candidates, bit-identical frame (checksum equal to the host topology's)",
             },
             "e2e": m["e2e"],
             "value_fast": m.get("value_fast"), "ms_per_step_fast": m.get("ms_per_step_fast"), "fast_vs_parity": m.get("fast_vs_parity"),
