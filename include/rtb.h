@@ -505,7 +505,7 @@ typedef enum rtb_option {
                                  * inner box of the reference's tree is the exact union of its children's (BvhNodeData.cs:205-212)
                                  * and the slab test is monotonic in the box, so a ray that passes a leaf's box passes its whole
                                  * chain: the reference's candidates are the entities of the leaves whose own box is hit, whatever
-                                 * lies above them (csrc/retree.hpp, DESIGN.md 3.1h) — same image bit for bit (config 3: 125.0 ->
+                                 * lies above them (csrc/retree.hpp, DESIGN.md 3.1a) — same image bit for bit (config 3: 125.0 ->
                                  * 115.0 ms), fewer boxes per ray.  2: also worlds with triangles and placed entities (mesh world
                                  * 69.0 -> 63.8 ms, Cornell box 114.5 -> 108.7): their entity tests run in entity space / on edge
                                  * vectors, a hit a few 1e-5 in FRONT of its own box can be pruned or not depending on what the walk

@@ -9,7 +9,7 @@
 // and P's t_exit >= C's: a ray that passes a box passes every box that contains it.  The only exception is 0 * inf = NaN
 // with a FLAT box (mn == mx == o on an axis whose direction component is 0): min / max drop the NaN and the axis stops
 // constraining C while P (mn < o or mx > o there) still sees +-inf.  For boxes with mn < mx on every axis the NaN cases are
-// misses of C itself (worked through in DESIGN.md §3.1h).  Hence, for such worlds,
+// misses of C itself (worked through in DESIGN.md §3.1a).  Hence, for such worlds,
 //     the reference's candidate set  ==  the entities of the leaves whose OWN box is hit,
 // whatever the inner topology.  The device may therefore walk ANY tree over the same leaves (same leaf boxes, same entity
 // ranges) whose inner boxes are unions of what lies below them: every decision the reference makes is reproduced, and
