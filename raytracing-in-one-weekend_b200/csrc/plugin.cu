@@ -444,6 +444,7 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   d.n_triangles = (uint32_t)triangle_count;
   d.n_placed = (uint32_t)placed_count;
   d.has_volumes = has_volumes ? 1u : 0u;
+  d.skip_root_test = out->retreed && d.has_root && d.root_ref >= 0 ? 1u : 0u;
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t off = 0;
