@@ -131,7 +131,7 @@ __device__ __noinline__ bool collect_hits(const int MODE, const SceneView<SMEM>&
   if (!aabb_hit(v3(sd.root_min), v3(sd.root_max), o, inv, &t_enter)) return false;
   int stack[kStackMax + 2];
   int sp = 0;
-  stack[sp++] = sd.root_ref;
+  stack[sp++] = sv.root(sd);
   while (sp > 0) {
     const int cur = stack[--sp];
     if (cur >= 0) {
@@ -274,7 +274,7 @@ __device__ __forceinline__ void gather_hits(const SceneView<SMEM>& sv, const Sce
   int stack[kStackMax + 2];
   int cand[kCandBatch], cand_first[kCandBatch];
   int sp = 0;
-  int cur = sd.root_ref;
+  int cur = sv.root(sd);
   bool have_cur = true;
   int leaf_first = 0, leaf_i = 0, leaf_n = 0;       // the leaf being unpacked into candidates
   const RayPairs rp{pack2(o.x, o.y), pack2(o.z, o.z), pack2(inv.x, inv.y), pack2(inv.z, inv.z)};

@@ -277,6 +277,10 @@ __global__ void __launch_bounds__(mega_block(FLAVOR), RTB_MEGA_MIN_BLOCKS) sampl
     __syncthreads();          // the barrier init is visible before anyone polls it
     mbar_wait(bar, 0);
     sv.bind(blob_smem, a.scene);
+    if (RTB_ABS_REFS) {
+      sv.rebias_inner_refs(a.scene.n_inner, threadIdx.x, blockDim.x);
+      __syncthreads();
+    }
   } else {
     __syncthreads();
     sv.bind(a.scene.blob, a.scene);
