@@ -167,3 +167,37 @@ def test_depth_is_bounded_for_a_degenerate_world(rtb):
     if new is not None:
         _, deepest = _leaves(new)
         assert deepest <= 62
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_candidates_do_not_depend_on_the_topology_random_worlds(rtb, seed):
+    """The same claim on random sphere worlds: overlapping, nested, tiny and huge spheres, negative radii (hollow glass),
+    random BVH depth limits (multi-entity leaves)."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(5, 300))
+    spheres = np.zeros(n, dtype=rtb.abi.SPHERE_DTYPE)
+    spheres["center"] = rng.normal(size=(n, 3)) * rng.choice([1.0, 10.0, 300.0])
+    spheres["radius"] = np.exp(rng.uniform(-4, 3, n)) * rng.choice([1.0, 1.0, 1.0, -1.0], n)
+    if seed % 2:
+        spheres["radius"][0] = 1000.0
+        spheres["center"][0] = (0.0, -1000.0, 0.0)
+    ordered, nodes = rtb.host.build_bvh(spheres, int(rng.integers(1, 20)))
+    new = rtb.plugin.retree_bvh(nodes)
+    if new is None:           # fewer than two non-empty leaves
+        assert sum(1 for x in nodes if x["first_entity"] >= 0 and x["entity_count"] > 0) < 2
+        return
+
+    class S:
+        pass
+    scene = S()
+    scene.spheres = ordered
+    o, d = _rays(scene, nodes, rng, 600)
+    own_ref = _slab_hits(nodes, o, d)
+    chain_ref = _chain_hits(nodes, own_ref)
+    chain_new = _chain_hits(new, _slab_hits(new, o, d))
+    for i, x in enumerate(nodes):
+        if x["first_entity"] >= 0 and x["entity_count"] > 0:
+            k = (int(x["first_entity"]), int(x["entity_count"]))
+            assert np.array_equal(chain_ref[k], own_ref[i]) and np.array_equal(chain_new[k], own_ref[i]), k
+    _, deepest = _leaves(new)
+    assert deepest <= 62
