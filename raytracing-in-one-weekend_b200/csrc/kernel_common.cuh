@@ -28,11 +28,12 @@ using um::f3;
 // path when it does not fit).
 //
 //   inner nodes  : n_inner * kNodeStride B   child boxes stored in the parent, 4 x float4 (+ padding up to the stride):
-//                    q0 = (Lmin.x, Lmin.y, Lmin.z, Lmax.x)
-//                    q1 = (Lmax.y, Lmax.z, Rmin.x, Rmin.y)
-//                    q2 = (Rmin.z, Rmax.x, Rmax.y, Rmax.z)
-//                    q3 = (left_ref, right_ref, -, -) as int32
-//                  ref >= 0: inner node, byte offset of its record (index * kNodeStride);
+//                    q0 = (Lmin.x, Lmin.y, Lmax.x, Lmax.y)   x and y of every corner as an aligned pair, the four z's as two
+//                    q1 = (Rmin.x, Rmin.y, Rmax.x, Rmax.y)   pairs: the operands of the packed slab arithmetic (aabb_range_pair)
+//                    q2 = (Lmin.z, Lmax.z, Rmin.z, Rmax.z)
+//                    q3 = (left_ref, right_ref, media flags, -) as int32
+//                  ref >= 0: inner node, byte offset of its record (index * kNodeStride) — in the copy staged to shared memory
+//                  the parity build turns these into addresses in the shared window once per launch (SceneView::rebias_inner_refs);
 //                  ref < 0: leaf, ~ref = byte offset of its first slot in `spheres` | (count - 1)
 //                  (count - 1 == 15: the count is leaf_count[first slot])
 //                  Entities are named by the byte offset of their slot ("slot" below) everywhere in the kernels.

@@ -239,7 +239,7 @@ class Optimizer {
     }
     return deepest;
   }
-  // depth-first order, root at 0; of two children the one with the larger box first (it is the likelier first visit)
+  // depth-first order, root at 0
   void emit(std::vector<rtb_bvh_node>& out) const {
     out.clear();
     out.reserve(n_);
