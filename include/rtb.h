@@ -507,9 +507,9 @@ typedef enum rtb_option {
                                  * chain: the reference's candidates are the entities of the leaves whose own box is hit, whatever
                                  * lies above them (csrc/retree.hpp) — same image bit for bit (config 3: 125.0 ->
                                  * 115.0 ms), fewer boxes per ray.  2: also worlds with triangles and placed entities (mesh world
-                                 * 69.0 -> 63.8 ms, Cornell box 114.5 -> 108.7): their entity tests run in entity space / on edge
-                                 * vectors, a hit a few 1e-5 in FRONT of its own box can be pruned or not depending on what the walk
-                                 * found first, and 1 path in 1.3e8 came out differently — hence opt-in.  Media worlds always keep the
+                                 * 69.0 -> 63.8 ms, Cornell box 114.5 -> 108.7): oracle parity at test sizes, but 1 path in 1.3e8 came
+                                 * out differently in each: exact ties in distance (entities that share an edge) go to whichever the
+                                 * walk visits first — the reference leaves them to an unstable sort — hence opt-in.  Media worlds always keep the
                                  * host's topology.  0: walk the host's topology.  Takes effect at the next upload; the traversal
                                  * counters of instrumented batches count the walk that ran */
   RTB_OPT_BALANCE_TILES = 8,    /* rtb_multi only. 1 (default): cost-model + kernel-time balanced row tiles; 0: equal row counts */

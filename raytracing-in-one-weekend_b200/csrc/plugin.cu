@@ -387,9 +387,9 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   // on the leaf boxes only; what is walked here is a surface-area-heuristic tree over the same leaves).  Everything below —
   // validation, flattening — sees it as "the host's tree".  retree == 1: worlds of plain spheres, where the pruned walk's
   // result provably does not depend on the visiting order (measured: one frame checksum on configs 3 and 5 with either
-  // tree); 2: every world without media that qualifies — placed entities are intersected in entity space, and a hit a
-  // few 1e-5 in front of its own box (large coordinates, rays leaving a neighbouring surface) can be pruned or not depending
-  // on what was found first: 1 path in 1.3e8 came out differently on the mesh and Cornell worlds.  Media worlds keep the
+  // tree); 2: every world without media that qualifies — 1 path in 1.3e8 came out differently on the mesh and Cornell worlds
+  // (exact ties in distance — two triangles sharing an edge report the same float distance for a ray that lands on it,
+  // tools/tie_probe.py — go to whichever entity the walk visits first; the reference leaves them to an unstable sort).  Media worlds keep the
   // host's topology (coincident medium boundaries: the hit list's order on ties follows the traversal).
   std::vector<rtb_bvh_node> rebuilt;
   out->retreed = false;
