@@ -466,9 +466,25 @@ __device__ __forceinline__ void aabb_range_fast(f3 mn, f3 mx, f3 inv, f3 noi, fl
 //   * fl(x / a) > 0 iff x > 0 (no float underflows when divided by a number in [0.9999, 1.0001]);
 //   * the prune limit best * kPruneMargin stays beyond the hit: fl(x / a) <= x * 1.00011 < x * kPruneMargin.
 // A ray with any other |d|, or one that already holds a hit, divides every candidate as before.
+// Equal distances (two triangles that share an edge report the SAME float distance for a third of the rays that land on it,
+// tools/tie_probe.py): the reference's candidate order and sort decide (FindHitCandidates pops the right child first, FindHits
+// pops candidates from the end and sorts: SampleBatchJob.cs:420-475; the oracle restates the sort as a stable one).  Of two
+// entities at the same distance the one in the LOWER slot wins across leaves and the HIGHER slot inside one leaf (slots are in
+// the reference's depth-first leaf order: plugin.cu; media.cuh: visited_later).  A leaf's entities are tested in ascending
+// order, so with `leaf_first` = the first slot of the leaf under test the newcomer wins a tie iff the holder's slot is not
+// below this leaf.  The triangle flavour applies it — meshes are where ties happen, and there the two extra instructions of an
+// accepted hit cost nothing (mesh world 69.2 -> 68.2 ms) — and its winner then depends neither on the walk's order nor on its
+// tree; so does the per-pixel validation kernel (sample_simple) for every world.  kNoTies (plain comparison, the first entity
+// visited keeps a tie): the megakernel's lean sphere builds, whose worlds' spheres do not intersect, and its placed-entity
+// flavours, which are instruction-fetch bound (Cornell box 114.5 -> 118.4 ms with the rule).
+constexpr int kNoTies = 0x7fffffff;
+__device__ __forceinline__ bool nearer(float t, float best_t, int best_idx, int leaf_first) {
+  return t < best_t || (leaf_first != kNoTies && t == best_t && best_idx >= leaf_first);
+}
+
 template <bool CHAINS, bool DEFER>
 __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int idx, f3 o, f3 d, f3 inv, float a,
-                                           float& best_t, int& best_idx) {
+                                           float& best_t, int& best_idx, const int leaf_first = kNoTies) {
   f3 oc = o + um::mk(-s.x, -s.y, -s.z);
   float b = um::dot(oc, d);
   float oc2 = um::dot(oc, oc);
@@ -490,7 +506,7 @@ __device__ __forceinline__ void sphere_hit(const SceneDesc& sd, float4 s, int id
       t = um::div(t, a);
       if (c > 0.0f && !(t > 0.0f)) t = um::div(-b + sq, a);
     }
-    if (t < best_t && t > 0.0f) {
+    if (nearer(t, best_t, best_idx, leaf_first) && t > 0.0f) {
       if (CHAINS && sd.has_chains && (sd.has_chains == 2u || !chain_guard(a, b, oc2, r2, disc)) && !chain_boxes_hit(sd, idx, o, inv)) return;
       best_t = t;
       best_idx = idx;
@@ -519,9 +535,10 @@ __device__ __forceinline__ bool triangle_uvt(const SceneView<SMEM>& sv, uint32_t
   return !(*t < 0.0f);
 }
 template <bool SMEM>
-__device__ __forceinline__ void triangle_hit(const SceneView<SMEM>& sv, uint32_t tri, int idx, f3 o, f3 d, float& best_t, int& best_idx) {
+__device__ __forceinline__ void triangle_hit(const SceneView<SMEM>& sv, uint32_t tri, int idx, f3 o, f3 d, float& best_t, int& best_idx,
+                                             const int leaf_first) {
   float u, v, t;
-  if (triangle_uvt(sv, tri, o, d, &u, &v, &t) && t < best_t) {
+  if (triangle_uvt(sv, tri, o, d, &u, &v, &t) && nearer(t, best_t, best_idx, leaf_first)) {
     best_t = t;
     best_idx = idx;
   }
@@ -637,10 +654,10 @@ __device__ __noinline__ bool placed_test(const SceneView<SMEM>& sv, uint32_t pid
 }
 template <bool SMEM>
 __device__ __forceinline__ void placed_hit(const SceneView<SMEM>& sv, uint32_t pidx, int idx, f3 o, f3 d, const RayClock& clk,
-                                           float& best_t, int& best_idx) {
+                                           float& best_t, int& best_idx, const int leaf_first) {
   float t;
   f3 n;
-  if (placed_test(sv, pidx, o, d, clk, &t, &n) && t < best_t) {
+  if (placed_test(sv, pidx, o, d, clk, &t, &n) && nearer(t, best_t, best_idx, leaf_first)) {
     best_t = t;
     best_idx = idx;
   }
@@ -730,7 +747,7 @@ __device__ __noinline__ float2 big_leaf_hit(SceneView<SMEM> sv, const SceneDesc&
   return make_float2(best_t, __int_as_float(best_idx));
 }
 
-template <bool SMEM, bool COUNTERS, int FLAVOR>
+template <bool SMEM, bool COUNTERS, int FLAVOR, bool TIES = (FLAVOR == kFlavorGeneral)>
 __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const SceneDesc& sd, f3 o, f3 d,
                                             float& best_t, int& best_idx, WorkCounters& wc, const RayClock& clk) {
   best_t = um::INF;
@@ -755,17 +772,18 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
   int stack[kStackMax];
   stack[0] = kTraversalDone;
   int cur = sv.root(sd);
-  auto test_prim = [&](int slot) {
+  auto test_prim = [&](int slot, int leaf_first) {
     const float4 prim = sv.sphere(slot);
-    if (FLAVOR >= kFlavorPlaced && prim.w != prim.w && __float_as_uint(prim.y) != 0u) placed_hit(sv, __float_as_uint(prim.x), slot, o, d, clk, best_t, best_idx);
-    else if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx);
-    else sphere_hit<(FLAVOR >= kFlavorChains), false>(sd, prim, slot, o, d, inv, a, best_t, best_idx);
+    const int ties = TIES ? leaf_first : kNoTies;
+    if (FLAVOR >= kFlavorPlaced && prim.w != prim.w && __float_as_uint(prim.y) != 0u) placed_hit(sv, __float_as_uint(prim.x), slot, o, d, clk, best_t, best_idx, ties);
+    else if (FLAVOR >= kFlavorGeneral && prim.w != prim.w) triangle_hit(sv, __float_as_uint(prim.x), slot, o, d, best_t, best_idx, ties);
+    else sphere_hit<(FLAVOR >= kFlavorChains), false>(sd, prim, slot, o, d, inv, a, best_t, best_idx, ties);
   };
   auto test_leaf = [&](int ref) {
     const uint32_t code = (uint32_t)~ref;
     const int first = (int)(code & ~15u);
     if ((code & 15u) == 0u) {            // the common leaf: one entity (BvhNodeData.cs:155 splits down to n <= 1)
-      test_prim(first);
+      test_prim(first, first);
       if (COUNTERS) wc.sphere_tests++;
       return;
     }
@@ -781,7 +799,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<SMEM>& sv, const Sce
       }
     }
 #pragma unroll 1
-    for (int i = 0; i < count; i++) test_prim(first + 16 * i);
+    for (int i = 0; i < count; i++) test_prim(first + 16 * i, first);
     if (COUNTERS) wc.sphere_tests += count;
   };
   if (FLAVOR < kFlavorGeneral) {

@@ -385,20 +385,24 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
 
   // Another topology over the host tree's leaves when the world qualifies (retree.hpp: the reference's candidate set depends
   // on the leaf boxes only; what is walked here is a surface-area-heuristic tree over the same leaves).  Everything below —
-  // validation, flattening — sees it as "the host's tree".  retree == 1: worlds of plain spheres, where the pruned walk's
-  // result provably does not depend on the visiting order (measured: one frame checksum on configs 3 and 5 with either
-  // tree); 2: every world without media that qualifies — 1 path in 1.3e8 came out differently on the mesh and Cornell worlds
-  // (exact ties in distance — two triangles sharing an edge report the same float distance for a ray that lands on it,
-  // tools/tie_probe.py — go to whichever entity the walk visits first; the reference leaves them to an unstable sort).  Media worlds keep the
-  // host's topology (coincident medium boundaries: the hit list's order on ties follows the traversal).
+  // validation, flattening — sees it as "the host's tree".  retree == 1: worlds of spheres and triangles, whose frames do not
+  // depend on the topology (measured: one frame checksum with either tree on configs 3, 4, 5 and on the mesh world — the
+  // triangle flavour resolves exact distance ties by the reference's candidate order, kernel_common.cuh: nearer); 2: also
+  // worlds with placed entities, whose flavour leaves a tie to the entity visited first (1 path in 1.3e8 came out differently
+  // on the Cornell box).  Media worlds keep the host's topology (no gain: their walks cannot prune boxes that hold media).
   std::vector<rtb_bvh_node> rebuilt;
+  const rtb_bvh_node* const host_nodes = nodes;     // the reference's topology: its depth-first leaf order is the candidate order
   out->retreed = false;
-  bool plain_spheres = true;
-  for (size_t i = 0; i < entity_count && plain_spheres; i++) plain_spheres = entities[i].type == RTB_ENTITY_SPHERE;
-  if (retree && !has_volumes && (plain_spheres || retree >= 2) && rtb_retree::retree(nodes, node_count, kStackMax - 2, rebuilt)) {
+  bool plain_spheres = true, no_placed = true;
+  for (size_t i = 0; i < entity_count; i++) {
+    plain_spheres = plain_spheres && entities[i].type == RTB_ENTITY_SPHERE;
+    no_placed = no_placed && !Flattener::is_placed_type(entities[i].type);
+  }
+  if (retree && !has_volumes && (no_placed || retree >= 2) && rtb_retree::retree(nodes, node_count, kStackMax - 2, rebuilt)) {
     nodes = rebuilt.data();
     node_count = rebuilt.size();
     out->retreed = true;
+    if (!plain_spheres) collapse_k = 1;              // the tie rule of the triangle / placed flavours needs one slot order (below)
   }
 
   Flattener f{};
@@ -433,6 +437,50 @@ const char* build_blob(const rtb_entity* entities, size_t entity_count, const rt
   if (f.max_depth > (uint32_t)kStackMax) {
     *status = RTB_ERR_UNSUPPORTED;
     return "BVH deeper than 64 levels";
+  }
+  // Slots in the REFERENCE's depth-first leaf order whatever topology was flattened: that order is the reference's candidate
+  // order, which decides between entities at exactly the same distance (kernel_common.cuh: nearer; media.cuh: visited_later).
+  // The flattener laid the slots out in the depth-first order of the tree it was given; for a re-built tree they are permuted
+  // here (a leaf's entities stay together: the reference visits them together too).
+  if (out->retreed && !f.collapsed_any && d.has_root) {
+    std::vector<uint32_t> rank(leaf_list_count, 0xFFFFFFFFu);
+    uint32_t r = 0;
+    std::vector<int32_t> st{0};
+    while (!st.empty()) {
+      const rtb_bvh_node& nd = host_nodes[st.back()];
+      st.pop_back();
+      if (nd.first_entity >= 0) {
+        for (int i = 0; i < nd.entity_count; i++) rank[(size_t)nd.first_entity + i] = r++;
+      } else {
+        st.push_back(nd.right);
+        st.push_back(nd.left);
+      }
+    }
+    const size_t n_slots = f.order.size();
+    bool ok = r == n_slots && f.leaf_count.size() == n_slots && f.chain_ref.size() == n_slots;
+    std::vector<uint32_t> perm(n_slots);
+    for (size_t s = 0; s < n_slots && ok; s++) {
+      const uint32_t h = f.order[s];
+      ok = h != 0xFFFFFFFFu && rank[h] != 0xFFFFFFFFu;
+      if (ok) perm[s] = rank[h];
+    }
+    if (ok) {
+      std::vector<uint32_t> order2(n_slots), count2(n_slots), chain2(n_slots);
+      for (size_t s = 0; s < n_slots; s++) { order2[perm[s]] = f.order[s]; count2[perm[s]] = f.leaf_count[s]; chain2[perm[s]] = f.chain_ref[s]; }
+      f.order.swap(order2); f.leaf_count.swap(count2); f.chain_ref.swap(chain2);
+      auto move_leaf = [&](int32_t ref) {
+        if (ref >= 0) return ref;
+        const uint32_t code = (uint32_t)~ref;
+        return ~(int32_t)((perm[code >> 4] << 4) | (code & 15u));
+      };
+      for (size_t i = 0; i < f.inner.size() / 16; i++) {
+        int32_t c[2];
+        memcpy(c, &f.inner[i * 16 + 12], 8);
+        c[0] = move_leaf(c[0]); c[1] = move_leaf(c[1]);
+        memcpy(&f.inner[i * 16 + 12], c, 8);
+      }
+      d.root_ref = move_leaf(d.root_ref);
+    }
   }
   d.max_depth = f.max_depth;
   d.n_inner = (uint32_t)(f.inner.size() / 16);

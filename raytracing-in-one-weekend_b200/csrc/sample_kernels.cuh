@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(128) sample_simple(const __grid_constant__ Bat
     for (; depth < p.trace_depth; depth++) {
       float t_hit;
       int hit_idx;
-      closest_hit<false, COUNTERS, kFlavorPlaced>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
+      closest_hit<false, COUNTERS, kFlavorPlaced, /*TIES*/ true>(sv, a.scene, ray.o, ray.d, t_hit, hit_idx, wc, clk);
       rays++;
       if (hit_idx >= 0) {
         const float4 sp = sv.sphere(hit_idx);

@@ -1514,3 +1514,72 @@ def test_retree_opt_in_for_the_wider_worlds_keeps_oracle_parity(rtb, oracle, ctx
     finally:
         ctx.set_option(rtb.abi.OPT_RETREE, 1)
     assert_parity(ref, got, exact=False)
+
+
+def _coincident_triangles_scene(rtb, max_bvh_depth):
+    """Every hit on the tilted quad is an EXACT TIE: its two triangles exist twice, at the same vertices, with different albedos.
+    The reference's winner is decided by its candidate order (which leaf is visited later, SampleBatchJob.cs:420-475); the
+    image shows which copy won."""
+    abi, host = rtb.abi, rtb.host
+    materials = np.zeros(4, dtype=abi.MATERIAL_DTYPE)
+    for i, albedo in enumerate([(0.9, 0.1, 0.1), (0.1, 0.9, 0.1), (0.1, 0.1, 0.9), (0.8, 0.8, 0.8)]):
+        materials[i]["type"], materials[i]["albedo"] = abi.MATERIAL_STANDARD, albedo
+    q = [(-3.0, 0.0, -3.0), (3.0, 0.6, -3.0), (3.0, 1.1, 3.0), (-3.0, 0.4, 3.0)]
+    tris = [host.make_triangle(q[0], q[2], q[1], 0), host.make_triangle(q[0], q[3], q[2], 0),
+            host.make_triangle(q[0], q[2], q[1], 1), host.make_triangle(q[0], q[3], q[2], 1),
+            host.make_triangle(q[0], q[2], q[1], 2),                                           # a third copy of one of them
+            host.make_triangle((-1.0, 2.0, -1.0), (1.0, 2.5, 0.0), (0.0, 2.2, 1.0), 3)]        # something else in the tree
+    spheres = np.zeros(1, dtype=abi.SPHERE_DTYPE)
+    spheres[0] = ((0.5, 1.6, 0.3), 0.5, 3, (0, 0, 0))
+    cam = abi.Camera()
+    cam.position[:] = (0.5, 7.0, -6.0)
+    cam.target[:] = (0.0, 0.5, 0.0)
+    cam.aperture = 0.0
+    cam.vertical_fov = 50.0
+    env = abi.Environment()
+    env.sky_type = abi.SKY_GRADIENT
+    env.sky_bottom_color[:] = (1.0, 1.0, 1.0)
+    env.sky_top_color[:] = (0.5, 0.7, 1.0)
+    return host.build_world(spheres, np.array(tris, dtype=abi.TRIANGLE_DTYPE), materials, max_bvh_depth, cam, env, 9.0, name="ties")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [16, 1, 0])
+def test_exact_distance_ties_go_to_the_references_candidate_order(rtb, oracle, ctx, depth):
+    """Coincident triangles of different colours (every hit a tie): the triangle flavour picks the oracle's winner — separate
+    leaves (depth 16), shared leaves (depth 1), one leaf (a linear list) — and the image does not depend on the walk's topology."""
+    scene = _coincident_triangles_scene(rtb, depth)
+    W, H, spp = 96, 54, 8
+    p = rtb.host.make_params(scene, W, H, spp, 12, aperture=0.0)
+    ref = oracle.Buffers(W, H)
+    oracle.sample_batch(scene, p, ref)
+    assert ref.out_albedo.std(axis=0).max() > 0.05          # the quad is in view
+    out = []
+    try:
+        for mode in (0, 1):
+            ctx.set_option(rtb.abi.OPT_RETREE, mode)
+            out.append(render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA))
+            assert_parity(ref, out[-1], exact=False)
+            assert_parity(ref, render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_SIMPLE), exact=True)
+    finally:
+        ctx.set_option(rtb.abi.OPT_RETREE, 1)
+    assert np.array_equal(out[0].out_color, out[1].out_color) and np.array_equal(out[0].out_albedo, out[1].out_albedo)
+
+
+@pytest.mark.gpu
+def test_retree_does_not_change_a_bit_on_the_mesh_world(rtb, ctx):
+    """Spheres + triangles: RTB_OPT_RETREE 0 and 1 (the default applies to this world) give the same words."""
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=16, subdivisions=3)
+    assert rtb.plugin.retree_bvh(scene.nodes) is not None
+    W, H, spp = 640, 360, 16
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.0)
+    out = []
+    try:
+        for mode in (0, 1):
+            ctx.set_option(rtb.abi.OPT_RETREE, mode)
+            out.append(render_gpu(rtb, ctx, scene, p, W, H, rtb.abi.KERNEL_MEGA))
+    finally:
+        ctx.set_option(rtb.abi.OPT_RETREE, 1)
+    a, b = out
+    assert np.array_equal(a.out_color, b.out_color) and np.array_equal(a.out_normal, b.out_normal)
+    assert np.array_equal(a.out_albedo, b.out_albedo) and np.array_equal(a.diagnostics["ray_count"], b.diagnostics["ray_count"])
