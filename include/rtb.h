@@ -498,20 +498,20 @@ typedef enum rtb_option {
                                  * parity build by a few flipped decisions per million paths (tools/fast_math_report.py).  Worlds
                                  * with triangles, placed entities, textures or media, and instrumented batches, keep the parity
                                  * kernels whatever this says. */
-  RTB_OPT_RETREE = 10,          /* 1 (default): worlds of plain spheres without media are walked through a surface-area-heuristic tree
-                                 * built over the LEAVES of the host's BVH (same leaf boxes, same entity ranges; rtb_retree_bvh) instead
-                                 * of the host's topology, when every leaf box has min < max on every axis and every inner box of
-                                 * the host's tree contains its children's.  An
-                                 * inner box of the reference's tree is the exact union of its children's (BvhNodeData.cs:205-212)
-                                 * and the slab test is monotonic in the box, so a ray that passes a leaf's box passes its whole
-                                 * chain: the reference's candidates are the entities of the leaves whose own box is hit, whatever
-                                 * lies above them (csrc/retree.hpp) — same image bit for bit (config 3: 125.0 ->
-                                 * 115.0 ms), fewer boxes per ray.  2: also worlds with triangles and placed entities (mesh world
-                                 * 69.0 -> 63.8 ms, Cornell box 114.5 -> 108.7): oracle parity at test sizes, but 1 path in 1.3e8 came
-                                 * out differently in each: exact ties in distance (entities that share an edge) go to whichever the
-                                 * walk visits first — the reference leaves them to an unstable sort — hence opt-in.  Media worlds always keep the
-                                 * host's topology.  0: walk the host's topology.  Takes effect at the next upload; the traversal
-                                 * counters of instrumented batches count the walk that ran */
+  RTB_OPT_RETREE = 10,          /* 1 (default): worlds of spheres and triangles without media are walked through a surface-area-heuristic
+                                 * tree built over the LEAVES of the host's BVH (same leaf boxes, same entity ranges; rtb_retree_bvh)
+                                 * instead of the host's topology, when every leaf box has min < max on every axis and every inner box
+                                 * of the host's tree contains its children's.  An inner box of the reference's tree is the exact
+                                 * union of its children's (BvhNodeData.cs:205-212) and the slab test is monotonic in the box, so a ray
+                                 * that passes a leaf's box passes its whole chain: the reference's candidates are the entities of the
+                                 * leaves whose own box is hit, whatever lies above them (csrc/retree.hpp) — same
+                                 * image bit for bit, fewer boxes per ray (config 3: 125.0 -> 112.6 ms, mesh world 69.2 -> 61.6).
+                                 * Entities at EXACTLY the same distance (triangles that share an edge) go to the one the reference's
+                                 * candidate order puts first, whatever tree is walked.  2: also worlds with placed entities (Rect,
+                                 * Box, rotated / moving entities): their kernel flavour leaves an exact tie to the entity visited
+                                 * first, so 1 path in 1e8 may come out differently from the host's topology — hence opt-in.  Media
+                                 * worlds always keep the host's topology.  0: walk the host's topology.  Takes effect at the next
+                                 * upload; the traversal counters of instrumented batches count the walk that ran */
   RTB_OPT_BALANCE_TILES = 8,    /* rtb_multi only. 1 (default): cost-model + kernel-time balanced row tiles; 0: equal row counts */
   RTB_OPT_ALWAYS_WALK_CHAINS = 5 /* test knob, 0/1: re-test the host boxes a collapsed leaf skipped for EVERY accepted hit
                                  * instead of only when the hit geometry does not already prove them (same results, slower) */
