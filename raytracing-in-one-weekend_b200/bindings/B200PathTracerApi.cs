@@ -77,6 +77,8 @@ namespace B200PathTracer
 		[DllImport(Lib)] public static extern IntPtr rtb_last_error(IntPtr ctx);
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_scene(IntPtr ctx, RtbSphere* spheres, UIntPtr sphereCount,
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
+		// the topology the device walks under RTB_OPT_RETREE (host-side, no device): same leaves as `nodes`, another tree above them
+		[DllImport(Lib)] public static extern RtbStatus rtb_retree_bvh(RtbBvhNode* nodes, UIntPtr nodeCount, RtbBvhNode* outNodes, UIntPtr capacity, out UIntPtr outCount);
 		[DllImport(Lib)] public static extern RtbStatus rtb_upload_world(IntPtr ctx, RtbEntity* entities, UIntPtr entityCount,
 			RtbSphere* spheres, UIntPtr sphereCount, RtbTriangle* triangles, UIntPtr triangleCount,
 			RtbMaterial* materials, UIntPtr materialCount, RtbBvhNode* nodes, UIntPtr nodeCount);
