@@ -201,3 +201,22 @@ def test_candidates_do_not_depend_on_the_topology_random_worlds(rtb, seed):
             assert np.array_equal(chain_ref[k], own_ref[i]) and np.array_equal(chain_new[k], own_ref[i]), k
     _, deepest = _leaves(new)
     assert deepest <= 62
+
+
+def test_candidates_do_not_depend_on_the_topology_mesh_world(rtb):
+    """The claim is about boxes, whatever the leaves hold: the mesh world (triangles + spheres, some leaves of several entities)."""
+    scene = rtb.host.make_mesh_scene(max_bvh_depth=16, subdivisions=2)
+    new = rtb.plugin.retree_bvh(scene.nodes)
+    assert new is not None
+    rng = np.random.default_rng(23)
+    o, d = _rays(scene, scene.nodes, rng, 800)
+    own_ref = _slab_hits(scene.nodes, o, d)
+    chain_ref = _chain_hits(scene.nodes, own_ref)
+    chain_new = _chain_hits(new, _slab_hits(new, o, d))
+    checked = 0
+    for i, x in enumerate(scene.nodes):
+        if x["first_entity"] >= 0 and x["entity_count"] > 0:
+            k = (int(x["first_entity"]), int(x["entity_count"]))
+            assert np.array_equal(chain_ref[k], own_ref[i]) and np.array_equal(chain_new[k], own_ref[i]), k
+            checked += 1
+    assert checked > 100
