@@ -220,3 +220,27 @@ def test_candidates_do_not_depend_on_the_topology_mesh_world(rtb):
             assert np.array_equal(chain_ref[k], own_ref[i]) and np.array_equal(chain_new[k], own_ref[i]), k
             checked += 1
     assert checked > 100
+
+
+def test_big_world_takes_the_binned_path(rtb):
+    """More leaves than the optimiser takes (65 536): binned splits down to 256 leaves, no optimisation passes — same guarantees."""
+    rng = np.random.default_rng(41)
+    n = 70_000
+    spheres = np.zeros(n, dtype=rtb.abi.SPHERE_DTYPE)
+    spheres["center"] = rng.uniform(-200, 200, (n, 3)) * np.array([1.0, 0.05, 1.0])
+    spheres["radius"] = rng.uniform(0.1, 0.6, n)
+    ordered, nodes = rtb.host.build_bvh(spheres, 20)
+    new = rtb.plugin.retree_bvh(nodes)
+    assert new is not None
+    ref_leaves, _ = _leaves(nodes)
+    new_leaves, deepest = _leaves(new)
+    assert ref_leaves.keys() == new_leaves.keys() and len(new) == 2 * len(new_leaves) - 1 and deepest <= 62
+    inner = new[new["first_entity"] < 0]
+    l, r = new[inner["left"]], new[inner["right"]]
+    assert np.array_equal(inner["bounds_min"], np.minimum(l["bounds_min"], r["bounds_min"]))
+    assert np.array_equal(inner["bounds_max"], np.maximum(l["bounds_max"], r["bounds_max"]))
+
+    def area_sum(t):
+        e = (t["bounds_max"] - t["bounds_min"]).astype(np.float64)[t["first_entity"] < 0]
+        return float((e[:, 0] * e[:, 1] + e[:, 1] * e[:, 2] + e[:, 2] * e[:, 0]).sum())
+    assert area_sum(new) < area_sum(nodes)          # fewer expected visits than the reference's median splits
