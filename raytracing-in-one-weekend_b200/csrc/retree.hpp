@@ -27,7 +27,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "rtb.h"
@@ -75,8 +77,23 @@ class Builder {
       return self;
     }
     size_t mid = split(begin, end, depth);
-    const int32_t l = build(begin, mid, depth + 1);
-    const int32_t r = build(mid, end, depth + 1);
+    int32_t l, r;
+    if (n >= kParallelLeaves && threads_ > 1) {
+      // big subtrees concurrently, each into its own array, spliced in the serial recursion's order (this node, the left
+      // subtree, the right subtree): the same array whatever the thread count.  The two halves of leaves_ are disjoint.
+      std::vector<rtb_bvh_node> lout, rout;
+      Builder lb(ref_, leaves_, depth_limit_, lout, sweep_max_), rb(ref_, leaves_, depth_limit_, rout, sweep_max_);
+      lb.threads_ = threads_ / 2;
+      rb.threads_ = threads_ - lb.threads_;
+      std::thread left_thread([&] { lb.build(begin, mid, depth + 1); });
+      rb.build(mid, end, depth + 1);
+      left_thread.join();
+      l = splice(lout);
+      r = splice(rout);
+    } else {
+      l = build(begin, mid, depth + 1);
+      r = build(mid, end, depth + 1);
+    }
     rtb_bvh_node nd;
     for (int k = 0; k < 3; k++) {
       nd.bounds_min[k] = std::min(out_[l].bounds_min[k], out_[r].bounds_min[k]);
@@ -90,7 +107,18 @@ class Builder {
     return self;
   }
 
+  int threads_ = 1;           // threads this subtree may use
+
  private:
+  static constexpr size_t kParallelLeaves = 32768;
+  int32_t splice(const std::vector<rtb_bvh_node>& sub) {
+    const int32_t base = (int32_t)out_.size();
+    for (rtb_bvh_node nd : sub) {
+      if (nd.first_entity < 0) { nd.left += base; nd.right += base; }
+      out_.push_back(nd);
+    }
+    return base;
+  }
   static int ceil_log2(size_t n) {
     int b = 0;
     while (((size_t)1 << b) < n) b++;
@@ -327,6 +355,13 @@ constexpr size_t kOptimizeMaxLeaves = 1u << 16;   // above this the sweep / binn
 #define RTB_RETREE_PASSES 8
 #endif
 
+// Threads for the re-build of big worlds: RTB_BUILD_THREADS (as the host library's builder), else the hardware's, at most 16.
+inline int build_threads() {
+  if (const char* e = getenv("RTB_BUILD_THREADS")) return std::max(1, atoi(e));
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::min(16u, std::max(1u, hw));
+}
+
 // -> true and `out` (root at 0, depth-first order, leaves = the reference's non-empty leaves) when the world qualifies.
 // depth_limit: the deepest leaf the device walk's stack allows.
 inline bool retree(const rtb_bvh_node* ref, size_t node_count, int depth_limit, std::vector<rtb_bvh_node>& out, int passes = RTB_RETREE_PASSES) {
@@ -368,6 +403,7 @@ inline bool retree(const rtb_bvh_node* ref, size_t node_count, int depth_limit, 
   if (leaves.size() < 2) return false;
   out.reserve(2 * leaves.size());
   Builder b(ref, leaves, depth_limit, out, leaves.size() <= kOptimizeMaxLeaves ? kSweepMax : kSweepMaxBigWorld);
+  b.threads_ = build_threads();
   b.build(0, leaves.size(), 0);
   if (passes > 0 && leaves.size() >= 4 && leaves.size() <= kOptimizeMaxLeaves) {
     Optimizer opt(out);

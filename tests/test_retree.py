@@ -244,3 +244,15 @@ def test_big_world_takes_the_binned_path(rtb):
         e = (t["bounds_max"] - t["bounds_min"]).astype(np.float64)[t["first_entity"] < 0]
         return float((e[:, 0] * e[:, 1] + e[:, 1] * e[:, 2] + e[:, 2] * e[:, 0]).sum())
     assert area_sum(new) < area_sum(nodes)          # fewer expected visits than the reference's median splits
+    # big subtrees are built concurrently and spliced in the serial order: the same array for any thread count
+    import os
+    was = os.environ.get("RTB_BUILD_THREADS")
+    try:
+        for threads in ("1", "3"):
+            os.environ["RTB_BUILD_THREADS"] = threads
+            assert rtb.plugin.retree_bvh(nodes).tobytes() == new.tobytes()
+    finally:
+        if was is None:
+            os.environ.pop("RTB_BUILD_THREADS", None)
+        else:
+            os.environ["RTB_BUILD_THREADS"] = was
