@@ -85,9 +85,15 @@ class Builder {
       Builder lb(ref_, leaves_, depth_limit_, lout, sweep_max_), rb(ref_, leaves_, depth_limit_, rout, sweep_max_);
       lb.threads_ = threads_ / 2;
       rb.threads_ = threads_ - lb.threads_;
-      std::thread left_thread([&] { lb.build(begin, mid, depth + 1); });
+      std::thread left_thread;
+      try {
+        left_thread = std::thread([&] { lb.build(begin, mid, depth + 1); });
+      } catch (...) {                     // no thread to be had: this one does both halves
+        lb.threads_ = 1;
+        lb.build(begin, mid, depth + 1);
+      }
       rb.build(mid, end, depth + 1);
-      left_thread.join();
+      if (left_thread.joinable()) left_thread.join();
       l = splice(lout);
       r = splice(rout);
     } else {
