@@ -1117,110 +1117,6 @@ def test_an_unused_volume_material_does_not_change_the_kernel(rtb, ctx):
     assert a.out_color.tobytes() == b.out_color.tobytes() and a.out_weight.tobytes() == b.out_weight.tobytes()
 
 
-def test_cancellation_token_set_mid_flight(rtb):
-    """CancellationToken (SampleBatchJob.cs:61; Raytracer.cs:189-192 flips it through a raw pointer while the job runs): the
-    batch is ONE launch whether or not a token is passed; the kernel polls the context's mapped flag when a warp claims a tile.
-    A token set from another thread in the middle of a ~120 ms batch ends the call within 5 ms with RTB_ERR_CANCELLED; a live
-    token that is never set costs nothing measurable (same kernel, same launch)."""
-    import threading
-    import time
-
-    abi = rtb.abi
-    W, H, spp = 1920, 1080, 256
-    scene = rtb.host.make_scene("final", max_bvh_depth=16)
-    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
-    c = rtb.plugin.Context(0)
-    try:
-        c.upload(scene)
-        b = rtb.plugin.HostBuffers(W, H, diagnostics=False)
-        c.register_host_buffers(b)
-        c.sample_batch(p, b)                                   # warm-up, and the time of an undisturbed batch
-        t_plain = []
-        for _ in range(2):
-            t = time.perf_counter()
-            c.sample_batch(p, b)
-            t_plain.append(time.perf_counter() - t)
-        cancel = np.zeros(1, np.uint8)
-        t_token = []
-        for _ in range(2):
-            t = time.perf_counter()
-            c.sample_batch(p, b, cancel=cancel)                # live token, never set
-            t_token.append(time.perf_counter() - t)
-        assert min(t_token) <= min(t_plain) * 1.02, (t_token, t_plain)
-        full = min(t_plain)
-        for delay in (0.010, 0.040):
-            cancel[0] = 0
-            set_at = [0.0]
-
-            def fire():
-                time.sleep(delay)
-                set_at[0] = time.perf_counter()
-                cancel[0] = 1
-
-            th = threading.Thread(target=fire)
-            th.start()
-            with pytest.raises(rtb.plugin.RtbError) as e:
-                c.sample_batch(p, b, cancel=cancel)
-            returned = time.perf_counter()
-            th.join()
-            assert e.value.code == abi.RTB_ERR_CANCELLED
-            assert returned - set_at[0] < 0.005, f"cancel took {1e3 * (returned - set_at[0]):.2f} ms"
-            assert returned - set_at[0] + delay < 0.8 * full          # it really stopped early
-        cancel[0] = 0
-        c.sample_batch(p, b, cancel=cancel)                    # and the context is usable afterwards
-        assert b.out_color[:, 3].min() > 0
-    finally:
-        c.close()
-
-
-def test_cancellation_stops_the_kernels_whose_warps_run_in_step(rtb):
-    """The placed-entity and media flavours synchronise their CTA's warps twice per trip and leave the loop by consensus
-    (sample_kernels.cuh: kPhased): a token set mid-flight must still end the batch at once — no warp may wait at a barrier
-    for one that has left —, and the context must render the full frame afterwards.  The media world also reads a status word
-    back after every batch, and the placed world is rendered through PAGEABLE host arrays here (staged copies): neither
-    read-back may keep the calling thread from watching the token while the kernel runs."""
-    import threading
-    import time
-
-    abi = rtb.abi
-    W, H, spp = 1920, 1080, 64
-    for fog in (False, True):
-        scene = rtb.host.make_cornell_scene(max_bvh_depth=16, fog=fog)
-        p = rtb.host.make_params(scene, W, H, spp, 50)
-        c = rtb.plugin.Context(0)
-        try:
-            c.upload(scene)
-            b = rtb.plugin.HostBuffers(W, H, diagnostics=False)
-            if fog:
-                c.register_host_buffers(b)
-            c.sample_batch(p, b)
-            t = time.perf_counter()
-            c.sample_batch(p, b)
-            full = time.perf_counter() - t
-            want = b.out_color.copy()
-            cancel = np.zeros(1, np.uint8)
-            set_at = [0.0]
-
-            def fire():
-                time.sleep(0.25 * full)
-                set_at[0] = time.perf_counter()
-                cancel[0] = 1
-
-            th = threading.Thread(target=fire)
-            th.start()
-            with pytest.raises(rtb.plugin.RtbError) as e:
-                c.sample_batch(p, b, cancel=cancel)
-            returned = time.perf_counter()
-            th.join()
-            assert e.value.code == abi.RTB_ERR_CANCELLED
-            assert returned - set_at[0] < 0.02, f"cancel took {1e3 * (returned - set_at[0]):.2f} ms"
-            cancel[0] = 0
-            c.sample_batch(p, b, cancel=cancel)
-            assert np.array_equal(b.out_color, want)               # same bits as the undisturbed batch
-        finally:
-            c.close()
-
-
 def test_accumulator_range_is_loud(rtb, oracle, ctx):
     """rtb.h "Accumulation range": the megakernel's per-pixel sums are 64-bit fixed point with 32 fraction bits.  Emitters far
     brighter than any display range still add up like the reference's floats (2^20 <= sample < 2^25 takes the one-at-a-time
@@ -1583,3 +1479,109 @@ def test_retree_does_not_change_a_bit_on_the_mesh_world(rtb, ctx):
     a, b = out
     assert np.array_equal(a.out_color, b.out_color) and np.array_equal(a.out_normal, b.out_normal)
     assert np.array_equal(a.out_albedo, b.out_albedo) and np.array_equal(a.diagnostics["ray_count"], b.diagnostics["ray_count"])
+
+
+# ---- mid-flight cancellation, last in the suite: these are the only tests that stop a running 100 ms kernel, and the one
+# place where a run ever ended with a sticky CUDA error — everything else has run by then ----------------------
+def test_cancellation_token_set_mid_flight(rtb):
+    """CancellationToken (SampleBatchJob.cs:61; Raytracer.cs:189-192 flips it through a raw pointer while the job runs): the
+    batch is ONE launch whether or not a token is passed; the kernel polls the context's mapped flag when a warp claims a tile.
+    A token set from another thread in the middle of a ~120 ms batch ends the call within 5 ms with RTB_ERR_CANCELLED; a live
+    token that is never set costs nothing measurable (same kernel, same launch)."""
+    import threading
+    import time
+
+    abi = rtb.abi
+    W, H, spp = 1920, 1080, 256
+    scene = rtb.host.make_scene("final", max_bvh_depth=16)
+    p = rtb.host.make_params(scene, W, H, spp, 50, aperture=0.1)
+    c = rtb.plugin.Context(0)
+    try:
+        c.upload(scene)
+        b = rtb.plugin.HostBuffers(W, H, diagnostics=False)
+        c.register_host_buffers(b)
+        c.sample_batch(p, b)                                   # warm-up, and the time of an undisturbed batch
+        t_plain = []
+        for _ in range(2):
+            t = time.perf_counter()
+            c.sample_batch(p, b)
+            t_plain.append(time.perf_counter() - t)
+        cancel = np.zeros(1, np.uint8)
+        t_token = []
+        for _ in range(2):
+            t = time.perf_counter()
+            c.sample_batch(p, b, cancel=cancel)                # live token, never set
+            t_token.append(time.perf_counter() - t)
+        assert min(t_token) <= min(t_plain) * 1.02, (t_token, t_plain)
+        full = min(t_plain)
+        for delay in (0.010, 0.040):
+            cancel[0] = 0
+            set_at = [0.0]
+
+            def fire():
+                time.sleep(delay)
+                set_at[0] = time.perf_counter()
+                cancel[0] = 1
+
+            th = threading.Thread(target=fire)
+            th.start()
+            with pytest.raises(rtb.plugin.RtbError) as e:
+                c.sample_batch(p, b, cancel=cancel)
+            returned = time.perf_counter()
+            th.join()
+            assert e.value.code == abi.RTB_ERR_CANCELLED
+            assert returned - set_at[0] < 0.005, f"cancel took {1e3 * (returned - set_at[0]):.2f} ms"
+            assert returned - set_at[0] + delay < 0.8 * full          # it really stopped early
+        cancel[0] = 0
+        c.sample_batch(p, b, cancel=cancel)                    # and the context is usable afterwards
+        assert b.out_color[:, 3].min() > 0
+    finally:
+        c.close()
+
+
+def test_cancellation_stops_the_kernels_whose_warps_run_in_step(rtb):
+    """The placed-entity and media flavours synchronise their CTA's warps twice per trip and leave the loop by consensus
+    (sample_kernels.cuh: kPhased): a token set mid-flight must still end the batch at once — no warp may wait at a barrier
+    for one that has left —, and the context must render the full frame afterwards.  The media world also reads a status word
+    back after every batch, and the placed world is rendered through PAGEABLE host arrays here (staged copies): neither
+    read-back may keep the calling thread from watching the token while the kernel runs."""
+    import threading
+    import time
+
+    abi = rtb.abi
+    W, H, spp = 1920, 1080, 64
+    for fog in (False, True):
+        scene = rtb.host.make_cornell_scene(max_bvh_depth=16, fog=fog)
+        p = rtb.host.make_params(scene, W, H, spp, 50)
+        c = rtb.plugin.Context(0)
+        try:
+            c.upload(scene)
+            b = rtb.plugin.HostBuffers(W, H, diagnostics=False)
+            if fog:
+                c.register_host_buffers(b)
+            c.sample_batch(p, b)
+            t = time.perf_counter()
+            c.sample_batch(p, b)
+            full = time.perf_counter() - t
+            want = b.out_color.copy()
+            cancel = np.zeros(1, np.uint8)
+            set_at = [0.0]
+
+            def fire():
+                time.sleep(0.25 * full)
+                set_at[0] = time.perf_counter()
+                cancel[0] = 1
+
+            th = threading.Thread(target=fire)
+            th.start()
+            with pytest.raises(rtb.plugin.RtbError) as e:
+                c.sample_batch(p, b, cancel=cancel)
+            returned = time.perf_counter()
+            th.join()
+            assert e.value.code == abi.RTB_ERR_CANCELLED
+            assert returned - set_at[0] < 0.02, f"cancel took {1e3 * (returned - set_at[0]):.2f} ms"
+            cancel[0] = 0
+            c.sample_batch(p, b, cancel=cancel)
+            assert np.array_equal(b.out_color, want)               # same bits as the undisturbed batch
+        finally:
+            c.close()
